@@ -1,0 +1,241 @@
+/*
+ * sdfr.h - C ABI of libsdfr.so, the B200 (sm_100a) implementation of the
+ * sdflabel differentiable SDF render / refine hot path.
+ *
+ * The reference (TRI-ML/sdflabel) has no FFI: its boundary is the Python object
+ * surface used by pipelines/optimizer.py and pipelines/refine_css.py
+ * (SURVEY.md section 8(b)).  Each entry point below replaces one of those
+ * Python-level operations; the citation after "replaces:" is the reference
+ * file:line.  The Python mirror classes in sdflabel_b200/ bind these symbols
+ * with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *  - every pointer named *_dev is a device pointer borrowed from the caller
+ *    (e.g. a torch tensor's data_ptr()); *_host pointers are host memory;
+ *  - the caller owns all memory except the opaque handles;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *  - every function returns 0 on success, a negative SDFR_E_* code otherwise;
+ *    sdfr_last_error() returns a thread-local message for the last failure;
+ *  - handles are thread-compatible, not thread-safe;
+ *  - nothing here ever falls back to the CPU: without a CUDA device the calls
+ *    fail with SDFR_E_CUDA.
+ */
+#ifndef SDFR_H_
+#define SDFR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFR_VERSION 100 /* 0.1.0 */
+
+enum {
+  SDFR_OK = 0,
+  SDFR_E_INVALID = -1,     /* bad argument */
+  SDFR_E_CUDA = -2,        /* CUDA runtime error (message has the detail) */
+  SDFR_E_UNSUPPORTED = -3, /* network spec outside what the kernels cover */
+  SDFR_E_CAPACITY = -4     /* a fixed-capacity buffer would overflow */
+};
+
+/* MLP kernel selection */
+enum {
+  SDFR_MLP_AUTO = 0,    /* tcgen05 kernel when the spec qualifies, else FFMA */
+  SDFR_MLP_FFMA = 1,    /* fp32 CUDA-core kernel (any supported spec) */
+  SDFR_MLP_TCGEN05 = 2  /* tensor-core kernel: fp16 hi/lo split operands, fp32 accumulate in TMEM */
+};
+
+enum { SDFR_ROT_DCM = 0, SDFR_ROT_QUAT = 1 };
+
+int sdfr_version(void);
+const char* sdfr_last_error(void);
+/* bit 0: a CUDA device is visible; bit 1: that device is sm_100 (tcgen05 path usable) */
+int sdfr_caps(void);
+
+/* ------------------------------------------------------------------------- *
+ * DeepSDF decoder.
+ * replaces: sdfrenderer/deepsdf/networks/deep_sdf_decoder_scale.py:10-114 (Decoder)
+ *           sdfrenderer/deepsdf/workspace.py:167-188 (setup_dsdf: the Python
+ *           side parses the .json/.pt and hands the folded weights over here)
+ * ------------------------------------------------------------------------- */
+typedef struct sdfr_decoder sdfr_decoder;
+
+typedef struct {
+  int32_t latent_size;      /* L */
+  int32_t num_layers;       /* number of Linear layers (stock: 9) */
+  const int32_t* in_dims;   /* [num_layers] fan-in of each Linear (after any concat) */
+  const int32_t* out_dims;  /* [num_layers] fan-out */
+  const int32_t* concat;    /* [num_layers] 0 none, 1 = cat[x, input] before this layer
+                               (latent_in, decoder.py:90-91), 2 = cat[x, xyz] (xyz_in_all, 92-93) */
+  const int32_t* layer_norm;/* [num_layers] 1 = LayerNorm(out) after the Linear (decoder.py:99-101) */
+  int32_t use_tanh;         /* extra tanh on the last Linear (decoder.py:96-97); the final
+                               tanh (decoder.py:106-107) is always applied */
+} sdfr_decoder_spec;
+
+/* weights_host[l]: row-major [out][in] effective weight (weight_norm already folded:
+ * W = g * v / ||v||_row, torch weight_norm dim=0); bias_host[l]: [out];
+ * ln_weight_host[l] / ln_bias_host[l]: [out] or NULL. */
+int sdfr_decoder_create(const sdfr_decoder_spec* spec, const float* const* weights_host,
+                        const float* const* bias_host, const float* const* ln_weight_host,
+                        const float* const* ln_bias_host, sdfr_decoder** out);
+void sdfr_decoder_destroy(sdfr_decoder* dec);
+/* 1 when the tcgen05 kernel covers this spec (all widths <= 512, no LayerNorm) */
+int sdfr_decoder_tcgen05_ok(const sdfr_decoder* dec);
+
+/* sdf[n] = Decoder(inputs[n, L+3]); if dinput_dev != NULL also the exact
+ * gradient d sdf[n] / d inputs[n, :] (what the reference obtains with
+ * pred_sdf_grid.sum().backward(), grid.py:55-56).
+ * replaces: Decoder.forward (deep_sdf_decoder_scale.py:78-114). */
+int sdfr_decoder_eval(sdfr_decoder* dec, const float* inputs_dev, int64_t n, float* sdf_dev,
+                      float* dinput_dev, int impl, void* stream);
+
+/* Same over the implicit Grid3D lattice: point k of detection b is lattice
+ * point k (grid.py:22-41) with latent latent_unit_dev[b, :]; no HBM traffic for
+ * the inputs.  sdf_dev: [batch, D^3]; dinput_dev: [batch, D^3, L+3] or NULL.
+ * replaces: optimizer.py:99-104 (inputs = cat[latent.expand, grid.points]; dsdf(inputs)). */
+int sdfr_decoder_eval_lattice(sdfr_decoder* dec, const float* latent_unit_dev, int batch, int density,
+                              float* sdf_dev, float* dinput_dev, int impl, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Grid3D.
+ * replaces: sdfrenderer/grid.py:18-41 (lattice) and 43-71 (get_surface_points)
+ * ------------------------------------------------------------------------- */
+/* points_dev: [D^3, 3], bit-identical to Grid3D.generate_point_grid */
+int sdfr_lattice_points(int density, float* points_dev, void* stream);
+
+/* Zero-isosurface projection + band select, order preserving (ascending index).
+ * points_dev [n,3] (NULL = implicit lattice of `density`), sdf_dev [n], grad_dev
+ * [n, grad_stride] with the xyz gradient at columns grad_col..grad_col+2.
+ * Outputs (capacity n rows each): out_pts [m,3] = p - sdf*n_hat, out_nrm [m,3],
+ * out_idx [m] source index; *out_count_dev = m.  scratch_dev: >= (n/1024+2) int32.
+ * replaces: Grid3D.get_surface_points (grid.py:43-71). */
+int sdfr_surface_extract(const float* points_dev, int density, const float* sdf_dev, const float* grad_dev,
+                         int grad_stride, int grad_col, int64_t n, float threshold, float* out_pts_dev,
+                         float* out_nrm_dev, int32_t* out_idx_dev, int32_t* out_count_dev,
+                         int32_t* scratch_dev, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Rasterer (disc / surfel primitive).
+ * replaces: sdfrenderer/renderer/rasterer.py:49-155 (forward, primitives='disc'),
+ *           renderer/projection.py:7-101 (dcm) and 104-199 (quat),
+ *           renderer/primitives.py:165-243 (inside_surfel),
+ *           renderer/utils_rasterer.py:6-24 (qrot)
+ * ------------------------------------------------------------------------- */
+typedef struct {
+  int32_t width, height;   /* resolution_px = (W, H) */
+  float kinv[9];           /* row-major K^-1 (inverted in fp32, primitives.py:204) */
+  float k[9];              /* row-major K (surfel bounding boxes, points_2d) */
+  int32_t rot;             /* SDFR_ROT_DCM: pose = 4x4 row-major (first 3 rows used)
+                              SDFR_ROT_QUAT: pose = [qw,qx,qy,qz,tx,ty,tz] */
+  int32_t output_nocs;     /* 1: colours = object coords (x negated in the dcm path) shown as (c+1)/2;
+                              0: colours = the given colour tensor, unscaled (rasterer.py:113-116) */
+} sdfr_raster_cfg;
+
+/* Workspace sizes (bytes) for m surfels at the configured resolution. */
+int64_t sdfr_splat_workspace_bytes(const sdfr_raster_cfg* cfg, int64_t m);
+
+/* Forward.  coords/normals/colors: [m,3]; pose: 16 or 7 floats (device).
+ * Outputs: color [3,H,W], mask [1,H,W], depth [1,H,W], normals [3,H,W] (any may
+ * be NULL), cam_pts [m,3] (points['xyz']), cam_rgb [m,3] (points['rgb']),
+ * front flags [m] (uint8, n.v < 0; all ones for quat), and the compacted
+ * front-facing lists xyzf/rgbf [<=m,3] with *front_count_dev (dcm only; NULL ok).
+ * workspace_dev keeps per-surfel / per-pixel state for the backward call. */
+int sdfr_splat_forward(const sdfr_raster_cfg* cfg, const float* coords_dev, const float* normals_dev,
+                       const float* colors_dev, const float* pose_dev, int64_t m, float* color_dev,
+                       float* mask_dev, float* depth_dev, float* nrm_map_dev, float* cam_pts_dev,
+                       float* cam_rgb_dev, uint8_t* front_dev, float* xyzf_dev, float* rgbf_dev,
+                       int32_t* front_count_dev, void* workspace_dev, void* stream);
+
+/* Backward.  Upstream gradients of the four maps (NULL = zero) and of the
+ * per-surfel outputs cam_pts / cam_rgb (NULL = zero; gradients of the xyzf/rgbf
+ * lists must be scattered into these by the caller).  Produces d coords [m,3],
+ * d normals [m,3], d colors [m,3] (only when output_nocs == 0, else NULL) and
+ * d pose (12 floats = rows of [R|t] for dcm, 7 for quat). */
+int sdfr_splat_backward(const sdfr_raster_cfg* cfg, const float* coords_dev, const float* normals_dev,
+                        const float* colors_dev, const float* pose_dev, int64_t m, const float* g_color_dev,
+                        const float* g_mask_dev, const float* g_depth_dev, const float* g_nrm_map_dev,
+                        const float* g_cam_pts_dev, const float* g_cam_rgb_dev, float* d_coords_dev,
+                        float* d_normals_dev, float* d_colors_dev, float* d_pose_dev, void* workspace_dev,
+                        void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Losses (value + gradient in one call).
+ * replaces: pipelines/optimizer.py:166-198 (compute_loss_3d; exact 1-NN on the
+ *           device instead of the sklearn KD-tree + D2H) and 200-237 (compute_loss_2d)
+ * ------------------------------------------------------------------------- */
+/* xyzf [q,3] query points; lidar_scaled [nl,3] (= lidar / scale); radius =
+ * 0.2/scale.  loss_dev[0] = mean ||L_nn - v|| over pairs with NN distance <
+ * radius (0 if none), loss_dev[1] = pair count.  d_xyzf [q,3] and d_lidar
+ * [nl,3] receive d loss (either may be NULL). */
+int sdfr_loss3d(const float* xyzf_dev, int64_t q, const float* lidar_scaled_dev, int64_t nl, double radius,
+                float* loss_dev, float* d_xyzf_dev, float* d_lidar_dev, void* stream);
+
+/* color, target: [3,H,W]; loss_dev[0] = loss (NaN when no pixel passes the
+ * threshold, exactly like the reference), loss_dev[1] = selected pixel count;
+ * d_color [3,H,W] = d loss / d color. */
+int sdfr_loss2d(const float* color_dev, const float* target_dev, int height, int width, float* loss_dev,
+                float* d_color_dev, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fused refine engine: the whole Optimizer.optimize loop on the device, all
+ * detections of a batch per launch, no host synchronisation inside the loop.
+ * replaces: pipelines/optimizer.py:26-54 (parameter groups, Adam + SGD) and
+ *           56-164 (optimize), utils/refinement.py:108-125 (rot_from_yaw)
+ * ------------------------------------------------------------------------- */
+typedef struct sdfr_refine sdfr_refine;
+
+typedef struct {
+  int32_t batch;        /* detections refined together */
+  int32_t density;      /* Grid3D density D (config_refine.ini:11) */
+  int32_t max_width;    /* crop capacity in pixels */
+  int32_t max_height;
+  int32_t max_lidar;    /* LIDAR points capacity per detection */
+  int32_t max_iters;    /* loss-history capacity */
+  float weight_2d;      /* config_refine.ini:26 */
+  float weight_3d;      /* config_refine.ini:27 */
+  int32_t mlp_impl;     /* SDFR_MLP_* */
+} sdfr_refine_cfg;
+
+int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg, sdfr_refine** out);
+void sdfr_refine_destroy(sdfr_refine* r);
+
+/* Host-side inputs of detection b (copied host->device asynchronously on
+ * `stream`; the host buffers must stay valid until the stream has run the copy).
+ * k_host: 3x3 row-major intrinsics of the crop; kinv_host: its fp32 inverse as
+ * the caller computed it (K.float().inverse(), primitives.py:204) or NULL to
+ * invert here; nocs_host: [3,th,tw] CSS NOCS
+ * prediction (nearest-resized to the crop on the device, optimizer.py:135-137);
+ * lidar_host: [n_lidar,3] un-scaled LIDAR crop (optimizer.py:84); the initial
+ * parameters follow get_opt_params (optimizer.py:26-40). */
+int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_host, const float* kinv_host, int width,
+                              int height, const float* nocs_host, int th, int tw, const float* lidar_host,
+                              int n_lidar, const float* yaw_host, const float* trans_host,
+                              const float* scale_host, const float* latent_host, void* stream);
+
+/* Enqueue `iters` iterations for all detections. */
+int sdfr_refine_run(sdfr_refine* r, int iters, void* stream);
+
+/* Synchronises `stream` and reads detection b back: params_host =
+ * [yaw, tx, ty, tz, scale, latent(L)]; history_host (may be NULL): per executed
+ * iteration [loss_2d, loss_3d, total, skipped] (4 floats), *n_history rows. */
+int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_host, int* n_history,
+                    void* stream);
+
+/* Device views of the last iteration's intermediates of detection b (for
+ * parity tests and label dumps): kind 0 sdf [D^3], 1 dinput [D^3,L+3],
+ * 2 surfel points [m,3], 3 surfel normals [m,3], 4 color [3,H,W], 5 mask,
+ * 6 normals map [3,H,W], 7 grads [dyaw,dt3,dscale,dlatent_unit(L),dlatent(L)],
+ * 8 surfel count (int32), 9 depth, 10 camera-space surfel centres [m,3],
+ * 11 front-facing flags [m] (uint8).  Returns the device pointer and element count. */
+int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev, int64_t* count);
+/* Asynchronous device-to-device copy of such a view into dst_dev (at most max_count elements). */
+int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_dev, int64_t max_count, void* stream);
+
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t sdfr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFR_H_ */

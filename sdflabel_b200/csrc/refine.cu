@@ -1,0 +1,643 @@
+// Fused refine engine: the whole Optimizer.optimize loop on the device.
+//
+// replaces: pipelines/optimizer.py:26-54 (parameter groups; Adam on yaw/trans,
+//           SGD on scale/latent) and 56-164 (the loop body), with
+//           utils/refinement.py:108-125 (rot_from_yaw) folded into the pose kernel.
+//
+// One iteration = 12 launches, no host synchronisation, all detections of the
+// batch per launch (blockIdx.y / blockIdx.z = detection):
+//   begin -> MLP lattice eval (sdf + d sdf/d[latent,x]) -> band count/scatter ->
+//   project -> splat forward -> 2D loss pixels -> 3D loss pairs -> pixel-gradient
+//   records -> splat backward -> chain to (R, t, latent_unit, scale) partials -> update.
+// Every reduction is an ordered two-level sum, so a run is bit-reproducible.
+#include <algorithm>
+#include <cstddef>
+#include <cstring>
+
+#include "loss.cuh"
+
+namespace sdfr {
+
+namespace {
+
+constexpr int kMaxLatent = 256;
+
+struct DetState {
+  int width, height, n_lidar, target_ready;
+  float yaw, trans[3], scale;
+  float adam_m[4], adam_v[4];
+  int adam_t;
+  int iter;                 // history rows written
+  float pose[16];           // render pose, row-major 4x4
+  float loss2d, loss3d, n2, n3;
+  int front_count, skip_reason;
+};
+
+struct EngineDev {          // passed by value to the engine kernels
+  int batch, L, in0;
+  long long ng;             // lattice points per detection
+  long long cap;            // surfel capacity per detection (= ng)
+  int max_pixels, max_lidar, max_iters;
+  float w2d, w3d;
+  int nb2, nb3, nbc;        // partial-sum blocks per detection
+  DetState* det;            // [B]
+  float* latent;            // [B,L]
+  float* latent_unit;       // [B,L]
+  float* sdf;               // [B,ng]
+  float* dinput;            // [B,ng,in0]
+  float* surf_pts;          // [B,cap,3]
+  float* surf_nrm;          // [B,cap,3]
+  float* surf_glat;         // [B,cap,L]
+  int* surf_idx;            // [B,cap]
+  int* surf_count;          // [B]
+  int* scan_scratch;
+  float* target;            // [B,3,max_pixels]
+  float* lidar;             // [B,max_lidar,3]
+  float* l3rec;             // [B,cap,4] unit direction, distance (-1 = unused)
+  float* l3dot;             // [B,cap]   u . L_nn
+  float* l2rec;             // [B,max_pixels,4]
+  double* part2;            // [B,nb2,3]
+  double* part3;            // [B,nb3,3]  sum, close count, front count
+  float* partc;             // [B,nbc,16+L]
+  float* history;           // [B,max_iters,4]
+  float* grads;             // [B,5+2L]
+  SplatView* views;         // [B]
+};
+
+// ---- iteration begin: pose + unit latent (optimizer.py:87-96) ----------------------
+__global__ void iter_begin_kernel(EngineDev E) {
+  const int b = blockIdx.x;
+  DetState& D = E.det[b];
+  if (threadIdx.x == 0) {
+    const float c = cosf(D.yaw), s = sinf(D.yaw);
+    float* P = D.pose;
+    // rot_from_yaw (refinement.py:124) with row 1 negated (optimizer.py:89), then translation (:90)
+    P[0] = c;    P[1] = 0.f;   P[2] = s;   P[3] = D.trans[0];
+    P[4] = -0.f; P[5] = -1.f;  P[6] = -0.f; P[7] = D.trans[1];
+    P[8] = -s;   P[9] = 0.f;   P[10] = c;  P[11] = D.trans[2];
+    P[12] = 0.f; P[13] = 0.f;  P[14] = 0.f; P[15] = 1.f;
+    // F.normalize(latent, p=2, dim=0), eps 1e-12 (optimizer.py:96)
+    float n2 = 0.f;
+    for (int k = 0; k < E.L; ++k) n2 += E.latent[b * E.L + k] * E.latent[b * E.L + k];
+    const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+    for (int k = 0; k < E.L; ++k) E.latent_unit[b * E.L + k] = E.latent[b * E.L + k] / nrm;
+  }
+}
+
+// ---- nearest resize of the CSS NOCS prediction to the crop (optimizer.py:135-137) ----
+__global__ void resize_target_kernel(const float* __restrict__ src, int th, int tw, float* __restrict__ dst, int H,
+                                     int W, int plane_stride) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H * W) return;
+  const int h = j / W, w = j - h * W;
+  const float sh = (float)th / (float)H, sw = (float)tw / (float)W;
+  const int ih = min((int)floorf((float)h * sh), th - 1), iw = min((int)floorf((float)w * sw), tw - 1);
+  for (int c = 0; c < 3; ++c) dst[c * plane_stride + j] = src[(c * th + ih) * tw + iw];
+}
+
+// ---- 2D loss: per rendered pixel (optimizer.py:200-237) --------------------------------
+constexpr int LB = 256;
+
+__global__ void __launch_bounds__(LB) loss2d_batch_kernel(EngineDev E) {
+  __shared__ double s_sum[LB / 32], s_hw[LB / 32];
+  __shared__ int s_cnt[LB / 32];
+  const int b = blockIdx.y;
+  const DetState& D = E.det[b];
+  const SplatView& V = E.views[b];
+  const int H = D.height, W = D.width, P = H * W;
+  const int j = blockIdx.x * LB + threadIdx.x;
+  double sum = 0.0, hw = 0.0;
+  int cnt = 0;
+  if (j < P) {
+    const float c0 = V.color[j], c1 = V.color[P + j], c2 = V.color[2 * P + j];
+    float4 r = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (c0 + c1 + c2 != 0.f) {
+      const int h = j / W, w = j - h * W;
+      hw = (double)(h + w);
+      float k0, k1, k2;
+      const float* T = E.target + (size_t)b * 3 * E.max_pixels;
+      // target planes are packed with stride P for this detection
+      const float d = loss2d_pixel(T, H, W, h, w, c0, c1, c2, k0, k1, k2);
+      if (d < kNocsThr) {
+        cnt = 1;
+        sum = (double)d;
+        if (d > 0.f) r = make_float4((c0 - k0) / d, (c1 - k1) / d, (c2 - k2) / d, d);
+        else r.w = d;
+      }
+    }
+    *reinterpret_cast<float4*>(E.l2rec + ((size_t)b * E.max_pixels + j) * 4) = r;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    hw += __shfl_xor_sync(0xffffffffu, hw, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_hw[threadIdx.x >> 5] = hw; s_cnt[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, th = 0.0;
+    int tc = 0;
+    for (int w = 0; w < LB / 32; ++w) { ts += s_sum[w]; th += s_hw[w]; tc += s_cnt[w]; }
+    double* o = E.part2 + ((size_t)b * E.nb2 + blockIdx.x) * 3;
+    o[0] = ts; o[1] = (double)tc; o[2] = th;
+  }
+}
+
+// ---- 3D loss: exact NN of every front-facing surfel in lidar/scale (optimizer.py:84,166-198) ----
+constexpr int STAGE = 1024;
+
+__global__ void __launch_bounds__(LB) loss3d_batch_kernel(EngineDev E) {
+  __shared__ float s_pts[STAGE * 3];
+  __shared__ double s_sum[LB / 32];
+  __shared__ int s_cnt[LB / 32], s_front[LB / 32];
+  const int b = blockIdx.y;
+  const DetState& D = E.det[b];
+  const SplatView& V = E.views[b];
+  const int m = min(E.surf_count[b], (int)E.cap);
+  if ((int)(blockIdx.x * LB) >= m) return;   // partials of these blocks are never read
+  const int i = blockIdx.x * LB + threadIdx.x;
+  const bool live = i < m && V.front[i];
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) { qx = V.cam_v[i * 3]; qy = V.cam_v[i * 3 + 1]; qz = V.cam_v[i * 3 + 2]; }
+  const float scale = D.scale;
+  const float* lidar = E.lidar + (size_t)b * E.max_lidar * 3;
+  double best = INFINITY;
+  int bi = -1;
+  for (int base = 0; base < D.n_lidar; base += STAGE) {
+    const int n = min(STAGE, D.n_lidar - base);
+    for (int k = threadIdx.x; k < n * 3; k += LB) s_pts[k] = lidar[base * 3 + k] / scale;   // optimizer.py:84
+    __syncthreads();
+    if (live) nn_scan(s_pts, n, base, qx, qy, qz, best, bi);
+    __syncthreads();
+  }
+  float dist = -1.f, ux = 0.f, uy = 0.f, uz = 0.f, dot = 0.f;
+  int close = 0;
+  const double radius = 0.2 / (double)scale;                       // optimizer.py:188
+  if (live && bi >= 0 && sqrt(best) < radius) {
+    close = 1;
+    const float lx = lidar[bi * 3] / scale, ly = lidar[bi * 3 + 1] / scale, lz = lidar[bi * 3 + 2] / scale;
+    const float ex = lx - qx, ey = ly - qy, ez = lz - qz;
+    dist = sqrtf(ex * ex + ey * ey + ez * ez);                      // optimizer.py:189
+    if (dist > 0.f) { ux = ex / dist; uy = ey / dist; uz = ez / dist; }
+    dot = ux * lx + uy * ly + uz * lz;
+  }
+  if (i < m) {
+    *reinterpret_cast<float4*>(E.l3rec + ((size_t)b * E.cap + i) * 4) = make_float4(ux, uy, uz, dist);
+    E.l3dot[(size_t)b * E.cap + i] = dot;
+  }
+  double s = close ? (double)dist : 0.0;
+  int c = close, f = live ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    f += __shfl_xor_sync(0xffffffffu, f, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = s; s_cnt[threadIdx.x >> 5] = c; s_front[threadIdx.x >> 5] = f; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0;
+    int tc = 0, tf = 0;
+    for (int w = 0; w < LB / 32; ++w) { ts += s_sum[w]; tc += s_cnt[w]; tf += s_front[w]; }
+    double* o = E.part3 + ((size_t)b * E.nb3 + blockIdx.x) * 3;
+    o[0] = ts; o[1] = (double)tc; o[2] = (double)tf;
+  }
+}
+
+// ---- per-pixel gradient records for the surfel gather -------------------------------------
+__global__ void __launch_bounds__(LB) grad_prep_kernel(EngineDev E) {
+  __shared__ float s_scale;
+  const int b = blockIdx.y;
+  DetState& D = E.det[b];
+  const SplatView& V = E.views[b];
+  const int P = D.width * D.height;
+  if (threadIdx.x == 0) {
+    const int nb = (P + LB - 1) / LB;
+    double s = 0.0, c = 0.0, hw = 0.0;
+    const double* p = E.part2 + (size_t)b * E.nb2 * 3;
+    for (int k = 0; k < nb; ++k) { s += p[k * 3]; c += p[k * 3 + 1]; hw += p[k * 3 + 2]; }
+    float loss, n;
+    if (hw == 0.0) { loss = 0.f; n = 0.f; }                         // optimizer.py:214 quirk
+    else { n = (float)c; loss = c > 0.0 ? (float)(s / c) : __int_as_float(0x7fc00000); }
+    s_scale = n > 0.f ? E.w2d / n : 0.f;
+    if (blockIdx.x == 0) { D.loss2d = loss; D.n2 = n; }
+  }
+  __syncthreads();
+  const int j = blockIdx.x * LB + threadIdx.x;
+  if (j >= P) return;
+  const float sc = s_scale;
+  const float4 r = *reinterpret_cast<const float4*>(E.l2rec + ((size_t)b * E.max_pixels + j) * 4);
+  const float* raw = V.pix_raw + (size_t)j * 8;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+  if (r.w >= 0.f) {
+    g0 = raw[0] <= 1.f ? r.x * sc : 0.f;
+    g1 = raw[1] <= 1.f ? r.y * sc : 0.f;
+    g2 = raw[2] <= 1.f ? r.z * sc : 0.f;
+  }
+  const float G = raw[0] * g0 + raw[1] * g1 + raw[2] * g2;
+  float* o = V.pix_grad + (size_t)j * 12;
+  *reinterpret_cast<float4*>(o) = make_float4(g0, g1, g2, 0.f);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(o + 8) = make_float4(G, 0.f, 0.f, 0.f);
+}
+
+// ---- chain surfel gradients to (t, R, scale, latent_unit) block partials --------------------
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < LB / 32; ++w) t += s_red[w];
+  return t;   // valid on thread 0
+}
+
+__global__ void __launch_bounds__(LB) chain_kernel(EngineDev E) {
+  __shared__ float s_red[LB / 32];
+  __shared__ float s_l3scale;
+  const int b = blockIdx.y;
+  DetState& D = E.det[b];
+  const SplatView& V = E.views[b];
+  const int m = min(E.surf_count[b], (int)E.cap);
+  if (blockIdx.x > 0 && (int)(blockIdx.x * LB) >= m) return;   // block 0 always publishes the loss
+  if (threadIdx.x == 0) {
+    const int nb = (m + LB - 1) / LB;
+    double s = 0.0, c = 0.0, f = 0.0;
+    const double* p = E.part3 + (size_t)b * E.nb3 * 3;
+    for (int k = 0; k < nb; ++k) { s += p[k * 3]; c += p[k * 3 + 1]; f += p[k * 3 + 2]; }
+    s_l3scale = c > 0.0 ? E.w3d / (float)c : 0.f;
+    if (blockIdx.x == 0) {
+      D.loss3d = c > 0.0 ? (float)(s / c) : 0.f;                    // optimizer.py:192-197
+      D.n3 = (float)c;
+      D.front_count = (int)f;
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * LB + threadIdx.x;
+  float dt[3] = {0.f, 0.f, 0.f}, dR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dscale = 0.f, df = 0.f;
+  if (i < m) {
+    const float* P = D.pose;
+    float dv[3] = {V.d_v[i * 3], V.d_v[i * 3 + 1], V.d_v[i * 3 + 2]};
+    const float dm[3] = {V.d_m[i * 3], V.d_m[i * 3 + 1], V.d_m[i * 3 + 2]};
+    const float dc[3] = {V.d_c[i * 3], V.d_c[i * 3 + 1], V.d_c[i * 3 + 2]};
+    const float4 r3 = *reinterpret_cast<const float4*>(E.l3rec + ((size_t)b * E.cap + i) * 4);
+    if (r3.w >= 0.f) {           // d loss3d / d v = -u/n ; d / d scale = -(u . L_nn)/(n scale)
+      const float k = s_l3scale;
+      dv[0] -= k * r3.x; dv[1] -= k * r3.y; dv[2] -= k * r3.z;
+      dscale = -k * E.l3dot[(size_t)b * E.cap + i] / D.scale;
+    }
+    const float* p = E.surf_pts + ((size_t)b * E.cap + i) * 3;
+    const float* n = E.surf_nrm + ((size_t)b * E.cap + i) * 3;
+    for (int a = 0; a < 3; ++a) {
+      dt[a] = dv[a];
+      for (int c = 0; c < 3; ++c) dR[a * 3 + c] = dv[a] * p[c] + dm[a] * n[c];
+    }
+    // d p = R^T d v + d colour path: C = ((-p_x, p_y, p_z) + 1)/2 (projection.py:53-55, rasterer.py:114)
+    float dp[3];
+    for (int c = 0; c < 3; ++c) dp[c] = P[0 * 4 + c] * dv[0] + P[1 * 4 + c] * dv[1] + P[2 * 4 + c] * dv[2];
+    dp[0] += -0.5f * dc[0]; dp[1] += 0.5f * dc[1]; dp[2] += 0.5f * dc[2];
+    // p = g - f n_hat with n_hat constant (grid.py:57-61): d f = - n_hat . d p
+    df = -(n[0] * dp[0] + n[1] * dp[1] + n[2] * dp[2]);
+  }
+  float* out = E.partc + ((size_t)b * E.nbc + blockIdx.x) * (16 + E.L);
+  float t;
+  for (int a = 0; a < 3; ++a) { t = block_sum(dt[a], s_red); if (threadIdx.x == 0) out[a] = t; }
+  for (int a = 0; a < 9; ++a) { t = block_sum(dR[a], s_red); if (threadIdx.x == 0) out[3 + a] = t; }
+  t = block_sum(dscale, s_red); if (threadIdx.x == 0) out[12] = t;
+  for (int k = 0; k < E.L; ++k) {
+    const float g = i < m ? df * E.surf_glat[((size_t)b * E.cap + i) * E.L + k] : 0.f;
+    t = block_sum(g, s_red);
+    if (threadIdx.x == 0) out[16 + k] = t;
+  }
+}
+
+// ---- gradient assembly, skip logic, Adam + SGD (optimizer.py:34-38,49-52,146-157) ----------
+__global__ void __launch_bounds__(LB) update_kernel(EngineDev E) {
+  __shared__ float s_tot[16 + kMaxLatent];
+  const int b = blockIdx.x;
+  DetState& D = E.det[b];
+  const int m = min(E.surf_count[b], (int)E.cap);
+  const int nb = (m + LB - 1) / LB;
+  const int ncomp = 16 + E.L;
+  for (int c = threadIdx.x; c < ncomp; c += LB) {
+    float s = 0.f;
+    const float* p = E.partc + (size_t)b * E.nbc * ncomp + c;
+    for (int k = 0; k < nb; ++k) s += p[(size_t)k * ncomp];
+    s_tot[c] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const int L = E.L;
+  float* g = E.grads + (size_t)b * (5 + 2 * L);
+  const float cy = cosf(D.yaw), sy = sinf(D.yaw);
+  const float* dR = s_tot + 3;
+  // R = diag(1,-1,1) R_y(yaw): dR/dyaw = [[-s,0,c],[0,0,0],[-c,0,-s]]
+  const float dyaw = dR[0] * (-sy) + dR[2] * cy + dR[6] * (-cy) + dR[8] * (-sy);
+  const float dtr[3] = {s_tot[0], s_tot[1], s_tot[2]};
+  const float dscale = s_tot[12];
+  // normalize backward: l_hat = l/||l||  ->  dl = (dl_hat - l_hat (l_hat . dl_hat)) / ||l||
+  float n2 = 0.f, dot = 0.f;
+  for (int k = 0; k < L; ++k) {
+    n2 += E.latent[b * L + k] * E.latent[b * L + k];
+    dot += E.latent_unit[b * L + k] * s_tot[16 + k];
+  }
+  const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+  g[0] = dyaw; g[1] = dtr[0]; g[2] = dtr[1]; g[3] = dtr[2]; g[4] = dscale;
+  for (int k = 0; k < L; ++k) {
+    g[5 + k] = s_tot[16 + k];
+    g[5 + L + k] = (s_tot[16 + k] - E.latent_unit[b * L + k] * dot) / nrm;
+  }
+  // skip logic
+  const float loss = E.w3d * D.loss3d + E.w2d * D.loss2d;
+  int skip = 0;
+  if (D.front_count == 0 || D.n_lidar == 0) skip = 1;               // optimizer.py:127-129
+  else if (isnan(loss) || loss == 0.f) skip = 2;                    // optimizer.py:149-151
+  D.skip_reason = skip;
+  if (D.iter < E.max_iters) {
+    float* h = E.history + ((size_t)b * E.max_iters + D.iter) * 4;
+    h[0] = D.loss2d; h[1] = D.loss3d; h[2] = loss; h[3] = (float)skip;
+  }
+  D.iter += 1;
+  if (skip) return;
+  // Adam(lr 0.01, betas (0.9, 0.999), eps 1e-8) on yaw, trans
+  D.adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999, lr = 0.01, eps = 1e-8;
+  const double bc1 = 1.0 - pow(b1, (double)D.adam_t), bc2 = 1.0 - pow(b2, (double)D.adam_t);
+  const float step = (float)(lr / bc1);
+  const float bc2s = (float)sqrt(bc2);
+  float grad4[4] = {dyaw, dtr[0], dtr[1], dtr[2]};
+  float* par[4] = {&D.yaw, &D.trans[0], &D.trans[1], &D.trans[2]};
+  for (int k = 0; k < 4; ++k) {
+    D.adam_m[k] = D.adam_m[k] * (float)b1 + (1.f - (float)b1) * grad4[k];
+    D.adam_v[k] = D.adam_v[k] * (float)b2 + (1.f - (float)b2) * grad4[k] * grad4[k];
+    const float denom = sqrtf(D.adam_v[k]) / bc2s + (float)eps;
+    *par[k] = *par[k] - step * (D.adam_m[k] / denom);
+  }
+  // SGD(momentum 0): scale lr 0.01, latent lr 3e-5
+  D.scale = D.scale - 0.01f * dscale;
+  for (int k = 0; k < L; ++k) E.latent[b * L + k] = E.latent[b * L + k] - 0.00003f * g[5 + L + k];
+}
+
+}  // namespace
+
+}  // namespace sdfr
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+using namespace sdfr;
+
+struct sdfr_refine {
+  sdfr_decoder* dec;
+  sdfr_refine_cfg cfg;
+  EngineDev E;
+  std::vector<void*> allocs;
+  std::vector<SplatView> views_host;
+  std::vector<float*> nocs_dev;       // per-detection staging of the un-resized NOCS prediction
+  std::vector<size_t> nocs_cap;
+  int max_w_set, max_h_set;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(sdfr_refine* r, T** p, size_t count) {
+  void* q = nullptr;
+  SDFR_CUDA(cudaMalloc(&q, count * sizeof(T) + 16));
+  SDFR_CUDA(cudaMemset(q, 0, count * sizeof(T) + 16));
+  r->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return SDFR_OK;
+}
+
+void invert3x3(const float* k, float* o) {
+  const double a = k[0], b = k[1], c = k[2], d = k[3], e = k[4], f = k[5], g = k[6], h = k[7], i = k[8];
+  const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+  o[0] = (float)((e * i - f * h) / det); o[1] = (float)((c * h - b * i) / det); o[2] = (float)((b * f - c * e) / det);
+  o[3] = (float)((f * g - d * i) / det); o[4] = (float)((a * i - c * g) / det); o[5] = (float)((c * d - a * f) / det);
+  o[6] = (float)((d * h - e * g) / det); o[7] = (float)((b * g - a * h) / det); o[8] = (float)((a * e - b * d) / det);
+}
+
+}  // namespace
+
+extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg, sdfr_refine** out) {
+  SDFR_REQUIRE(dec && cfg && out, SDFR_E_INVALID, "null argument");
+  SDFR_REQUIRE(cfg->batch > 0 && cfg->density > 1 && cfg->max_width > 0 && cfg->max_height > 0, SDFR_E_INVALID,
+               "bad refine configuration");
+  SDFR_REQUIRE(dec->dev.latent_size <= kMaxLatent, SDFR_E_UNSUPPORTED, "latent size %d > %d", dec->dev.latent_size,
+               kMaxLatent);
+  sdfr_refine* r = new sdfr_refine();
+  r->dec = dec;
+  r->cfg = *cfg;
+  r->max_w_set = r->max_h_set = 0;
+  EngineDev& E = r->E;
+  const int B = cfg->batch, L = dec->dev.latent_size;
+  E.batch = B; E.L = L; E.in0 = L + 3;
+  E.ng = (long long)cfg->density * cfg->density * cfg->density;
+  E.cap = E.ng;
+  E.max_pixels = cfg->max_width * cfg->max_height;
+  E.max_lidar = cfg->max_lidar > 0 ? cfg->max_lidar : 1;
+  E.max_iters = cfg->max_iters > 0 ? cfg->max_iters : 1;
+  E.w2d = cfg->weight_2d; E.w3d = cfg->weight_3d;
+  E.nb2 = (E.max_pixels + LB - 1) / LB;
+  E.nb3 = (int)((E.cap + LB - 1) / LB);
+  E.nbc = E.nb3;
+  int rc = 0;
+#define A(ptr, count) if ((rc = dev_alloc(r, &(ptr), (size_t)(count)))) { sdfr_refine_destroy(r); return rc; }
+  A(E.det, B); A(E.latent, B * L); A(E.latent_unit, B * L);
+  A(E.sdf, B * E.ng); A(E.dinput, B * E.ng * E.in0);
+  A(E.surf_pts, B * E.cap * 3); A(E.surf_nrm, B * E.cap * 3); A(E.surf_glat, B * E.cap * L);
+  A(E.surf_idx, B * E.cap); A(E.surf_count, B);
+  A(E.scan_scratch, (size_t)B * (E.ng / 1024 + 4));
+  A(E.target, (size_t)B * 3 * E.max_pixels); A(E.lidar, (size_t)B * E.max_lidar * 3);
+  A(E.l3rec, B * E.cap * 4); A(E.l3dot, B * E.cap); A(E.l2rec, (size_t)B * E.max_pixels * 4);
+  A(E.part2, (size_t)B * E.nb2 * 3); A(E.part3, (size_t)B * E.nb3 * 3); A(E.partc, (size_t)B * E.nbc * (16 + L));
+  A(E.history, (size_t)B * E.max_iters * 4); A(E.grads, (size_t)B * (5 + 2 * L));
+  A(E.views, B);
+  r->views_host.resize(B);
+  r->nocs_dev.assign(B, nullptr);
+  r->nocs_cap.assign(B, 0);
+  for (int b = 0; b < B; ++b) {
+    SplatView& V = r->views_host[b];
+    memset(&V, 0, sizeof(V));
+    V.rot = SDFR_ROT_DCM;
+    V.output_nocs = 1;
+    V.coords = E.surf_pts + (size_t)b * E.cap * 3;
+    V.normals = E.surf_nrm + (size_t)b * E.cap * 3;
+    V.colors = nullptr;
+    V.pose = reinterpret_cast<const float*>(reinterpret_cast<const char*>(E.det + b) + offsetof(DetState, pose));
+    V.count = E.surf_count + b;
+    V.capacity = (int)E.cap;
+    A(V.cam_v, E.cap * 3); A(V.cam_m, E.cap * 3); A(V.cam_c, E.cap * 3); A(V.plane_a, E.cap);
+    A(V.bbox, E.cap * 4); A(V.front, E.cap);
+    V.cam_rgb = nullptr;
+    A(V.color, (size_t)3 * E.max_pixels); A(V.mask, E.max_pixels); A(V.depth, E.max_pixels);
+    A(V.nmap, (size_t)3 * E.max_pixels);
+    A(V.pix_stat, (size_t)4 * E.max_pixels); A(V.pix_raw, (size_t)8 * E.max_pixels);
+    A(V.pix_grad, (size_t)12 * E.max_pixels);
+    A(V.d_v, E.cap * 3); A(V.d_m, E.cap * 3); A(V.d_c, E.cap * 3);
+  }
+#undef A
+  *out = r;
+  return SDFR_OK;
+}
+
+extern "C" void sdfr_refine_destroy(sdfr_refine* r) {
+  if (!r) return;
+  for (void* p : r->allocs) cudaFree(p);
+  for (float* p : r->nocs_dev) if (p) cudaFree(p);
+  delete r;
+}
+
+extern "C" int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_host, const float* kinv_host,
+                                         int width, int height, const float* nocs_host, int th, int tw,
+                                         const float* lidar_host, int n_lidar, const float* yaw_host,
+                                         const float* trans_host, const float* scale_host,
+                                         const float* latent_host, void* stream) {
+  SDFR_REQUIRE(r && k_host && nocs_host && yaw_host && trans_host && scale_host && latent_host, SDFR_E_INVALID,
+               "null argument");
+  SDFR_REQUIRE(b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "detection index %d out of range", b);
+  SDFR_REQUIRE(width > 0 && height > 0 && width * height <= r->E.max_pixels, SDFR_E_CAPACITY,
+               "crop %dx%d exceeds the configured capacity of %d pixels", width, height, r->E.max_pixels);
+  SDFR_REQUIRE(n_lidar >= 0 && n_lidar <= r->E.max_lidar, SDFR_E_CAPACITY, "%d lidar points exceed capacity %d",
+               n_lidar, r->E.max_lidar);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  EngineDev& E = r->E;
+  DetState D;
+  memset(&D, 0, sizeof(D));
+  D.width = width; D.height = height; D.n_lidar = n_lidar; D.target_ready = 1;
+  D.yaw = yaw_host[0];
+  D.trans[0] = trans_host[0]; D.trans[1] = trans_host[1]; D.trans[2] = trans_host[2];
+  D.scale = scale_host[0];
+  SDFR_CUDA(cudaMemcpyAsync(E.det + b, &D, sizeof(D), cudaMemcpyHostToDevice, s));
+  SDFR_CUDA(cudaMemcpyAsync(E.latent + (size_t)b * E.L, latent_host, E.L * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (n_lidar > 0)
+    SDFR_CUDA(cudaMemcpyAsync(E.lidar + (size_t)b * E.max_lidar * 3, lidar_host, (size_t)n_lidar * 3 * sizeof(float),
+                              cudaMemcpyHostToDevice, s));
+  const size_t nocs_count = (size_t)3 * th * tw;
+  if (r->nocs_cap[b] < nocs_count) {
+    if (r->nocs_dev[b]) SDFR_CUDA(cudaFree(r->nocs_dev[b]));
+    r->nocs_dev[b] = nullptr;
+    r->nocs_cap[b] = 0;
+    SDFR_CUDA(cudaMalloc(&r->nocs_dev[b], nocs_count * sizeof(float)));
+    r->nocs_cap[b] = nocs_count;
+  }
+  SDFR_CUDA(cudaMemcpyAsync(r->nocs_dev[b], nocs_host, nocs_count * sizeof(float), cudaMemcpyHostToDevice, s));
+  const int P = width * height;
+  resize_target_kernel<<<(P + 255) / 256, 256, 0, s>>>(r->nocs_dev[b], th, tw, E.target + (size_t)b * 3 * E.max_pixels,
+                                                        height, width, P);
+  SDFR_LAUNCH_CHECK();
+  SplatView& V = r->views_host[b];
+  V.width = width; V.height = height;
+  for (int i = 0; i < 9; ++i) V.k[i] = k_host[i];
+  if (kinv_host) for (int i = 0; i < 9; ++i) V.kinv[i] = kinv_host[i];
+  else invert3x3(k_host, V.kinv);
+  SDFR_CUDA(cudaMemcpyAsync(E.views + b, &V, sizeof(V), cudaMemcpyHostToDevice, s));
+  r->max_w_set = std::max(r->max_w_set, width);
+  r->max_h_set = std::max(r->max_h_set, height);
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
+  SDFR_REQUIRE(r && iters >= 0, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  EngineDev& E = r->E;
+  const int B = E.batch;
+  MlpInputs in;
+  in.inputs = nullptr;
+  in.latent_unit = E.latent_unit;
+  in.lattice = make_lattice(r->cfg.density);
+  in.points_per_batch = E.ng;
+  in.n = E.ng * B;
+  int impl = r->cfg.mlp_impl;
+  if (impl == SDFR_MLP_AUTO) impl = r->dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
+  SurfaceArgs sa;
+  sa.points = nullptr; sa.lattice = in.lattice; sa.sdf = E.sdf; sa.grad = E.dinput;
+  sa.grad_stride = E.in0; sa.grad_col = E.L; sa.n = E.ng; sa.batch = B; sa.threshold = 0.03f;   // grid.py:43
+  sa.out_pts = E.surf_pts; sa.out_nrm = E.surf_nrm; sa.out_idx = E.surf_idx; sa.out_glat = E.surf_glat;
+  sa.glat_dim = E.L; sa.cap = E.cap; sa.out_count = E.surf_count; sa.scratch = E.scan_scratch;
+  const int maxw = r->max_w_set, maxh = r->max_h_set;
+  SDFR_REQUIRE(maxw > 0 && maxh > 0, SDFR_E_INVALID, "no detection has been set");
+  int rc;
+  for (int it = 0; it < iters; ++it) {
+    iter_begin_kernel<<<B, 32, 0, s>>>(E);
+    SDFR_LAUNCH_CHECK();
+    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in, E.sdf, E.dinput, s)
+                                  : launch_mlp_ffma(r->dec, in, E.sdf, E.dinput, s);
+    if (rc) return rc;
+    if ((rc = launch_surface_extract(sa, s))) return rc;
+    if ((rc = launch_project(E.views, B, (int)E.cap, s))) return rc;
+    if ((rc = launch_splat_forward(E.views, B, maxw, maxh, s))) return rc;
+    loss2d_batch_kernel<<<dim3((maxw * maxh + LB - 1) / LB, B), LB, 0, s>>>(E);
+    SDFR_LAUNCH_CHECK();
+    loss3d_batch_kernel<<<dim3(E.nb3, B), LB, 0, s>>>(E);
+    SDFR_LAUNCH_CHECK();
+    grad_prep_kernel<<<dim3((maxw * maxh + LB - 1) / LB, B), LB, 0, s>>>(E);
+    SDFR_LAUNCH_CHECK();
+    if ((rc = launch_splat_backward(E.views, B, (int)E.cap, s))) return rc;
+    chain_kernel<<<dim3(E.nbc, B), LB, 0, s>>>(E);
+    SDFR_LAUNCH_CHECK();
+    update_kernel<<<B, LB, 0, s>>>(E);
+    SDFR_LAUNCH_CHECK();
+  }
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_host, int* n_history,
+                               void* stream) {
+  SDFR_REQUIRE(r && params_host && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  EngineDev& E = r->E;
+  DetState D;
+  SDFR_CUDA(cudaMemcpyAsync(&D, E.det + b, sizeof(D), cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(params_host + 5, E.latent + (size_t)b * E.L, E.L * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaStreamSynchronize(s));
+  params_host[0] = D.yaw; params_host[1] = D.trans[0]; params_host[2] = D.trans[1]; params_host[3] = D.trans[2];
+  params_host[4] = D.scale;
+  const int nh = std::min(D.iter, E.max_iters);
+  if (n_history) *n_history = nh;
+  if (history_host && nh > 0) {
+    SDFR_CUDA(cudaMemcpyAsync(history_host, E.history + (size_t)b * E.max_iters * 4, (size_t)nh * 4 * sizeof(float),
+                              cudaMemcpyDeviceToHost, s));
+    SDFR_CUDA(cudaStreamSynchronize(s));
+  }
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev, int64_t* count) {
+  SDFR_REQUIRE(r && ptr_dev && count && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
+  EngineDev& E = r->E;
+  const SplatView& V = r->views_host[b];
+  const int64_t P = (int64_t)V.width * V.height;
+  switch (kind) {
+    case 0: *ptr_dev = E.sdf + (size_t)b * E.ng; *count = E.ng; break;
+    case 1: *ptr_dev = E.dinput + (size_t)b * E.ng * E.in0; *count = E.ng * E.in0; break;
+    case 2: *ptr_dev = E.surf_pts + (size_t)b * E.cap * 3; *count = E.cap * 3; break;
+    case 3: *ptr_dev = E.surf_nrm + (size_t)b * E.cap * 3; *count = E.cap * 3; break;
+    case 4: *ptr_dev = V.color; *count = 3 * P; break;
+    case 5: *ptr_dev = V.mask; *count = P; break;
+    case 6: *ptr_dev = V.nmap; *count = 3 * P; break;
+    case 7: *ptr_dev = E.grads + (size_t)b * (5 + 2 * E.L); *count = 5 + 2 * E.L; break;
+    case 8: *ptr_dev = E.surf_count + b; *count = 1; break;
+    case 9: *ptr_dev = V.depth; *count = P; break;
+    case 10: *ptr_dev = V.cam_v; *count = E.cap * 3; break;
+    case 11: *ptr_dev = V.front; *count = E.cap; break;
+    default: SDFR_REQUIRE(false, SDFR_E_INVALID, "unknown view kind %d", kind);
+  }
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_dev, int64_t max_count, void* stream) {
+  void* src = nullptr;
+  int64_t count = 0;
+  int rc = sdfr_refine_view(r, b, kind, &src, &count);
+  if (rc) return rc;
+  SDFR_REQUIRE(dst_dev && max_count >= 0, SDFR_E_INVALID, "bad argument");
+  const size_t elem = kind == 11 ? 1 : 4;
+  const size_t n = (size_t)std::min<int64_t>(count, max_count);
+  if (n) SDFR_CUDA(cudaMemcpyAsync(dst_dev, src, n * elem, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return SDFR_OK;
+}

@@ -1,0 +1,387 @@
+// Surfel ("disc") splatting: projection, per-pixel depth-softmax forward and
+// the per-surfel gather backward.
+//
+// replaces: project_in_2D / project_in_2D_quat (sdfrenderer/renderer/projection.py:7-101,104-199),
+//           qrot (renderer/utils_rasterer.py:6-24), inside_surfel (renderer/primitives.py:165-243,
+//           diam=0.04, softclamp=False, add_bg=False) and the composition in
+//           Rasterer.forward (renderer/rasterer.py:113-144).
+//
+// The reference materialises >= 6 tensors of N_surf x P x {1,3}; here nothing of
+// that size exists.  Every hit lies inside the ball of radius 0.04 around the
+// surfel centre, so a surfel can only touch pixels inside the projected bounding
+// box of that ball: the forward is a gather per 16x16 pixel tile over the surfels
+// whose box meets the tile (two sweeps: sum zeta^2 / max, then the softmax), the
+// backward a gather per surfel (one warp) over the pixels of its box.  Both are
+// deterministic (no atomics).  Traffic: 44 B per surfel in, 8 floats per pixel out.
+#include "common.cuh"
+
+namespace sdfr {
+
+namespace {
+
+struct Rot {
+  float r[9];
+  float t[3];
+};
+
+// Linear map applied to points/normals.  dcm: rows of pose[:3,:3].  quat: the matrix of
+// v -> v + 2 (qw (u x v) + u x (u x v)), u = q_xyz (not normalised, utils_rasterer.py:21-24).
+__device__ __forceinline__ Rot load_rot(const SplatView& V) {
+  Rot R;
+  const float* p = V.pose;
+  if (V.rot == SDFR_ROT_DCM) {
+    R.r[0] = p[0]; R.r[1] = p[1]; R.r[2] = p[2];  R.t[0] = p[3];
+    R.r[3] = p[4]; R.r[4] = p[5]; R.r[5] = p[6];  R.t[1] = p[7];
+    R.r[6] = p[8]; R.r[7] = p[9]; R.r[8] = p[10]; R.t[2] = p[11];
+  } else {
+    const float w = p[0], x = p[1], y = p[2], z = p[3];
+    R.r[0] = 1.f - 2.f * (y * y + z * z); R.r[1] = 2.f * (x * y - w * z);       R.r[2] = 2.f * (x * z + w * y);
+    R.r[3] = 2.f * (x * y + w * z);       R.r[4] = 1.f - 2.f * (x * x + z * z); R.r[5] = 2.f * (y * z - w * x);
+    R.r[6] = 2.f * (x * z - w * y);       R.r[7] = 2.f * (y * z + w * x);       R.r[8] = 1.f - 2.f * (x * x + y * y);
+    R.t[0] = p[4]; R.t[1] = p[5]; R.t[2] = p[6];
+  }
+  return R;
+}
+
+__device__ __forceinline__ void interval_div(float lo, float hi, float zlo, float zhi, float& qlo, float& qhi) {
+  // [lo,hi] / [zlo,zhi] with zlo > 0
+  qlo = lo >= 0.f ? lo / zhi : lo / zlo;
+  qhi = hi >= 0.f ? hi / zlo : hi / zhi;
+}
+
+__global__ void __launch_bounds__(256) project_kernel(const SplatView* __restrict__ views) {
+  const SplatView& V = views[blockIdx.y];
+  const int m = V.count ? *V.count : V.static_count;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m || i >= V.capacity) return;
+  const Rot R = load_rot(V);
+  const float px = V.coords[i * 3], py = V.coords[i * 3 + 1], pz = V.coords[i * 3 + 2];
+  const float nx = V.normals[i * 3], ny = V.normals[i * 3 + 1], nz = V.normals[i * 3 + 2];
+  float vx, vy, vz, mx, my, mz;
+  if (V.rot == SDFR_ROT_DCM) {
+    vx = R.r[0] * px + R.r[1] * py + R.r[2] * pz + R.t[0];
+    vy = R.r[3] * px + R.r[4] * py + R.r[5] * pz + R.t[1];
+    vz = R.r[6] * px + R.r[7] * py + R.r[8] * pz + R.t[2];
+    mx = R.r[0] * nx + R.r[1] * ny + R.r[2] * nz;
+    my = R.r[3] * nx + R.r[4] * ny + R.r[5] * nz;
+    mz = R.r[6] * nx + R.r[7] * ny + R.r[8] * nz;
+  } else {
+    // qrot evaluated as written in the reference (two cross products)
+    const float w = V.pose[0], ux = V.pose[1], uy = V.pose[2], uz = V.pose[3];
+    {
+      const float ax = uy * pz - uz * py, ay = uz * px - ux * pz, az = ux * py - uy * px;
+      const float bx = uy * az - uz * ay, by = uz * ax - ux * az, bz = ux * ay - uy * ax;
+      vx = px + 2.f * (w * ax + bx) + R.t[0];
+      vy = py + 2.f * (w * ay + by) + R.t[1];
+      vz = pz + 2.f * (w * az + bz) + R.t[2];
+    }
+    {
+      const float ax = uy * nz - uz * ny, ay = uz * nx - ux * nz, az = ux * ny - uy * nx;
+      const float bx = uy * az - uz * ay, by = uz * ax - ux * az, bz = ux * ay - uy * ax;
+      mx = nx + 2.f * (w * ax + bx);
+      my = ny + 2.f * (w * ay + by);
+      mz = nz + 2.f * (w * az + bz);
+    }
+  }
+  float cx, cy, cz;
+  if (V.output_nocs) {   // projection.py:53-55 (dcm negates x) / 147-149 (quat does not)
+    cx = V.rot == SDFR_ROT_DCM ? -px : px; cy = py; cz = pz;
+  } else {
+    cx = V.colors[i * 3]; cy = V.colors[i * 3 + 1]; cz = V.colors[i * 3 + 2];
+  }
+  V.cam_v[i * 3] = vx; V.cam_v[i * 3 + 1] = vy; V.cam_v[i * 3 + 2] = vz;
+  V.cam_m[i * 3] = mx; V.cam_m[i * 3 + 1] = my; V.cam_m[i * 3 + 2] = mz;
+  if (V.output_nocs) {   // rasterer.py:113-114
+    V.cam_c[i * 3] = (cx + 1.f) / 2.f; V.cam_c[i * 3 + 1] = (cy + 1.f) / 2.f; V.cam_c[i * 3 + 2] = (cz + 1.f) / 2.f;
+  } else {
+    V.cam_c[i * 3] = cx; V.cam_c[i * 3 + 1] = cy; V.cam_c[i * 3 + 2] = cz;
+  }
+  if (V.cam_rgb) {       // rasterer.py:150
+    V.cam_rgb[i * 3] = (cx + 1.f) / 2.f; V.cam_rgb[i * 3 + 1] = (cy + 1.f) / 2.f; V.cam_rgb[i * 3 + 2] = (cz + 1.f) / 2.f;
+  }
+  const float a = mx * vx + my * vy + mz * vz;
+  V.plane_a[i] = a;
+  V.front[i] = (V.rot == SDFR_ROT_DCM) ? (a < 0.f ? 1 : 0) : 1;   // projection.py:61-66
+
+  // conservative pixel box of the ball B(v, radius)
+  int x0 = 0, y0 = 0, x1 = V.width - 1, y1 = V.height - 1;
+  const float rad = kDiscRadius * 1.001f;
+  const bool affine_k = V.k[6] == 0.f && V.k[7] == 0.f && V.k[8] == 1.f;
+  if (affine_k && vz - rad > 1e-6f && isfinite(vx) && isfinite(vy) && isfinite(vz)) {
+    float ulo, uhi, wlo, whi;
+    interval_div(vx - rad, vx + rad, vz - rad, vz + rad, ulo, uhi);
+    interval_div(vy - rad, vy + rad, vz - rad, vz + rad, wlo, whi);
+    const float k00 = V.k[0], k01 = V.k[1], k02 = V.k[2], k10 = V.k[3], k11 = V.k[4], k12 = V.k[5];
+    const float xa = fminf(k00 * ulo, k00 * uhi) + fminf(k01 * wlo, k01 * whi) + k02;
+    const float xb = fmaxf(k00 * ulo, k00 * uhi) + fmaxf(k01 * wlo, k01 * whi) + k02;
+    const float ya = fminf(k10 * ulo, k10 * uhi) + fminf(k11 * wlo, k11 * whi) + k12;
+    const float yb = fmaxf(k10 * ulo, k10 * uhi) + fmaxf(k11 * wlo, k11 * whi) + k12;
+    const float big = 1e8f;
+    x0 = max(0, (int)floorf(fmaxf(xa, -big)) - 1);
+    y0 = max(0, (int)floorf(fmaxf(ya, -big)) - 1);
+    x1 = min(V.width - 1, (int)ceilf(fminf(xb, big)) + 1);
+    y1 = min(V.height - 1, (int)ceilf(fminf(yb, big)) + 1);
+  }
+  V.bbox[i * 4] = x0; V.bbox[i * 4 + 1] = y0; V.bbox[i * 4 + 2] = x1; V.bbox[i * 4 + 3] = y1;
+}
+
+// ---------------------------------------------------------------------------
+// ray / tangent-disc test shared by forward and backward (primitives.py:202-226)
+// ---------------------------------------------------------------------------
+struct Hit {
+  bool hit, overwritten;
+  float b, z;
+};
+
+__device__ __forceinline__ Hit disc_test(float rx, float ry, float rz, float vx, float vy, float vz, float mx,
+                                         float my, float mz, float a) {
+  Hit h;
+  float b = rx * mx + ry * my + rz * mz;
+  h.overwritten = fabsf(b) < kRayCutoff;
+  if (h.overwritten) b = kEps32;
+  h.b = b;
+  h.z = a / b;
+  const float dx = vx - rx * h.z, dy = vy - ry * h.z, dz = vz - rz * h.z;
+  const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+  h.hit = (kDiscRadius - dist) > 0.f;
+  return h;
+}
+
+constexpr int TILE = 16;
+constexpr int CHUNK = 256;
+
+__global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatView* __restrict__ views) {
+  const SplatView& V = views[blockIdx.z];
+  const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+  if (tx0 >= V.width || ty0 >= V.height) return;
+  const int m = min(V.count ? *V.count : V.static_count, V.capacity);
+  const int tid = threadIdx.y * TILE + threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+  const bool live = x < V.width && y < V.height;
+  const int tx1 = min(tx0 + TILE - 1, V.width - 1), ty1 = min(ty0 + TILE - 1, V.height - 1);
+
+  __shared__ float s_v[CHUNK][3], s_m[CHUNK][3], s_c[CHUNK][3], s_a[CHUNK];
+  __shared__ int s_warp_cnt[TILE * TILE / 32];
+  __shared__ int s_total;
+
+  const float fx = (float)x, fy = (float)y;
+  const float rx = V.kinv[0] * fx + V.kinv[1] * fy + V.kinv[2];
+  const float ry = V.kinv[3] * fx + V.kinv[4] * fy + V.kinv[5];
+  const float rz = V.kinv[6] * fx + V.kinv[7] * fy + V.kinv[8];
+
+  float sumsq = 0.f, zeta_max = -INFINITY;
+  int hits = 0;
+  float nu = 0.f, smax = 0.f, den = 0.f;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // colour3, mask, depth, normals3
+
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    if (sweep == 1) {
+      nu = sqrtf(sumsq);
+      smax = fmaxf(zeta_max / (nu + kEps32) + 1.f, 0.f) * kDepthGain;
+    }
+    for (int base = 0; base < m; base += CHUNK) {
+      // cull this chunk of surfels against the tile, compact survivors into shared memory
+      const int i = base + tid;
+      bool take = false;
+      if (i < m) {
+        const int4 bb = *reinterpret_cast<const int4*>(V.bbox + i * 4);
+        take = bb.x <= tx1 && bb.z >= tx0 && bb.y <= ty1 && bb.w >= ty0;
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, take);
+      if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+      __syncthreads();
+      int off = __popc(ballot & ((1u << lane) - 1u));
+      for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
+      if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < TILE * TILE / 32; ++w) t += s_warp_cnt[w];
+        s_total = t;
+      }
+      if (take) {
+        s_v[off][0] = V.cam_v[i * 3]; s_v[off][1] = V.cam_v[i * 3 + 1]; s_v[off][2] = V.cam_v[i * 3 + 2];
+        s_m[off][0] = V.cam_m[i * 3]; s_m[off][1] = V.cam_m[i * 3 + 1]; s_m[off][2] = V.cam_m[i * 3 + 2];
+        s_a[off] = V.plane_a[i];
+        if (sweep == 1) {
+          s_c[off][0] = V.cam_c[i * 3]; s_c[off][1] = V.cam_c[i * 3 + 1]; s_c[off][2] = V.cam_c[i * 3 + 2];
+        }
+      }
+      __syncthreads();
+      const int cnt = s_total;
+      if (live) {
+        for (int k = 0; k < cnt; ++k) {
+          const Hit h = disc_test(rx, ry, rz, s_v[k][0], s_v[k][1], s_v[k][2], s_m[k][0], s_m[k][1], s_m[k][2], s_a[k]);
+          if (!h.hit) continue;
+          const float zeta = -h.z;                      // primitives.py:227
+          if (sweep == 0) {
+            sumsq += zeta * zeta;                       // primitives.py:228
+            zeta_max = fmaxf(zeta_max, zeta);
+            ++hits;
+          } else {
+            const float sc = fmaxf(zeta / (nu + kEps32) + 1.f, 0.f) * kDepthGain;   // primitives.py:229-230
+            const float e = expf(sc - smax);            // softmax numerator (primitives.py:240)
+            den += e;
+            acc[0] += e * s_c[k][0]; acc[1] += e * s_c[k][1]; acc[2] += e * s_c[k][2];
+            acc[3] += e;
+            acc[4] += e * s_v[k][2];                    // rasterer.py:136 (surfel-centre z)
+            acc[5] += e * ((s_m[k][0] + 1.f) / 2.f);
+            acc[6] += e * ((s_m[k][1] + 1.f) / 2.f);
+            acc[7] += e * ((s_m[k][2] + 1.f) / 2.f);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!live) return;
+  const int P = V.width * V.height, j = y * V.width + x;
+  const float inv_den = hits > 0 ? 1.f / den : 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) acc[c] *= inv_den;
+  if (V.color) {   // clamp(max=1): rasterer.py:124
+    V.color[j] = fminf(acc[0], 1.f); V.color[P + j] = fminf(acc[1], 1.f); V.color[2 * P + j] = fminf(acc[2], 1.f);
+  }
+  if (V.mask) V.mask[j] = fminf(acc[3], 1.f);
+  if (V.depth) V.depth[j] = acc[4];
+  if (V.nmap) {
+    V.nmap[j] = fminf(acc[5], 1.f); V.nmap[P + j] = fminf(acc[6], 1.f); V.nmap[2 * P + j] = fminf(acc[7], 1.f);
+  }
+  if (V.pix_stat) *reinterpret_cast<float4*>(V.pix_stat + (size_t)j * 4) = make_float4(nu, smax, inv_den, (float)hits);
+  if (V.pix_raw) {
+    *reinterpret_cast<float4*>(V.pix_raw + (size_t)j * 8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(V.pix_raw + (size_t)j * 8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// Upstream map gradients -> per-pixel record used by the surfel gather.
+// g' = g * [unclamped <= 1] (clamp(max=1) backward); G = sum_k w_kj gbar_kj = <raw, g'>.
+__global__ void pixel_grad_prep_kernel(const SplatView* __restrict__ views, const float* __restrict__ g_color,
+                                       const float* __restrict__ g_mask, const float* __restrict__ g_depth,
+                                       const float* __restrict__ g_nmap) {
+  const SplatView& V = views[blockIdx.y];
+  const int P = V.width * V.height;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P) return;
+  const float* raw = V.pix_raw + (size_t)j * 8;
+  float g[8];
+  g[0] = g_color ? g_color[j] : 0.f; g[1] = g_color ? g_color[P + j] : 0.f; g[2] = g_color ? g_color[2 * P + j] : 0.f;
+  g[3] = g_mask ? g_mask[j] : 0.f;
+  g[4] = g_depth ? g_depth[j] : 0.f;
+  g[5] = g_nmap ? g_nmap[j] : 0.f; g[6] = g_nmap ? g_nmap[P + j] : 0.f; g[7] = g_nmap ? g_nmap[2 * P + j] : 0.f;
+  float G = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (c != 4 && !(raw[c] <= 1.f)) g[c] = 0.f;
+    G += raw[c] * g[c];
+  }
+  float* o = V.pix_grad + (size_t)j * 12;
+  *reinterpret_cast<float4*>(o) = make_float4(g[0], g[1], g[2], g[4]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(g[5], g[6], g[7], g[3]);
+  *reinterpret_cast<float4*>(o + 8) = make_float4(G, 0.f, 0.f, 0.f);
+}
+
+// One warp per surfel: gathers d loss / d (v, m, composited colour) over the surfel's pixel box.
+__global__ void __launch_bounds__(256) splat_backward_kernel(const SplatView* __restrict__ views) {
+  const SplatView& V = views[blockIdx.y];
+  const int m = min(V.count ? *V.count : V.static_count, V.capacity);
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const float vx = V.cam_v[i * 3], vy = V.cam_v[i * 3 + 1], vz = V.cam_v[i * 3 + 2];
+  const float mx = V.cam_m[i * 3], my = V.cam_m[i * 3 + 1], mz = V.cam_m[i * 3 + 2];
+  const float cx = V.cam_c[i * 3], cy = V.cam_c[i * 3 + 1], cz = V.cam_c[i * 3 + 2];
+  const float a = V.plane_a[i];
+  const int4 bb = *reinterpret_cast<const int4*>(V.bbox + i * 4);
+  const int bw = bb.z - bb.x + 1, bh = bb.w - bb.y + 1;
+  const int npx = (bw > 0 && bh > 0) ? bw * bh : 0;
+  float da = 0.f, dmx = 0.f, dmy = 0.f, dmz = 0.f, dcx = 0.f, dcy = 0.f, dcz = 0.f, dvz = 0.f;
+  float dnx = 0.f, dny = 0.f, dnz = 0.f;
+  const float nxd = (mx + 1.f) / 2.f, nyd = (my + 1.f) / 2.f, nzd = (mz + 1.f) / 2.f;
+  for (int idx = lane; idx < npx; idx += 32) {
+    const int yy = idx / bw, x = bb.x + (idx - yy * bw), y = bb.y + yy;
+    const int j = y * V.width + x;
+    const float4 st = *reinterpret_cast<const float4*>(V.pix_stat + (size_t)j * 4);
+    if (st.w == 0.f) continue;
+    const float fx = (float)x, fy = (float)y;
+    const float rx = V.kinv[0] * fx + V.kinv[1] * fy + V.kinv[2];
+    const float ry = V.kinv[3] * fx + V.kinv[4] * fy + V.kinv[5];
+    const float rz = V.kinv[6] * fx + V.kinv[7] * fy + V.kinv[8];
+    const Hit h = disc_test(rx, ry, rz, vx, vy, vz, mx, my, mz, a);
+    if (!h.hit) continue;
+    const float zeta = -h.z;
+    const float t = zeta / (st.x + kEps32) + 1.f;
+    const float sc = fmaxf(t, 0.f) * kDepthGain;
+    const float w = expf(sc - st.y) * st.z;
+    const float* pg = V.pix_grad + (size_t)j * 12;
+    const float4 g0 = *reinterpret_cast<const float4*>(pg);       // g_colour'(3), g_depth
+    const float4 g1 = *reinterpret_cast<const float4*>(pg + 4);   // g_normals'(3), g_mask'
+    const float G = pg[8];
+    const float gbar = cx * g0.x + cy * g0.y + cz * g0.z + vz * g0.w + nxd * g1.x + nyd * g1.y + nzd * g1.z + g1.w;
+    const float ds = w * (gbar - G);                               // softmax backward
+    const float dzeta = t > 0.f ? ds * kDepthGain / (st.x + kEps32) : 0.f;
+    const float dz = -dzeta;                                       // zeta = -z * mu
+    da += dz / h.b;                                                // z = a / b
+    if (!h.overwritten) {                                          // in-place overwrite kills this path (primitives.py:210)
+      const float db = -dz * h.z / h.b;
+      dmx += db * rx; dmy += db * ry; dmz += db * rz;
+    }
+    dcx += w * g0.x; dcy += w * g0.y; dcz += w * g0.z;
+    dvz += w * g0.w;
+    dnx += w * g1.x; dny += w * g1.y; dnz += w * g1.z;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    da += __shfl_xor_sync(0xffffffffu, da, o);
+    dmx += __shfl_xor_sync(0xffffffffu, dmx, o); dmy += __shfl_xor_sync(0xffffffffu, dmy, o);
+    dmz += __shfl_xor_sync(0xffffffffu, dmz, o);
+    dcx += __shfl_xor_sync(0xffffffffu, dcx, o); dcy += __shfl_xor_sync(0xffffffffu, dcy, o);
+    dcz += __shfl_xor_sync(0xffffffffu, dcz, o);
+    dvz += __shfl_xor_sync(0xffffffffu, dvz, o);
+    dnx += __shfl_xor_sync(0xffffffffu, dnx, o); dny += __shfl_xor_sync(0xffffffffu, dny, o);
+    dnz += __shfl_xor_sync(0xffffffffu, dnz, o);
+  }
+  if (lane == 0) {
+    // a = m.v  ->  dv += da*m, dm += da*v ; depth uses v.z ; normals map uses (m+1)/2
+    V.d_v[i * 3] = da * mx; V.d_v[i * 3 + 1] = da * my; V.d_v[i * 3 + 2] = da * mz + dvz;
+    V.d_m[i * 3] = dmx + da * vx + 0.5f * dnx;
+    V.d_m[i * 3 + 1] = dmy + da * vy + 0.5f * dny;
+    V.d_m[i * 3 + 2] = dmz + da * vz + 0.5f * dnz;
+    V.d_c[i * 3] = dcx; V.d_c[i * 3 + 1] = dcy; V.d_c[i * 3 + 2] = dcz;
+  }
+}
+
+}  // namespace
+
+int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStream_t s) {
+  if (max_count <= 0 || batch <= 0) return SDFR_OK;
+  dim3 grid((max_count + 255) / 256, batch);
+  project_kernel<<<grid, 256, 0, s>>>(views_dev);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, cudaStream_t s) {
+  if (max_w <= 0 || max_h <= 0 || batch <= 0) return SDFR_OK;
+  dim3 grid((max_w + TILE - 1) / TILE, (max_h + TILE - 1) / TILE, batch);
+  splat_forward_kernel<<<grid, dim3(TILE, TILE), 0, s>>>(views_dev);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+int launch_pixel_grad_prep(const SplatView* views_dev, int batch, int max_pixels, const float* g_color,
+                           const float* g_mask, const float* g_depth, const float* g_nmap, cudaStream_t s) {
+  if (max_pixels <= 0 || batch <= 0) return SDFR_OK;
+  dim3 grid((max_pixels + 255) / 256, batch);
+  pixel_grad_prep_kernel<<<grid, 256, 0, s>>>(views_dev, g_color, g_mask, g_depth, g_nmap);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+int launch_splat_backward(const SplatView* views_dev, int batch, int max_count, cudaStream_t s) {
+  if (max_count <= 0 || batch <= 0) return SDFR_OK;
+  dim3 grid((max_count + 7) / 8, batch);
+  splat_backward_kernel<<<grid, 256, 0, s>>>(views_dev);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+}  // namespace sdfr

@@ -1,0 +1,245 @@
+"""Pose / shape refinement loop on the device.
+
+Mirror of the reference's pipelines/optimizer.py: ``MultipleOptimizer`` (13-23),
+``get_opt_params`` (26-40), ``Optimizer.__init__`` (43-54) and
+``Optimizer.optimize`` (56-164) with the same signatures; results are read back
+from the same ``params`` dict, mutated in place to tensors, exactly as
+``refine_css.py:229-231`` expects.
+
+The loop body does not run in PyTorch.  ``optimize`` hands the host inputs to the
+fused engine of libsdfr.so (``sdfr_refine_*``): per iteration the DeepSDF lattice
+evaluation with its input gradient, the band extraction, the surfel splat, both
+losses, every gradient and the Adam/SGD update are CUDA kernels chained on one
+stream without host synchronisation (the reference does one H2D, one D2H + a CPU
+KD-tree and two ``.item()`` syncs per iteration).  ``BatchOptimizer`` refines all
+detections of a frame (or many frames) in the same launches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class MultipleOptimizer:
+    def __init__(self, *op):
+        self.optimizers = op
+
+    def zero_grad(self):
+        for op in self.optimizers:
+            op.zero_grad()
+
+    def step(self):
+        for op in self.optimizers:
+            op.step()
+
+
+def get_opt_params(params, device):
+    """numpy -> leaf tensors and the four parameter groups with the reference's
+    learning rates (optimizer.py:26-40).  The fused engine applies the same rates."""
+    for key, value in params.items():
+        if isinstance(value, torch.Tensor):
+            params[key] = value.detach().to(device, torch.float32).requires_grad_(True)
+        else:
+            params[key] = torch.tensor(np.asarray(value, dtype=np.float32)).to(device).requires_grad_(True)
+    optim_params = [
+        {'params': params['yaw'], 'lr': 0.01},
+        {'params': params['trans'], 'lr': 0.01},
+        {'params': params['scale'], 'lr': 0.01},
+        {'params': params['latent'], 'lr': 0.00003},
+    ]
+    return params, optim_params
+
+
+class _Engine:
+    """One sdfr_refine handle (fixed capacities); cached on the decoder object."""
+
+    def __init__(self, native_decoder, batch, density, max_w, max_h, max_lidar, max_iters, w2d, w3d, impl):
+        lib = _lib.load()
+        self.cfg = _lib.RefineCfg(batch=batch, density=density, max_width=max_w, max_height=max_h,
+                                  max_lidar=max_lidar, max_iters=max_iters, weight_2d=w2d, weight_3d=w3d,
+                                  mlp_impl=impl)
+        self.native_decoder = native_decoder     # keeps the decoder handle alive
+        self.latent_size = native_decoder.latent_size
+        h = _lib.vp()
+        _lib.check(lib.sdfr_refine_create(native_decoder.handle, C.byref(self.cfg), C.byref(h)))
+        self.handle = h
+        self._pinned: List[torch.Tensor] = []
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().sdfr_refine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def key(self):
+        c = self.cfg
+        return (c.batch, c.density, c.max_width, c.max_height, c.max_lidar, c.max_iters, c.weight_2d, c.weight_3d,
+                c.mlp_impl)
+
+    def _pin(self, arr) -> torch.Tensor:
+        """float32 host copy in pinned memory so the H2D copy is a true async DMA."""
+        t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)) if not isinstance(arr, torch.Tensor) \
+            else arr.detach().to('cpu', torch.float32).contiguous()
+        p = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
+        p.copy_(t)
+        self._pinned.append(p)
+        return p
+
+    def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw, trans, scale, latent):
+        lib = _lib.load()
+        k32 = K.detach().float().cpu().contiguous()
+        kinv = k32.inverse().contiguous()          # K.float().inverse() (primitives.py:204)
+        nocs = self._pin(nocs_pred)
+        lidar = self._pin(np.asarray(lidar_np, dtype=np.float32).reshape(-1, 3))
+        par = [self._pin(np.asarray(v, dtype=np.float32).reshape(-1)) for v in (yaw, trans, scale, latent)]
+        fp = lambda t: C.cast(t.data_ptr(), _lib.c_float_p)
+        _lib.check(lib.sdfr_refine_set_detection(
+            self.handle, b, fp(k32), fp(kinv), int(width), int(height), nocs.data_ptr(), int(nocs.shape[1]),
+            int(nocs.shape[2]), lidar.data_ptr(), int(lidar.shape[0]), fp(par[0]), fp(par[1]), fp(par[2]), fp(par[3]),
+            _lib.stream_ptr()))
+
+    def run(self, iters):
+        _lib.check(_lib.load().sdfr_refine_run(self.handle, int(iters), _lib.stream_ptr()))
+
+    def get(self, b):
+        L = self.latent_size
+        params = np.zeros(5 + L, dtype=np.float32)
+        hist = np.zeros((self.cfg.max_iters, 4), dtype=np.float32)
+        nh = C.c_int(0)
+        _lib.check(_lib.load().sdfr_refine_get(self.handle, b, _lib.fptr(params), _lib.fptr(hist), C.byref(nh),
+                                               _lib.stream_ptr()))
+        self._pinned.clear()
+        return params, hist[:nh.value]
+
+    VIEW_KINDS = {'sdf': 0, 'dinput': 1, 'surf_pts': 2, 'surf_nrm': 3, 'color': 4, 'mask': 5, 'normals': 6,
+                  'grads': 7, 'surf_count': 8, 'depth': 9, 'cam_pts': 10, 'front': 11}
+
+    def view(self, b, kind):
+        """Device copy of an intermediate of the last iteration (tests, label dumps)."""
+        lib = _lib.load()
+        kind = self.VIEW_KINDS[kind] if isinstance(kind, str) else int(kind)
+        p = _lib.vp()
+        n = C.c_int64(0)
+        _lib.check(lib.sdfr_refine_view(self.handle, b, kind, C.byref(p), C.byref(n)))
+        dtype = torch.int32 if kind == 8 else torch.uint8 if kind == 11 else torch.float32
+        out = torch.empty((n.value,), device='cuda', dtype=dtype)
+        _lib.check(lib.sdfr_refine_copy_view(self.handle, b, kind, out.data_ptr(), n.value, _lib.stream_ptr()))
+        return out
+
+
+def _engine_for(dsdf, batch, density, w, h, n_lidar, iters, weights, impl) -> _Engine:
+    native = dsdf.native()
+    cache = dsdf.__dict__.setdefault('_sdfr_engines', {})
+    # round capacities up so a sequence of slightly different crops reuses one engine
+    cap_w = max(32, 1 << (int(w) - 1).bit_length())
+    cap_h = max(32, 1 << (int(h) - 1).bit_length())
+    cap_l = max(1024, 1 << (int(max(n_lidar, 1)) - 1).bit_length())
+    cap_i = max(64, int(iters))
+    key = (id(native), batch, density, cap_w, cap_h, cap_l, cap_i, float(weights['2d']), float(weights['3d']), impl)
+    eng = cache.get(key)
+    if eng is None:
+        eng = _Engine(native, batch, density, cap_w, cap_h, cap_l, cap_i, float(weights['2d']), float(weights['3d']),
+                      impl)
+        cache.clear()          # one live engine per decoder keeps the memory footprint bounded
+        cache[key] = eng
+    return eng
+
+
+class Optimizer:
+    def __init__(self, params, device, weights, rot='dcm'):
+        self.params, self.optim_params = get_opt_params(params, device)
+        self.optim_params_adam = self.optim_params[:2]
+        self.optim_params_sgd = self.optim_params[2:]
+        self.weights = weights
+        self.rot = rot
+        self.verbose = False
+        self.history = None
+
+    def optimize(self, iters_optim, nocs_pred, pcd_frustum_np, dsdf, grid, K, crop_size, viz_type=None,
+                 frame_vis=None):
+        """
+        Optimization loop (same arguments as the reference).
+        Args:
+            iters_optim (int): number of iterations
+            nocs_pred (torch.Tensor): CSS network prediction (3,h,w)
+            pcd_frustum_np (np.array): LIDAR point cloud (N,3)
+            dsdf: sdflabel_b200 Decoder
+            grid: sdflabel_b200 Grid3D
+            K (torch.Tensor): camera matrix (3,3) of the crop
+            crop_size (list): [H, W] of the optimized crop
+            viz_type: must be None (open3d / cv2 visualisation is out of scope)
+        """
+        if viz_type not in (None, 'none'):
+            raise NotImplementedError("visualisation is not part of the device refine loop")
+        if self.rot != 'dcm':
+            raise NotImplementedError("the refine loop optimises yaw/translation (rot='dcm'), as the reference does")
+        self.device = grid.points.device
+        self.precision = grid.points.dtype
+        height, width = int(crop_size[0]), int(crop_size[1])
+        lidar = np.asarray(pcd_frustum_np, dtype=np.float32).reshape(-1, 3)
+        with torch.cuda.device(self.device):
+            eng = _engine_for(dsdf, 1, int(grid.density), width, height, lidar.shape[0], iters_optim, self.weights,
+                              getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
+            p = self.params
+            eng.set_detection(0, K, width, height, nocs_pred, lidar, p['yaw'].detach().cpu().numpy(),
+                              p['trans'].detach().cpu().numpy(), p['scale'].detach().cpu().numpy(),
+                              p['latent'].detach().cpu().numpy())
+            eng.run(iters_optim)
+            out, hist = eng.get(0)
+        self.engine = eng
+        self.history = hist
+        with torch.no_grad():
+            p['yaw'].copy_(torch.from_numpy(out[0:1]))
+            p['trans'].copy_(torch.from_numpy(out[1:4]))
+            p['scale'].copy_(torch.from_numpy(out[4:5]))
+            p['latent'].copy_(torch.from_numpy(out[5:]))
+        if self.verbose:
+            w2, w3 = self.weights['2d'], self.weights['3d']
+            for e, (l2, l3, tot, skip) in enumerate(hist):
+                if skip:
+                    print('Skip frame')
+                else:
+                    print('ITER {} | Losses: 2D - {}, 3D - {}, Total - {}'.format(e, w2 * l2, w3 * l3, tot))
+
+
+class BatchOptimizer:
+    """All detections of one or more frames refined in the same kernel launches.
+
+    ``detections`` is a sequence of dicts with the arguments ``Optimizer`` takes
+    per detection: ``params`` (yaw/trans/scale/latent), ``nocs_pred``, ``lidar``,
+    ``K``, ``crop_size``.  This is the per-GPU unit of the multi-GPU pipeline
+    (frames are sharded across ranks)."""
+
+    def __init__(self, weights, device='cuda'):
+        self.weights = weights
+        self.device = torch.device(device)
+
+    def optimize(self, iters_optim, detections: Sequence[Dict], dsdf, grid):
+        B = len(detections)
+        if B == 0:
+            return []
+        max_w = max(int(d['crop_size'][1]) for d in detections)
+        max_h = max(int(d['crop_size'][0]) for d in detections)
+        max_l = max(int(np.asarray(d['lidar']).reshape(-1, 3).shape[0]) for d in detections)
+        with torch.cuda.device(self.device):
+            eng = _engine_for(dsdf, B, int(grid.density), max_w, max_h, max_l, iters_optim, self.weights,
+                              getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
+            for b, d in enumerate(detections):
+                p = d['params']
+                eng.set_detection(b, d['K'], int(d['crop_size'][1]), int(d['crop_size'][0]), d['nocs_pred'],
+                                  d['lidar'], p['yaw'], p['trans'], p['scale'], p['latent'])
+            eng.run(iters_optim)
+            results = []
+            for b in range(B):
+                out, hist = eng.get(b)
+                results.append({'yaw': out[0:1].copy(), 'trans': out[1:4].copy(), 'scale': out[4:5].copy(),
+                                'latent': out[5:].copy(), 'history': hist.copy()})
+        self.engine = eng
+        return results
