@@ -1,0 +1,117 @@
+"""Pins the oracle restatement against outputs of the UNMODIFIED reference.
+
+The golden files were written by ``python -m oracle.make_golden`` in the build
+container (reference imported from /root/reference).  Tolerances: the restatement
+uses the same fp32 torch ops in a different order, so agreement is at the fp32
+rounding floor (SURVEY.md Appendix B measured 1e-7 abs for sdf, 1e-6 for maps).
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prior as P
+from oracle import sdf_oracle as O
+
+
+def _load(golden_dir, name):
+    path = os.path.join(golden_dir, name)
+    if not os.path.isfile(path):
+        pytest.skip(f"{name} not generated")
+    return np.load(path)
+
+
+def test_lattice_bit_exact(golden_dir):
+    g = _load(golden_dir, "lattice.npz")
+    for d in (8, 9, 12):
+        assert np.array_equal(O.lattice(d).numpy(), g[f"points_{d}"]), d
+    for d in (30, 40, 41):
+        h = hashlib.sha256(O.lattice(d).numpy().tobytes()).digest()
+        assert np.array_equal(np.frombuffer(h, dtype=np.uint8), g[f"sha256_{d}"]), d
+
+
+@pytest.mark.parametrize("name", ["wn_skip", "layernorm", "xyz_in_all", "use_tanh", "latent8"])
+def test_decoder_variants(golden_dir, name):
+    g = _load(golden_dir, f"decoder_{name}.npz")
+    spec = O.DecoderSpec.from_json(json.loads(bytes(g["spec_json"]).decode()))
+    sd = {k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}
+    params = O.params_from_state_dict(spec, sd)
+    inp = torch.from_numpy(g["inputs"]).requires_grad_(True)
+    sdf = O.decoder_forward(params, inp)
+    (grad,) = torch.autograd.grad(sdf.sum(), inp)
+    assert np.abs(sdf.detach().numpy() - g["sdf"]).max() < 2e-6
+    assert np.abs(grad.numpy() - g["dinput"]).max() < 2e-5 * max(1.0, np.abs(g["dinput"]).max())
+
+
+def test_stock_surface(golden_dir, stock_prior_path):
+    g = _load(golden_dir, "stock_surface_d16.npz")
+    prior = P.load_prior(stock_prior_path)
+    pts = O.lattice(16)
+    sdf, nrm, _ = O.sdf_and_normals(prior, torch.from_numpy(g["latent_unit"]), pts)
+    assert np.abs(sdf.detach().numpy() - g["sdf"]).max() < 1e-6
+    sp, nocs, sn, keep = O.surface_points(pts, sdf.detach(), nrm)
+    assert np.array_equal(keep.numpy(), g["keep"])
+    assert np.abs(sp.numpy() - g["surf_pts"]).max() < 1e-6
+    assert np.abs(nocs.numpy() - g["surf_nocs"]).max() < 1e-6
+    assert np.abs(sn.numpy() - g["surf_nrm"]).max() < 2e-5
+
+
+@pytest.mark.parametrize("tag,rot", [("dcm_45x22", "dcm"), ("dcm_32x32", "dcm"), ("quat_40x30", "quat")])
+def test_raster_maps_and_gradients(golden_dir, tag, rot):
+    g = _load(golden_dir, f"raster_{tag}.npz")
+    w, h = int(g["width"]), int(g["height"])
+    coords = torch.from_numpy(g["coords"]).requires_grad_(True)
+    normals = torch.from_numpy(g["normals"]).requires_grad_(True)
+    pose = torch.from_numpy(g["pose"]).requires_grad_(True)
+    r = O.render(torch.from_numpy(g["K"]), w, h, coords, normals, normals, pose, rot=rot, output_nocs=True)
+    scalar = 0
+    for k in ("color", "mask", "depth", "normals"):
+        ref = g["r_" + k]
+        assert np.abs(r[k].detach().numpy() - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), k
+        scalar = scalar + (r[k] * torch.from_numpy(g["cot_" + k])).sum()
+    if rot == "dcm":
+        assert np.abs(r["xyzf"].detach().numpy() - g["p_xyzf"]).max() < 1e-6
+        assert np.abs(r["rgbf"].detach().numpy() - g["p_rgbf"]).max() < 1e-6
+        assert np.abs(r["xyz"].detach().numpy() - g["p_xyz"]).max() < 1e-6
+        scalar = scalar + (r["xyzf"] * torch.from_numpy(g["cot_xyzf"])).sum()
+    gc, gn, gp = torch.autograd.grad(scalar, [coords, normals, pose])
+    for ours, ref in ((gc, g["g_coords"]), (gn, g["g_normals"]), (gp, g["g_pose"])):
+        assert np.abs(ours.numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_losses(golden_dir):
+    g = _load(golden_dir, "losses.npz")
+    xyzf = torch.from_numpy(g["xyzf"]).requires_grad_(True)
+    lidar = torch.from_numpy(g["lidar_scaled"]).requires_grad_(True)
+    l3 = O.loss_3d(xyzf, lidar, float(g["scale"][0]))
+    gx, gl = torch.autograd.grad(l3, [xyzf, lidar])
+    assert abs(float(l3) - float(g["loss3d"])) < 1e-6
+    assert np.abs(gx.numpy() - g["g_xyzf"]).max() < 1e-6
+    assert np.abs(gl.numpy() - g["g_lidar"]).max() < 1e-6
+    color = torch.from_numpy(g["color"]).requires_grad_(True)
+    target = torch.from_numpy(g["target"])
+    for dense in (False, True):
+        l2 = O.loss_2d(color, target, dense=dense)
+        (gcol,) = torch.autograd.grad(l2, [color])
+        assert abs(float(l2) - float(g["loss2d"])) < 1e-6, dense
+        assert np.abs(gcol.numpy() - g["g_color"]).max() < 1e-6, dense
+
+
+def test_refine_trajectory(golden_dir, stock_prior_path):
+    """Five iterations of the reference's Optimizer.optimize vs the oracle loop."""
+    g = _load(golden_dir, "refine_traj.npz")
+    prior = P.load_prior(stock_prior_path)
+    pts = O.lattice(int(g["density"]))
+    st = O.RefineState.create(g["init_yaw"], g["init_trans"], g["init_scale"], g["init_latent"])
+    h, w = [int(v) for v in g["crop_size"]]
+    traj = []
+    for _ in range(g["traj"].shape[0]):
+        O.refine_iteration(prior, pts, torch.from_numpy(g["K"]), w, h, st, torch.from_numpy(g["nocs_pred"]),
+                           g["lidar"], float(g["w2d"]), float(g["w3d"]))
+        p = st.as_numpy()
+        traj.append(np.concatenate([p[k].reshape(-1) for k in ("yaw", "trans", "scale", "latent")]))
+    traj = np.stack(traj)
+    assert np.abs(traj - g["traj"]).max() < 2e-5, np.abs(traj - g["traj"]).max(0)
