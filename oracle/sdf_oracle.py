@@ -189,7 +189,10 @@ def sdf_and_normals(p: DecoderParams, latent_unit: torch.Tensor, pts: torch.Tens
     x = pts.detach().clone().requires_grad_(True)
     inp = torch.cat([latent_unit.expand(x.shape[0], -1), x], dim=1)
     sdf = decoder_forward(p, inp)
-    (g,) = torch.autograd.grad(sdf.sum(), x, retain_graph=True)
+    # When the decoder tensors require grad (bench.py's reference-cost mode) the backward also
+    # produces dW for every layer, as the reference's sdf.sum().backward() does (grid.py:55).
+    extra = [t for t in list(p.weight) + list(p.bias) if t.requires_grad]
+    g = torch.autograd.grad(sdf.sum(), [x] + extra, retain_graph=True)[0]
     nrm = g / g.norm(dim=1, keepdim=True)
     return sdf, nrm.detach(), g.detach()
 
@@ -467,7 +470,8 @@ def refine_iteration(p, pts, K, width, height, state: RefineState, target_full, 
     if out["skip"]:
         out["grads"] = None
         return out
-    grads = torch.autograd.grad(out["loss"], list(leaves.values()), allow_unused=True)
+    extra = [t for t in list(p.weight) + list(p.bias) if t.requires_grad]   # reference-cost mode (optimizer.py:156)
+    grads = torch.autograd.grad(out["loss"], list(leaves.values()) + extra, allow_unused=True)[:len(leaves)]
     grads = {k: (g if g is not None else torch.zeros_like(leaves[k])) for k, g in zip(leaves, grads)}
     out["grads"] = grads
     state.adam_t += 1

@@ -1,0 +1,365 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the Python mirrors) against the
+oracle on the same seeded inputs and against the golden files written from the
+unmodified reference.  Tolerances follow SURVEY.md Appendix C:
+
+  * lattice: bit exact;
+  * sdf: max abs <= 2e-6 (fp32 floor 1e-7; the tensor-core kernel's split operands 4e-7);
+  * input gradient / normals: rel <= 1e-4 on >= 99.9 % of the points (ReLU-kink flips
+    exist between any two fp32 evaluations, including the reference against itself);
+  * maps / losses / gradients: 1e-4 relative to the map maximum (north_star tolerance);
+  * set membership (band, front-facing, disc hits) may flip only within 1e-6 of a threshold.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import prior as P
+from oracle import scenes
+from oracle import sdf_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+cuda = torch.device("cuda")
+
+
+def _impls(dec):
+    from sdflabel_b200 import _lib
+    out = [("ffma", _lib.MLP_FFMA)]
+    if dec.native().tcgen05:
+        out.append(("tcgen05", _lib.MLP_TCGEN05))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# T1 lattice
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [8, 9, 12, 30, 40, 41])
+def test_lattice_bit_exact(d):
+    from sdflabel_b200.grid import Grid3D
+    ours = Grid3D(d, device=cuda).points.detach().cpu().numpy()
+    assert np.array_equal(ours, O.lattice(d).numpy())
+
+
+# ------------------------------------------------------------------------------------------
+# T2/T3 decoder variants (golden = reference outputs)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["wn_skip", "layernorm", "xyz_in_all", "use_tanh", "latent8"])
+def test_decoder_variants_vs_reference(golden_dir, name):
+    g, spec, sd = H.golden_decoder(golden_dir, name)
+    dec = H.our_decoder_from_state(spec, sd)
+    for tag, impl in _impls(dec):
+        dec.mlp_impl = impl
+        inp = torch.from_numpy(g["inputs"]).to(cuda).requires_grad_(True)
+        sdf, scale = dec(inp)
+        (grad,) = torch.autograd.grad(sdf.sum(), inp)
+        err = np.abs(sdf.detach().cpu().numpy() - g["sdf"]).max()
+        assert err < 2e-6, (tag, err)
+        gmax = np.abs(g["dinput"]).max()
+        frac = H.frac_within(grad.cpu().numpy(), g["dinput"], 1e-4, atol=1e-5 * gmax)
+        assert frac >= 0.995, (tag, frac)
+
+
+def test_decoder_ragged_sizes(golden_dir):
+    """Point counts that are not multiples of the tile, including 1 and 0."""
+    g, spec, sd = H.golden_decoder(golden_dir, "wn_skip")
+    dec = H.our_decoder_from_state(spec, sd)
+    params = O.params_from_state_dict(spec, sd)
+    for tag, impl in _impls(dec):
+        dec.mlp_impl = impl
+        for n in (1, 31, 33, 64, 65, 300):
+            inp = torch.from_numpy(g["inputs"][:n].copy())
+            ref = O.decoder_forward(params, inp).detach().numpy()
+            ours, _ = dec(inp.to(cuda))
+            assert np.abs(ours.cpu().numpy() - ref).max() < 2e-6, (tag, n)
+
+
+def test_stock_decoder_full_lattice(stock_prior_path):
+    """Stock 8x512 prior over the 40^3 lattice through the implicit-lattice entry point."""
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200 import _lib
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    prior = P.load_prior(stock_prior_path)
+    lat = torch.nn.functional.normalize(torch.tensor([0.5, 0.7, 0.5]), dim=0)
+    pts = O.lattice(40)
+    sdf_ref, nrm_ref, g_ref = O.sdf_and_normals(prior, lat, pts)
+    lib = _lib.load()
+    for tag, impl in _impls(dec):
+        sdf = torch.empty(pts.shape[0], device=cuda)
+        dinp = torch.empty(pts.shape[0], 6, device=cuda)
+        lat_d = lat.to(cuda).contiguous()
+        _lib.check(lib.sdfr_decoder_eval_lattice(dec.native().handle, lat_d.data_ptr(), 1, 40, sdf.data_ptr(),
+                                                 dinp.data_ptr(), impl, _lib.stream_ptr()))
+        err = np.abs(sdf.cpu().numpy() - sdf_ref.detach().numpy().ravel()).max()
+        assert err < 2e-6, (tag, err)
+        gx = dinp[:, 3:].cpu().numpy()
+        gmax = np.abs(g_ref.numpy()).max()
+        frac = H.frac_within(gx, g_ref.numpy(), 1e-4, atol=1e-5 * gmax)
+        assert frac >= 0.999, (tag, frac)
+        # latent gradient of sdf against autograd
+        latv = lat.clone().requires_grad_(True)
+        sub = slice(0, 64000, 97)
+        s2 = O.decoder_forward(prior, torch.cat([latv.expand(pts[sub].shape[0], -1), pts[sub]], 1))
+        jac = []
+        for k in range(0, s2.shape[0], 40):
+            (gk,) = torch.autograd.grad(s2[k, 0], latv, retain_graph=True)
+            jac.append(gk.numpy())
+        ours = dinp[sub][::40, :3].cpu().numpy()
+        assert np.abs(ours - np.stack(jac)).max() < 1e-4 * max(1.0, np.abs(np.stack(jac)).max()), tag
+
+
+# ------------------------------------------------------------------------------------------
+# T4 surface extraction
+# ------------------------------------------------------------------------------------------
+def test_surface_vs_reference_golden(golden_dir, stock_prior_path):
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    g = np.load(os.path.join(golden_dir, "stock_surface_d16.npz"))
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    grid = Grid3D(16, device=cuda)
+    lat = torch.from_numpy(g["latent_unit"]).to(cuda)
+    inputs = torch.cat([lat.expand(grid.points.size(0), -1), grid.points], 1)
+    sdf, _ = dec(inputs)
+    pts, nocs, nrm = grid.get_surface_points(sdf)
+    assert np.abs(sdf.detach().cpu().numpy() - g["sdf"]).max() < 2e-6
+    keep = (sdf.detach().abs() < 0.03).squeeze(1).cpu().numpy()
+    flips = keep != g["keep"]
+    assert np.all(np.abs(np.abs(g["sdf"][flips.nonzero()[0], 0]) - 0.03) < 2e-6)
+    if not flips.any():
+        assert np.abs(pts.detach().cpu().numpy() - g["surf_pts"]).max() < 2e-6
+        assert np.abs(nocs.detach().cpu().numpy() - g["surf_nocs"]).max() < 2e-6
+        assert H.frac_within(nrm.cpu().numpy(), g["surf_nrm"], 1e-4, atol=1e-5) >= 0.999
+
+
+# ------------------------------------------------------------------------------------------
+# T5 rasteriser (maps, point lists, gradients) vs the reference's outputs
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,rot", [("dcm_45x22", "dcm"), ("dcm_32x32", "dcm"), ("quat_40x30", "quat")])
+def test_rasterer_vs_reference_golden(golden_dir, tag, rot):
+    from sdflabel_b200.renderer.rasterer import Rasterer
+    g = np.load(os.path.join(golden_dir, f"raster_{tag}.npz"))
+    w, h = int(g["width"]), int(g["height"])
+    coords = torch.from_numpy(g["coords"]).to(cuda).requires_grad_(True)
+    normals = torch.from_numpy(g["normals"]).to(cuda).requires_grad_(True)
+    pose = torch.from_numpy(g["pose"]).to(cuda).requires_grad_(True)
+    ras = Rasterer(torch.from_numpy(g["K"]), (w, h)).to(cuda)
+    rendering, points = ras(coords, normals, normals, pose, rot=rot, primitives='disc', bg=None, output_depth=True,
+                            output_normals=True, output_nocs=True, output_mask=True, output_points=True)
+    scalar = 0
+    for k in ("color", "mask", "depth", "normals"):
+        ref = g["r_" + k]
+        ours = rendering[k].detach().cpu().numpy()
+        bad = np.abs(ours - ref) > 1e-4 * max(1.0, np.abs(ref).max())
+        assert bad.mean() < 2e-3, (k, bad.sum(), np.abs(ours - ref).max())
+        scalar = scalar + (rendering[k] * torch.from_numpy(g["cot_" + k]).to(cuda)).sum()
+    if rot == "dcm":
+        assert np.abs(points["xyz"].detach().cpu().numpy() - g["p_xyz"]).max() < 2e-6
+        assert points["xyzf"].shape == tuple(g["p_xyzf"].shape)
+        assert np.abs(points["xyzf"].detach().cpu().numpy() - g["p_xyzf"]).max() < 2e-6
+        assert np.abs(points["rgbf"].detach().cpu().numpy() - g["p_rgbf"]).max() < 2e-6
+        scalar = scalar + (points["xyzf"] * torch.from_numpy(g["cot_xyzf"]).to(cuda)).sum()
+    gc, gn, gp = torch.autograd.grad(scalar, [coords, normals, pose])
+    for name, ours, ref in (("coords", gc, g["g_coords"]), ("normals", gn, g["g_normals"]), ("pose", gp, g["g_pose"])):
+        tol = 1e-4 if name == "pose" else 1e-3
+        err = np.abs(ours.cpu().numpy() - ref).max() / max(1.0, np.abs(ref).max())
+        assert err < tol, (name, err)
+
+
+def test_rasterer_empty_and_single():
+    from sdflabel_b200.renderer.rasterer import Rasterer
+    K = scenes.intrinsics(32)
+    ras = Rasterer(K, (32, 24)).to(cuda)
+    pose = O.yaw_pose(torch.tensor([0.3]), torch.tensor([0.0, 0.0, 3.0])).to(cuda)
+    e = torch.zeros((0, 3), device=cuda)
+    rendering, points = ras(e, e, e, pose, rot='dcm', output_mask=True, output_depth=True, output_normals=True,
+                            output_nocs=True)
+    assert float(rendering['color'].abs().max()) == 0.0 and points['xyzf'].shape[0] == 0
+    p = torch.tensor([[0.0, 0.0, 0.0]], device=cuda)
+    n = torch.tensor([[0.0, 0.0, -1.0]], device=cuda)
+    rendering, points = ras(p, n, n, pose, rot='dcm', output_mask=True, output_depth=True, output_nocs=True)
+    ref = O.render(K, 32, 24, p.cpu(), n.cpu(), n.cpu(), pose.cpu())
+    assert np.abs(rendering['mask'].cpu().numpy() - ref['mask'].numpy()).max() < 1e-6
+    assert np.abs(rendering['depth'].cpu().numpy() - ref['depth'].numpy()).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# T6 losses
+# ------------------------------------------------------------------------------------------
+def test_losses_vs_reference_golden(golden_dir):
+    from sdflabel_b200 import _lib
+    lib = _lib.load()
+    g = np.load(os.path.join(golden_dir, "losses.npz"))
+    xyzf = torch.from_numpy(g["xyzf"]).to(cuda).contiguous()
+    lidar = torch.from_numpy(g["lidar_scaled"]).to(cuda).contiguous()
+    loss = torch.zeros(2, device=cuda)
+    dx = torch.empty_like(xyzf)
+    dl = torch.empty_like(lidar)
+    radius = 0.2 / float(g["scale"][0])
+    _lib.check(lib.sdfr_loss3d(xyzf.data_ptr(), xyzf.shape[0], lidar.data_ptr(), lidar.shape[0], radius,
+                               loss.data_ptr(), dx.data_ptr(), dl.data_ptr(), _lib.stream_ptr()))
+    assert abs(float(loss[0]) - float(g["loss3d"])) < 1e-5 * max(1.0, abs(float(g["loss3d"])))
+    assert np.abs(dx.cpu().numpy() - g["g_xyzf"]).max() < 1e-6
+    assert np.abs(dl.cpu().numpy() - g["g_lidar"]).max() < 1e-6
+    color = torch.from_numpy(g["color"]).to(cuda).contiguous()
+    target = torch.from_numpy(g["target"]).to(cuda).contiguous()
+    dc = torch.empty_like(color)
+    _lib.check(lib.sdfr_loss2d(color.data_ptr(), target.data_ptr(), color.shape[1], color.shape[2], loss.data_ptr(),
+                               dc.data_ptr(), _lib.stream_ptr()))
+    assert abs(float(loss[0]) - float(g["loss2d"])) < 1e-5 * max(1.0, abs(float(g["loss2d"])))
+    assert np.abs(dc.cpu().numpy() - g["g_color"]).max() < 1e-6
+
+
+def test_loss_edge_cases():
+    from sdflabel_b200 import _lib
+    lib = _lib.load()
+    loss = torch.ones(2, device=cuda)
+    q = torch.rand(10, 3, device=cuda)
+    # empty lidar -> 0 (optimizer.py:177,197)
+    _lib.check(lib.sdfr_loss3d(q.data_ptr(), 10, 0, 0, 0.1, loss.data_ptr(), 0, 0, _lib.stream_ptr()))
+    assert float(loss[0]) == 0.0
+    # no pair within the radius -> 0 (optimizer.py:192-195)
+    far = q + 100.0
+    _lib.check(lib.sdfr_loss3d(q.data_ptr(), 10, far.data_ptr(), 10, 0.1, loss.data_ptr(), 0, 0, _lib.stream_ptr()))
+    assert float(loss[0]) == 0.0
+    # 2D: nothing rendered -> 0; rendered but every delta >= 1 -> NaN like the reference
+    z = torch.zeros(3, 16, 16, device=cuda)
+    _lib.check(lib.sdfr_loss2d(z.data_ptr(), z.data_ptr(), 16, 16, loss.data_ptr(), 0, _lib.stream_ptr()))
+    assert float(loss[0]) == 0.0
+    c = torch.zeros(3, 16, 16, device=cuda)
+    c[:, 8, 8] = 1.0
+    _lib.check(lib.sdfr_loss2d(c.data_ptr(), z.data_ptr(), 16, 16, loss.data_ptr(), 0, _lib.stream_ptr()))
+    ref = O.loss_2d(c.cpu(), z.cpu())
+    assert np.isnan(float(loss[0])) and bool(torch.isnan(ref))
+
+
+# ------------------------------------------------------------------------------------------
+# T7/T8 the refine loop
+# ------------------------------------------------------------------------------------------
+def _run_engine(prior_path, sc, iters, impl=None):
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import Optimizer
+    dec, L = setup_dsdf(prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    if impl is not None:
+        dec.mlp_impl = impl
+    grid = Grid3D(sc["density"], device=cuda)
+    params = {k: v.copy() for k, v in sc["init"].items()}
+    opt = Optimizer(params, cuda, sc["weights"])
+    opt.optimize(iters, torch.from_numpy(sc["nocs_pred"]), sc["lidar"], dec, grid, torch.from_numpy(sc["K"]),
+                 sc["crop_size"], viz_type=None)
+    return opt, params, dec
+
+
+def test_refine_trajectory_vs_reference_golden(golden_dir, stock_prior_path):
+    """The reference's own Optimizer.optimize, 5 iterations (32x32, D=20): parameters after every step."""
+    g = np.load(os.path.join(golden_dir, "refine_traj.npz"))
+    sc = {"K": g["K"], "crop_size": [int(v) for v in g["crop_size"]], "density": int(g["density"]),
+          "nocs_pred": g["nocs_pred"], "lidar": g["lidar"], "weights": {"2d": float(g["w2d"]), "3d": float(g["w3d"])},
+          "init": {k: g["init_" + k] for k in ("yaw", "trans", "scale", "latent")}}
+    for n in range(1, g["traj"].shape[0] + 1):
+        opt, params, dec = _run_engine(stock_prior_path, sc, n)
+        got = np.concatenate([params[k].detach().cpu().numpy().reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
+        ref = g["traj"][n - 1]
+        err = np.abs(got - ref) / np.maximum(1e-3, np.abs(ref))
+        assert err.max() < 2e-4 * n, (n, got, ref)
+
+
+@pytest.mark.parametrize("size,density", [(64, 40)])
+def test_refine_iteration_vs_oracle(stock_prior_path, size, density):
+    """cfg1: one full iteration (forward maps, both losses, every gradient, the update) vs the oracle."""
+    prior = P.load_prior(stock_prior_path)
+    sc = scenes.make_scene(prior, size=size, density=density)
+    st = O.RefineState.create(**sc["init"])
+    out = O.refine_iteration(prior, O.lattice(density), torch.from_numpy(sc["K"]), size, size, st,
+                             torch.from_numpy(sc["nocs_pred"]), sc["lidar"], 0.3, 0.5)
+    opt, params, dec = _run_engine(stock_prior_path, sc, 1)
+    eng = opt.engine
+    m = int(eng.view(0, 'surf_count').item())
+    assert m == out["surf_pts"].shape[0]
+    assert np.abs(eng.view(0, 'surf_pts')[:m * 3].view(-1, 3).cpu().numpy() - out["surf_pts"].detach().numpy()).max() < 2e-6
+    col = eng.view(0, 'color').view(3, size, size).cpu().numpy()
+    ref = out["render"]["color"].detach().numpy()
+    bad = np.abs(col - ref) > 1e-4
+    assert bad.mean() < 1e-3, (bad.sum(), np.abs(col - ref).max())
+    l2, l3, tot, skip = opt.history[0]
+    assert skip == 0
+    assert abs(l2 - float(out["loss_2d"])) < 1e-4 * abs(float(out["loss_2d"]))
+    assert abs(l3 - float(out["loss_3d"])) < 1e-4 * abs(float(out["loss_3d"]))
+    grads = eng.view(0, 'grads').cpu().numpy()
+    gref = np.concatenate([out["grads"][k].numpy().reshape(-1) for k in ("yaw", "trans", "scale")])
+    assert np.abs(grads[:5] - gref).max() < 1e-3 * np.abs(gref).max(), (grads[:5], gref)
+    glat = out["grads"]["latent"].numpy()
+    assert np.abs(grads[8:11] - glat).max() < 1e-3 * np.abs(glat).max(), (grads[8:11], glat)
+    got = np.concatenate([params[k].detach().cpu().numpy().reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
+    want = np.concatenate([st.as_numpy()[k].reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
+    assert np.abs(got - want).max() < 1e-5, (got, want)
+
+
+def test_refine_256_forward_and_gradients(stock_prior_path):
+    """cfg2: 256x256 fwd+bwd of one latent; the oracle evaluates the pixels in row tiles."""
+    prior = P.load_prior(stock_prior_path)
+    sc = scenes.make_scene(prior, size=256, density=40)
+    st = O.RefineState.create(**sc["init"])
+    out = O.refine_iteration(prior, O.lattice(40), torch.from_numpy(sc["K"]), 256, 256, st,
+                             torch.from_numpy(sc["nocs_pred"]), sc["lidar"], 0.3, 0.5, tile_rows=16)
+    opt, params, dec = _run_engine(stock_prior_path, sc, 1)
+    eng = opt.engine
+    for kind, key in (("color", "color"), ("mask", "mask"), ("normals", "normals")):
+        ours = eng.view(0, kind).cpu().numpy().reshape(out["render"][key].shape)
+        ref = out["render"][key].detach().numpy()
+        bad = np.abs(ours - ref) > 1e-4
+        assert bad.mean() < 1e-3, (kind, bad.sum(), np.abs(ours - ref).max())
+    grads = eng.view(0, 'grads').cpu().numpy()
+    gref = np.concatenate([out["grads"][k].numpy().reshape(-1) for k in ("yaw", "trans", "scale")])
+    assert np.abs(grads[:5] - gref).max() < 1e-3 * np.abs(gref).max(), (grads[:5], gref)
+    glat = out["grads"]["latent"].numpy()
+    assert np.abs(grads[8:11] - glat).max() < 1e-3 * np.abs(glat).max(), (grads[8:11], glat)
+
+
+def test_refine_is_deterministic_and_converges(stock_prior_path):
+    """Size-independent properties at the full configuration: two runs are bit-identical and
+    60 iterations move the pose towards the ground truth."""
+    prior = P.load_prior(stock_prior_path)
+    sc = scenes.make_scene(prior, size=64, density=40)
+    a = _run_engine(stock_prior_path, sc, 60)
+    b = _run_engine(stock_prior_path, sc, 60)
+    for k in ("yaw", "trans", "scale", "latent"):
+        assert torch.equal(a[1][k], b[1][k]), k
+    h = a[0].history
+    assert h.shape[0] == 60 and h[-1, 2] < h[0, 2]
+    yaw0, yaw1, yaw_gt = float(sc["init"]["yaw"][0]), float(a[1]["yaw"][0]), float(sc["gt"]["yaw"][0])
+    assert abs(yaw1 - yaw_gt) < abs(yaw0 - yaw_gt)
+
+
+def test_refine_skip_paths(stock_prior_path):
+    """Empty LIDAR crop: the reference prints 'Skip frame' and leaves the parameters untouched."""
+    prior = P.load_prior(stock_prior_path)
+    sc = scenes.make_scene(prior, size=32, density=20, n_lidar=0)
+    opt, params, dec = _run_engine(stock_prior_path, sc, 3)
+    assert np.all(opt.history[:, 3] == 1)
+    for k in ("yaw", "trans", "scale", "latent"):
+        assert np.allclose(params[k].detach().cpu().numpy(), sc["init"][k])
+
+
+def test_batch_matches_single(stock_prior_path):
+    """Ragged batch (different crop sizes / LIDAR counts) == the same detections refined one by one."""
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import BatchOptimizer
+    prior = P.load_prior(stock_prior_path)
+    dets = [scenes.random_detection(prior, s, density=20) for s in range(3)]
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    grid = Grid3D(20, device=cuda)
+    bo = BatchOptimizer({"2d": 0.3, "3d": 0.5})
+    res = bo.optimize(4, [{"params": d["init"], "nocs_pred": d["nocs_pred"], "lidar": d["lidar"],
+                           "K": torch.from_numpy(d["K"]), "crop_size": d["crop_size"]} for d in dets], dec, grid)
+    for d, r in zip(dets, res):
+        opt, params, _ = _run_engine(stock_prior_path, d, 4)
+        for k in ("yaw", "trans", "scale", "latent"):
+            assert np.array_equal(params[k].detach().cpu().numpy().reshape(-1), r[k].reshape(-1)), k
