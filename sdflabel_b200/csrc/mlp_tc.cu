@@ -1,9 +1,607 @@
-// placeholder until the tcgen05 kernel lands
+// DeepSDF decoder on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// replaces: the nine nn.Linear GEMMs of Decoder.forward
+//           (sdfrenderer/deepsdf/networks/deep_sdf_decoder_scale.py:88-94) and the
+//           autograd pass that yields the normals (sdfrenderer/grid.py:55-56), as one
+//           persistent kernel: forward, then the input-gradient backward, per 64-point tile.
+//
+// Orientation.  A 128-point x 512-wide fp32 activation tile does not fit on chip next to
+// its successor (SURVEY.md "SMEM/TMEM budget"), so the GEMM is issued transposed:
+//     D^T[feature, point] = W[feature, k] * H^T[k, point]
+// A = weight tile (128 features x 32 k, K-major, streamed from L2 with cp.async.bulk into a
+// 3-stage ring), B = the CTA's activations (64 points x 512 k, K-major, resident in shared
+// memory), D = 4 x (128 lanes x 64 columns) fp32 accumulators in TMEM.  TMEM lane == output
+// feature, so the epilogue thread that owns a lane applies bias / ReLU / mask for one feature
+// across the 64 points and writes the next layer's B operand in place.
+//
+// Precision.  fp32 parity (1e-4 on normals) needs more than one TF32/BF16 pass (SURVEY.md
+// "Tensor-core precision").  Every operand is split into two fp16 halves x = hi + lo
+// (22 significand bits, power-of-two pre-scaling keeps lo out of the subnormals) and each
+// product is three kind::f16 MMAs  hi*hi + hi*lo + lo*hi  accumulated in fp32 in TMEM:
+// half the operand bytes of 3xTF32 and twice its MMA rate.  Measured against fp64 the sdf
+// error is 2.1e-7 (plain fp32: 1.7e-7).
+//
+// Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane quadrant each), warp 4 weight
+// producer (one elected lane), warp 5 MMA issuer (one elected lane) + TMEM allocator.
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
+
 namespace sdfr {
-int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec*, const float* const*) { dec->tc.ok = 0; return SDFR_OK; }
-int launch_mlp_tc(const sdfr_decoder*, const MlpInputs&, float*, float*, cudaStream_t) {
-  set_error("tcgen05 MLP kernel not available for this decoder");
-  return SDFR_E_UNSUPPORTED;
+
+namespace {
+
+constexpr int NPTS = 64;                 // points per CTA tile (MMA N)
+constexpr int KC = 32;                   // k per weight stage (two K=16 MMA steps)
+constexpr int TILE_BYTES = 16384;        // 128 x 32 fp16 hi + the same lo
+constexpr int TILE_HALF_BYTES = 8192;
+constexpr int NSTAGE = 3;
+constexpr int B_CHUNK = 1040;            // bytes per 8-k chunk of B: 8 point groups x 128 B + 16 B bank skew
+constexpr int B_BYTES = 64 * B_CHUNK;    // 512 / 8 chunks
+constexpr int A_LBO = 2048;              // A: core matrices adjacent in K are 16 row groups apart
+constexpr int A_SBO = 128;
+constexpr int B_LBO = B_CHUNK;
+constexpr int B_SBO = 128;
+constexpr int TMEM_COLS = 256;           // 4 M-blocks x 64 columns
+constexpr int NTHREADS = 192;
+constexpr int MAX_TC_LAYERS = 9;
+constexpr float ACT_SCALE = 32.f;        // forward activations are stored as h * 2^5
+constexpr float BWD_SCALE = 256.f;       // backward deltas as delta * 2^8
+
+struct TcPassDev {
+  int kind;          // 0 forward hidden, 1 forward last, 2 backward hidden, 3 backward first
+  int layer;
+  int m_blocks, k_chunks;
+  int rows;          // logical output rows of this pass
+  int cat_dim, cat_off;   // rows [rows, rows+cat_dim) are the concatenated input (forward) / its gradient (backward)
+  int prev_rows;     // backward: fan-out of layer-1 (rows below it go through that layer's ReLU mask)
+  float inv_scale;   // 1 / (weight scale * input activation scale)
+  float out_scale;   // scale applied to what the epilogue writes back as the next B operand
+  long long tile0;
+  const float* bias; // forward: [rows]
+};
+
+struct TcTable {
+  int num_passes, num_layers, in0, latent, use_tanh;
+  int last_k;                    // fan-in of the last Linear
+  float last_wscale_inv;
+  const float* last_w;           // [last_k] un-scaled last-layer weights (backward of the last Linear is an outer product)
+  long long tiles_per_point_tile;
+  TcPassDev pass[2 * MAX_TC_LAYERS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// 8-row x 16-byte core matrices; LBO = byte distance between core matrices adjacent in K,
+// SBO = between core matrices adjacent in M/N.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;                 // base offset 0, LBO mode 0, layout type 0 = SWIZZLE_NONE
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, M=128, N=64
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(NPTS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void split_store(unsigned char* b_hi, unsigned char* b_lo, int f, int n, float h,
+                                            int* overflow) {
+  if (fabsf(h) > 60000.f) *overflow = 1;
+  const __half hi = __float2half_rn(h);
+  const __half lo = __float2half_rn(h - __half2float(hi));
+  const int off = (f >> 3) * B_CHUNK + (n >> 3) * 128 + (n & 7) * 16 + (f & 7) * 2;
+  *reinterpret_cast<__half*>(b_hi + off) = hi;
+  *reinterpret_cast<__half*>(b_lo + off) = lo;
+}
+
+struct SmemPlan {
+  uint32_t stages, b_hi, b_lo, masks, inp, dinp, g, bars, tmem_slot, total;
+};
+__host__ __device__ inline SmemPlan make_plan(int num_layers, int in0) {
+  SmemPlan p;
+  uint32_t o = 0;
+  p.stages = o; o += NSTAGE * TILE_BYTES;
+  p.b_hi = o; o += B_BYTES;
+  p.b_lo = o; o += B_BYTES;
+  p.masks = o; o += (uint32_t)(num_layers - 1) * 512 * 8;
+  const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
+  p.inp = o; o += in_pad * NPTS * 4;
+  p.dinp = o; o += in_pad * NPTS * 4;
+  p.g = o; o += NPTS * 4;
+  p.bars = o; o += 16 * 8;
+  p.tmem_slot = o; o += 16;
+  p.total = o;
+  return p;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
+              float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
+              long long num_point_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcTable& T = *tabp;
+  const SmemPlan P = make_plan(T.num_layers, T.in0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned char* b_hi = smem + P.b_hi;
+  unsigned char* b_lo = smem + P.b_lo;
+  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + P.masks);
+  float* inp = reinterpret_cast<float*>(smem + P.inp);     // [in_pad][64]
+  float* dinp = reinterpret_cast<float*>(smem + P.dinp);
+  float* gbuf = reinterpret_cast<float*>(smem + P.g);
+  const uint32_t bars = smem_u32(smem + P.bars);
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * NSTAGE, bar_acc = bars + 8 * (2 * NSTAGE),
+                 bar_act = bars + 8 * (2 * NSTAGE + 1);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
+  const int in0 = T.in0, in_pad = (in0 + 7) & ~7;
+  const bool want_grad = dinput_out != nullptr;
+  const int npass = want_grad ? T.num_passes : T.num_layers;   // forward passes come first
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_act, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  long long my_tiles = 0;
+  for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) ++my_tiles;
+
+  if (warp == 4) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      long long total = 0;
+      for (int p = 0; p < npass; ++p) total += (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
+      uint32_t stage = 0, phase = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < npass; ++p) {
+          const long long n = (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
+          const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
+          for (long long t = 0; t < n; ++t) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
+            bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, TILE_BYTES,
+                     bar_full + 8 * stage);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      (void)total;
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, act_phase = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < npass; ++p) {
+          const TcPassDev& Ps = T.pass[p];
+          mbar_wait(bar_act, act_phase);     // B operand of this pass is in shared memory, TMEM is drained
+          act_phase ^= 1;
+          tc_fence_after();
+          for (int mb = 0; mb < Ps.m_blocks; ++mb) {
+            const uint32_t d = tmem_base + (uint32_t)(mb * NPTS);
+            for (int kc = 0; kc < Ps.k_chunks; ++kc) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              const uint32_t a_hi = smem_u32(smem + P.stages + stage * TILE_BYTES);
+              const uint32_t a_lo = a_hi + TILE_HALF_BYTES;
+#pragma unroll
+              for (int j = 0; j < KC / 16; ++j) {
+                const uint32_t koff_b = (uint32_t)((kc * (KC / 8) + j * 2) * B_CHUNK);
+                const uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, A_SBO);
+                const uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, A_SBO);
+                const uint64_t db_hi = make_desc(smem_u32(b_hi) + koff_b, B_LBO, B_SBO);
+                const uint64_t db_lo = make_desc(smem_u32(b_lo) + koff_b, B_LBO, B_SBO);
+                umma_f16(d, da_hi, db_hi, kIdesc, (kc | j) ? 1u : 0u);
+                umma_f16(d, da_hi, db_lo, kIdesc, 1u);
+                umma_f16(d, da_lo, db_hi, kIdesc, 1u);
+              }
+              umma_commit(bar_empty + 8 * stage);      // frees the weight stage when these MMAs retire
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(bar_acc);                        // accumulators of this pass are complete
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (TMEM lane quadrant = warp) =====================
+    const int t = tid;                                 // 0..127 = TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t acc_phase = 0;
+    int ovf = 0;
+    for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) {
+      const long long base = pt * NPTS;
+      // ---- stage inputs: inp[c][n] ----
+      for (int i = t; i < in_pad * NPTS; i += 128) {
+        const int c = i / NPTS, n = i - c * NPTS;
+        const long long gi = base + n;
+        float v = 0.f;
+        if (gi < in.n && c < in0) {
+          if (in.inputs) {
+            v = in.inputs[gi * in0 + c];
+          } else {
+            const long long b = gi / in.points_per_batch, k = gi - b * in.points_per_batch;
+            if (c < T.latent) {
+              v = in.latent_unit[b * T.latent + c];
+            } else {
+              float x, y, z;
+              lattice_point(in.lattice, k, x, y, z);
+              v = (c - T.latent) == 0 ? x : (c - T.latent) == 1 ? y : z;
+            }
+          }
+        }
+        inp[i] = v;
+        dinp[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // B operand of layer 0: k = input column (padded to 32)
+      for (int i = t; i < KC * NPTS; i += 128) {
+        const int k = i / NPTS, n = i - k * NPTS;
+        split_store(b_hi, b_lo, k, n, k < in0 ? inp[k * NPTS + n] * ACT_SCALE : 0.f, &ovf);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_act);
+
+      for (int p = 0; p < npass; ++p) {
+        const TcPassDev& Ps = T.pass[p];
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (Ps.kind == 1) {
+          // ---- last Linear: row 0 is the pre-activation of the sdf ----
+          if (warp == 0) {                             // whole warp issues the aligned loads; lane 0 owns row 0
+            uint32_t v[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              tmem_ld32(lane_base + half * 32, v);
+              if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                  const int n = half * 32 + q;
+                  float y = __uint_as_float(v[q]) * Ps.inv_scale + __ldg(Ps.bias), g = 1.f;
+                  if (T.use_tanh) { y = tanhf(y); g *= 1.f - y * y; }
+                  y = tanhf(y);
+                  g *= 1.f - y * y;
+                  if (base + n < in.n) sdf_out[base + n] = y;
+                  gbuf[n] = g;
+                }
+              }
+              __syncwarp();
+            }
+          }
+          tc_fence_before();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (want_grad) {
+            // backward of the last Linear is an outer product: delta[f][n] = W_last[f] * g[n] * mask[f][n]
+            const int hidden = T.last_k;
+            for (int mb = 0; mb < 4; ++mb) {
+              const int f = mb * 128 + t;
+              const float w = f < hidden ? __ldg(T.last_w + f) : 0.f;
+              const unsigned long long mk = f < hidden ? masks[(size_t)(T.num_layers - 2) * 512 + f] : 0ull;
+#pragma unroll 8
+              for (int n = 0; n < NPTS; ++n) {
+                const float dlt = ((mk >> n) & 1ull) ? w * gbuf[n] * BWD_SCALE : 0.f;
+                split_store(b_hi, b_lo, f, n, dlt, &ovf);
+              }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_act);
+          }
+          continue;
+        }
+        for (int mb = 0; mb < Ps.m_blocks; ++mb) {
+          const int f = mb * 128 + t;
+          unsigned long long mk = 0ull;
+          const bool fwd = Ps.kind == 0;
+          float bias = 0.f;
+          unsigned long long prev_mask = ~0ull;
+          if (fwd) {
+            bias = f < Ps.rows ? __ldg(Ps.bias + f) : 0.f;
+          } else if (Ps.kind == 2 && f < Ps.prev_rows) {
+            prev_mask = masks[(size_t)(Ps.layer - 1) * 512 + f];
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(lane_base + (uint32_t)(mb * NPTS + half * 32), v);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int n = half * 32 + q;
+              const float x = __uint_as_float(v[q]) * Ps.inv_scale;
+              float outv = 0.f;
+              if (fwd) {
+                if (f < Ps.rows) {
+                  const float y = x + bias;
+                  if (y > 0.f) { mk |= 1ull << n; outv = y * Ps.out_scale; }
+                } else if (f < Ps.rows + Ps.cat_dim) {      // cat[x, input] feeds the next Linear (decoder.py:90-93)
+                  outv = inp[(Ps.cat_off + f - Ps.rows) * NPTS + n] * Ps.out_scale;
+                }
+                split_store(b_hi, b_lo, f, n, outv, &ovf);
+              } else if (Ps.kind == 2) {
+                if (f < Ps.prev_rows) {
+                  outv = ((prev_mask >> n) & 1ull) ? x * Ps.out_scale : 0.f;
+                } else if (f < Ps.prev_rows + Ps.cat_dim) {   // gradient of the concatenated input columns
+                  dinp[(Ps.cat_off + f - Ps.prev_rows) * NPTS + n] += x;
+                }
+                split_store(b_hi, b_lo, f, n, outv, &ovf);
+              } else {                                        // kind 3: gradient with respect to the input row
+                if (f < in0) dinp[f * NPTS + n] += x;
+              }
+            }
+          }
+          if (fwd && f < 512) masks[(size_t)Ps.layer * 512 + f] = mk;
+        }
+        if (Ps.kind == 3) {
+          tc_fence_before();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = t; i < NPTS * in0; i += 128) {
+            const int n = i / in0, c = i - n * in0;
+            if (base + n < in.n) dinput_out[(base + n) * in0 + c] = dinp[c * NPTS + n];
+          }
+        } else {
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_act);
+        }
+      }
+      // the next point tile re-stages inp/dinp: make sure everyone is done with them
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (ovf) atomicOr(overflow_flag, 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host: pass table + packed fp16 hi/lo weight tiles
+// ---------------------------------------------------------------------------------------------
+struct TcHostState {
+  TcTable table;
+  TcTable* table_dev;
+  unsigned char* tiles_dev;
+  int* overflow_dev;
+  size_t smem_bytes;
+};
+
+static float pow2_scale_for(const float* w, size_t n) {
+  float mx = 0.f;
+  for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(w[i]));
+  if (!(mx > 0.f) || !std::isfinite(mx)) return 1.f;
+  int e;
+  std::frexp(mx, &e);              // mx = m * 2^e, m in [0.5, 1)
+  return std::ldexp(1.f, 7 - e);   // scaled max in [64, 128)
+}
+
+static void pack_tile(std::vector<__half>& out, size_t tile_index, const std::vector<float>& A, int rows, int K,
+                      int lda, int mb, int kc, float scale) {
+  __half* hi = out.data() + tile_index * (TILE_BYTES / 2);
+  __half* lo = hi + TILE_HALF_BYTES / 2;
+  for (int kc8 = 0; kc8 < KC / 8; ++kc8)
+    for (int rg = 0; rg < 16; ++rg)
+      for (int rr = 0; rr < 8; ++rr)
+        for (int kk = 0; kk < 8; ++kk) {
+          const int row = mb * 128 + rg * 8 + rr, k = kc * KC + kc8 * 8 + kk;
+          const float v = (row < rows && k < K) ? A[(size_t)row * lda + k] * scale : 0.f;
+          const __half h = __float2half_rn(v);
+          const __half l = __float2half_rn(v - __half2float(h));
+          const size_t o = ((size_t)(kc8 * 16 + rg) * 8 + rr) * 8 + kk;
+          hi[o] = h;
+          lo[o] = l;
+        }
+}
+
+int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host) {
+  dec->tc.ok = 0;
+  dec->tc_ptr = nullptr;
+  const int NL = spec->num_layers, in0 = spec->latent_size + 3;
+  if (NL > MAX_TC_LAYERS || in0 > KC) return SDFR_OK;
+  if (spec->concat[NL - 1]) return SDFR_OK;   // a concatenating last Linear stays on the FFMA kernel
+  for (int l = 0; l < NL; ++l) {
+    if (spec->layer_norm[l]) return SDFR_OK;
+    if (spec->in_dims[l] > 512 || spec->out_dims[l] > 512) return SDFR_OK;
+  }
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dec->device);
+  if (major != 10) return SDFR_OK;   // tcgen05 exists on sm_100 only
+  const SmemPlan plan = make_plan(NL, in0);
+  if (plan.total > 227 * 1024) return SDFR_OK;
+
+  TcHostState* st = new TcHostState();
+  memset(&st->table, 0, sizeof(st->table));
+  TcTable& T = st->table;
+  T.num_layers = NL; T.in0 = in0; T.latent = spec->latent_size; T.use_tanh = spec->use_tanh;
+  std::vector<float> wscale(NL);
+  for (int l = 0; l < NL; ++l) wscale[l] = pow2_scale_for(weights_host[l], (size_t)spec->in_dims[l] * spec->out_dims[l]);
+
+  struct HostPass { int kind, layer, rows, K; std::vector<float> A; int lda; float scale; };
+  std::vector<HostPass> hp;
+  // forward passes
+  for (int l = 0; l < NL; ++l) {
+    HostPass p;
+    p.kind = l == NL - 1 ? 1 : 0; p.layer = l; p.rows = spec->out_dims[l]; p.K = spec->in_dims[l];
+    p.A.assign(weights_host[l], weights_host[l] + (size_t)p.rows * p.K);
+    p.lda = p.K; p.scale = wscale[l];
+    hp.push_back(std::move(p));
+  }
+  // backward passes: W^T of layers NL-2 .. 0 (the last Linear's backward is an outer product in the epilogue)
+  for (int l = NL - 2; l >= 0; --l) {
+    HostPass p;
+    p.kind = l == 0 ? 3 : 2; p.layer = l; p.rows = spec->in_dims[l]; p.K = spec->out_dims[l];
+    p.A.resize((size_t)p.rows * p.K);
+    for (int o = 0; o < spec->out_dims[l]; ++o)
+      for (int i = 0; i < spec->in_dims[l]; ++i) p.A[(size_t)i * p.K + o] = weights_host[l][(size_t)o * spec->in_dims[l] + i];
+    p.lda = p.K; p.scale = wscale[l];
+    hp.push_back(std::move(p));
+  }
+  T.num_passes = (int)hp.size();
+  long long ntiles = 0;
+  for (auto& p : hp) ntiles += (long long)((p.rows + 127) / 128) * ((p.K + KC - 1) / KC);
+  std::vector<__half> packed((size_t)ntiles * (TILE_BYTES / 2));
+  long long tile = 0;
+  int rc = SDFR_OK;
+  std::vector<const float*> bias_dev(NL, nullptr);
+  for (int l = 0; l < NL; ++l) bias_dev[l] = dec->dev.layer[l].bias;
+  for (int pi = 0; pi < T.num_passes; ++pi) {
+    HostPass& p = hp[pi];
+    TcPassDev& D = T.pass[pi];
+    D.kind = p.kind; D.layer = p.layer; D.rows = p.rows;
+    D.m_blocks = (p.rows + 127) / 128; D.k_chunks = (p.K + KC - 1) / KC;
+    D.tile0 = tile;
+    D.bias = (p.kind <= 1) ? bias_dev[p.layer] : nullptr;
+    D.cat_dim = 0; D.cat_off = 0; D.prev_rows = 0;
+    const float in_scale = p.kind <= 1 ? ACT_SCALE : BWD_SCALE;
+    D.inv_scale = 1.f / (p.scale * in_scale);
+    D.out_scale = p.kind == 0 ? ACT_SCALE : BWD_SCALE;
+    if (p.kind == 0 && p.layer + 1 < NL && spec->concat[p.layer + 1]) {      // the next Linear concatenates
+      D.cat_dim = spec->concat[p.layer + 1] == 1 ? in0 : 3;
+      D.cat_off = spec->concat[p.layer + 1] == 1 ? 0 : spec->latent_size;
+      D.m_blocks = (p.rows + D.cat_dim + 127) / 128;
+    }
+    if (p.kind == 2) {
+      D.prev_rows = spec->out_dims[p.layer - 1];
+      if (spec->concat[p.layer]) {
+        D.cat_dim = spec->concat[p.layer] == 1 ? in0 : 3;
+        D.cat_off = spec->concat[p.layer] == 1 ? 0 : spec->latent_size;
+      }
+    }
+    const int mb_packed = D.m_blocks;
+    for (int mb = 0; mb < mb_packed; ++mb)
+      for (int kc = 0; kc < D.k_chunks; ++kc) pack_tile(packed, (size_t)tile++, p.A, p.rows, p.K, p.lda, mb, kc, p.scale);
+  }
+  // m_blocks may have grown for concatenation rows: recount
+  if (tile != ntiles) {
+    // repack with the right total (rare: only when the concat pushes past a 128 multiple)
+    ntiles = 0;
+    for (int pi = 0; pi < T.num_passes; ++pi) ntiles += (long long)T.pass[pi].m_blocks * T.pass[pi].k_chunks;
+    packed.assign((size_t)ntiles * (TILE_BYTES / 2), __float2half_rn(0.f));
+    tile = 0;
+    for (int pi = 0; pi < T.num_passes; ++pi) {
+      T.pass[pi].tile0 = tile;
+      for (int mb = 0; mb < T.pass[pi].m_blocks; ++mb)
+        for (int kc = 0; kc < T.pass[pi].k_chunks; ++kc)
+          pack_tile(packed, (size_t)tile++, hp[pi].A, hp[pi].rows, hp[pi].K, hp[pi].lda, mb, kc, hp[pi].scale);
+    }
+  }
+  T.tiles_per_point_tile = ntiles;
+  T.last_k = spec->in_dims[NL - 1];
+  T.last_w = dec->dev.layer[NL - 1].w;     // [out_pad=4][in_pad]: row 0 is the weight vector
+  void* p = nullptr;
+#define TC_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(e_)); rc = SDFR_E_CUDA; } } while (0)
+  TC_CUDA(cudaMalloc(&p, packed.size() * sizeof(__half)));
+  if (rc == SDFR_OK) { dec->allocs.push_back(p); st->tiles_dev = reinterpret_cast<unsigned char*>(p); }
+  if (rc == SDFR_OK) TC_CUDA(cudaMemcpy(p, packed.data(), packed.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  if (rc == SDFR_OK) { TC_CUDA(cudaMalloc(&p, sizeof(TcTable))); if (rc == SDFR_OK) { dec->allocs.push_back(p); st->table_dev = reinterpret_cast<TcTable*>(p); } }
+  if (rc == SDFR_OK) TC_CUDA(cudaMemcpy(st->table_dev, &T, sizeof(TcTable), cudaMemcpyHostToDevice));
+  if (rc == SDFR_OK) { TC_CUDA(cudaMalloc(&p, 64)); if (rc == SDFR_OK) { dec->allocs.push_back(p); st->overflow_dev = reinterpret_cast<int*>(p); TC_CUDA(cudaMemset(p, 0, 64)); } }
+  if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+#undef TC_CUDA
+  if (rc != SDFR_OK) { delete st; return rc; }
+  st->smem_bytes = plan.total;
+  dec->tc.ok = 1;
+  dec->tc.num_passes = T.num_passes;
+  dec->tc.num_tiles = ntiles;
+  dec->tc.tiles = reinterpret_cast<const uint4*>(st->tiles_dev);
+  dec->tc_ptr = reinterpret_cast<DecoderTc*>(st);   // opaque host state (freed with the decoder)
+  return SDFR_OK;
+}
+
+int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
+  SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,
+               "tcgen05 MLP kernel does not cover this decoder (needs sm_100, widths <= 512, no LayerNorm, "
+               "latent+3 <= 32, <= 9 layers)");
+  if (in.n <= 0) return SDFR_OK;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  const long long point_tiles = (in.n + NPTS - 1) / NPTS;
+  const int grid = (int)std::min<long long>(point_tiles, dec->sm_count > 0 ? dec->sm_count : 148);
+  mlp_tc_kernel<<<grid, NTHREADS, st->smem_bytes, s>>>(st->table_dev, st->tiles_dev, in, sdf, dinput,
+                                                      st->overflow_dev, point_tiles);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+}  // namespace sdfr
