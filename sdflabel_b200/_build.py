@@ -46,6 +46,7 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compiles every CUDA source and links libsdfr.so; returns its path."""
     nvcc = _nvcc()
+    extra = os.environ.get("SDFR_NVCC_FLAGS", "").split()   # e.g. -DSDFR_TC_PROFILE for the in-kernel timers
     os.makedirs(OBJ_DIR, exist_ok=True)
     jobs = []
     objs = []
@@ -53,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, _deps(src)):
-            jobs.append([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj])
+            jobs.append([nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj])
 
     def run(cmd):
         if verbose:

@@ -9,17 +9,21 @@
 // its successor (SURVEY.md "SMEM/TMEM budget"), so the GEMM is issued transposed:
 //     D^T[feature, point] = W[feature, k] * H^T[k, point]
 // A = weight tile (128 features x 32 k, K-major, streamed from L2 with cp.async.bulk into a
-// 3-stage ring), B = the CTA's activations (64 points x 512 k, K-major, resident in shared
-// memory), D = 4 x (128 lanes x 64 columns) fp32 accumulators in TMEM.  TMEM lane == output
-// feature, so the epilogue thread that owns a lane applies bias / ReLU / mask for one feature
-// across the 64 points and writes the next layer's B operand in place.
+// 3-stage ring), B = the CTA's activations (64 points x 512 k, resident in shared memory,
+// MN-major so that the 8 points one epilogue thread packs are one 16-byte store),
+// D = 4 x (128 lanes x 128 columns) fp32 accumulators in TMEM.  TMEM lane == output feature,
+// so the epilogue thread that owns a lane applies bias / ReLU / mask for one feature across
+// the 64 points and writes the next layer's B operand in place.
 //
 // Precision.  fp32 parity (1e-4 on normals) needs more than one TF32/BF16 pass (SURVEY.md
 // "Tensor-core precision").  Every operand is split into two fp16 halves x = hi + lo
 // (22 significand bits, power-of-two pre-scaling keeps lo out of the subnormals) and each
-// product is three kind::f16 MMAs  hi*hi + hi*lo + lo*hi  accumulated in fp32 in TMEM:
-// half the operand bytes of 3xTF32 and twice its MMA rate.  Measured against fp64 the sdf
-// error is 2.1e-7 (plain fp32: 1.7e-7).
+// product is  hi*hi + hi*lo + lo*hi  with fp32 accumulation in TMEM.  Per K=16 step that is
+// two MMAs: W_hi x [H_hi ; H_lo] (N = 128: columns 0-63 collect hi*hi, 64-127 hi*lo) and
+// W_lo x H_hi (N = 64) accumulated onto columns 64-127.  Keeping the 2^-11-sized cross terms
+// in their own accumulator shortens the (truncating) accumulation chain of the main sum from
+// 96 to 32 adds; the epilogue adds the two columns in fp32.  Half the operand bytes of 3xTF32
+// and twice its MMA rate.
 //
 // Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane quadrant each), warp 4 weight
 // producer (one elected lane), warp 5 MMA issuer (one elected lane) + TMEM allocator.
@@ -35,18 +39,21 @@ namespace sdfr {
 
 namespace {
 
-constexpr int NPTS = 64;                 // points per CTA tile (MMA N)
+constexpr int NPTS = 64;                 // points per CTA tile
 constexpr int KC = 32;                   // k per weight stage (two K=16 MMA steps)
 constexpr int TILE_BYTES = 16384;        // 128 x 32 fp16 hi + the same lo
 constexpr int TILE_HALF_BYTES = 8192;
 constexpr int NSTAGE = 3;
-constexpr int B_CHUNK = 1040;            // bytes per 8-k chunk of B: 8 point groups x 128 B + 16 B bank skew
-constexpr int B_BYTES = 64 * B_CHUNK;    // 512 / 8 chunks
-constexpr int A_LBO = 2048;              // A: core matrices adjacent in K are 16 row groups apart
+// B operand (activations), MN-major, no swizzle: core matrix = 8 k-rows x (8 points = 16 B).
+// Per 8-k chunk: 8 point groups of the hi halves (1024 B) followed by 8 point groups of the lo
+// halves (1024 B), so one descriptor with N = 128 covers [hi ; lo] and N = 64 covers hi only.
+constexpr int B_CHUNK = 2048;
+constexpr int B_BYTES = 64 * B_CHUNK;    // 512 / 8 chunks = 128 KB
+constexpr int A_LBO = 2048;              // A (K-major): core matrices adjacent in K are 16 row groups apart
 constexpr int A_SBO = 128;
-constexpr int B_LBO = B_CHUNK;
-constexpr int B_SBO = 128;
-constexpr int TMEM_COLS = 256;           // 4 M-blocks x 64 columns
+constexpr int B_LBO = B_CHUNK;           // B (MN-major): next 8-k chunk
+constexpr int B_SBO = 128;               //               next 8-point group
+constexpr int TMEM_COLS = 512;           // 4 M-blocks x (64 main + 64 cross-term) columns
 constexpr int NTHREADS = 192;
 constexpr int MAX_TC_LAYERS = 9;
 constexpr float ACT_SCALE = 32.f;        // forward activations are stored as h * 2^5
@@ -141,6 +148,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 // 8-row x 16-byte core matrices; LBO = byte distance between core matrices adjacent in K,
 // SBO = between core matrices adjacent in M/N.
@@ -153,28 +166,51 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return d;                 // base offset 0, LBO mode 0, layout type 0 = SWIZZLE_NONE
 }
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, M=128, N=64
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(NPTS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, A K-major, B MN-major, M=128
+constexpr uint32_t idesc_for(int n) {
+  return (1u << 4) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+constexpr uint32_t kIdesc128 = idesc_for(128), kIdesc64 = idesc_for(64);
 
-__device__ __forceinline__ void split_store(unsigned char* b_hi, unsigned char* b_lo, int f, int n, float h,
-                                            int* overflow) {
-  if (fabsf(h) > 60000.f) *overflow = 1;
-  const __half hi = __float2half_rn(h);
-  const __half lo = __float2half_rn(h - __half2float(hi));
-  const int off = (f >> 3) * B_CHUNK + (n >> 3) * 128 + (n & 7) * 16 + (f & 7) * 2;
-  *reinterpret_cast<__half*>(b_hi + off) = hi;
-  *reinterpret_cast<__half*>(b_lo + off) = lo;
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 8 consecutive points of one feature -> one 16-byte store of the hi halves and one of the lo halves
+__device__ __forceinline__ float pack8_store(unsigned char* chunk_row, int pg, const float (&h)[8]) {
+  uint4 hi, lo;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 a = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+    const float2 b = __half22float2(a);
+    const __half2 l = __floats2half2_rn(h[2 * i] - b.x, h[2 * i + 1] - b.y);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
+    lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    amax = fmaxf(amax, fmaxf(fabsf(h[2 * i]), fabsf(h[2 * i + 1])));
+  }
+  *reinterpret_cast<uint4*>(chunk_row + pg * 128) = hi;
+  *reinterpret_cast<uint4*>(chunk_row + 1024 + pg * 128) = lo;
+  return amax;
 }
 
 struct SmemPlan {
-  uint32_t stages, b_hi, b_lo, masks, inp, dinp, g, bars, tmem_slot, total;
+  uint32_t stages, b, masks, inp, dinp, g, bars, tmem_slot, total;
 };
 __host__ __device__ inline SmemPlan make_plan(int num_layers, int in0) {
   SmemPlan p;
   uint32_t o = 0;
   p.stages = o; o += NSTAGE * TILE_BYTES;
-  p.b_hi = o; o += B_BYTES;
-  p.b_lo = o; o += B_BYTES;
+  p.b = o; o += B_BYTES;
   p.masks = o; o += (uint32_t)(num_layers - 1) * 512 * 8;
   const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
   p.inp = o; o += in_pad * NPTS * 4;
@@ -186,16 +222,25 @@ __host__ __device__ inline SmemPlan make_plan(int num_layers, int in0) {
   return p;
 }
 
+#ifdef SDFR_TC_PROFILE
+__device__ unsigned long long g_tc_prof[16];
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(slot) do { if (blockIdx.x == 0) atomicAdd(&g_tc_prof[slot], (unsigned long long)(clock64() - _t0)); } while (0)
+#else
+#define PROF_T0() do {} while (0)
+#define PROF_ADD(slot) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
               long long num_point_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const TcTable& T = *tabp;
-  const SmemPlan P = make_plan(T.num_layers, T.in0);
+  const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
+  const SmemPlan P = make_plan(num_layers, in0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned char* b_hi = smem + P.b_hi;
-  unsigned char* b_lo = smem + P.b_lo;
+  unsigned char* bop = smem + P.b;
   unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + P.masks);
   float* inp = reinterpret_cast<float*>(smem + P.inp);     // [in_pad][64]
   float* dinp = reinterpret_cast<float*>(smem + P.dinp);
@@ -204,9 +249,9 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   const uint32_t bar_full = bars, bar_empty = bars + 8 * NSTAGE, bar_acc = bars + 8 * (2 * NSTAGE),
                  bar_act = bars + 8 * (2 * NSTAGE + 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
-  const int in0 = T.in0, in_pad = (in0 + 7) & ~7;
+  const int in_pad = (in0 + 7) & ~7;
   const bool want_grad = dinput_out != nullptr;
-  const int npass = want_grad ? T.num_passes : T.num_layers;   // forward passes come first
+  const int npass = want_grad ? T.num_passes : num_layers;   // forward passes come first
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -226,15 +271,13 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   if (warp == 4) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      long long total = 0;
-      for (int p = 0; p < npass; ++p) total += (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < my_tiles; ++it) {
         for (int p = 0; p < npass; ++p) {
           const long long n = (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
           const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
           for (long long t = 0; t < n; ++t) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            { PROF_T0(); mbar_wait(bar_empty + 8 * stage, phase ^ 1); PROF_ADD(0); }
             mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
             bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, TILE_BYTES,
                      bar_full + 8 * stage);
@@ -242,52 +285,58 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           }
         }
       }
-      (void)total;
     }
     __syncwarp();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, act_phase = 0;
-      for (long long it = 0; it < my_tiles; ++it) {
-        for (int p = 0; p < npass; ++p) {
-          const TcPassDev& Ps = T.pass[p];
-          mbar_wait(bar_act, act_phase);     // B operand of this pass is in shared memory, TMEM is drained
-          act_phase ^= 1;
-          tc_fence_after();
-          for (int mb = 0; mb < Ps.m_blocks; ++mb) {
-            const uint32_t d = tmem_base + (uint32_t)(mb * NPTS);
-            for (int kc = 0; kc < Ps.k_chunks; ++kc) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              tc_fence_after();
-              const uint32_t a_hi = smem_u32(smem + P.stages + stage * TILE_BYTES);
-              const uint32_t a_lo = a_hi + TILE_HALF_BYTES;
+    // All 32 lanes run the loop with identical (warp-uniform) values so that the descriptor
+    // arithmetic stays on the uniform datapath; one elected lane issues the tcgen05 instructions.
+    // (A single thread executing ~80 dependent scalar instructions per K step takes ~240 cycles,
+    // 2.5x the 96 cycles of tensor work it feeds - measured with tools/umma_bench.cu.)
+    uint32_t stage = 0, phase = 0, act_phase = 0;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc_a_base =
+        make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);             // + (stage*TILE_BYTES + ...) >> 4
+    const uint64_t desc_b_base = make_desc(smem_u32(bop), B_LBO, B_SBO);
+    for (long long it = 0; it < my_tiles; ++it) {
+      for (int p = 0; p < npass; ++p) {
+        const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
+        { PROF_T0(); mbar_wait(bar_act, act_phase); if (lane == 0) PROF_ADD(1); }   // B operand staged, TMEM drained
+        act_phase ^= 1;
+        tc_fence_after();
+        for (int mb = 0; mb < m_blocks; ++mb) {
+          const uint32_t d_main = tm + (uint32_t)(mb * 128);    // columns [0,64): hi*hi, [64,128): cross terms
+          const uint32_t d_cross = d_main + 64;
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            { PROF_T0(); mbar_wait(bar_full + 8 * stage, phase); if (lane == 0) PROF_ADD(2); }
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t da_hi = desc_a_base + (uint64_t)((stage * TILE_BYTES) >> 4);
+              const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
+              const uint64_t db = desc_b_base + (uint64_t)((kc * (KC / 8) * B_CHUNK) >> 4);
 #pragma unroll
               for (int j = 0; j < KC / 16; ++j) {
-                const uint32_t koff_b = (uint32_t)((kc * (KC / 8) + j * 2) * B_CHUNK);
-                const uint64_t da_hi = make_desc(a_hi + j * 2 * A_LBO, A_LBO, A_SBO);
-                const uint64_t da_lo = make_desc(a_lo + j * 2 * A_LBO, A_LBO, A_SBO);
-                const uint64_t db_hi = make_desc(smem_u32(b_hi) + koff_b, B_LBO, B_SBO);
-                const uint64_t db_lo = make_desc(smem_u32(b_lo) + koff_b, B_LBO, B_SBO);
-                umma_f16(d, da_hi, db_hi, kIdesc, (kc | j) ? 1u : 0u);
-                umma_f16(d, da_hi, db_lo, kIdesc, 1u);
-                umma_f16(d, da_lo, db_hi, kIdesc, 1u);
+                umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
+                         kIdesc128, (kc | j) ? 1u : 0u);                                  // W_hi x [H_hi ; H_lo]
+                umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
+                         kIdesc64, 1u);                                                    // W_lo x H_hi
               }
               umma_commit(bar_empty + 8 * stage);      // frees the weight stage when these MMAs retire
-              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
-          umma_commit(bar_acc);                        // accumulators of this pass are complete
         }
+        if (elect_one()) umma_commit(bar_acc);         // accumulators of this pass are complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM lane quadrant = warp) =====================
     const int t = tid;                                 // 0..127 = TMEM lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t acc_phase = 0;
-    int ovf = 0;
+    float amax = 0.f;
     for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) {
       const long long base = pt * NPTS;
       // ---- stage inputs: inp[c][n] ----
@@ -300,12 +349,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             v = in.inputs[gi * in0 + c];
           } else {
             const long long b = gi / in.points_per_batch, k = gi - b * in.points_per_batch;
-            if (c < T.latent) {
-              v = in.latent_unit[b * T.latent + c];
+            if (c < latent) {
+              v = in.latent_unit[b * latent + c];
             } else {
               float x, y, z;
               lattice_point(in.lattice, k, x, y, z);
-              v = (c - T.latent) == 0 ? x : (c - T.latent) == 1 ? y : z;
+              v = (c - latent) == 0 ? x : (c - latent) == 1 ? y : z;
             }
           }
         }
@@ -313,33 +362,43 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         dinp[i] = 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      // B operand of layer 0: k = input column (padded to 32)
-      for (int i = t; i < KC * NPTS; i += 128) {
-        const int k = i / NPTS, n = i - k * NPTS;
-        split_store(b_hi, b_lo, k, n, k < in0 ? inp[k * NPTS + n] * ACT_SCALE : 0.f, &ovf);
+      // B operand of layer 0: k = input column (padded to one 32-k chunk)
+      if (t < KC) {
+        unsigned char* row = bop + (t >> 3) * B_CHUNK + (t & 7) * 16;
+#pragma unroll
+        for (int pg = 0; pg < 8; ++pg) {
+          float h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = t < in0 ? inp[t * NPTS + pg * 8 + e] * ACT_SCALE : 0.f;
+          amax = fmaxf(amax, pack8_store(row, pg, h));
+        }
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(bar_act);
 
       for (int p = 0; p < npass; ++p) {
-        const TcPassDev& Ps = T.pass[p];
-        mbar_wait(bar_acc, acc_phase);
+        const TcPassDev Ps = T.pass[p];               // by value: keeps the fields in registers
+        { PROF_T0(); mbar_wait(bar_acc, acc_phase); if (t == 0) PROF_ADD(3); }
         acc_phase ^= 1;
         tc_fence_after();
+        PROF_T0();
         if (Ps.kind == 1) {
-          // ---- last Linear: row 0 is the pre-activation of the sdf ----
+          // ---- last Linear: row 0 holds the pre-activation of the sdf ----
           if (warp == 0) {                             // whole warp issues the aligned loads; lane 0 owns row 0
-            uint32_t v[32];
+            const float bias0 = __ldg(Ps.bias);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              tmem_ld32(lane_base + half * 32, v);
+            for (int g4 = 0; g4 < 4; ++g4) {
+              uint32_t vm[16], vc[16];
+              tmem_ld16(lane_base + g4 * 16, vm);
+              tmem_ld16(lane_base + 64 + g4 * 16, vc);
+              tmem_ld_wait();
               if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                  const int n = half * 32 + q;
-                  float y = __uint_as_float(v[q]) * Ps.inv_scale + __ldg(Ps.bias), g = 1.f;
-                  if (T.use_tanh) { y = tanhf(y); g *= 1.f - y * y; }
+                for (int q = 0; q < 16; ++q) {
+                  const int n = g4 * 16 + q;
+                  float y = (__uint_as_float(vm[q]) + __uint_as_float(vc[q])) * Ps.inv_scale + bias0, g = 1.f;
+                  if (use_tanh) { y = tanhf(y); g *= 1.f - y * y; }
                   y = tanhf(y);
                   g *= 1.f - y * y;
                   if (base + n < in.n) sdf_out[base + n] = y;
@@ -356,12 +415,15 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             const int hidden = T.last_k;
             for (int mb = 0; mb < 4; ++mb) {
               const int f = mb * 128 + t;
-              const float w = f < hidden ? __ldg(T.last_w + f) : 0.f;
-              const unsigned long long mk = f < hidden ? masks[(size_t)(T.num_layers - 2) * 512 + f] : 0ull;
-#pragma unroll 8
-              for (int n = 0; n < NPTS; ++n) {
-                const float dlt = ((mk >> n) & 1ull) ? w * gbuf[n] * BWD_SCALE : 0.f;
-                split_store(b_hi, b_lo, f, n, dlt, &ovf);
+              const float w = f < hidden ? __ldg(T.last_w + f) * BWD_SCALE : 0.f;
+              const unsigned long long mk = f < hidden ? masks[(size_t)(num_layers - 2) * 512 + f] : 0ull;
+              unsigned char* row = bop + (f >> 3) * B_CHUNK + (f & 7) * 16;
+#pragma unroll
+              for (int pg = 0; pg < 8; ++pg) {
+                float h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (pg * 8 + e)) & 1ull) ? w * gbuf[pg * 8 + e] : 0.f;
+                amax = fmaxf(amax, pack8_store(row, pg, h));
               }
             }
             fence_async_smem();
@@ -370,48 +432,74 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           }
           continue;
         }
+        const bool fwd = Ps.kind == 0;
+        const int split = fwd ? Ps.rows : (Ps.kind == 2 ? Ps.prev_rows : in0);   // rows below: regular outputs
         for (int mb = 0; mb < Ps.m_blocks; ++mb) {
           const int f = mb * 128 + t;
+          const int cls = f < split ? 0 : (f < split + Ps.cat_dim ? 1 : 2);
+          const uint32_t tb = lane_base + (uint32_t)(mb * 128);
+          unsigned char* row = bop + (f >> 3) * B_CHUNK + (f & 7) * 16;
+          const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
+          const unsigned long long pmask = (Ps.kind == 2 && cls == 0) ? masks[(size_t)(Ps.layer - 1) * 512 + f] : 0ull;
+          const int cat_row = (Ps.cat_off + f - split) * NPTS;
           unsigned long long mk = 0ull;
-          const bool fwd = Ps.kind == 0;
-          float bias = 0.f;
-          unsigned long long prev_mask = ~0ull;
-          if (fwd) {
-            bias = f < Ps.rows ? __ldg(Ps.bias + f) : 0.f;
-          } else if (Ps.kind == 2 && f < Ps.prev_rows) {
-            prev_mask = masks[(size_t)(Ps.layer - 1) * 512 + f];
-          }
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32(lane_base + (uint32_t)(mb * NPTS + half * 32), v);
+          for (int g4 = 0; g4 < 4; ++g4) {
+            uint32_t vm[16], vc[16];
+            tmem_ld16(tb + g4 * 16, vm);
+            tmem_ld16(tb + 64 + g4 * 16, vc);
+            tmem_ld_wait();
+            float x[16];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const int n = half * 32 + q;
-              const float x = __uint_as_float(v[q]) * Ps.inv_scale;
-              float outv = 0.f;
-              if (fwd) {
-                if (f < Ps.rows) {
-                  const float y = x + bias;
-                  if (y > 0.f) { mk |= 1ull << n; outv = y * Ps.out_scale; }
-                } else if (f < Ps.rows + Ps.cat_dim) {      // cat[x, input] feeds the next Linear (decoder.py:90-93)
-                  outv = inp[(Ps.cat_off + f - Ps.rows) * NPTS + n] * Ps.out_scale;
+            for (int q = 0; q < 16; ++q) x[q] = (__uint_as_float(vm[q]) + __uint_as_float(vc[q])) * Ps.inv_scale;
+            if (Ps.kind == 3) {                                    // gradient with respect to the input row
+              if (cls == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) dinp[f * NPTS + g4 * 16 + q] += x[q];
+              }
+              continue;
+            }
+            float h[16];
+            if (fwd) {
+              if (cls == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  const float y = x[q] + bias;
+                  const bool on = y > 0.f;
+                  if (on) mk |= 1ull << (g4 * 16 + q);
+                  h[q] = on ? y * Ps.out_scale : 0.f;
                 }
-                split_store(b_hi, b_lo, f, n, outv, &ovf);
-              } else if (Ps.kind == 2) {
-                if (f < Ps.prev_rows) {
-                  outv = ((prev_mask >> n) & 1ull) ? x * Ps.out_scale : 0.f;
-                } else if (f < Ps.prev_rows + Ps.cat_dim) {   // gradient of the concatenated input columns
-                  dinp[(Ps.cat_off + f - Ps.prev_rows) * NPTS + n] += x;
+              } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
+#pragma unroll
+                for (int q = 0; q < 16; ++q) h[q] = inp[cat_row + g4 * 16 + q] * Ps.out_scale;
+              } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) h[q] = 0.f;
+              }
+            } else {
+              if (cls == 0) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) h[q] = ((pmask >> (g4 * 16 + q)) & 1ull) ? x[q] * Ps.out_scale : 0.f;
+              } else {
+                if (cls == 1) {                                    // gradient of the concatenated input columns
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) dinp[cat_row + g4 * 16 + q] += x[q];
                 }
-                split_store(b_hi, b_lo, f, n, outv, &ovf);
-              } else {                                        // kind 3: gradient with respect to the input row
-                if (f < in0) dinp[f * NPTS + n] += x;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) h[q] = 0.f;
               }
             }
+            float h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h8[e] = h[e];
+            amax = fmaxf(amax, pack8_store(row, g4 * 2, h8));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h8[e] = h[8 + e];
+            amax = fmaxf(amax, pack8_store(row, g4 * 2 + 1, h8));
           }
-          if (fwd && f < 512) masks[(size_t)Ps.layer * 512 + f] = mk;
+          if (fwd) masks[(size_t)Ps.layer * 512 + f] = mk;
         }
+        if (t == 0) PROF_ADD(4 + (Ps.kind == 0 ? 0 : Ps.kind == 2 ? 1 : 2));
         if (Ps.kind == 3) {
           tc_fence_before();
           asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -428,7 +516,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
       // the next point tile re-stages inp/dinp: make sure everyone is done with them
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    if (ovf) atomicOr(overflow_flag, 1);
+    if (amax > 60000.f) atomicOr(overflow_flag, 1);   // a scaled operand left the fp16 range
   }
   tc_fence_before();
   __syncthreads();
@@ -589,6 +677,14 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   dec->tc_ptr = reinterpret_cast<DecoderTc*>(st);   // opaque host state (freed with the decoder)
   return SDFR_OK;
 }
+
+#ifdef SDFR_TC_PROFILE
+extern "C" int sdfr_debug_tc_prof(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
   SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,

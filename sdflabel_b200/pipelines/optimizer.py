@@ -68,7 +68,8 @@ class _Engine:
         h = _lib.vp()
         _lib.check(lib.sdfr_refine_create(native_decoder.handle, C.byref(self.cfg), C.byref(h)))
         self.handle = h
-        self._pinned: List[torch.Tensor] = []
+        self._pinned: Dict = {}     # persistent pinned staging buffers, keyed by (name, detection)
+        self._dirty = set()         # detections whose staging buffers may still be in flight
 
     def __del__(self):
         try:
@@ -83,27 +84,38 @@ class _Engine:
         return (c.batch, c.density, c.max_width, c.max_height, c.max_lidar, c.max_iters, c.weight_2d, c.weight_3d,
                 c.mlp_impl)
 
-    def _pin(self, arr) -> torch.Tensor:
-        """float32 host copy in pinned memory so the H2D copy is a true async DMA."""
+    def _pin(self, key, arr) -> torch.Tensor:
+        """float32 host copy in a persistent pinned buffer, so the H2D copy is a true async DMA
+        and no cudaHostAlloc happens per call."""
         t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)) if not isinstance(arr, torch.Tensor) \
             else arr.detach().to('cpu', torch.float32).contiguous()
-        p = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
-        p.copy_(t)
-        self._pinned.append(p)
-        return p
+        buf = self._pinned.get(key)
+        if buf is None or buf.numel() < t.numel():
+            buf = torch.empty((max(t.numel(), 1),), dtype=torch.float32, pin_memory=True)
+            self._pinned[key] = buf
+        view = buf[:t.numel()].view(t.shape)
+        view.copy_(t)
+        return view
 
     def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw, trans, scale, latent):
         lib = _lib.load()
         k32 = K.detach().float().cpu().contiguous()
         kinv = k32.inverse().contiguous()          # K.float().inverse() (primitives.py:204)
-        nocs = self._pin(nocs_pred)
-        lidar = self._pin(np.asarray(lidar_np, dtype=np.float32).reshape(-1, 3))
-        par = [self._pin(np.asarray(v, dtype=np.float32).reshape(-1)) for v in (yaw, trans, scale, latent)]
+        # the previous use of these staging buffers must have been consumed by the device
+        torch.cuda.current_stream().synchronize() if self._pinned_dirty(b) else None
+        nocs = self._pin(('nocs', b), nocs_pred)
+        lidar = self._pin(('lidar', b), np.asarray(lidar_np, dtype=np.float32).reshape(-1, 3))
+        par = [self._pin((n, b), np.asarray(v, dtype=np.float32).reshape(-1))
+               for n, v in (('yaw', yaw), ('trans', trans), ('scale', scale), ('latent', latent))]
+        self._dirty.add(b)
         fp = lambda t: C.cast(t.data_ptr(), _lib.c_float_p)
         _lib.check(lib.sdfr_refine_set_detection(
             self.handle, b, fp(k32), fp(kinv), int(width), int(height), nocs.data_ptr(), int(nocs.shape[1]),
             int(nocs.shape[2]), lidar.data_ptr(), int(lidar.shape[0]), fp(par[0]), fp(par[1]), fp(par[2]), fp(par[3]),
             _lib.stream_ptr()))
+
+    def _pinned_dirty(self, b) -> bool:
+        return b in self._dirty
 
     def run(self, iters):
         _lib.check(_lib.load().sdfr_refine_run(self.handle, int(iters), _lib.stream_ptr()))
@@ -115,7 +127,7 @@ class _Engine:
         nh = C.c_int(0)
         _lib.check(_lib.load().sdfr_refine_get(self.handle, b, _lib.fptr(params), _lib.fptr(hist), C.byref(nh),
                                                _lib.stream_ptr()))
-        self._pinned.clear()
+        self._dirty.clear()         # sdfr_refine_get synchronised the stream: all staged copies are done
         return params, hist[:nh.value]
 
     VIEW_KINDS = {'sdf': 0, 'dinput': 1, 'surf_pts': 2, 'surf_nrm': 3, 'color': 4, 'mask': 5, 'normals': 6,

@@ -12,3 +12,6 @@ fi
 if [ -n "$RUN_NCU_LIST" ]; then
 echo "== ncu launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu ${BENCH_ARGS} > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?"; tail -3 gpurun_out/ncu_bench.log
 fi
+if [ -n "$RUN_NCU_FULL" ]; then
+echo "== ncu full capture of ${NCU_KERNEL:-mlp_tc_kernel}"; timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-mlp_tc_kernel} -s 2 -c 1 -f -o gpurun_out/prof_${NCU_KERNEL:-mlp_tc_kernel} python bench.py --steps 1 --warmup 1 --no-cpu ${BENCH_ARGS} > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+fi
