@@ -9,7 +9,7 @@
 // its successor (SURVEY.md "SMEM/TMEM budget"), so the GEMM is issued transposed:
 //     D^T[feature, point] = W[feature, k] * H^T[k, point]
 // A = weight tile (128 features x 32 k, K-major, streamed from L2 with cp.async.bulk into a
-// 3-stage ring), B = the CTA's activations (64 points x 512 k, resident in shared memory,
+// 5-stage ring), B = the CTA's activations (64 points x 512 k, resident in shared memory,
 // MN-major so that the 8 points one epilogue thread packs are one 16-byte store),
 // D = 4 x (128 lanes x 128 columns) fp32 accumulators in TMEM.  TMEM lane == output feature,
 // so the epilogue thread that owns a lane applies bias / ReLU / mask for one feature across
@@ -25,12 +25,13 @@
 // 96 to 32 adds; the epilogue adds the two columns in fp32.  Half the operand bytes of 3xTF32
 // and twice its MMA rate.
 //
-// Warp roles (192 threads): warps 0-3 epilogue (one TMEM lane quadrant each), warp 4 weight
-// producer (one elected lane), warp 5 MMA issuer (one elected lane) + TMEM allocator.
+// Warp roles (320 threads): warps 0-7 epilogue (TMEM lane quadrant = warp & 3, point half =
+// warp >> 2), warp 8 weight producer (one lane), warp 9 MMA issuer (one elected lane) + TMEM allocator.
 #include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -43,7 +44,7 @@ constexpr int NPTS = 64;                 // points per CTA tile
 constexpr int KC = 32;                   // k per weight stage (two K=16 MMA steps)
 constexpr int TILE_BYTES = 16384;        // 128 x 32 fp16 hi + the same lo
 constexpr int TILE_HALF_BYTES = 8192;
-constexpr int NSTAGE = 3;
+constexpr int NSTAGE = 5;
 // B operand (activations), MN-major, no swizzle: core matrix = 8 k-rows x (8 points = 16 B).
 // Per 8-k chunk: 8 point groups of the hi halves (1024 B) followed by 8 point groups of the lo
 // halves (1024 B), so one descriptor with N = 128 covers [hi ; lo] and N = 64 covers hi only.
@@ -54,7 +55,8 @@ constexpr int A_SBO = 128;
 constexpr int B_LBO = B_CHUNK;           // B (MN-major): next 8-k chunk
 constexpr int B_SBO = 128;               //               next 8-point group
 constexpr int TMEM_COLS = 512;           // 4 M-blocks x (64 main + 64 cross-term) columns
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;          // 8 epilogue warps + producer + MMA issuer
+constexpr int NEPI = 256;
 constexpr int MAX_TC_LAYERS = 9;
 constexpr float ACT_SCALE = 32.f;        // forward activations are stored as h * 2^5
 constexpr float BWD_SCALE = 256.f;       // backward deltas as delta * 2^8
@@ -109,6 +111,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// multicast variant: the slice lands at the same offset in every CTA of ctaMask and completes
+// tx bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -133,6 +156,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // arrives on the mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -204,19 +232,18 @@ __device__ __forceinline__ float pack8_store(unsigned char* chunk_row, int pg, c
 }
 
 struct SmemPlan {
-  uint32_t stages, b, masks, inp, dinp, g, bars, tmem_slot, total;
+  uint32_t stages, b, inp, dinp, g, bars, tmem_slot, total;
 };
 __host__ __device__ inline SmemPlan make_plan(int num_layers, int in0) {
   SmemPlan p;
   uint32_t o = 0;
   p.stages = o; o += NSTAGE * TILE_BYTES;
   p.b = o; o += B_BYTES;
-  p.masks = o; o += (uint32_t)(num_layers - 1) * 512 * 8;
   const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
   p.inp = o; o += in_pad * NPTS * 4;
   p.dinp = o; o += in_pad * NPTS * 4;
   p.g = o; o += NPTS * 4;
-  p.bars = o; o += 16 * 8;
+  p.bars = o; o += 32 * 8;
   p.tmem_slot = o; o += 16;
   p.total = o;
   return p;
@@ -234,14 +261,16 @@ __device__ unsigned long long g_tc_prof[16];
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
-              long long num_point_tiles) {
+              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
   const SmemPlan P = make_plan(num_layers, in0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* bop = smem + P.b;
-  unsigned long long* masks = reinterpret_cast<unsigned long long*>(smem + P.masks);
+  // ReLU sign words (one u64 per feature per hidden layer) live in an L2-resident global scratch:
+  // written and read back by the same thread, 32 KB per CTA, which buys two more weight stages.
+  unsigned long long* masks = mask_scratch + (size_t)blockIdx.x * (size_t)(num_layers - 1) * 512;
   float* inp = reinterpret_cast<float*>(smem + P.inp);     // [in_pad][64]
   float* dinp = reinterpret_cast<float*>(smem + P.dinp);
   float* gbuf = reinterpret_cast<float*>(smem + P.g);
@@ -252,23 +281,32 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   const int in_pad = (in0 + 7) & ~7;
   const bool want_grad = dinput_out != nullptr;
   const int npass = want_grad ? T.num_passes : num_layers;   // forward passes come first
+  // Thread-block cluster: every CTA of the cluster consumes the same weight-tile sequence, so each
+  // loads 1/CL of every tile and multicasts it to all of them (one L2 read per cluster instead of per CTA).
+  const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
+  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
     mbar_init(bar_acc, 1);
-    mbar_init(bar_act, 128);
+    mbar_init(bar_act, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 5) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
+  if (warp == 9) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // peers' barriers must exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Every CTA of a cluster runs the same number of iterations (it shares the weight ring with its
+  // peers); a CTA whose own point tile is past the end computes on masked (zero) points.
+  // Iteration `it` of cluster c covers point tiles (it * num_clusters + c) * CL + rank.
+  const long long num_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
   long long my_tiles = 0;
-  for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) ++my_tiles;
+  for (long long it = 0; (it * num_clusters + cluster_id) * CL < num_point_tiles; ++it) ++my_tiles;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== weight producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
@@ -279,15 +317,21 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           for (long long t = 0; t < n; ++t) {
             { PROF_T0(); mbar_wait(bar_empty + 8 * stage, phase ^ 1); PROF_ADD(0); }
             mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
-            bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, TILE_BYTES,
-                     bar_full + 8 * stage);
+            if (CL == 1) {
+              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, TILE_BYTES,
+                       bar_full + 8 * stage);
+            } else {
+              const uint32_t slice = TILE_BYTES / CL, off = crank * slice;
+              bulk_g2s_mcast(smem_u32(smem + P.stages + stage * TILE_BYTES) + off, src + t * TILE_BYTES + off, slice,
+                             bar_full + 8 * stage, cmask);
+            }
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     // All 32 lanes run the loop with identical (warp-uniform) values so that the descriptor
     // arithmetic stays on the uniform datapath; one elected lane issues the tcgen05 instructions.
@@ -321,7 +365,9 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
                 umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
                          kIdesc64, 1u);                                                    // W_lo x H_hi
               }
-              umma_commit(bar_empty + 8 * stage);      // frees the weight stage when these MMAs retire
+              // frees the weight stage (in every CTA of the cluster: all of them write into it)
+              if (CL == 1) umma_commit(bar_empty + 8 * stage);
+              else umma_commit_mcast(bar_empty + 8 * stage, cmask);
             }
             __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -332,15 +378,19 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM lane quadrant = warp) =====================
-    const int t = tid;                                 // 0..127 = TMEM lane
-    const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+    // ===================== epilogue warps =====================
+    const int q = warp & 3, ph = warp >> 2;            // TMEM lane quadrant, point half (32 points)
+    const int t = q * 32 + lane;                       // 0..127 = TMEM lane = feature within the M block
+    const int et = tid;                                // 0..255 index among the epilogue threads
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t* masks32 = reinterpret_cast<uint32_t*>(masks);   // [layer][feature][point half]
     uint32_t acc_phase = 0;
     float amax = 0.f;
-    for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) {
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long pt = (it * num_clusters + cluster_id) * CL + crank;   // may be past the end: masked
       const long long base = pt * NPTS;
       // ---- stage inputs: inp[c][n] ----
-      for (int i = t; i < in_pad * NPTS; i += 128) {
+      for (int i = et; i < in_pad * NPTS; i += NEPI) {
         const int c = i / NPTS, n = i - c * NPTS;
         const long long gi = base + n;
         float v = 0.f;
@@ -361,16 +411,17 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         inp[i] = v;
         dinp[i] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // B operand of layer 0: k = input column (padded to one 32-k chunk)
-      if (t < KC) {
-        unsigned char* row = bop + (t >> 3) * B_CHUNK + (t & 7) * 16;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // B operand of layer 0: k = input column (padded to one 32-k chunk); thread = (k, point half)
+      if (q == 0) {
+        const int k = lane;
+        unsigned char* row = bop + (k >> 3) * B_CHUNK + (k & 7) * 16;
 #pragma unroll
-        for (int pg = 0; pg < 8; ++pg) {
+        for (int pg = 0; pg < 4; ++pg) {
           float h[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = t < in0 ? inp[t * NPTS + pg * 8 + e] * ACT_SCALE : 0.f;
-          amax = fmaxf(amax, pack8_store(row, pg, h));
+          for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NPTS + ph * 32 + pg * 8 + e] * ACT_SCALE : 0.f;
+          amax = fmaxf(amax, pack8_store(row, ph * 4 + pg, h));
         }
       }
       fence_async_smem();
@@ -379,25 +430,26 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
 
       for (int p = 0; p < npass; ++p) {
         const TcPassDev Ps = T.pass[p];               // by value: keeps the fields in registers
-        { PROF_T0(); mbar_wait(bar_acc, acc_phase); if (t == 0) PROF_ADD(3); }
+        { PROF_T0(); mbar_wait(bar_acc, acc_phase); if (et == 0) PROF_ADD(3); }
         acc_phase ^= 1;
         tc_fence_after();
         PROF_T0();
         if (Ps.kind == 1) {
           // ---- last Linear: row 0 holds the pre-activation of the sdf ----
-          if (warp == 0) {                             // whole warp issues the aligned loads; lane 0 owns row 0
+          if (q == 0) {                                // whole warp issues the aligned loads; lane 0 owns row 0
             const float bias0 = __ldg(Ps.bias);
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const int g4 = ph * 2 + g2;
               uint32_t vm[16], vc[16];
               tmem_ld16(lane_base + g4 * 16, vm);
               tmem_ld16(lane_base + 64 + g4 * 16, vc);
               tmem_ld_wait();
               if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  const int n = g4 * 16 + q;
-                  float y = (__uint_as_float(vm[q]) + __uint_as_float(vc[q])) * Ps.inv_scale + bias0, g = 1.f;
+                for (int qq = 0; qq < 16; ++qq) {
+                  const int n = g4 * 16 + qq;
+                  float y = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale + bias0, g = 1.f;
                   if (use_tanh) { y = tanhf(y); g *= 1.f - y * y; }
                   y = tanhf(y);
                   g *= 1.f - y * y;
@@ -409,21 +461,21 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             }
           }
           tc_fence_before();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
           if (want_grad) {
             // backward of the last Linear is an outer product: delta[f][n] = W_last[f] * g[n] * mask[f][n]
             const int hidden = T.last_k;
             for (int mb = 0; mb < 4; ++mb) {
               const int f = mb * 128 + t;
               const float w = f < hidden ? __ldg(T.last_w + f) * BWD_SCALE : 0.f;
-              const unsigned long long mk = f < hidden ? masks[(size_t)(num_layers - 2) * 512 + f] : 0ull;
+              const uint32_t mk = f < hidden ? masks32[((size_t)(num_layers - 2) * 512 + f) * 2 + ph] : 0u;
               unsigned char* row = bop + (f >> 3) * B_CHUNK + (f & 7) * 16;
 #pragma unroll
-              for (int pg = 0; pg < 8; ++pg) {
+              for (int pg = 0; pg < 4; ++pg) {
                 float h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (pg * 8 + e)) & 1ull) ? w * gbuf[pg * 8 + e] : 0.f;
-                amax = fmaxf(amax, pack8_store(row, pg, h));
+                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (pg * 8 + e)) & 1u) ? w * gbuf[ph * 32 + pg * 8 + e] : 0.f;
+                amax = fmaxf(amax, pack8_store(row, ph * 4 + pg, h));
               }
             }
             fence_async_smem();
@@ -440,22 +492,23 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           const uint32_t tb = lane_base + (uint32_t)(mb * 128);
           unsigned char* row = bop + (f >> 3) * B_CHUNK + (f & 7) * 16;
           const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
-          const unsigned long long pmask = (Ps.kind == 2 && cls == 0) ? masks[(size_t)(Ps.layer - 1) * 512 + f] : 0ull;
-          const int cat_row = (Ps.cat_off + f - split) * NPTS;
-          unsigned long long mk = 0ull;
+          const uint32_t pmask = (Ps.kind == 2 && cls == 0) ? masks32[((size_t)(Ps.layer - 1) * 512 + f) * 2 + ph] : 0u;
+          const int cat_row = (Ps.cat_off + f - split) * NPTS + ph * 32;
+          uint32_t mk = 0u;
 #pragma unroll
-          for (int g4 = 0; g4 < 4; ++g4) {
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int g4 = ph * 2 + g2;
             uint32_t vm[16], vc[16];
             tmem_ld16(tb + g4 * 16, vm);
             tmem_ld16(tb + 64 + g4 * 16, vc);
             tmem_ld_wait();
             float x[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) x[q] = (__uint_as_float(vm[q]) + __uint_as_float(vc[q])) * Ps.inv_scale;
+            for (int qq = 0; qq < 16; ++qq) x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
             if (Ps.kind == 3) {                                    // gradient with respect to the input row
               if (cls == 0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) dinp[f * NPTS + g4 * 16 + q] += x[q];
+                for (int qq = 0; qq < 16; ++qq) dinp[f * NPTS + g4 * 16 + qq] += x[qq];
               }
               continue;
             }
@@ -463,30 +516,30 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             if (fwd) {
               if (cls == 0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  const float y = x[q] + bias;
+                for (int qq = 0; qq < 16; ++qq) {
+                  const float y = x[qq] + bias;
                   const bool on = y > 0.f;
-                  if (on) mk |= 1ull << (g4 * 16 + q);
-                  h[q] = on ? y * Ps.out_scale : 0.f;
+                  if (on) mk |= 1u << (g2 * 16 + qq);
+                  h[qq] = on ? y * Ps.out_scale : 0.f;
                 }
               } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
 #pragma unroll
-                for (int q = 0; q < 16; ++q) h[q] = inp[cat_row + g4 * 16 + q] * Ps.out_scale;
+                for (int qq = 0; qq < 16; ++qq) h[qq] = inp[cat_row + g2 * 16 + qq] * Ps.out_scale;
               } else {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) h[q] = 0.f;
+                for (int qq = 0; qq < 16; ++qq) h[qq] = 0.f;
               }
             } else {
               if (cls == 0) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) h[q] = ((pmask >> (g4 * 16 + q)) & 1ull) ? x[q] * Ps.out_scale : 0.f;
+                for (int qq = 0; qq < 16; ++qq) h[qq] = ((pmask >> (g2 * 16 + qq)) & 1u) ? x[qq] * Ps.out_scale : 0.f;
               } else {
                 if (cls == 1) {                                    // gradient of the concatenated input columns
 #pragma unroll
-                  for (int q = 0; q < 16; ++q) dinp[cat_row + g4 * 16 + q] += x[q];
+                  for (int qq = 0; qq < 16; ++qq) dinp[cat_row + g2 * 16 + qq] += x[qq];
                 }
 #pragma unroll
-                for (int q = 0; q < 16; ++q) h[q] = 0.f;
+                for (int qq = 0; qq < 16; ++qq) h[qq] = 0.f;
               }
             }
             float h8[8];
@@ -497,13 +550,13 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             for (int e = 0; e < 8; ++e) h8[e] = h[8 + e];
             amax = fmaxf(amax, pack8_store(row, g4 * 2 + 1, h8));
           }
-          if (fwd) masks[(size_t)Ps.layer * 512 + f] = mk;
+          if (fwd) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;
         }
-        if (t == 0) PROF_ADD(4 + (Ps.kind == 0 ? 0 : Ps.kind == 2 ? 1 : 2));
+        if (et == 0) PROF_ADD(4 + (Ps.kind == 0 ? 0 : Ps.kind == 2 ? 1 : 2));
         if (Ps.kind == 3) {
           tc_fence_before();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = t; i < NPTS * in0; i += 128) {
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int i = et; i < NPTS * in0; i += NEPI) {
             const int n = i / in0, c = i - n * in0;
             if (base + n < in.n) dinput_out[(base + n) * in0 + c] = dinp[c * NPTS + n];
           }
@@ -514,13 +567,14 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         }
       }
       // the next point tile re-stages inp/dinp: make sure everyone is done with them
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (amax > 60000.f) atomicOr(overflow_flag, 1);   // a scaled operand left the fp16 range
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CL > 1) cluster_sync_all();      // no CTA may exit while a peer can still write into it
+  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace
@@ -533,6 +587,7 @@ struct TcHostState {
   TcTable* table_dev;
   unsigned char* tiles_dev;
   int* overflow_dev;
+  unsigned long long* mask_dev;
   size_t smem_bytes;
 };
 
@@ -666,6 +721,11 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   if (rc == SDFR_OK) { TC_CUDA(cudaMalloc(&p, sizeof(TcTable))); if (rc == SDFR_OK) { dec->allocs.push_back(p); st->table_dev = reinterpret_cast<TcTable*>(p); } }
   if (rc == SDFR_OK) TC_CUDA(cudaMemcpy(st->table_dev, &T, sizeof(TcTable), cudaMemcpyHostToDevice));
   if (rc == SDFR_OK) { TC_CUDA(cudaMalloc(&p, 64)); if (rc == SDFR_OK) { dec->allocs.push_back(p); st->overflow_dev = reinterpret_cast<int*>(p); TC_CUDA(cudaMemset(p, 0, 64)); } }
+  if (rc == SDFR_OK) {
+    const size_t mask_bytes = (size_t)(dec->sm_count > 0 ? dec->sm_count : 148) * (size_t)(NL - 1) * 512 * 8;
+    TC_CUDA(cudaMalloc(&p, mask_bytes));
+    if (rc == SDFR_OK) { dec->allocs.push_back(p); st->mask_dev = reinterpret_cast<unsigned long long*>(p); }
+  }
   if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
 #undef TC_CUDA
   if (rc != SDFR_OK) { delete st; return rc; }
@@ -693,9 +753,33 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
   if (in.n <= 0) return SDFR_OK;
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
   const long long point_tiles = (in.n + NPTS - 1) / NPTS;
-  const int grid = (int)std::min<long long>(point_tiles, dec->sm_count > 0 ? dec->sm_count : 148);
-  mlp_tc_kernel<<<grid, NTHREADS, st->smem_bytes, s>>>(st->table_dev, st->tiles_dev, in, sdf, dinput,
-                                                      st->overflow_dev, point_tiles);
+  static int cluster = -1;
+  if (cluster < 0) {
+    const char* e = getenv("SDFR_TC_CLUSTER");
+    cluster = e ? atoi(e) : 1;   // multicast measured slower than per-CTA streaming with a 3-stage ring
+    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+  }
+  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  int grid = (int)std::min<long long>(point_tiles, sms);
+  int cl = cluster;
+  while (cl > 1 && (grid % cl != 0 || grid < cl)) {
+    if (grid >= cl) grid -= grid % cl; else cl >>= 1;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = st->smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev, in,
+                               sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles));
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
