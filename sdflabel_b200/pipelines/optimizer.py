@@ -85,17 +85,23 @@ class _Engine:
                 c.mlp_impl)
 
     def _pin(self, key, arr) -> torch.Tensor:
-        """float32 host copy in a persistent pinned buffer, so the H2D copy is a true async DMA
-        and no cudaHostAlloc happens per call."""
-        t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)) if not isinstance(arr, torch.Tensor) \
-            else arr.detach().to('cpu', torch.float32).contiguous()
-        buf = self._pinned.get(key)
-        if buf is None or buf.numel() < t.numel():
-            buf = torch.empty((max(t.numel(), 1),), dtype=torch.float32, pin_memory=True)
-            self._pinned[key] = buf
-        view = buf[:t.numel()].view(t.shape)
-        view.copy_(t)
-        return view
+        """float32 host copy in a persistent pinned buffer, so the H2D copy is a true async DMA and
+        no cudaHostAlloc happens per call.  The copy is a plain single-threaded numpy memcpy: torch's
+        CPU copy_ goes through the OpenMP pool above 32 K elements, and waking a sleeping pool on a
+        128-core host costs tens of milliseconds every few calls (measured)."""
+        if isinstance(arr, torch.Tensor):
+            src = arr.detach()
+            src = (src if src.device.type == 'cpu' else src.cpu()).numpy()
+        else:
+            src = np.asarray(arr)
+        n = int(src.size)
+        ent = self._pinned.get(key)
+        if ent is None or ent[0].numel() < n:
+            buf = torch.empty((max(n, 1),), dtype=torch.float32, pin_memory=True)
+            ent = (buf, buf.numpy())
+            self._pinned[key] = ent
+        np.copyto(ent[1][:n], src.reshape(-1), casting='same_kind')
+        return ent[0][:n].view(tuple(src.shape))
 
     def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw, trans, scale, latent):
         lib = _lib.load()
