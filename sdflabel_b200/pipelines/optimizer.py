@@ -170,6 +170,53 @@ def _engine_for(dsdf, batch, density, w, h, n_lidar, iters, weights, impl) -> _E
     return eng
 
 
+class _Loss3D(torch.autograd.Function):
+    """mean ||L_nn - v|| over pairs closer than `radius` (sdfr_loss3d: exact brute-force 1-NN on the device)."""
+
+    @staticmethod
+    def forward(ctx, xyzf, lidar_scaled, radius):
+        lib = _lib.load()
+        q = xyzf.detach().contiguous().float()
+        l = lidar_scaled.detach().contiguous().float()
+        loss = torch.zeros(2, device=q.device)
+        dq = torch.zeros_like(q)
+        dl = torch.zeros_like(l)
+        with torch.cuda.device(q.device):
+            _lib.check(lib.sdfr_loss3d(q.data_ptr(), q.shape[0], l.data_ptr(), l.shape[0], float(radius),
+                                       loss.data_ptr(), dq.data_ptr(), dl.data_ptr(), _lib.stream_ptr()))
+        ctx.save_for_backward(dq, dl)
+        ctx.dtypes = (xyzf.dtype, lidar_scaled.dtype)
+        return loss[0].to(xyzf.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        dq, dl = ctx.saved_tensors
+        return (g * dq).to(ctx.dtypes[0]), (g * dl).to(ctx.dtypes[1]), None
+
+
+class _Loss2D(torch.autograd.Function):
+    """Windowed form of the reference's O(M*H*W) NOCS loss (sdfr_loss2d)."""
+
+    @staticmethod
+    def forward(ctx, color, target):
+        lib = _lib.load()
+        c = color.detach().contiguous().float()
+        t = target.detach().contiguous().float()
+        loss = torch.zeros(2, device=c.device)
+        dc = torch.zeros_like(c)
+        with torch.cuda.device(c.device):
+            _lib.check(lib.sdfr_loss2d(c.data_ptr(), t.data_ptr(), c.shape[1], c.shape[2], loss.data_ptr(),
+                                       dc.data_ptr(), _lib.stream_ptr()))
+        ctx.save_for_backward(dc)
+        ctx.dtype = color.dtype
+        return loss[0].to(color.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dc,) = ctx.saved_tensors
+        return (g * dc).to(ctx.dtype), None
+
+
 class Optimizer:
     def __init__(self, params, device, weights, rot='dcm'):
         self.params, self.optim_params = get_opt_params(params, device)
@@ -225,6 +272,23 @@ class Optimizer:
                     print('Skip frame')
                 else:
                     print('ITER {} | Losses: 2D - {}, 3D - {}, Total - {}'.format(e, w2 * l2, w3 * l3, tot))
+
+
+    # ---- stand-alone losses with the reference's signatures (optimizer.py:166-237) -------------------
+    def compute_loss_3d(self, pcd_dsdf_trans, pcd_frustum, threshold=0.2):
+        """3D loss between the estimated and LIDAR point clouds; returns (loss, None, None): the
+        neighbour distances / indices the reference also returns only feed its open3d visualiser."""
+        if pcd_dsdf_trans.nelement() == 0 or pcd_frustum.nelement() == 0:
+            return torch.zeros((), device=pcd_dsdf_trans.device, dtype=pcd_dsdf_trans.dtype), None, None
+        radius = threshold / self.params['scale'][0].item()
+        return _Loss3D.apply(pcd_dsdf_trans, pcd_frustum, radius), None, None
+
+    def compute_loss_2d(self, rendering_nocs, css_nocs, diam=5, threshold_nocs=1):
+        """2D loss between the CSS net output and the rendering (diam / threshold are the reference's
+        fixed 5 px / 1.0; other values are not supported by the kernel)."""
+        if diam != 5 or threshold_nocs != 1:
+            raise NotImplementedError("sdfr_loss2d implements the reference defaults diam=5, threshold_nocs=1")
+        return _Loss2D.apply(rendering_nocs, css_nocs.to(rendering_nocs.device))
 
 
 class BatchOptimizer:
