@@ -662,19 +662,14 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
     hp.push_back(std::move(p));
   }
   T.num_passes = (int)hp.size();
-  long long ntiles = 0;
-  for (auto& p : hp) ntiles += (long long)((p.rows + 127) / 128) * ((p.K + KC - 1) / KC);
-  std::vector<__half> packed((size_t)ntiles * (TILE_BYTES / 2));
-  long long tile = 0;
-  int rc = SDFR_OK;
   std::vector<const float*> bias_dev(NL, nullptr);
   for (int l = 0; l < NL; ++l) bias_dev[l] = dec->dev.layer[l].bias;
+  long long ntiles = 0;
   for (int pi = 0; pi < T.num_passes; ++pi) {
     HostPass& p = hp[pi];
     TcPassDev& D = T.pass[pi];
     D.kind = p.kind; D.layer = p.layer; D.rows = p.rows;
     D.m_blocks = (p.rows + 127) / 128; D.k_chunks = (p.K + KC - 1) / KC;
-    D.tile0 = tile;
     D.bias = (p.kind <= 1) ? bias_dev[p.layer] : nullptr;
     D.cat_dim = 0; D.cat_off = 0; D.prev_rows = 0;
     const float in_scale = p.kind <= 1 ? ACT_SCALE : BWD_SCALE;
@@ -683,7 +678,7 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
     if (p.kind == 0 && p.layer + 1 < NL && spec->concat[p.layer + 1]) {      // the next Linear concatenates
       D.cat_dim = spec->concat[p.layer + 1] == 1 ? in0 : 3;
       D.cat_off = spec->concat[p.layer + 1] == 1 ? 0 : spec->latent_size;
-      D.m_blocks = (p.rows + D.cat_dim + 127) / 128;
+      D.m_blocks = (p.rows + D.cat_dim + 127) / 128;                          // the concat rows are written by this pass
     }
     if (p.kind == 2) {
       D.prev_rows = spec->out_dims[p.layer - 1];
@@ -692,23 +687,17 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
         D.cat_off = spec->concat[p.layer] == 1 ? 0 : spec->latent_size;
       }
     }
-    const int mb_packed = D.m_blocks;
-    for (int mb = 0; mb < mb_packed; ++mb)
-      for (int kc = 0; kc < D.k_chunks; ++kc) pack_tile(packed, (size_t)tile++, p.A, p.rows, p.K, p.lda, mb, kc, p.scale);
+    D.tile0 = ntiles;
+    ntiles += (long long)D.m_blocks * D.k_chunks;
   }
-  // m_blocks may have grown for concatenation rows: recount
-  if (tile != ntiles) {
-    // repack with the right total (rare: only when the concat pushes past a 128 multiple)
-    ntiles = 0;
-    for (int pi = 0; pi < T.num_passes; ++pi) ntiles += (long long)T.pass[pi].m_blocks * T.pass[pi].k_chunks;
-    packed.assign((size_t)ntiles * (TILE_BYTES / 2), __float2half_rn(0.f));
-    tile = 0;
-    for (int pi = 0; pi < T.num_passes; ++pi) {
-      T.pass[pi].tile0 = tile;
-      for (int mb = 0; mb < T.pass[pi].m_blocks; ++mb)
-        for (int kc = 0; kc < T.pass[pi].k_chunks; ++kc)
-          pack_tile(packed, (size_t)tile++, hp[pi].A, hp[pi].rows, hp[pi].K, hp[pi].lda, mb, kc, hp[pi].scale);
-    }
+  std::vector<__half> packed((size_t)ntiles * (TILE_BYTES / 2));
+  long long tile = 0;
+  int rc = SDFR_OK;
+  for (int pi = 0; pi < T.num_passes; ++pi) {
+    HostPass& p = hp[pi];
+    const TcPassDev& D = T.pass[pi];
+    for (int mb = 0; mb < D.m_blocks; ++mb)
+      for (int kc = 0; kc < D.k_chunks; ++kc) pack_tile(packed, (size_t)tile++, p.A, p.rows, p.K, p.lda, mb, kc, p.scale);
   }
   T.tiles_per_point_tile = ntiles;
   T.last_k = spec->in_dims[NL - 1];

@@ -43,15 +43,20 @@ struct Variant {
   int a_kstep, b_kstep;   // byte advance of the start address per K=16 step
   int ksteps;       // K=16 steps cycled over
   int two;          // 1: alternate N / 64 like the MLP kernel (second MMA uses N=64)
+  int commit_every; // >0: tcgen05.commit to a scratch mbarrier after every this many rounds (no wait)
+  int wait_ready;   // 1: also try_wait on an already-completed mbarrier + tcgen05.fence before each group
+  int nacc;         // >1: rotate over this many accumulators (128 columns apart), all MMAs use N=n
 };
 
 __global__ void __launch_bounds__(128, 1) bench(Variant v, int rounds, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t scratch_bar[8];
+  __shared__ uint64_t done_bar;
   __shared__ uint32_t slot;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&scratch_bar[i]), 1 << 20); mbar_init(smem_u32(&done_bar), 1); asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&done_bar)) : "memory"); mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -74,15 +79,24 @@ __global__ void __launch_bounds__(128, 1) bench(Variant v, int rounds, long long
     long long best = 1ll << 60;
     for (int rep = 0; rep < 5; ++rep) {
       const long long t0 = clock64();
-      for (int r = 0; r < rounds; r += 4) {
+      for (int r = 0; r < rounds; r += 16) {
+        if (v.wait_ready) {
+          mbar_wait(smem_u32(&done_bar), 0);     // phase 0 completed at start-up: returns immediately
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         uint32_t pred;
         asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
         if (pred) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 16; ++u) {
             const int j = u % 2;   // two K steps per operand stage, like the MLP kernel
-            umma(tmu, da0 + j * ak, db0 + j * bk, idn, (r | u) ? 1u : 0u);
-            if (v.two) umma(tmu + 64, da1 + j * ak, db0 + j * bk, id64, 1u);
+            if (v.nacc > 1) {
+              umma(tmu + (uint32_t)((u % v.nacc) * 128), da0 + j * ak, db0 + j * bk, idn, (r | (u / v.nacc)) ? 1u : 0u);
+            } else {
+              umma(tmu, da0 + j * ak, db0 + j * bk, idn, (r | u) ? 1u : 0u);
+              if (v.two) umma(tmu + 64, da1 + j * ak, db0 + j * bk, id64, 1u);
+            }
+            if (v.commit_every && ((u + 1) % (v.commit_every < 0 ? -v.commit_every : v.commit_every)) == 0) { commit(smem_u32(&scratch_bar[(r / 16 + u) & 7])); if (v.commit_every < 0) commit(smem_u32(&scratch_bar[(r / 16 + u + 1) & 7])); }
           }
         }
         __syncwarp();
@@ -123,8 +137,24 @@ int main() {
       // swizzled A, MN-major unswizzled B
       {"A:K/sw128 B:MN/none N=128       ", {128, 2, 0, 1, 16, 1024, 2048, 128, 32, 4096, 2, 0}},
       {"A:K/sw128 B:MN/none N=128+64    ", {128, 2, 0, 1, 16, 1024, 2048, 128, 32, 4096, 2, 1}},
+      {"pair, commit every 2 rounds     ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 2, 0}},
+      {"pair, commit every 4 rounds     ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 4, 0}},
+      {"pair, try_wait+fence per 4 rnds ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 0, 1}},
+      {"pair, commit/2 + wait per 16    ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 2, 1}},
+      {"pair, commit every 1 round      ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 1, 0}},
+      {"pair, commit every 8 rounds     ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 8, 0}},
+      {"pair, commit every 16 rounds    ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, 16, 0}},
+      {"pair, 2 commits every 4 rounds  ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 1, -4, 0}},
+      {"N=128 x1 acc, commit every 2    ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 0, 2, 0, 1}},
+      {"N=128 x2 acc, commit every 2    ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 0, 2, 0, 2}},
+      {"N=128 x4 acc, commit every 2    ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 0, 2, 0, 4}},
+      {"N=128 x4 acc, no commit         ", {128, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 0, 0, 0, 4}},
+      {"N=64  x4 acc, commit every 2    ", {64, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 0, 2, 0, 4}},
+      {"N=64  x4 acc, no commit         ", {64, 0, 0, 1, 2048, 128, 2048, 128, 4096, 4096, 2, 0, 0, 0, 4}},
+      {"N=256 single, commit every 2    ", {256, 0, 0, 1, 2048, 128, 4096, 128, 4096, 8192, 2, 0, 2, 0}},
+      {"N=256 single, commit every 4    ", {256, 0, 0, 1, 2048, 128, 4096, 128, 4096, 8192, 2, 0, 4, 0}},
   };
-  const int rounds = 2000;
+  const int rounds = 2048;
   for (auto& nv : vs) {
     bench<<<148, 128, 200 * 1024>>>(nv.v, rounds, out);
     cudaError_t e = cudaDeviceSynchronize();
