@@ -223,7 +223,8 @@ int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_ho
                     void* stream);
 
 /* Device views of the last iteration's intermediates of detection b (for
- * parity tests and label dumps): kind 0 sdf [D^3], 1 dinput [D^3,L+3],
+ * parity tests and label dumps): kind 0 sdf [D^3], 1 d sdf/d[latent,x] of the band points of the
+ * whole batch (compact, [sum m, L+3]),
  * 2 surfel points [m,3], 3 surfel normals [m,3], 4 color [3,H,W], 5 mask,
  * 6 normals map [3,H,W], 7 grads [dyaw,dt3,dscale,dlatent_unit(L),dlatent(L)],
  * 8 surfel count (int32), 9 depth, 10 camera-space surfel centres [m,3],

@@ -210,8 +210,16 @@ struct MlpInputs {
   const float* latent_unit;   // [batch, L] for lattice mode
   LatticeParams lattice;
   long long points_per_batch; // D^3 in lattice mode
-  long long n;                // total points
+  long long n;                // total points (capacity when count_dev is set)
+  const int* index;           // optional gather: row r evaluates source point index[r] (null = r)
+  const int* count_dev;       // optional: number of rows, read on the device (no host sync)
 };
+
+__device__ __forceinline__ long long mlp_rows(const MlpInputs& in) {
+  if (!in.count_dev) return in.n;
+  const long long c = (long long)*in.count_dev;
+  return c < in.n ? c : in.n;
+}
 
 int launch_mlp_ffma(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s);
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s);
@@ -238,6 +246,34 @@ struct SurfaceArgs {
   int* scratch;             // [batch, blocks+1]
 };
 int launch_surface_extract(const SurfaceArgs& a, cudaStream_t s);
+
+// Band-restricted flow of the fused engine: (1) select |sdf| < thr over all detections into one
+// compact source-index list, (2) evaluate the decoder with its input gradient on that list only,
+// (3) project the band points onto the zero isosurface.
+struct BandArgs {
+  LatticeParams lattice;
+  const float* sdf;         // [batch, n] from the forward-only lattice pass
+  long long n;              // lattice points per detection
+  int batch;
+  float threshold;
+  int* block_counts;        // [batch, nblocks]
+  int* block_prefix;        // [batch, nblocks] exclusive, detection-major
+  int* det_start;           // [batch]
+  int* det_count;           // [batch]  (also the surfel count the splat stages read)
+  int* total;               // [1]
+  int* band_src;            // [batch * n] global source index b*n + k, ascending
+  // after the band evaluation
+  const float* band_sdf;    // [total]
+  const float* band_dinput; // [total, in0]
+  int in0, latent;
+  float* out_pts;           // [batch, cap, 3]
+  float* out_nrm;
+  int* out_idx;
+  float* out_glat;          // [batch, cap, latent]
+  long long cap;
+};
+int launch_band_select(const BandArgs& a, cudaStream_t s);
+int launch_band_surface(const BandArgs& a, cudaStream_t s);
 
 // loss.cu
 int launch_loss3d_standalone(const float* xyzf, long long q, const float* lidar, long long nl, double radius,

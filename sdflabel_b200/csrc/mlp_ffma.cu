@@ -143,6 +143,8 @@ mlp_ffma_kernel(const DecoderDev* __restrict__ decp, MlpInputs in, float* __rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = warp * PPW;
   const long long base = (long long)blockIdx.x * TP;
+  const long long n_rows = mlp_rows(in);
+  if (base >= n_rows) return;            // launched for the capacity; the row count lives on the device
   const int in0 = dec.in0, Ls = dec.latent_size, NL = dec.num_layers;
   const int AS = L.act_stride, IS = L.in_stride;
   float* xhat_scratch = ln_scratch ? ln_scratch + (size_t)blockIdx.x * ln_scratch_per_cta : nullptr;
@@ -152,11 +154,12 @@ mlp_ffma_kernel(const DecoderDev* __restrict__ decp, MlpInputs in, float* __rest
     const int p = i / IS, c = i - p * IS;
     const long long gi = base + p;
     float v = 0.f;
-    if (gi < in.n && c < in0) {
+    if (gi < n_rows && c < in0) {
+      const long long src = in.index ? (long long)in.index[gi] : gi;
       if (in.inputs) {
-        v = in.inputs[gi * in0 + c];
+        v = in.inputs[src * in0 + c];
       } else {
-        const long long b = gi / in.points_per_batch, k = gi - b * in.points_per_batch;
+        const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
         if (c < Ls) {
           v = in.latent_unit[b * Ls + c];
         } else {
@@ -281,7 +284,7 @@ mlp_ffma_kernel(const DecoderDev* __restrict__ decp, MlpInputs in, float* __rest
           v = tanhf(v);
           g *= 1.f - v * v;
           const long long gi = base + row0 + pp;
-          if (gi < in.n) sdf_out[gi] = v;
+          if (gi < n_rows) sdf_out[gi] = v;
           gbuf[row0 + pp] = g;
         }
       }
@@ -400,7 +403,7 @@ mlp_ffma_kernel(const DecoderDev* __restrict__ decp, MlpInputs in, float* __rest
   for (int i = tid; i < TP * in0; i += NT) {
     const int p = i / in0, c = i - p * in0;
     const long long gi = base + p;
-    if (gi < in.n) dinput_out[gi * in0 + c] = dinp[p * IS + c];
+    if (gi < n_rows) dinput_out[gi * in0 + c] = dinp[p * IS + c];
   }
 }
 

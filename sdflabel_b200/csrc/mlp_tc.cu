@@ -283,6 +283,8 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   const int npass = want_grad ? T.num_passes : num_layers;   // forward passes come first
   // Thread-block cluster: every CTA of the cluster consumes the same weight-tile sequence, so each
   // loads 1/CL of every tile and multicasts it to all of them (one L2 read per cluster instead of per CTA).
+  const long long n_rows = mlp_rows(in);           // the row count may live on the device (band pass)
+  if (in.count_dev) num_point_tiles = (n_rows + NPTS - 1) / NPTS;
   const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
@@ -394,11 +396,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         const int c = i / NPTS, n = i - c * NPTS;
         const long long gi = base + n;
         float v = 0.f;
-        if (gi < in.n && c < in0) {
+        if (gi < n_rows && c < in0) {
+          const long long src = in.index ? (long long)in.index[gi] : gi;
           if (in.inputs) {
-            v = in.inputs[gi * in0 + c];
+            v = in.inputs[src * in0 + c];
           } else {
-            const long long b = gi / in.points_per_batch, k = gi - b * in.points_per_batch;
+            const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
             if (c < latent) {
               v = in.latent_unit[b * latent + c];
             } else {
@@ -453,7 +456,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
                   if (use_tanh) { y = tanhf(y); g *= 1.f - y * y; }
                   y = tanhf(y);
                   g *= 1.f - y * y;
-                  if (base + n < in.n) sdf_out[base + n] = y;
+                  if (base + n < n_rows) sdf_out[base + n] = y;
                   gbuf[n] = g;
                 }
               }
@@ -558,7 +561,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           asm volatile("bar.sync 1, 256;" ::: "memory");
           for (int i = et; i < NPTS * in0; i += NEPI) {
             const int n = i / in0, c = i - n * in0;
-            if (base + n < in.n) dinput_out[(base + n) * in0 + c] = dinp[c * NPTS + n];
+            if (base + n < n_rows) dinput_out[(base + n) * in0 + c] = dinp[c * NPTS + n];
           }
         } else {
           fence_async_smem();

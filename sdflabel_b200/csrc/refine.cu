@@ -4,11 +4,13 @@
 //           SGD on scale/latent) and 56-164 (the loop body), with
 //           utils/refinement.py:108-125 (rot_from_yaw) folded into the pose kernel.
 //
-// One iteration = 12 launches, no host synchronisation, all detections of the
+// One iteration = 16 launches, no host synchronisation, all detections of the
 // batch per launch (blockIdx.y / blockIdx.z = detection):
-//   begin -> MLP lattice eval (sdf + d sdf/d[latent,x]) -> band count/scatter ->
-//   project -> splat forward -> 2D loss pixels -> 3D loss pairs -> pixel-gradient
-//   records -> splat backward -> chain to (R, t, latent_unit, scale) partials -> update.
+//   begin -> MLP forward over the lattice -> band select (count / prefix / index) ->
+//   MLP forward + input-gradient over the band points only (the normals and d sdf/d latent
+//   are needed nowhere else: ~2.5 % of the lattice) -> isosurface projection -> project ->
+//   splat forward -> 2D loss pixels -> 3D loss pairs -> pixel-gradient records ->
+//   splat backward -> chain to (R, t, latent_unit, scale) partials -> update.
 // Every reduction is an ordered two-level sum, so a run is bit-reproducible.
 #include <algorithm>
 #include <cstddef>
@@ -43,14 +45,19 @@ struct EngineDev {          // passed by value to the engine kernels
   DetState* det;            // [B]
   float* latent;            // [B,L]
   float* latent_unit;       // [B,L]
-  float* sdf;               // [B,ng]
-  float* dinput;            // [B,ng,in0]
+  float* sdf;               // [B,ng]   forward-only lattice pass
+  float* dinput;            // [B*ng,in0] d sdf / d [latent, x] of the BAND points only (compact)
   float* surf_pts;          // [B,cap,3]
   float* surf_nrm;          // [B,cap,3]
   float* surf_glat;         // [B,cap,L]
   int* surf_idx;            // [B,cap]
-  int* surf_count;          // [B]
-  int* scan_scratch;
+  int* surf_count;          // [B]  (= band count per detection)
+  int* band_block_counts;   // [B,nblk]
+  int* band_block_prefix;   // [B,nblk]
+  int* band_det_start;      // [B]
+  int* band_total;          // [1]
+  int* band_src;            // [B*ng] compact global source indices of the band points
+  float* band_sdf;          // [B*ng] sdf of the band points (second, gradient-carrying evaluation)
   float* target;            // [B,3,max_pixels]
   float* lidar;             // [B,max_lidar,3]
   float* l3rec;             // [B,cap,4] unit direction, distance (-1 = unused)
@@ -451,7 +458,8 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.sdf, B * E.ng); A(E.dinput, B * E.ng * E.in0);
   A(E.surf_pts, B * E.cap * 3); A(E.surf_nrm, B * E.cap * 3); A(E.surf_glat, B * E.cap * L);
   A(E.surf_idx, B * E.cap); A(E.surf_count, B);
-  A(E.scan_scratch, (size_t)B * (E.ng / 1024 + 4));
+  A(E.band_block_counts, (size_t)B * (E.ng / 1024 + 2)); A(E.band_block_prefix, (size_t)B * (E.ng / 1024 + 2));
+  A(E.band_det_start, B); A(E.band_total, 4); A(E.band_src, (size_t)B * E.ng); A(E.band_sdf, (size_t)B * E.ng);
   A(E.target, (size_t)B * 3 * E.max_pixels); A(E.lidar, (size_t)B * E.max_lidar * 3);
   A(E.l3rec, B * E.cap * 4); A(E.l3dot, B * E.cap); A(E.l2rec, (size_t)B * E.max_pixels * 4);
   A(E.part2, (size_t)B * E.nb2 * 3); A(E.part3, (size_t)B * E.nb3 * 3); A(E.partc, (size_t)B * E.nbc * (16 + L));
@@ -552,23 +560,33 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   in.lattice = make_lattice(r->cfg.density);
   in.points_per_batch = E.ng;
   in.n = E.ng * B;
+  in.index = nullptr;
+  in.count_dev = nullptr;
+  MlpInputs in_band = in;               // same lattice / latents, rows gathered through band_src
+  in_band.index = E.band_src;
+  in_band.count_dev = E.band_total;
   int impl = r->cfg.mlp_impl;
   if (impl == SDFR_MLP_AUTO) impl = r->dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
-  SurfaceArgs sa;
-  sa.points = nullptr; sa.lattice = in.lattice; sa.sdf = E.sdf; sa.grad = E.dinput;
-  sa.grad_stride = E.in0; sa.grad_col = E.L; sa.n = E.ng; sa.batch = B; sa.threshold = 0.03f;   // grid.py:43
-  sa.out_pts = E.surf_pts; sa.out_nrm = E.surf_nrm; sa.out_idx = E.surf_idx; sa.out_glat = E.surf_glat;
-  sa.glat_dim = E.L; sa.cap = E.cap; sa.out_count = E.surf_count; sa.scratch = E.scan_scratch;
+  BandArgs ba;
+  ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B; ba.threshold = 0.03f;   // grid.py:43
+  ba.block_counts = E.band_block_counts; ba.block_prefix = E.band_block_prefix; ba.det_start = E.band_det_start;
+  ba.det_count = E.surf_count; ba.total = E.band_total; ba.band_src = E.band_src;
+  ba.band_sdf = E.band_sdf; ba.band_dinput = E.dinput; ba.in0 = E.in0; ba.latent = E.L;
+  ba.out_pts = E.surf_pts; ba.out_nrm = E.surf_nrm; ba.out_idx = E.surf_idx; ba.out_glat = E.surf_glat; ba.cap = E.cap;
   const int maxw = r->max_w_set, maxh = r->max_h_set;
   SDFR_REQUIRE(maxw > 0 && maxh > 0, SDFR_E_INVALID, "no detection has been set");
   int rc;
   for (int it = 0; it < iters; ++it) {
     iter_begin_kernel<<<B, 32, 0, s>>>(E);
     SDFR_LAUNCH_CHECK();
-    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in, E.sdf, E.dinput, s)
-                                  : launch_mlp_ffma(r->dec, in, E.sdf, E.dinput, s);
+    // sdf over the whole lattice (forward only), then sdf + input gradient for the band points
+    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in, E.sdf, nullptr, s) : launch_mlp_ffma(r->dec, in, E.sdf, nullptr, s);
     if (rc) return rc;
-    if ((rc = launch_surface_extract(sa, s))) return rc;
+    if ((rc = launch_band_select(ba, s))) return rc;
+    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in_band, E.band_sdf, E.dinput, s)
+                                  : launch_mlp_ffma(r->dec, in_band, E.band_sdf, E.dinput, s);
+    if (rc) return rc;
+    if ((rc = launch_band_surface(ba, s))) return rc;
     if ((rc = launch_project(E.views, B, (int)E.cap, s))) return rc;
     if ((rc = launch_splat_forward(E.views, B, maxw, maxh, s))) return rc;
     loss2d_batch_kernel<<<dim3((maxw * maxh + LB - 1) / LB, B), LB, 0, s>>>(E);
