@@ -160,6 +160,30 @@ int sdfr_splat_backward(const sdfr_raster_cfg* cfg, const float* coords_dev, con
                         void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Trace mode: per-ray sphere tracing against the decoder (BASELINE.json north_star).  Not a
+ * reference function (the reference renderer is the surfel splat above); same decoder, same
+ * camera conventions, validated against oracle/trace_oracle.py.
+ * ------------------------------------------------------------------------- */
+int64_t sdfr_trace_workspace_bytes(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec);
+
+/* Marches every pixel ray (r = K^-1 [x,y,1], object frame through pose_host = 4x4 row-major
+ * [R|t], R orthogonal) by tau += sdf for at most max_steps decoder evaluations; a ray hits when
+ * |sdf| < eps.  Outputs (device, may be NULL): depth [1,H,W] = z of the hit in the camera frame,
+ * normals [3,H,W] = (R grad sdf/|grad sdf| + 1)/2, nocs [3,H,W] = ((-x,y,z)+1)/2 of the hit in
+ * the object frame, mask [1,H,W]; zero where no hit.  latent_unit_dev: [L] normalised latent. */
+int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg, const float* latent_unit_dev,
+                       const float* pose_host, int max_steps, float eps, float* depth_dev, float* nmap_dev,
+                       float* nocs_dev, float* mask_dev, int32_t* hit_count_dev, void* workspace_dev, int impl,
+                       void* stream);
+
+/* Gradient of a loss on the depth / NOCS maps with respect to the pose (12 floats, rows of
+ * [R|t]) and the unit latent, by implicit differentiation of sdf(l, o + tau d) = 0 at the hits
+ * found by the preceding forward call on the same workspace. */
+int sdfr_trace_backward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg, const float* pose_host, float eps,
+                        const float* g_depth_dev, const float* g_nocs_dev, float* d_pose_dev,
+                        float* d_latent_unit_dev, void* workspace_dev, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Losses (value + gradient in one call).
  * replaces: pipelines/optimizer.py:166-198 (compute_loss_3d; exact 1-NN on the
  *           device instead of the sklearn KD-tree + D2H) and 200-237 (compute_loss_2d)

@@ -1,0 +1,93 @@
+"""Trace-mode renderer: per-ray sphere tracing of the DeepSDF decoder on the device.
+
+This is the renderer BASELINE.json's north_star describes; the reference has no counterpart
+(its renderer is the surfel splat, mirrored in ``rasterer.py``).  Same camera conventions as
+``Rasterer``: ``K`` (3,3), resolution ``(W, H)``, ``camera_matrix`` a 4x4 object-to-camera DCM
+pose with an orthogonal rotation (e.g. the refine loop's ``diag(1,-1,1) R_y(yaw)``, optimizer.py:87-90).
+
+    tracer = SphereTracer(K, (W, H)).to(device)
+    rendering = tracer(dsdf, latent, pose)      # dict: depth (1,H,W), normals (3,H,W), color = NOCS (3,H,W), mask
+
+``depth`` and ``color`` are differentiable with respect to ``pose`` and ``latent`` (implicit
+differentiation at the hit, ``sdfr_trace_backward``); ``normals`` and ``mask`` are constants,
+like the normals in the reference's graph (grid.py:55-58).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class _Trace(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, latent_unit, pose, native, cfg_tuple, max_steps, eps, impl):
+        lib = _lib.load()
+        width, height, kinv, kmat = cfg_tuple
+        dev = latent_unit.device
+        cfg = _lib.RasterCfg(width=width, height=height, rot=_lib.ROT_DCM, output_nocs=1)
+        cfg.kinv[:] = kinv
+        cfg.k[:] = kmat
+        lat = latent_unit.detach().contiguous().float()
+        pose_h = np.ascontiguousarray(pose.detach().cpu().float().numpy().reshape(16))
+        f32 = dict(device=dev, dtype=torch.float32)
+        depth = torch.empty((1, height, width), **f32)
+        nmap = torch.empty((3, height, width), **f32)
+        nocs = torch.empty((3, height, width), **f32)
+        mask = torch.empty((1, height, width), **f32)
+        ws = torch.empty((lib.sdfr_trace_workspace_bytes(cfg, native.handle),), device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sdfr_trace_forward(native.handle, cfg, lat.data_ptr(), _lib.fptr(pose_h), int(max_steps),
+                                              float(eps), depth.data_ptr(), nmap.data_ptr(), nocs.data_ptr(),
+                                              mask.data_ptr(), 0, ws.data_ptr(), impl, _lib.stream_ptr()))
+        ctx.native, ctx.cfg, ctx.ws, ctx.pose_h, ctx.eps = native, cfg, ws, pose_h, float(eps)
+        ctx.meta = (latent_unit.dtype, pose.dtype, pose.device, tuple(pose.shape), latent_unit.shape[0])
+        ctx.mark_non_differentiable(nmap, mask)
+        return depth, nmap, nocs, mask
+
+    @staticmethod
+    def backward(ctx, g_depth, _g_nmap, g_nocs, _g_mask):
+        lib = _lib.load()
+        lat_dtype, pose_dtype, pose_dev, pose_shape, L = ctx.meta
+        dev = ctx.ws.device
+        gd = g_depth.contiguous().float() if g_depth is not None else None
+        gn = g_nocs.contiguous().float() if g_nocs is not None else None
+        d_pose = torch.zeros(12, device=dev, dtype=torch.float32)
+        d_lat = torch.zeros(L, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _lib.check(lib.sdfr_trace_backward(ctx.native.handle, ctx.cfg, _lib.fptr(ctx.pose_h), ctx.eps, _lib.ptr(gd),
+                                               _lib.ptr(gn), d_pose.data_ptr(), d_lat.data_ptr(), ctx.ws.data_ptr(),
+                                               _lib.stream_ptr()))
+        g_pose = torch.zeros(pose_shape, device=dev, dtype=torch.float32)
+        g_pose[:3, :4] = d_pose.view(3, 4)
+        return d_lat.to(lat_dtype), g_pose.to(pose_dev, pose_dtype), None, None, None, None, None
+
+
+class SphereTracer(torch.nn.Module):
+    def __init__(self, K, resolution_px, max_steps=64, eps=1e-4, precision=torch.float32):
+        super().__init__()
+        self.res_x_px, self.res_y_px = resolution_px
+        self.max_steps, self.eps = int(max_steps), float(eps)
+        self.register_buffer('K', K.to(precision))
+        self._k_cache = None
+
+    def _intrinsics(self):
+        key = (self.K.data_ptr(), self.K._version)
+        if self._k_cache is None or self._k_cache[0] != key:
+            k32 = self.K.detach().float().cpu()
+            self._k_cache = (key, k32.inverse().reshape(-1).tolist(), k32.reshape(-1).tolist())
+        return self._k_cache[1], self._k_cache[2]
+
+    def forward(self, dsdf, latent, camera_matrix, normalize_latent=True):
+        """latent: (L,) (normalised like the refine loop does, optimizer.py:96, unless told otherwise)."""
+        if not latent.is_cuda:
+            raise _lib.SdfrError("SphereTracer runs on a CUDA device only (no CPU path)")
+        lat = torch.nn.functional.normalize(latent, p=2, dim=0) if normalize_latent else latent
+        kinv, kmat = self._intrinsics()
+        cfg = (int(self.res_x_px), int(self.res_y_px), kinv, kmat)
+        depth, nmap, nocs, mask = _Trace.apply(lat, camera_matrix, dsdf.native(), cfg, self.max_steps, self.eps,
+                                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
+        return {'depth': depth, 'normals': nmap, 'color': nocs, 'mask': mask}

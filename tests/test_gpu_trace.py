@@ -1,0 +1,94 @@
+"""Trace mode (sphere tracing) on the GPU vs its torch oracle (T9) and vs splat mode (T10, sanity)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import prior as P
+from oracle import scenes
+from oracle import sdf_oracle as O
+from oracle import trace_oracle as T
+
+pytestmark = pytest.mark.gpu
+cuda = torch.device("cuda")
+
+
+def _setup(stock_prior_path, size):
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.renderer.tracer import SphereTracer
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    prior = P.load_prior(stock_prior_path)
+    K = scenes.intrinsics(size)
+    tracer = SphereTracer(K, (size, size)).to(cuda)
+    return dec, prior, K, tracer
+
+
+@pytest.mark.parametrize("size", [48, 96])
+def test_trace_maps_and_gradients_vs_oracle(stock_prior_path, size):
+    dec, prior, K, tracer = _setup(stock_prior_path, size)
+    lat_raw = torch.tensor([0.5, 0.7, 0.5])
+    pose0 = O.yaw_pose(torch.tensor([0.6]), torch.tensor([0.05, -0.02, 5.0]))
+    # oracle
+    lat_o = torch.nn.functional.normalize(lat_raw, dim=0).requires_grad_(True)
+    pose_o = pose0.clone().requires_grad_(True)
+    ro = T.trace(prior, lat_o, K, size, size, pose_o)
+    gen = torch.Generator().manual_seed(0)
+    cd, cn = torch.rand(ro["depth"].shape, generator=gen), torch.rand(ro["nocs"].shape, generator=gen)
+    lo = (ro["depth"] * cd).sum() + (ro["nocs"] * cn).sum()
+    g_lat_o, g_pose_o = torch.autograd.grad(lo, [lat_o, pose_o])
+    # ours (latent passed already normalised so the two gradients are of the same variable)
+    lat_g = torch.nn.functional.normalize(lat_raw, dim=0).to(cuda).requires_grad_(True)
+    pose_g = pose0.clone().to(cuda).requires_grad_(True)
+    r = tracer(dec, lat_g, pose_g, normalize_latent=False)
+    both = (r["mask"][0].cpu() > 0.5) & (ro["mask"][0] > 0.5)
+    either = (r["mask"][0].cpu() > 0.5) | (ro["mask"][0] > 0.5)
+    assert both.sum() >= 0.995 * either.sum(), (int(both.sum()), int(either.sum()))   # hit sets agree up to borderline rays
+    d_err = (r["depth"][0].cpu() - ro["depth"][0].detach())[both].abs().max()
+    assert d_err < 1e-4 * 5.0, d_err
+    c_err = (r["color"].cpu() - ro["nocs"].detach())[:, both].abs().max()
+    assert c_err < 1e-4, c_err
+    n_err = (r["normals"].cpu() - ro["normals"].detach())[:, both].abs()
+    assert (n_err > 1e-3).float().mean() < 2e-3, float(n_err.max())
+    # gradients: restrict the cotangents to the common hit set so borderline rays do not enter
+    w = both.float()
+    lo2 = (ro["depth"] * cd * w).sum() + (ro["nocs"] * cn * w).sum()
+    g_lat_o, g_pose_o = torch.autograd.grad(lo2, [lat_o, pose_o])
+    lg = (r["depth"] * (cd * w).to(cuda)).sum() + (r["color"] * (cn * w).to(cuda)).sum()
+    g_lat, g_pose = torch.autograd.grad(lg, [lat_g, pose_g])
+    assert np.abs(g_lat.cpu().numpy() - g_lat_o.numpy()).max() < 2e-3 * np.abs(g_lat_o.numpy()).max()
+    gp, gpo = g_pose.cpu().numpy()[:3], g_pose_o.numpy()[:3]
+    assert np.abs(gp - gpo).max() < 2e-3 * np.abs(gpo).max(), (gp, gpo)
+
+
+def test_trace_agrees_with_splat_mode(stock_prior_path):
+    """Sanity (not parity): both renderers see the same surface (SURVEY.md T10 bands)."""
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.renderer.rasterer import Rasterer
+    size = 96
+    dec, prior, K, tracer = _setup(stock_prior_path, size)
+    lat = torch.nn.functional.normalize(torch.tensor([0.5, 0.7, 0.5]), dim=0).to(cuda)
+    pose = O.yaw_pose(torch.tensor([0.6]), torch.tensor([0.0, 0.0, 5.0])).to(cuda)
+    r = tracer(dec, lat, pose, normalize_latent=False)
+    grid = Grid3D(40, device=cuda)
+    sdf, _ = dec(torch.cat([lat.expand(grid.points.size(0), -1), grid.points], 1))
+    pts, _, nrm = grid.get_surface_points(sdf)
+    ras = Rasterer(K, (size, size)).to(cuda)
+    rendering, _ = ras(pts, nrm, nrm, pose, rot='dcm', output_mask=True, output_depth=True, output_normals=True,
+                       output_nocs=True)
+    a, b = r["mask"][0] > 0.5, rendering["mask"][0] > 0.5
+    iou = float((a & b).sum()) / float((a | b).sum())
+    assert iou > 0.95, iou
+    m = a & b
+    assert float((r["depth"][0][m] - rendering["depth"][0][m]).abs().median()) < 1e-2
+    assert float((r["normals"][:, m] - rendering["normals"][:, m]).abs().median()) < 3e-2
+
+
+def test_trace_empty_view(stock_prior_path):
+    """Camera looking away from the object: no hits, zero maps, zero gradients."""
+    dec, prior, K, tracer = _setup(stock_prior_path, 32)
+    lat = torch.tensor([0.5, 0.7, 0.5], device=cuda, requires_grad=True)
+    pose = O.yaw_pose(torch.tensor([0.0]), torch.tensor([30.0, 0.0, 5.0])).to(cuda).requires_grad_(True)
+    r = tracer(dec, lat, pose)
+    assert float(r["mask"].sum()) == 0.0 and float(r["depth"].abs().sum()) == 0.0
+    g = torch.autograd.grad(r["depth"].sum() + r["color"].sum(), [lat, pose], allow_unused=True)
+    assert all(x is None or float(x.abs().sum()) == 0.0 for x in g)
