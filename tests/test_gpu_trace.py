@@ -34,8 +34,6 @@ def test_trace_maps_and_gradients_vs_oracle(stock_prior_path, size):
     ro = T.trace(prior, lat_o, K, size, size, pose_o)
     gen = torch.Generator().manual_seed(0)
     cd, cn = torch.rand(ro["depth"].shape, generator=gen), torch.rand(ro["nocs"].shape, generator=gen)
-    lo = (ro["depth"] * cd).sum() + (ro["nocs"] * cn).sum()
-    g_lat_o, g_pose_o = torch.autograd.grad(lo, [lat_o, pose_o])
     # ours (latent passed already normalised so the two gradients are of the same variable)
     lat_g = torch.nn.functional.normalize(lat_raw, dim=0).to(cuda).requires_grad_(True)
     pose_g = pose0.clone().to(cuda).requires_grad_(True)
