@@ -263,6 +263,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
               unsigned long long* __restrict__ mask_scratch, long long num_point_tiles) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  if (in.count_dev && *in.count_dev <= 0) return;   // nothing to evaluate (uniform over the whole grid)
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
   const SmemPlan P = make_plan(num_layers, in0);
