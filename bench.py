@@ -271,13 +271,15 @@ def run_ours(args, rank, world, local_rank):
     sdf = torch.empty(B * ng, device=dev)
     dinp = torch.empty(B * ng, L + 3, device=dev)
     impl = dec.mlp_impl if dec.mlp_impl else (_lib.MLP_TCGEN05 if dec.native().tcgen05 else _lib.MLP_FFMA)
+    # the engine's lattice pass: fp16-operand (hi-only) forward when the tensor-core decoder is in use
+    k_impl = _lib.MLP_TCGEN05_COARSE if impl == _lib.MLP_TCGEN05 else impl
     kev = []
     for i in range(3 + args.steps):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         _lib.check(lib.sdfr_decoder_eval_lattice(dec.native().handle, lat.data_ptr(), B, DENSITY, sdf.data_ptr(),
-                                                 0, impl, _lib.stream_ptr()))
+                                                 0, k_impl, _lib.stream_ptr()))
         b.record()
         if i >= 3:
             kev.append((a, b))
@@ -298,7 +300,9 @@ def run_ours(args, rank, world, local_rank):
                 "traffic": traffic, "kernel": "mlp_tc_kernel" if impl == _lib.MLP_TCGEN05 else "mlp_ffma_kernel",
                 "kernel_ms": k_ms, "share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": alg_flops,
-                "issued_over_algorithmic": 3.0 if impl == _lib.MLP_TCGEN05 else 1.0}
+                "issued_over_algorithmic": 1.0,
+                "note": "lattice pass of the engine (forward, one fp16 MMA per product); the accurate 3-MMA "
+                        "forward+gradient pass runs on the pre-selected band points only"}
 
     clocks = sampler.stop() if rank == 0 else None
 

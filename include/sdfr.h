@@ -43,7 +43,9 @@ enum {
 enum {
   SDFR_MLP_AUTO = 0,    /* tcgen05 kernel when the spec qualifies, else FFMA */
   SDFR_MLP_FFMA = 1,    /* fp32 CUDA-core kernel (any supported spec) */
-  SDFR_MLP_TCGEN05 = 2  /* tensor-core kernel: fp16 hi/lo split operands, fp32 accumulate in TMEM */
+  SDFR_MLP_TCGEN05 = 2, /* tensor-core kernel: fp16 hi/lo split operands, fp32 accumulate in TMEM */
+  SDFR_MLP_TCGEN05_COARSE = 3 /* tensor-core kernel, hi halves only (fp16 operand precision, sdf to ~3e-4),
+                                 forward only: the band pre-selection pass of the fused engine */
 };
 
 enum { SDFR_ROT_DCM = 0, SDFR_ROT_QUAT = 1 };
@@ -251,8 +253,9 @@ int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_ho
  * whole batch (compact, [sum m, L+3]),
  * 2 surfel points [m,3], 3 surfel normals [m,3], 4 color [3,H,W], 5 mask,
  * 6 normals map [3,H,W], 7 grads [dyaw,dt3,dscale,dlatent_unit(L),dlatent(L)],
- * 8 surfel count (int32), 9 depth, 10 camera-space surfel centres [m,3],
- * 11 front-facing flags [m] (uint8).  Returns the device pointer and element count. */
+ * 8 pre-selected point count m (int32; with the tensor-core decoder a superset of the band), 9 depth,
+ * 10 camera-space surfel centres [m,3], 11 front-facing flags [m] (uint8), 12 band flags [m] (uint8: 1 =
+ * inside the reference's band |sdf| < 0.03; rows with 0 are ignored by every stage).  Returns the device pointer and element count. */
 int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev, int64_t* count);
 /* Asynchronous device-to-device copy of such a view into dst_dev (at most max_count elements). */
 int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_dev, int64_t max_count, void* stream);

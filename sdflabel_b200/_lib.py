@@ -16,7 +16,7 @@ c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
 vp = C.c_void_p
 
-MLP_AUTO, MLP_FFMA, MLP_TCGEN05 = 0, 1, 2
+MLP_AUTO, MLP_FFMA, MLP_TCGEN05, MLP_TCGEN05_COARSE = 0, 1, 2, 3
 ROT_DCM, ROT_QUAT = 0, 1
 
 

@@ -330,6 +330,10 @@ int sdfr_decoder_eval(sdfr_decoder* dec, const float* inputs_dev, int64_t n, flo
   impl = pick_impl(dec, impl);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (impl == SDFR_MLP_TCGEN05) return launch_mlp_tc(dec, in, sdf_dev, dinput_dev, s);
+  if (impl == SDFR_MLP_TCGEN05_COARSE) {
+    SDFR_REQUIRE(!dinput_dev, SDFR_E_INVALID, "the coarse decoder pass is forward only");
+    return launch_mlp_tc_coarse(dec, in, sdf_dev, s);
+  }
   SDFR_REQUIRE(impl == SDFR_MLP_FFMA, SDFR_E_INVALID, "unknown MLP implementation %d", impl);
   return launch_mlp_ffma(dec, in, sdf_dev, dinput_dev, s);
 }
@@ -345,6 +349,10 @@ int sdfr_decoder_eval_lattice(sdfr_decoder* dec, const float* latent_unit_dev, i
   impl = pick_impl(dec, impl);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (impl == SDFR_MLP_TCGEN05) return launch_mlp_tc(dec, in, sdf_dev, dinput_dev, s);
+  if (impl == SDFR_MLP_TCGEN05_COARSE) {
+    SDFR_REQUIRE(!dinput_dev, SDFR_E_INVALID, "the coarse decoder pass is forward only");
+    return launch_mlp_tc_coarse(dec, in, sdf_dev, s);
+  }
   SDFR_REQUIRE(impl == SDFR_MLP_FFMA, SDFR_E_INVALID, "unknown MLP implementation %d", impl);
   return launch_mlp_ffma(dec, in, sdf_dev, dinput_dev, s);
 }

@@ -171,6 +171,7 @@ struct SplatView {
   const float* normals;   // [m,3]
   const float* colors;    // [m,3] or null
   const float* pose;      // 16 (dcm) or 7 (quat) floats
+  const unsigned char* valid;   // optional per-surfel flag: 0 = not a surfel (skipped by every stage)
   const int* count;       // surfel count on the device (null -> static_count)
   int static_count;
   int capacity;
@@ -223,6 +224,8 @@ __device__ __forceinline__ long long mlp_rows(const MlpInputs& in) {
 
 int launch_mlp_ffma(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s);
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s);
+// forward only, fp16 operand precision (hi halves only): the band pre-selection pass of the fused engine
+int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s);
 int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host);
 
 // surface.cu
@@ -270,6 +273,8 @@ struct BandArgs {
   float* out_nrm;
   int* out_idx;
   float* out_glat;          // [batch, cap, latent]
+  unsigned char* out_valid; // [batch, cap] 1 where |band_sdf| < final_threshold (the true band)
+  float final_threshold;
   long long cap;
 };
 int launch_band_select(const BandArgs& a, cudaStream_t s);

@@ -211,6 +211,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// coarse pass: only the hi halves are ever read by the MMAs
+__device__ __forceinline__ void pack8_store_hi(unsigned char* chunk_row, int pg, const float (&h)[8]) {
+  uint4 hi;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 a = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
+  }
+  *reinterpret_cast<uint4*>(chunk_row + pg * 128) = hi;
+}
+
 // 8 consecutive points of one feature -> one 16-byte store of the hi halves and one of the lo halves
 __device__ __forceinline__ float pack8_store(unsigned char* chunk_row, int pg, const float (&h)[8]) {
   uint4 hi, lo;
@@ -261,7 +273,7 @@ __device__ unsigned long long g_tc_prof[16];
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
-              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles) {
+              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles, int coarse) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (in.count_dev && *in.count_dev <= 0) return;   // nothing to evaluate (uniform over the whole grid)
   const TcTable& T = *tabp;
@@ -280,8 +292,11 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
                  bar_act = bars + 8 * (2 * NSTAGE + 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
   const int in_pad = (in0 + 7) & ~7;
-  const bool want_grad = dinput_out != nullptr;
+  // coarse: forward only with the hi halves alone (one MMA per K step, fp16 operand precision,
+  // ~3e-4 absolute on the sdf).  Used by the fused engine to pre-select a superset of the band.
+  const bool want_grad = dinput_out != nullptr && !coarse;
   const int npass = want_grad ? T.num_passes : num_layers;   // forward passes come first
+  const uint32_t tile_copy_bytes = coarse ? TILE_HALF_BYTES : TILE_BYTES;
   // Thread-block cluster: every CTA of the cluster consumes the same weight-tile sequence, so each
   // loads 1/CL of every tile and multicasts it to all of them (one L2 read per cluster instead of per CTA).
   const long long n_rows = mlp_rows(in);           // the row count may live on the device (band pass)
@@ -319,12 +334,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
           for (long long t = 0; t < n; ++t) {
             { PROF_T0(); mbar_wait(bar_empty + 8 * stage, phase ^ 1); PROF_ADD(0); }
-            mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
+            mbar_expect_tx(bar_full + 8 * stage, tile_copy_bytes);
             if (CL == 1) {
-              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, TILE_BYTES,
+              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, tile_copy_bytes,
                        bar_full + 8 * stage);
             } else {
-              const uint32_t slice = TILE_BYTES / CL, off = crank * slice;
+              const uint32_t slice = tile_copy_bytes / CL, off = crank * slice;
               bulk_g2s_mcast(smem_u32(smem + P.stages + stage * TILE_BYTES) + off, src + t * TILE_BYTES + off, slice,
                              bar_full + 8 * stage, cmask);
             }
@@ -361,12 +376,19 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
               const uint64_t da_hi = desc_a_base + (uint64_t)((stage * TILE_BYTES) >> 4);
               const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
               const uint64_t db = desc_b_base + (uint64_t)((kc * (KC / 8) * B_CHUNK) >> 4);
+              if (coarse) {
 #pragma unroll
-              for (int j = 0; j < KC / 16; ++j) {
-                umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
-                         kIdesc128, (kc | j) ? 1u : 0u);                                  // W_hi x [H_hi ; H_lo]
-                umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
-                         kIdesc64, 1u);                                                    // W_lo x H_hi
+                for (int j = 0; j < KC / 16; ++j)
+                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
+                           kIdesc64, (kc | j) ? 1u : 0u);                                  // W_hi x H_hi only
+              } else {
+#pragma unroll
+                for (int j = 0; j < KC / 16; ++j) {
+                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
+                           kIdesc128, (kc | j) ? 1u : 0u);                                  // W_hi x [H_hi ; H_lo]
+                  umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
+                           kIdesc64, 1u);                                                    // W_lo x H_hi
+                }
               }
               // frees the weight stage (in every CTA of the cluster: all of them write into it)
               if (CL == 1) umma_commit(bar_empty + 8 * stage);
@@ -425,7 +447,8 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           float h[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NPTS + ph * 32 + pg * 8 + e] * ACT_SCALE : 0.f;
-          amax = fmaxf(amax, pack8_store(row, ph * 4 + pg, h));
+          if (coarse) pack8_store_hi(row, ph * 4 + pg, h);
+          else amax = fmaxf(amax, pack8_store(row, ph * 4 + pg, h));
         }
       }
       fence_async_smem();
@@ -447,8 +470,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
               const int g4 = ph * 2 + g2;
               uint32_t vm[16], vc[16];
               tmem_ld16(lane_base + g4 * 16, vm);
-              tmem_ld16(lane_base + 64 + g4 * 16, vc);
+              if (!coarse) tmem_ld16(lane_base + 64 + g4 * 16, vc);
               tmem_ld_wait();
+              if (coarse) {
+#pragma unroll
+                for (int qq = 0; qq < 16; ++qq) vc[qq] = 0u;
+              }
               if (lane == 0) {
 #pragma unroll
                 for (int qq = 0; qq < 16; ++qq) {
@@ -504,8 +531,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             const int g4 = ph * 2 + g2;
             uint32_t vm[16], vc[16];
             tmem_ld16(tb + g4 * 16, vm);
-            tmem_ld16(tb + 64 + g4 * 16, vc);
+            if (!coarse) tmem_ld16(tb + 64 + g4 * 16, vc);
             tmem_ld_wait();
+            if (coarse) {
+#pragma unroll
+              for (int qq = 0; qq < 16; ++qq) vc[qq] = 0u;
+            }
             float x[16];
 #pragma unroll
             for (int qq = 0; qq < 16; ++qq) x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
@@ -549,12 +580,14 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             float h8[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) h8[e] = h[e];
-            amax = fmaxf(amax, pack8_store(row, g4 * 2, h8));
+            if (coarse) pack8_store_hi(row, g4 * 2, h8);
+            else amax = fmaxf(amax, pack8_store(row, g4 * 2, h8));
 #pragma unroll
             for (int e = 0; e < 8; ++e) h8[e] = h[8 + e];
-            amax = fmaxf(amax, pack8_store(row, g4 * 2 + 1, h8));
+            if (coarse) pack8_store_hi(row, g4 * 2 + 1, h8);
+            else amax = fmaxf(amax, pack8_store(row, g4 * 2 + 1, h8));
           }
-          if (fwd) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;
+          if (fwd && want_grad) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;   // only the backward reads them
         }
         if (et == 0) PROF_ADD(4 + (Ps.kind == 0 ? 0 : Ps.kind == 2 ? 1 : 2));
         if (Ps.kind == 3) {
@@ -739,7 +772,19 @@ extern "C" int sdfr_debug_tc_prof(unsigned long long* out16, int reset) {
 }
 #endif
 
+static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, int coarse,
+                              cudaStream_t s);
+
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
+  return launch_mlp_tc_impl(dec, in, sdf, dinput, 0, s);
+}
+
+int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s) {
+  return launch_mlp_tc_impl(dec, in, sdf, nullptr, 1, s);
+}
+
+static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, int coarse,
+                              cudaStream_t s) {
   SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,
                "tcgen05 MLP kernel does not cover this decoder (needs sm_100, widths <= 512, no LayerNorm, "
                "latent+3 <= 32, <= 9 layers)");
@@ -772,7 +817,7 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev, in,
-                               sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles));
+                               sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }

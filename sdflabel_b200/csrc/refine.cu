@@ -57,7 +57,8 @@ struct EngineDev {          // passed by value to the engine kernels
   int* band_det_start;      // [B]
   int* band_total;          // [1]
   int* band_src;            // [B*ng] compact global source indices of the band points
-  float* band_sdf;          // [B*ng] sdf of the band points (second, gradient-carrying evaluation)
+  float* band_sdf;          // [B*ng] sdf of the pre-selected points (second, gradient-carrying evaluation)
+  unsigned char* surf_valid;// [B,cap] 1 where the accurate |sdf| < 0.03: the reference's band (grid.py:64)
   float* target;            // [B,3,max_pixels]
   float* lidar;             // [B,max_lidar,3]
   float* l3rec;             // [B,cap,4] unit direction, distance (-1 = unused)
@@ -460,6 +461,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.surf_idx, B * E.cap); A(E.surf_count, B);
   A(E.band_block_counts, (size_t)B * (E.ng / 1024 + 2)); A(E.band_block_prefix, (size_t)B * (E.ng / 1024 + 2));
   A(E.band_det_start, B); A(E.band_total, 4); A(E.band_src, (size_t)B * E.ng); A(E.band_sdf, (size_t)B * E.ng);
+  A(E.surf_valid, (size_t)B * E.cap);
   A(E.target, (size_t)B * 3 * E.max_pixels); A(E.lidar, (size_t)B * E.max_lidar * 3);
   A(E.l3rec, B * E.cap * 4); A(E.l3dot, B * E.cap); A(E.l2rec, (size_t)B * E.max_pixels * 4);
   A(E.part2, (size_t)B * E.nb2 * 3); A(E.part3, (size_t)B * E.nb3 * 3); A(E.partc, (size_t)B * E.nbc * (16 + L));
@@ -478,6 +480,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
     V.colors = nullptr;
     V.pose = reinterpret_cast<const float*>(reinterpret_cast<const char*>(E.det + b) + offsetof(DetState, pose));
     V.count = E.surf_count + b;
+    V.valid = E.surf_valid + (size_t)b * E.cap;
     V.capacity = (int)E.cap;
     A(V.cam_v, E.cap * 3); A(V.cam_m, E.cap * 3); A(V.cam_c, E.cap * 3); A(V.plane_a, E.cap);
     A(V.bbox, E.cap * 4); A(V.front, E.cap);
@@ -568,7 +571,12 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   int impl = r->cfg.mlp_impl;
   if (impl == SDFR_MLP_AUTO) impl = r->dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
   BandArgs ba;
-  ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B; ba.threshold = 0.03f;   // grid.py:43
+  // Pre-selection threshold = band (grid.py:43) + margin.  With the tensor-core decoder the lattice pass runs
+  // at fp16 operand precision (error ~3e-4, checked in tests to stay below half the margin); the accurate
+  // second pass then decides the real band, so the result is the same set the accurate kernel alone gives.
+  const bool coarse = impl == SDFR_MLP_TCGEN05;
+  ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B; ba.threshold = 0.03f + (coarse ? 0.005f : 0.f);
+  ba.out_valid = E.surf_valid; ba.final_threshold = 0.03f;
   ba.block_counts = E.band_block_counts; ba.block_prefix = E.band_block_prefix; ba.det_start = E.band_det_start;
   ba.det_count = E.surf_count; ba.total = E.band_total; ba.band_src = E.band_src;
   ba.band_sdf = E.band_sdf; ba.band_dinput = E.dinput; ba.in0 = E.in0; ba.latent = E.L;
@@ -580,7 +588,7 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
     iter_begin_kernel<<<B, 32, 0, s>>>(E);
     SDFR_LAUNCH_CHECK();
     // sdf over the whole lattice (forward only), then sdf + input gradient for the band points
-    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in, E.sdf, nullptr, s) : launch_mlp_ffma(r->dec, in, E.sdf, nullptr, s);
+    rc = coarse ? launch_mlp_tc_coarse(r->dec, in, E.sdf, s) : launch_mlp_ffma(r->dec, in, E.sdf, nullptr, s);
     if (rc) return rc;
     if ((rc = launch_band_select(ba, s))) return rc;
     rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in_band, E.band_sdf, E.dinput, s)
@@ -643,6 +651,7 @@ extern "C" int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev,
     case 9: *ptr_dev = V.depth; *count = P; break;
     case 10: *ptr_dev = V.cam_v; *count = E.cap * 3; break;
     case 11: *ptr_dev = V.front; *count = E.cap; break;
+    case 12: *ptr_dev = E.surf_valid + (size_t)b * E.cap; *count = E.cap; break;
     default: SDFR_REQUIRE(false, SDFR_E_INVALID, "unknown view kind %d", kind);
   }
   return SDFR_OK;
@@ -654,7 +663,7 @@ extern "C" int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_
   int rc = sdfr_refine_view(r, b, kind, &src, &count);
   if (rc) return rc;
   SDFR_REQUIRE(dst_dev && max_count >= 0, SDFR_E_INVALID, "bad argument");
-  const size_t elem = kind == 11 ? 1 : 4;
+  const size_t elem = (kind == 11 || kind == 12) ? 1 : 4;
   const size_t n = (size_t)std::min<int64_t>(count, max_count);
   if (n) SDFR_CUDA(cudaMemcpyAsync(dst_dev, src, n * elem, cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
   return SDFR_OK;

@@ -102,6 +102,11 @@ __global__ void __launch_bounds__(256) project_kernel(const SplatView* __restric
   const float a = mx * vx + my * vy + mz * vz;
   V.plane_a[i] = a;
   V.front[i] = (V.rot == SDFR_ROT_DCM) ? (a < 0.f ? 1 : 0) : 1;   // projection.py:61-66
+  if (V.valid && !V.valid[i]) {     // pre-selected but outside the band: invisible to every later stage
+    V.front[i] = 0;
+    V.bbox[i * 4] = 1; V.bbox[i * 4 + 1] = 1; V.bbox[i * 4 + 2] = 0; V.bbox[i * 4 + 3] = 0;
+    return;
+  }
 
   // conservative pixel box of the ball B(v, radius)
   int x0 = 0, y0 = 0, x1 = V.width - 1, y1 = V.height - 1;

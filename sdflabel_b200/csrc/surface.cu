@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256) band_surface_kernel(BandArgs a) {
   if (a.out_idx) a.out_idx[o] = (int)k;
   if (a.out_glat)
     for (int c = 0; c < a.latent; ++c) a.out_glat[o * a.latent + c] = g[c];
+  if (a.out_valid) a.out_valid[o] = in_band(f, a.final_threshold) ? 1 : 0;
 }
 
 }  // namespace

@@ -137,7 +137,7 @@ class _Engine:
         return params, hist[:nh.value]
 
     VIEW_KINDS = {'sdf': 0, 'dinput': 1, 'surf_pts': 2, 'surf_nrm': 3, 'color': 4, 'mask': 5, 'normals': 6,
-                  'grads': 7, 'surf_count': 8, 'depth': 9, 'cam_pts': 10, 'front': 11}
+                  'grads': 7, 'surf_count': 8, 'depth': 9, 'cam_pts': 10, 'front': 11, 'surf_valid': 12}
 
     def view(self, b, kind):
         """Device copy of an intermediate of the last iteration (tests, label dumps)."""
@@ -146,10 +146,16 @@ class _Engine:
         p = _lib.vp()
         n = C.c_int64(0)
         _lib.check(lib.sdfr_refine_view(self.handle, b, kind, C.byref(p), C.byref(n)))
-        dtype = torch.int32 if kind == 8 else torch.uint8 if kind == 11 else torch.float32
+        dtype = torch.int32 if kind == 8 else torch.uint8 if kind in (11, 12) else torch.float32
         out = torch.empty((n.value,), device='cuda', dtype=dtype)
         _lib.check(lib.sdfr_refine_copy_view(self.handle, b, kind, out.data_ptr(), n.value, _lib.stream_ptr()))
         return out
+
+    def surfels(self, b):
+        """(points (M,3), normals (M,3)) of the band of detection b after the last iteration."""
+        m = int(self.view(b, 'surf_count').item())
+        keep = self.view(b, 'surf_valid')[:m].bool()
+        return self.view(b, 'surf_pts')[:m * 3].view(-1, 3)[keep], self.view(b, 'surf_nrm')[:m * 3].view(-1, 3)[keep]
 
 
 def _engine_for(dsdf, batch, density, w, h, n_lidar, iters, weights, impl) -> _Engine:
