@@ -84,6 +84,10 @@ int sdfr_decoder_create(const sdfr_decoder_spec* spec, const float* const* weigh
 void sdfr_decoder_destroy(sdfr_decoder* dec);
 /* 1 when the tcgen05 kernel covers this spec (all widths <= 512, no LayerNorm) */
 int sdfr_decoder_tcgen05_ok(const sdfr_decoder* dec);
+/* Synchronises the device and fails with SDFR_E_UNSUPPORTED if, since the last check, a scaled
+ * activation of the split-fp16 tensor-core kernel left the fp16 range (its results are then invalid
+ * and the caller should select SDFR_MLP_FFMA); SDFR_OK otherwise. */
+int sdfr_decoder_check(sdfr_decoder* dec);
 
 /* sdf[n] = Decoder(inputs[n, L+3]); if dinput_dev != NULL also the exact
  * gradient d sdf[n] / d inputs[n, :] (what the reference obtains with

@@ -58,6 +58,7 @@ SIGNATURES = {
                                       C.POINTER(c_float_p), C.POINTER(c_float_p), C.POINTER(vp)]),
     "sdfr_decoder_destroy": (None, [vp]),
     "sdfr_decoder_tcgen05_ok": (C.c_int, [vp]),
+    "sdfr_decoder_check": (C.c_int, [vp]),
     "sdfr_decoder_eval": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int, vp]),
     "sdfr_decoder_eval_lattice": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, C.c_int, vp]),
     "sdfr_lattice_points": (C.c_int, [C.c_int, vp, vp]),

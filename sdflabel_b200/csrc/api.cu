@@ -309,12 +309,23 @@ int sdfr_decoder_create(const sdfr_decoder_spec* spec, const float* const* weigh
 
 void sdfr_decoder_destroy(sdfr_decoder* dec) {
   if (!dec) return;
+  free_tc_tables(dec);
   for (void* p : dec->allocs) cudaFree(p);
   if (dec->scratch) cudaFree(dec->scratch);
   delete dec;
 }
 
 int sdfr_decoder_tcgen05_ok(const sdfr_decoder* dec) { return dec ? dec->tc.ok : 0; }
+
+int sdfr_decoder_check(sdfr_decoder* dec) {
+  SDFR_REQUIRE(dec, SDFR_E_INVALID, "null decoder");
+  int flag = 0;
+  int rc = tc_overflow_flag(dec, &flag);
+  if (rc) return rc;
+  SDFR_REQUIRE(!flag, SDFR_E_UNSUPPORTED,
+               "an activation left the fp16 range of the split-operand tensor-core kernel; use SDFR_MLP_FFMA for this network");
+  return SDFR_OK;
+}
 
 static int pick_impl(const sdfr_decoder* dec, int impl) {
   if (impl == SDFR_MLP_AUTO) return dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;

@@ -227,6 +227,8 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
 // forward only, fp16 operand precision (hi halves only): the band pre-selection pass of the fused engine
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s);
 int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host);
+void free_tc_tables(sdfr_decoder* dec);
+int tc_overflow_flag(const sdfr_decoder* dec, int* flag);
 
 // surface.cu
 int launch_lattice_points(int density, float* pts, cudaStream_t s);

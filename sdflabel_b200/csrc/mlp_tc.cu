@@ -775,6 +775,22 @@ extern "C" int sdfr_debug_tc_prof(unsigned long long* out16, int reset) {
 static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, int coarse,
                               cudaStream_t s);
 
+void free_tc_tables(sdfr_decoder* dec) {
+  if (dec->tc_ptr) delete reinterpret_cast<TcHostState*>(dec->tc_ptr);   // device memory is owned by dec->allocs
+  dec->tc_ptr = nullptr;
+}
+
+// 1 when a scaled operand of the split-fp16 kernel has left the fp16 range since the last query
+// (results of that launch are then invalid); synchronises the device.
+int tc_overflow_flag(const sdfr_decoder* dec, int* flag) {
+  *flag = 0;
+  if (!dec->tc.ok || !dec->tc_ptr) return SDFR_OK;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  SDFR_CUDA(cudaMemcpy(flag, st->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost));
+  if (*flag) SDFR_CUDA(cudaMemset(st->overflow_dev, 0, sizeof(int)));
+  return SDFR_OK;
+}
+
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
   return launch_mlp_tc_impl(dec, in, sdf, dinput, 0, s);
 }

@@ -220,16 +220,24 @@ __global__ void __launch_bounds__(LB) grad_prep_kernel(EngineDev E) {
   DetState& D = E.det[b];
   const SplatView& V = E.views[b];
   const int P = D.width * D.height;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {     // warp 0: fixed-order (deterministic) reduction of the block partials
     const int nb = (P + LB - 1) / LB;
     double s = 0.0, c = 0.0, hw = 0.0;
     const double* p = E.part2 + (size_t)b * E.nb2 * 3;
-    for (int k = 0; k < nb; ++k) { s += p[k * 3]; c += p[k * 3 + 1]; hw += p[k * 3 + 2]; }
-    float loss, n;
-    if (hw == 0.0) { loss = 0.f; n = 0.f; }                         // optimizer.py:214 quirk
-    else { n = (float)c; loss = c > 0.0 ? (float)(s / c) : __int_as_float(0x7fc00000); }
-    s_scale = n > 0.f ? E.w2d / n : 0.f;
-    if (blockIdx.x == 0) { D.loss2d = loss; D.n2 = n; }
+    for (int k = threadIdx.x; k < nb; k += 32) { s += p[k * 3]; c += p[k * 3 + 1]; hw += p[k * 3 + 2]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      hw += __shfl_xor_sync(0xffffffffu, hw, o);
+    }
+    if (threadIdx.x == 0) {
+      float loss, n;
+      if (hw == 0.0) { loss = 0.f; n = 0.f; }                         // optimizer.py:214 quirk
+      else { n = (float)c; loss = c > 0.0 ? (float)(s / c) : __int_as_float(0x7fc00000); }
+      s_scale = n > 0.f ? E.w2d / n : 0.f;
+      if (blockIdx.x == 0) { D.loss2d = loss; D.n2 = n; }
+    }
   }
   __syncthreads();
   const int j = blockIdx.x * LB + threadIdx.x;
@@ -271,16 +279,24 @@ __global__ void __launch_bounds__(LB) chain_kernel(EngineDev E) {
   const SplatView& V = E.views[b];
   const int m = min(E.surf_count[b], (int)E.cap);
   if (blockIdx.x > 0 && (int)(blockIdx.x * LB) >= m) return;   // block 0 always publishes the loss
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {     // warp 0: fixed-order reduction of the 3D-loss block partials
     const int nb = (m + LB - 1) / LB;
     double s = 0.0, c = 0.0, f = 0.0;
     const double* p = E.part3 + (size_t)b * E.nb3 * 3;
-    for (int k = 0; k < nb; ++k) { s += p[k * 3]; c += p[k * 3 + 1]; f += p[k * 3 + 2]; }
-    s_l3scale = c > 0.0 ? E.w3d / (float)c : 0.f;
-    if (blockIdx.x == 0) {
-      D.loss3d = c > 0.0 ? (float)(s / c) : 0.f;                    // optimizer.py:192-197
-      D.n3 = (float)c;
-      D.front_count = (int)f;
+    for (int k = threadIdx.x; k < nb; k += 32) { s += p[k * 3]; c += p[k * 3 + 1]; f += p[k * 3 + 2]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      f += __shfl_xor_sync(0xffffffffu, f, o);
+    }
+    if (threadIdx.x == 0) {
+      s_l3scale = c > 0.0 ? E.w3d / (float)c : 0.f;
+      if (blockIdx.x == 0) {
+        D.loss3d = c > 0.0 ? (float)(s / c) : 0.f;                    // optimizer.py:192-197
+        D.n3 = (float)c;
+        D.front_count = (int)f;
+      }
     }
   }
   __syncthreads();

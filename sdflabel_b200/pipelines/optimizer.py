@@ -70,6 +70,7 @@ class _Engine:
         self.handle = h
         self._pinned: Dict = {}     # persistent pinned staging buffers, keyed by (name, detection)
         self._dirty = set()         # detections whose staging buffers may still be in flight
+        self._kcache: Dict = {}
 
     def __del__(self):
         try:
@@ -103,10 +104,22 @@ class _Engine:
         np.copyto(ent[1][:n], src.reshape(-1), casting='same_kind')
         return ent[0][:n].view(tuple(src.shape))
 
+    def _intrinsics(self, K):
+        """(K, K^-1) as contiguous fp32 host tensors; the inverse is torch's own K.float().inverse()
+        (primitives.py:204), cached by value because a crop's K rarely changes between calls."""
+        k32 = K.detach().float().cpu().contiguous()
+        key = k32.numpy().tobytes()
+        hit = self._kcache.get(key)
+        if hit is None:
+            if len(self._kcache) > 256:
+                self._kcache.clear()
+            hit = (k32.clone(), k32.inverse().contiguous())
+            self._kcache[key] = hit
+        return hit
+
     def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw, trans, scale, latent):
         lib = _lib.load()
-        k32 = K.detach().float().cpu().contiguous()
-        kinv = k32.inverse().contiguous()          # K.float().inverse() (primitives.py:204)
+        k32, kinv = self._intrinsics(K)
         # the previous use of these staging buffers must have been consumed by the device
         torch.cuda.current_stream().synchronize() if self._pinned_dirty(b) else None
         nocs = self._pin(('nocs', b), nocs_pred)
@@ -232,6 +245,7 @@ class Optimizer:
         self.rot = rot
         self.verbose = False
         self.history = None
+        self._host = None           # (versions, host copies) of the parameter tensors after the last optimize()
 
     def optimize(self, iters_optim, nocs_pred, pcd_frustum_np, dsdf, grid, K, crop_size, viz_type=None,
                  frame_vis=None):
@@ -259,18 +273,24 @@ class Optimizer:
             eng = _engine_for(dsdf, 1, int(grid.density), width, height, lidar.shape[0], iters_optim, self.weights,
                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
             p = self.params
-            eng.set_detection(0, K, width, height, nocs_pred, lidar, p['yaw'].detach().cpu().numpy(),
-                              p['trans'].detach().cpu().numpy(), p['scale'].detach().cpu().numpy(),
-                              p['latent'].detach().cpu().numpy())
+            keys = ('yaw', 'trans', 'scale', 'latent')
+            versions = tuple((p[k].data_ptr(), p[k]._version) for k in keys)
+            if self._host is not None and self._host[0] == versions:
+                host = self._host[1]        # nobody touched the tensors since we wrote them: skip four D2H syncs
+            else:
+                host = {k: p[k].detach().cpu().numpy() for k in keys}
+            eng.set_detection(0, K, width, height, nocs_pred, lidar, host['yaw'], host['trans'], host['scale'],
+                              host['latent'])
             eng.run(iters_optim)
             out, hist = eng.get(0)
+            _lib.check(_lib.load().sdfr_decoder_check(eng.native_decoder.handle))   # fp16-range guard of the TC kernel
         self.engine = eng
         self.history = hist
+        new = {'yaw': out[0:1].copy(), 'trans': out[1:4].copy(), 'scale': out[4:5].copy(), 'latent': out[5:].copy()}
         with torch.no_grad():
-            p['yaw'].copy_(torch.from_numpy(out[0:1]))
-            p['trans'].copy_(torch.from_numpy(out[1:4]))
-            p['scale'].copy_(torch.from_numpy(out[4:5]))
-            p['latent'].copy_(torch.from_numpy(out[5:]))
+            for k, v in new.items():
+                p[k].copy_(torch.from_numpy(v), non_blocking=True)
+        self._host = (tuple((p[k].data_ptr(), p[k]._version) for k in ('yaw', 'trans', 'scale', 'latent')), new)
         if self.verbose:
             w2, w3 = self.weights['2d'], self.weights['3d']
             for e, (l2, l3, tot, skip) in enumerate(hist):
