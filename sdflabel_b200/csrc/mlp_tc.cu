@@ -614,6 +614,270 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coarse lattice pass, ping-pong version.
+//
+// Forward only, hi halves only (one MMA per product).  With the lo halves gone the B operand of a
+// 64-point tile is 64 KB and its accumulators 256 TMEM columns, so TWO point tiles (X, Y) are
+// resident per CTA and the epilogue of one overlaps the MMAs of the other:
+//     MMA  X(p)   Y(p)   X(p+1) Y(p+1) ...
+//     EPI         X(p)   Y(p)   X(p+1) ...
+// Each pass's weight tiles (hi halves, 8 KB) are streamed once per point tile (L2 has the headroom:
+// 31 % utilised before).  Same pass table, same layouts, same epilogue math as mlp_tc_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int C_STAGES = 8;              // 8 KB stages (hi half of a weight tile)
+constexpr int CB_CHUNK = 1024;           // B (hi only): 8 point groups x 128 B per 8-k chunk
+constexpr int CB_BYTES = 64 * CB_CHUNK;  // 64 KB per point tile
+
+struct CoarsePlan {
+  uint32_t stages, b[2], inp[2], bars, tmem_slot, total;
+};
+__host__ __device__ inline CoarsePlan make_coarse_plan(int in0) {
+  CoarsePlan p;
+  uint32_t o = 0;
+  p.stages = o; o += C_STAGES * TILE_HALF_BYTES;
+  p.b[0] = o; o += CB_BYTES;
+  p.b[1] = o; o += CB_BYTES;
+  const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
+  p.inp[0] = o; o += in_pad * NPTS * 4;
+  p.inp[1] = o; o += in_pad * NPTS * 4;
+  p.bars = o; o += 32 * 8;
+  p.tmem_slot = o; o += 16;
+  p.total = o;
+  return p;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
+                     float* __restrict__ sdf_out, long long num_point_tiles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (in.count_dev && *in.count_dev <= 0) return;
+  const TcTable& T = *tabp;
+  const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
+  const CoarsePlan P = make_coarse_plan(in0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bars = smem_u32(smem + P.bars);
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * C_STAGES, bar_acc = bars + 8 * (2 * C_STAGES),
+                 bar_act = bars + 8 * (2 * C_STAGES + 2);          // [2] each: one per resident point tile
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
+  const int in_pad = (in0 + 7) & ~7;
+  const long long n_rows = mlp_rows(in);
+  if (in.count_dev) num_point_tiles = (n_rows + NPTS - 1) / NPTS;
+
+  if (tid == 0) {
+    for (int s = 0; s < C_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, NEPI); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // this CTA's point tiles: blockIdx.x, blockIdx.x + grid, ... processed two at a time
+  long long my_tiles = 0;
+  for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) ++my_tiles;
+  const long long my_pairs = (my_tiles + 1) / 2;
+
+  if (warp == 8) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long pr = 0; pr < my_pairs; ++pr) {
+        const int nt = (2 * pr + 1 < my_tiles) ? 2 : 1;
+        for (int p = 0; p < num_layers; ++p) {
+          const long long n = (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
+          const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
+          for (int t = 0; t < nt; ++t)
+            for (long long w = 0; w < n; ++w) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(bar_full + 8 * stage, TILE_HALF_BYTES);
+              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_HALF_BYTES), src + w * TILE_BYTES, TILE_HALF_BYTES,
+                       bar_full + 8 * stage);
+              if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane) =====================
+    uint32_t stage = 0, phase = 0, act_phase[2] = {0, 0};
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc_a_base = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);
+    const uint64_t desc_b_base[2] = {make_desc(smem_u32(smem + P.b[0]), CB_CHUNK, B_SBO),
+                                     make_desc(smem_u32(smem + P.b[1]), CB_CHUNK, B_SBO)};
+    for (long long pr = 0; pr < my_pairs; ++pr) {
+      const int nt = (2 * pr + 1 < my_tiles) ? 2 : 1;
+      for (int p = 0; p < num_layers; ++p) {
+        const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(bar_act + 8 * t, act_phase[t]);      // tile t: B operand staged, its accumulators drained
+          act_phase[t] ^= 1;
+          tc_fence_after();
+          for (int mb = 0; mb < m_blocks; ++mb) {
+            const uint32_t d = tm + (uint32_t)(t * 256 + mb * 64);
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t da = desc_a_base + (uint64_t)((stage * TILE_HALF_BYTES) >> 4);
+                const uint64_t db = desc_b_base[t] + (uint64_t)((kc * (KC / 8) * CB_CHUNK) >> 4);
+#pragma unroll
+                for (int j = 0; j < KC / 16; ++j)
+                  umma_f16(d, da + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * CB_CHUNK) >> 4), kIdesc64,
+                           (kc | j) ? 1u : 0u);
+                umma_commit(bar_empty + 8 * stage);
+              }
+              __syncwarp();
+              if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          if (elect_one()) umma_commit(bar_acc + 8 * t);
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3, ph = warp >> 2;
+    const int tl = q * 32 + lane;                      // TMEM lane = feature within the M block
+    const int et = tid;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t acc_phase[2] = {0, 0};
+    for (long long pr = 0; pr < my_pairs; ++pr) {
+      const int nt = (2 * pr + 1 < my_tiles) ? 2 : 1;
+      long long base[2];
+      for (int t = 0; t < nt; ++t) {
+        const long long pt = (2 * pr + t) * gridDim.x + blockIdx.x;
+        base[t] = pt * NPTS;
+        float* inp = reinterpret_cast<float*>(smem + P.inp[t]);
+        for (int i = et; i < in_pad * NPTS; i += NEPI) {
+          const int c = i / NPTS, n = i - c * NPTS;
+          const long long gi = base[t] + n;
+          float v = 0.f;
+          if (gi < n_rows && c < in0) {
+            const long long src = in.index ? (long long)in.index[gi] : gi;
+            if (in.inputs) {
+              v = in.inputs[src * in0 + c];
+            } else {
+              const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
+              if (c < latent) {
+                v = in.latent_unit[b * latent + c];
+              } else {
+                float x, y, z;
+                lattice_point(in.lattice, k, x, y, z);
+                v = (c - latent) == 0 ? x : (c - latent) == 1 ? y : z;
+              }
+            }
+          }
+          inp[i] = v;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int t = 0; t < nt; ++t) {                    // B operand of layer 0 for both tiles
+        if (q == 0) {
+          const float* inp = reinterpret_cast<const float*>(smem + P.inp[t]);
+          const int k = lane;
+          unsigned char* row = smem + P.b[t] + (k >> 3) * CB_CHUNK + (k & 7) * 16;
+#pragma unroll
+          for (int pg = 0; pg < 4; ++pg) {
+            float h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NPTS + ph * 32 + pg * 8 + e] * ACT_SCALE : 0.f;
+            pack8_store_hi(row, ph * 4 + pg, h);
+          }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_act + 8 * t);
+      }
+      for (int p = 0; p < num_layers; ++p) {
+        const TcPassDev Ps = T.pass[p];
+        for (int t = 0; t < nt; ++t) {
+          mbar_wait(bar_acc + 8 * t, acc_phase[t]);
+          acc_phase[t] ^= 1;
+          tc_fence_after();
+          const uint32_t tbuf = lane_base + (uint32_t)(t * 256);
+          const float* inp = reinterpret_cast<const float*>(smem + P.inp[t]);
+          unsigned char* bop = smem + P.b[t];
+          if (Ps.kind == 1) {                           // last Linear: row 0 is the pre-activation of the sdf
+            if (q == 0) {
+              const float bias0 = __ldg(Ps.bias);
+#pragma unroll
+              for (int g2 = 0; g2 < 2; ++g2) {
+                const int g4 = ph * 2 + g2;
+                uint32_t vm[16];
+                tmem_ld16(tbuf + g4 * 16, vm);
+                tmem_ld_wait();
+                if (lane == 0) {
+#pragma unroll
+                  for (int qq = 0; qq < 16; ++qq) {
+                    const int n = g4 * 16 + qq;
+                    float y = __uint_as_float(vm[qq]) * Ps.inv_scale + bias0;
+                    if (use_tanh) y = tanhf(y);
+                    y = tanhf(y);
+                    if (base[t] + n < n_rows) sdf_out[base[t] + n] = y;
+                  }
+                }
+                __syncwarp();
+              }
+            }
+            tc_fence_before();
+            // accumulators of tile t are drained: the next pair's first pass may overwrite them
+            continue;
+          }
+          for (int mb = 0; mb < Ps.m_blocks; ++mb) {
+            const int f = mb * 128 + tl;
+            const int cls = f < Ps.rows ? 0 : (f < Ps.rows + Ps.cat_dim ? 1 : 2);
+            const uint32_t tb = tbuf + (uint32_t)(mb * 64);
+            unsigned char* row = bop + (f >> 3) * CB_CHUNK + (f & 7) * 16;
+            const float bias = cls == 0 ? __ldg(Ps.bias + f) : 0.f;
+            const int cat_row = (Ps.cat_off + f - Ps.rows) * NPTS + ph * 32;
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const int g4 = ph * 2 + g2;
+              uint32_t vm[16];
+              tmem_ld16(tb + g4 * 16, vm);
+              tmem_ld_wait();
+              float h[16];
+              if (cls == 0) {
+#pragma unroll
+                for (int qq = 0; qq < 16; ++qq) {
+                  const float y = __uint_as_float(vm[qq]) * Ps.inv_scale + bias;
+                  h[qq] = y > 0.f ? y * Ps.out_scale : 0.f;
+                }
+              } else if (cls == 1) {
+#pragma unroll
+                for (int qq = 0; qq < 16; ++qq) h[qq] = inp[cat_row + g2 * 16 + qq] * Ps.out_scale;
+              } else {
+#pragma unroll
+                for (int qq = 0; qq < 16; ++qq) h[qq] = 0.f;
+              }
+              float h8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h8[e] = h[e];
+              pack8_store_hi(row, g4 * 2, h8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h8[e] = h[8 + e];
+              pack8_store_hi(row, g4 * 2 + 1, h8);
+            }
+          }
+          fence_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_act + 8 * t);
+        }
+      }
+      // both tiles' inputs are dead once every epilogue thread is past the last pass
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -796,7 +1060,24 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
 }
 
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s) {
-  return launch_mlp_tc_impl(dec, in, sdf, nullptr, 1, s);
+  SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED, "tcgen05 MLP kernel does not cover this decoder");
+  if (in.n <= 0) return SDFR_OK;
+  static int pingpong = -1;
+  if (pingpong < 0) { const char* e = getenv("SDFR_TC_PINGPONG"); pingpong = e ? atoi(e) : 1; }
+  if (!pingpong) return launch_mlp_tc_impl(dec, in, sdf, nullptr, 1, s);
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  const long long point_tiles = (in.n + NPTS - 1) / NPTS;
+  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  const int grid = (int)std::min<long long>((point_tiles + 1) / 2, sms);
+  const CoarsePlan plan = make_coarse_plan(dec->dev.in0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+    attr_set = true;
+  }
+  mlp_tc_coarse_kernel<<<grid, NTHREADS, plan.total, s>>>(st->table_dev, st->tiles_dev, in, sdf, point_tiles);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
 }
 
 static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, int coarse,
