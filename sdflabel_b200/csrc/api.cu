@@ -337,7 +337,7 @@ int sdfr_decoder_eval(sdfr_decoder* dec, const float* inputs_dev, int64_t n, flo
   SDFR_REQUIRE(dec && sdf_dev && (inputs_dev || n == 0) && n >= 0, SDFR_E_INVALID, "bad argument");
   MlpInputs in;
   in.inputs = inputs_dev; in.latent_unit = nullptr; in.lattice = make_lattice(2); in.points_per_batch = 1; in.n = n;
-  in.index = nullptr; in.count_dev = nullptr;
+  in.index = nullptr; in.count_dev = nullptr; in.small_tiles = 0;
   impl = pick_impl(dec, impl);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (impl == SDFR_MLP_TCGEN05) return launch_mlp_tc(dec, in, sdf_dev, dinput_dev, s);
@@ -356,7 +356,7 @@ int sdfr_decoder_eval_lattice(sdfr_decoder* dec, const float* latent_unit_dev, i
   in.inputs = nullptr; in.latent_unit = latent_unit_dev; in.lattice = make_lattice(density);
   in.points_per_batch = (long long)density * density * density;
   in.n = in.points_per_batch * batch;
-  in.index = nullptr; in.count_dev = nullptr;
+  in.index = nullptr; in.count_dev = nullptr; in.small_tiles = 0;
   impl = pick_impl(dec, impl);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (impl == SDFR_MLP_TCGEN05) return launch_mlp_tc(dec, in, sdf_dev, dinput_dev, s);

@@ -214,6 +214,7 @@ struct MlpInputs {
   long long n;                // total points (capacity when count_dev is set)
   const int* index;           // optional gather: row r evaluates source point index[r] (null = r)
   const int* count_dev;       // optional: number of rows, read on the device (no host sync)
+  int small_tiles;            // hint: the row list is short, use 16-point tiles in the tensor-core kernel
 };
 
 __device__ __forceinline__ long long mlp_rows(const MlpInputs& in) {

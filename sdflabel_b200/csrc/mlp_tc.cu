@@ -49,10 +49,8 @@ constexpr int NSTAGE = 5;
 // Per 8-k chunk: 8 point groups of the hi halves (1024 B) followed by 8 point groups of the lo
 // halves (1024 B), so one descriptor with N = 128 covers [hi ; lo] and N = 64 covers hi only.
 constexpr int B_CHUNK = 2048;
-constexpr int B_BYTES = 64 * B_CHUNK;    // 512 / 8 chunks = 128 KB
 constexpr int A_LBO = 2048;              // A (K-major): core matrices adjacent in K are 16 row groups apart
 constexpr int A_SBO = 128;
-constexpr int B_LBO = B_CHUNK;           // B (MN-major): next 8-k chunk
 constexpr int B_SBO = 128;               //               next 8-point group
 constexpr int TMEM_COLS = 512;           // 4 M-blocks x (64 main + 64 cross-term) columns
 constexpr int NTHREADS = 320;          // 8 epilogue warps + producer + MMA issuer
@@ -162,20 +160,6 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
                "h"(mask)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -195,10 +179,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, A K-major, B MN-major, M=128
-constexpr uint32_t idesc_for(int n) {
+__host__ __device__ constexpr uint32_t idesc_for(int n) {
   return (1u << 4) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-constexpr uint32_t kIdesc128 = idesc_for(128), kIdesc64 = idesc_for(64);
+constexpr uint32_t kIdesc64 = idesc_for(64);
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -223,38 +207,21 @@ __device__ __forceinline__ void pack8_store_hi(unsigned char* chunk_row, int pg,
   *reinterpret_cast<uint4*>(chunk_row + pg * 128) = hi;
 }
 
-// 8 consecutive points of one feature -> one 16-byte store of the hi halves and one of the lo halves
-__device__ __forceinline__ float pack8_store(unsigned char* chunk_row, int pg, const float (&h)[8]) {
-  uint4 hi, lo;
-  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
-  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
-  float amax = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __half2 a = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
-    const float2 b = __half22float2(a);
-    const __half2 l = __floats2half2_rn(h[2 * i] - b.x, h[2 * i + 1] - b.y);
-    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
-    lw[i] = *reinterpret_cast<const uint32_t*>(&l);
-    amax = fmaxf(amax, fmaxf(fabsf(h[2 * i]), fabsf(h[2 * i + 1])));
-  }
-  *reinterpret_cast<uint4*>(chunk_row + pg * 128) = hi;
-  *reinterpret_cast<uint4*>(chunk_row + 1024 + pg * 128) = lo;
-  return amax;
-}
-
 struct SmemPlan {
   uint32_t stages, b, inp, dinp, g, bars, tmem_slot, total;
 };
+// NP = points per CTA tile: 64 for throughput, 16 to spread a short row list (the band pass of a
+// single detection: ~1 850 rows) over enough CTAs to fill the machine.
+template <int NP>
 __host__ __device__ inline SmemPlan make_plan(int num_layers, int in0) {
   SmemPlan p;
   uint32_t o = 0;
   p.stages = o; o += NSTAGE * TILE_BYTES;
-  p.b = o; o += B_BYTES;
+  p.b = o; o += 64 * (NP * 32);            // 64 k-chunks x (hi + lo) point groups
   const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
-  p.inp = o; o += in_pad * NPTS * 4;
-  p.dinp = o; o += in_pad * NPTS * 4;
-  p.g = o; o += NPTS * 4;
+  p.inp = o; o += in_pad * NP * 4;
+  p.dinp = o; o += in_pad * NP * 4;
+  p.g = o; o += 64 * 4;
   p.bars = o; o += 32 * 8;
   p.tmem_slot = o; o += 16;
   p.total = o;
@@ -270,6 +237,38 @@ __device__ unsigned long long g_tc_prof[16];
 #define PROF_ADD(slot) do {} while (0)
 #endif
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+
+// hi halves at row + pg*128, lo halves LO bytes further
+template <int LO>
+__device__ __forceinline__ float pack8_store_t(unsigned char* chunk_row, int pg, const float (&h)[8]) {
+  uint4 hi, lo;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 a = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+    const float2 b = __half22float2(a);
+    const __half2 l = __floats2half2_rn(h[2 * i] - b.x, h[2 * i + 1] - b.y);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
+    lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    amax = fmaxf(amax, fmaxf(fabsf(h[2 * i]), fabsf(h[2 * i + 1])));
+  }
+  *reinterpret_cast<uint4*>(chunk_row + pg * 128) = hi;
+  *reinterpret_cast<uint4*>(chunk_row + LO + pg * 128) = lo;
+  return amax;
+}
+
+template <int NP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
@@ -278,7 +277,15 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   if (in.count_dev && *in.count_dev <= 0) return;   // nothing to evaluate (uniform over the whole grid)
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
-  const SmemPlan P = make_plan(num_layers, in0);
+  constexpr int BCH = NP * 32;            // bytes per 8-k chunk of B: NP/8 hi groups then NP/8 lo groups
+  constexpr int LO = NP * 16;             // offset of the lo groups inside a chunk
+  constexpr int PT = NP / 2;              // points per epilogue thread (the two point halves)
+  constexpr int GW = PT >= 16 ? 16 : 8;   // points per TMEM load group
+  constexpr int G = PT / GW;              // load groups per thread
+  constexpr int PG = GW / 8;              // 8-point packs (16-byte stores) per load group
+  constexpr int TCOLS = 8 * NP < 32 ? 32 : 8 * NP;   // 4 M-blocks x (NP main + NP cross) columns
+  constexpr uint32_t kIdMain = idesc_for(2 * NP), kIdCross = idesc_for(NP);
+  const SmemPlan P = make_plan<NP>(num_layers, in0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   unsigned char* bop = smem + P.b;
   // ReLU sign words (one u64 per feature per hidden layer) live in an L2-resident global scratch:
@@ -300,7 +307,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   // Thread-block cluster: every CTA of the cluster consumes the same weight-tile sequence, so each
   // loads 1/CL of every tile and multicasts it to all of them (one L2 read per cluster instead of per CTA).
   const long long n_rows = mlp_rows(in);           // the row count may live on the device (band pass)
-  if (in.count_dev) num_point_tiles = (n_rows + NPTS - 1) / NPTS;
+  if (in.count_dev) num_point_tiles = (n_rows + NP - 1) / NP;
   const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
   const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
@@ -310,7 +317,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
     mbar_init(bar_act, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
+  if (warp == 9) tmem_alloc(smem_u32(smem + P.tmem_slot), TCOLS);
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();      // peers' barriers must exist before anything arrives on them
@@ -359,7 +366,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t desc_a_base =
         make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);             // + (stage*TILE_BYTES + ...) >> 4
-    const uint64_t desc_b_base = make_desc(smem_u32(bop), B_LBO, B_SBO);
+    const uint64_t desc_b_base = make_desc(smem_u32(bop), BCH, B_SBO);
     for (long long it = 0; it < my_tiles; ++it) {
       for (int p = 0; p < npass; ++p) {
         const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
@@ -367,27 +374,27 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         act_phase ^= 1;
         tc_fence_after();
         for (int mb = 0; mb < m_blocks; ++mb) {
-          const uint32_t d_main = tm + (uint32_t)(mb * 128);    // columns [0,64): hi*hi, [64,128): cross terms
-          const uint32_t d_cross = d_main + 64;
+          const uint32_t d_main = tm + (uint32_t)(mb * 2 * NP);  // columns [0,NP): hi*hi, [NP,2NP): cross terms
+          const uint32_t d_cross = d_main + NP;
           for (int kc = 0; kc < k_chunks; ++kc) {
             { PROF_T0(); mbar_wait(bar_full + 8 * stage, phase); if (lane == 0) PROF_ADD(2); }
             tc_fence_after();
             if (elect_one()) {
               const uint64_t da_hi = desc_a_base + (uint64_t)((stage * TILE_BYTES) >> 4);
               const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
-              const uint64_t db = desc_b_base + (uint64_t)((kc * (KC / 8) * B_CHUNK) >> 4);
+              const uint64_t db = desc_b_base + (uint64_t)((kc * (KC / 8) * BCH) >> 4);
               if (coarse) {
 #pragma unroll
                 for (int j = 0; j < KC / 16; ++j)
-                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
-                           kIdesc64, (kc | j) ? 1u : 0u);                                  // W_hi x H_hi only
+                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                           kIdCross, (kc | j) ? 1u : 0u);                                  // W_hi x H_hi only
               } else {
 #pragma unroll
                 for (int j = 0; j < KC / 16; ++j) {
-                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
-                           kIdesc128, (kc | j) ? 1u : 0u);                                  // W_hi x [H_hi ; H_lo]
-                  umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * B_CHUNK) >> 4),
-                           kIdesc64, 1u);                                                    // W_lo x H_hi
+                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                           kIdMain, (kc | j) ? 1u : 0u);                                    // W_hi x [H_hi ; H_lo]
+                  umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                           kIdCross, 1u);                                                    // W_lo x H_hi
                 }
               }
               // frees the weight stage (in every CTA of the cluster: all of them write into it)
@@ -404,7 +411,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3, ph = warp >> 2;            // TMEM lane quadrant, point half (32 points)
+    const int q = warp & 3, ph = warp >> 2;            // TMEM lane quadrant, point half (PT points)
     const int t = q * 32 + lane;                       // 0..127 = TMEM lane = feature within the M block
     const int et = tid;                                // 0..255 index among the epilogue threads
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -413,10 +420,10 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
     float amax = 0.f;
     for (long long it = 0; it < my_tiles; ++it) {
       const long long pt = (it * num_clusters + cluster_id) * CL + crank;   // may be past the end: masked
-      const long long base = pt * NPTS;
+      const long long base = pt * NP;
       // ---- stage inputs: inp[c][n] ----
-      for (int i = et; i < in_pad * NPTS; i += NEPI) {
-        const int c = i / NPTS, n = i - c * NPTS;
+      for (int i = et; i < in_pad * NP; i += NEPI) {
+        const int c = i / NP, n = i - c * NP;
         const long long gi = base + n;
         float v = 0.f;
         if (gi < n_rows && c < in0) {
@@ -441,14 +448,14 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
       // B operand of layer 0: k = input column (padded to one 32-k chunk); thread = (k, point half)
       if (q == 0) {
         const int k = lane;
-        unsigned char* row = bop + (k >> 3) * B_CHUNK + (k & 7) * 16;
+        unsigned char* row = bop + (k >> 3) * BCH + (k & 7) * 16;
 #pragma unroll
-        for (int pg = 0; pg < 4; ++pg) {
+        for (int g = 0; g < PT / 8; ++g) {
           float h[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NPTS + ph * 32 + pg * 8 + e] * ACT_SCALE : 0.f;
-          if (coarse) pack8_store_hi(row, ph * 4 + pg, h);
-          else amax = fmaxf(amax, pack8_store(row, ph * 4 + pg, h));
+          for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NP + ph * PT + g * 8 + e] * ACT_SCALE : 0.f;
+          if (coarse) pack8_store_hi(row, ph * (PT / 8) + g, h);
+          else amax = fmaxf(amax, pack8_store_t<LO>(row, ph * (PT / 8) + g, h));
         }
       }
       fence_async_smem();
@@ -466,26 +473,22 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           if (q == 0) {                                // whole warp issues the aligned loads; lane 0 owns row 0
             const float bias0 = __ldg(Ps.bias);
 #pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-              const int g4 = ph * 2 + g2;
-              uint32_t vm[16], vc[16];
-              tmem_ld16(lane_base + g4 * 16, vm);
-              if (!coarse) tmem_ld16(lane_base + 64 + g4 * 16, vc);
+            for (int g = 0; g < G; ++g) {
+              uint32_t vm[GW], vc[GW];
+              tmem_ldg(lane_base + ph * PT + g * GW, vm);
+              if (!coarse) tmem_ldg(lane_base + NP + ph * PT + g * GW, vc);
               tmem_ld_wait();
-              if (coarse) {
-#pragma unroll
-                for (int qq = 0; qq < 16; ++qq) vc[qq] = 0u;
-              }
               if (lane == 0) {
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) {
-                  const int n = g4 * 16 + qq;
-                  float y = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale + bias0, g = 1.f;
-                  if (use_tanh) { y = tanhf(y); g *= 1.f - y * y; }
+                for (int qq = 0; qq < GW; ++qq) {
+                  const int n = ph * PT + g * GW + qq;
+                  const float cross = coarse ? 0.f : __uint_as_float(vc[qq]);
+                  float y = (__uint_as_float(vm[qq]) + cross) * Ps.inv_scale + bias0, gg = 1.f;
+                  if (use_tanh) { y = tanhf(y); gg *= 1.f - y * y; }
                   y = tanhf(y);
-                  g *= 1.f - y * y;
+                  gg *= 1.f - y * y;
                   if (base + n < n_rows) sdf_out[base + n] = y;
-                  gbuf[n] = g;
+                  gbuf[n] = gg;
                 }
               }
               __syncwarp();
@@ -500,13 +503,13 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
               const int f = mb * 128 + t;
               const float w = f < hidden ? __ldg(T.last_w + f) * BWD_SCALE : 0.f;
               const uint32_t mk = f < hidden ? masks32[((size_t)(num_layers - 2) * 512 + f) * 2 + ph] : 0u;
-              unsigned char* row = bop + (f >> 3) * B_CHUNK + (f & 7) * 16;
+              unsigned char* row = bop + (f >> 3) * BCH + (f & 7) * 16;
 #pragma unroll
-              for (int pg = 0; pg < 4; ++pg) {
+              for (int g = 0; g < PT / 8; ++g) {
                 float h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (pg * 8 + e)) & 1u) ? w * gbuf[ph * 32 + pg * 8 + e] : 0.f;
-                amax = fmaxf(amax, pack8_store(row, ph * 4 + pg, h));
+                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (g * 8 + e)) & 1u) ? w * gbuf[ph * PT + g * 8 + e] : 0.f;
+                amax = fmaxf(amax, pack8_store_t<LO>(row, ph * (PT / 8) + g, h));
               }
             }
             fence_async_smem();
@@ -520,72 +523,68 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         for (int mb = 0; mb < Ps.m_blocks; ++mb) {
           const int f = mb * 128 + t;
           const int cls = f < split ? 0 : (f < split + Ps.cat_dim ? 1 : 2);
-          const uint32_t tb = lane_base + (uint32_t)(mb * 128);
-          unsigned char* row = bop + (f >> 3) * B_CHUNK + (f & 7) * 16;
+          const uint32_t tb = lane_base + (uint32_t)(mb * 2 * NP);
+          unsigned char* row = bop + (f >> 3) * BCH + (f & 7) * 16;
           const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
           const uint32_t pmask = (Ps.kind == 2 && cls == 0) ? masks32[((size_t)(Ps.layer - 1) * 512 + f) * 2 + ph] : 0u;
-          const int cat_row = (Ps.cat_off + f - split) * NPTS + ph * 32;
+          const int cat_row = (Ps.cat_off + f - split) * NP + ph * PT;
           uint32_t mk = 0u;
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            const int g4 = ph * 2 + g2;
-            uint32_t vm[16], vc[16];
-            tmem_ld16(tb + g4 * 16, vm);
-            if (!coarse) tmem_ld16(tb + 64 + g4 * 16, vc);
+          for (int g = 0; g < G; ++g) {
+            uint32_t vm[GW], vc[GW];
+            tmem_ldg(tb + ph * PT + g * GW, vm);
+            if (!coarse) tmem_ldg(tb + NP + ph * PT + g * GW, vc);
             tmem_ld_wait();
-            if (coarse) {
+            float x[GW];
 #pragma unroll
-              for (int qq = 0; qq < 16; ++qq) vc[qq] = 0u;
-            }
-            float x[16];
-#pragma unroll
-            for (int qq = 0; qq < 16; ++qq) x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
+            for (int qq = 0; qq < GW; ++qq)
+              x[qq] = (__uint_as_float(vm[qq]) + (coarse ? 0.f : __uint_as_float(vc[qq]))) * Ps.inv_scale;
             if (Ps.kind == 3) {                                    // gradient with respect to the input row
               if (cls == 0) {
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) dinp[f * NPTS + g4 * 16 + qq] += x[qq];
+                for (int qq = 0; qq < GW; ++qq) dinp[f * NP + ph * PT + g * GW + qq] += x[qq];
               }
               continue;
             }
-            float h[16];
+            float h[GW];
             if (fwd) {
               if (cls == 0) {
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) {
+                for (int qq = 0; qq < GW; ++qq) {
                   const float y = x[qq] + bias;
                   const bool on = y > 0.f;
-                  if (on) mk |= 1u << (g2 * 16 + qq);
+                  if (on) mk |= 1u << (g * GW + qq);
                   h[qq] = on ? y * Ps.out_scale : 0.f;
                 }
               } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) h[qq] = inp[cat_row + g2 * 16 + qq] * Ps.out_scale;
+                for (int qq = 0; qq < GW; ++qq) h[qq] = inp[cat_row + g * GW + qq] * Ps.out_scale;
               } else {
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) h[qq] = 0.f;
+                for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
               }
             } else {
               if (cls == 0) {
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) h[qq] = ((pmask >> (g2 * 16 + qq)) & 1u) ? x[qq] * Ps.out_scale : 0.f;
+                for (int qq = 0; qq < GW; ++qq) h[qq] = ((pmask >> (g * GW + qq)) & 1u) ? x[qq] * Ps.out_scale : 0.f;
               } else {
                 if (cls == 1) {                                    // gradient of the concatenated input columns
 #pragma unroll
-                  for (int qq = 0; qq < 16; ++qq) dinp[cat_row + g2 * 16 + qq] += x[qq];
+                  for (int qq = 0; qq < GW; ++qq) dinp[cat_row + g * GW + qq] += x[qq];
                 }
 #pragma unroll
-                for (int qq = 0; qq < 16; ++qq) h[qq] = 0.f;
+                for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
               }
             }
-            float h8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) h8[e] = h[e];
-            if (coarse) pack8_store_hi(row, g4 * 2, h8);
-            else amax = fmaxf(amax, pack8_store(row, g4 * 2, h8));
+            for (int pk = 0; pk < PG; ++pk) {
+              float h8[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) h8[e] = h[8 + e];
-            if (coarse) pack8_store_hi(row, g4 * 2 + 1, h8);
-            else amax = fmaxf(amax, pack8_store(row, g4 * 2 + 1, h8));
+              for (int e = 0; e < 8; ++e) h8[e] = h[pk * 8 + e];
+              const int pgi = ph * (PT / 8) + g * PG + pk;
+              if (coarse) pack8_store_hi(row, pgi, h8);
+              else amax = fmaxf(amax, pack8_store_t<LO>(row, pgi, h8));
+            }
           }
           if (fwd && want_grad) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;   // only the backward reads them
         }
@@ -593,9 +592,9 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         if (Ps.kind == 3) {
           tc_fence_before();
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          for (int i = et; i < NPTS * in0; i += NEPI) {
+          for (int i = et; i < NP * in0; i += NEPI) {
             const int n = i / in0, c = i - n * in0;
-            if (base + n < n_rows) dinput_out[(base + n) * in0 + c] = dinp[c * NPTS + n];
+            if (base + n < n_rows) dinput_out[(base + n) * in0 + c] = dinp[c * NP + n];
           }
         } else {
           fence_async_smem();
@@ -611,7 +610,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();      // no CTA may exit while a peer can still write into it
-  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == 9) tmem_dealloc(tmem_base, TCOLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -932,7 +931,7 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   int major = 0;
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dec->device);
   if (major != 10) return SDFR_OK;   // tcgen05 exists on sm_100 only
-  const SmemPlan plan = make_plan(NL, in0);
+  const SmemPlan plan = make_plan<64>(NL, in0);
   if (plan.total > 227 * 1024) return SDFR_OK;
 
   TcHostState* st = new TcHostState();
@@ -1016,7 +1015,9 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
     TC_CUDA(cudaMalloc(&p, mask_bytes));
     if (rc == SDFR_OK) { dec->allocs.push_back(p); st->mask_dev = reinterpret_cast<unsigned long long*>(p); }
   }
-  if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+  if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
+  if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)make_plan<16>(NL, in0).total));
 #undef TC_CUDA
   if (rc != SDFR_OK) { delete st; return rc; }
   st->smem_bytes = plan.total;
@@ -1087,16 +1088,20 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
                "latent+3 <= 32, <= 9 layers)");
   if (in.n <= 0) return SDFR_OK;
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
-  const long long point_tiles = (in.n + NPTS - 1) / NPTS;
+  // 16-point tiles when the caller expects a short row list (MlpInputs::small_tiles: the band pass of a
+  // few detections), so that ~2 000 rows still fill the machine; 64-point tiles otherwise.
+  const bool small = in.small_tiles && !coarse;
+  const int np = small ? 16 : 64;
+  const long long point_tiles = (in.n + np - 1) / np;
   static int cluster = -1;
   if (cluster < 0) {
     const char* e = getenv("SDFR_TC_CLUSTER");
-    cluster = e ? atoi(e) : 1;   // multicast measured slower than per-CTA streaming with a 3-stage ring
+    cluster = e ? atoi(e) : 1;   // multicast measured slower than per-CTA streaming
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
   }
   const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
   int grid = (int)std::min<long long>(point_tiles, sms);
-  int cl = cluster;
+  int cl = small ? 1 : cluster;
   while (cl > 1 && (grid % cl != 0 || grid < cl)) {
     if (grid >= cl) grid -= grid % cl; else cl >>= 1;
   }
@@ -1104,7 +1109,7 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = st->smem_bytes;
+  cfg.dynamicSmemBytes = small ? make_plan<16>(dec->dev.num_layers, dec->dev.in0).total : st->smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1113,8 +1118,13 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev, in,
-                               sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+  if (small) {
+    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<16>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
+                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+  } else {
+    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<64>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
+                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+  }
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }

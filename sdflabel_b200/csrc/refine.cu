@@ -581,9 +581,11 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   in.n = E.ng * B;
   in.index = nullptr;
   in.count_dev = nullptr;
+  in.small_tiles = 0;
   MlpInputs in_band = in;               // same lattice / latents, rows gathered through band_src
   in_band.index = E.band_src;
   in_band.count_dev = E.band_total;
+  in_band.small_tiles = B <= 4;         // a few detections: ~2 000 rows each, spread them over all SMs
   int impl = r->cfg.mlp_impl;
   if (impl == SDFR_MLP_AUTO) impl = r->dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
   BandArgs ba;

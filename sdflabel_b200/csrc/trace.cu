@@ -274,7 +274,7 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
   SDFR_LAUNCH_CHECK();
   MlpInputs in;
   in.inputs = w.inputs; in.latent_unit = nullptr; in.lattice = make_lattice(2); in.points_per_batch = 1; in.n = P;
-  in.index = nullptr;
+  in.index = nullptr; in.small_tiles = 0;
   int rc;
   for (int step = 0; step < max_steps; ++step) {
     const int cur = step & 1, nxt = cur ^ 1;
