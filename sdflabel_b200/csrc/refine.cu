@@ -14,6 +14,7 @@
 // Every reduction is an ordered two-level sum, so a run is bit-reproducible.
 #include <algorithm>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 
 #include "loss.cuh"
@@ -423,6 +424,11 @@ struct sdfr_refine {
   std::vector<float*> nocs_dev;       // per-detection staging of the un-resized NOCS prediction
   std::vector<size_t> nocs_cap;
   int max_w_set, max_h_set;
+  // one refine iteration captured as a CUDA graph (16 kernel nodes, all arguments are device-resident
+  // state, so the same executable graph is replayed every iteration)
+  cudaGraphExec_t graph_exec;
+  cudaStream_t capture_stream;   // the caller's stream may be the legacy default stream, which cannot be captured
+  int graph_w, graph_h, graph_nodes, runs;
 };
 
 namespace {
@@ -457,6 +463,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   r->dec = dec;
   r->cfg = *cfg;
   r->max_w_set = r->max_h_set = 0;
+  r->graph_exec = nullptr; r->capture_stream = nullptr; r->graph_w = r->graph_h = 0; r->graph_nodes = 0; r->runs = 0;
   EngineDev& E = r->E;
   const int B = cfg->batch, L = dec->dev.latent_size;
   E.batch = B; E.L = L; E.in0 = L + 3;
@@ -514,6 +521,8 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
 
 extern "C" void sdfr_refine_destroy(sdfr_refine* r) {
   if (!r) return;
+  if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
+  if (r->capture_stream) cudaStreamDestroy(r->capture_stream);
   for (void* p : r->allocs) cudaFree(p);
   for (float* p : r->nocs_dev) if (p) cudaFree(p);
   delete r;
@@ -568,9 +577,8 @@ extern "C" int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_h
   return SDFR_OK;
 }
 
-extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
-  SDFR_REQUIRE(r && iters >= 0, SDFR_E_INVALID, "bad argument");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+// enqueues the kernels of ONE refine iteration on `s`
+static int enqueue_iteration(sdfr_refine* r, cudaStream_t s) {
   EngineDev& E = r->E;
   const int B = E.batch;
   MlpInputs in;
@@ -600,9 +608,8 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   ba.band_sdf = E.band_sdf; ba.band_dinput = E.dinput; ba.in0 = E.in0; ba.latent = E.L;
   ba.out_pts = E.surf_pts; ba.out_nrm = E.surf_nrm; ba.out_idx = E.surf_idx; ba.out_glat = E.surf_glat; ba.cap = E.cap;
   const int maxw = r->max_w_set, maxh = r->max_h_set;
-  SDFR_REQUIRE(maxw > 0 && maxh > 0, SDFR_E_INVALID, "no detection has been set");
   int rc;
-  for (int it = 0; it < iters; ++it) {
+  {
     iter_begin_kernel<<<B, 32, 0, s>>>(E);
     SDFR_LAUNCH_CHECK();
     // sdf over the whole lattice (forward only), then sdf + input gradient for the band points
@@ -626,6 +633,44 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
     SDFR_LAUNCH_CHECK();
     update_kernel<<<B, LB, 0, s>>>(E);
     SDFR_LAUNCH_CHECK();
+  }
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
+  SDFR_REQUIRE(r && iters >= 0, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  SDFR_REQUIRE(r->max_w_set > 0 && r->max_h_set > 0, SDFR_E_INVALID, "no detection has been set");
+  static int use_graph = -1;
+  if (use_graph < 0) { const char* e = getenv("SDFR_REFINE_GRAPH"); use_graph = e ? atoi(e) : 1; }
+  int rc;
+  int done = 0;
+  // The first call runs un-captured (lazy attribute setup inside the launchers must not happen during capture).
+  if (!use_graph || r->runs == 0) {
+    for (; done < (use_graph ? std::min(iters, 1) : iters); ++done)
+      if ((rc = enqueue_iteration(r, s))) return rc;
+  }
+  r->runs += 1;
+  if (done == iters) return SDFR_OK;
+  if (!r->graph_exec || r->graph_w != r->max_w_set || r->graph_h != r->max_h_set) {
+    if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const long long before = sdfr_launch_count();
+    if (!r->capture_stream) SDFR_CUDA(cudaStreamCreateWithFlags(&r->capture_stream, cudaStreamNonBlocking));
+    SDFR_CUDA(cudaStreamBeginCapture(r->capture_stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_iteration(r, r->capture_stream);
+    cudaError_t ce = cudaStreamEndCapture(r->capture_stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    SDFR_CUDA(ce);
+    r->graph_nodes = (int)(sdfr_launch_count() - before);
+    count_launch(-r->graph_nodes);            // capturing launched nothing
+    SDFR_CUDA(cudaGraphInstantiate(&r->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    r->graph_w = r->max_w_set; r->graph_h = r->max_h_set;
+  }
+  for (; done < iters; ++done) {
+    SDFR_CUDA(cudaGraphLaunch(r->graph_exec, s));
+    count_launch(r->graph_nodes);
   }
   return SDFR_OK;
 }
