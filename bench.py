@@ -297,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get("bytes_per_launch")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "mlp_tc_kernel" if impl == _lib.MLP_TCGEN05 else "mlp_ffma_kernel",
+                "traffic": traffic, "kernel": _lattice_kernel_name(impl),
                 "kernel_ms": k_ms, "share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
                 "algorithmic_flops_per_launch": alg_flops,
                 "issued_over_algorithmic": 1.0,
@@ -337,6 +337,16 @@ def run_ours(args, rank, world, local_rank):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _lattice_kernel_name(impl):
+    """Name of the kernel the lattice pass launches (the dispatch of csrc/mlp_tc.cu:launch_mlp_tc_coarse)."""
+    from sdflabel_b200 import _lib
+    if impl != _lib.MLP_TCGEN05:
+        return "mlp_ffma_kernel"
+    if os.environ.get("SDFR_TC_PINGPONG", "1") == "0":
+        return "mlp_tc_kernel"
+    return "mlp_tc_coarse_wide_kernel" if os.environ.get("SDFR_TC_WIDE", "1") != "0" else "mlp_tc_coarse_kernel"
 
 
 def main():

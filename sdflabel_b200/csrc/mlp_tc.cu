@@ -98,6 +98,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// wait with back-off: for warps that wait long (epilogue waiting for a whole MMA phase) and must not
+// compete for issue slots with the single MMA-issuing warp
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(64);
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -648,7 +661,7 @@ __host__ __device__ inline CoarsePlan make_coarse_plan(int in0) {
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
-                     float* __restrict__ sdf_out, long long num_point_tiles) {
+                     float* __restrict__ sdf_out, long long num_point_tiles, int interleave) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (in.count_dev && *in.count_dev <= 0) return;
   const TcTable& T = *tabp;
@@ -688,14 +701,20 @@ mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __re
         for (int p = 0; p < num_layers; ++p) {
           const long long n = (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
           const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
-          for (int t = 0; t < nt; ++t)
-            for (long long w = 0; w < n; ++w) {
+          const int m_blocks = T.pass[p].m_blocks, k_chunks = T.pass[p].k_chunks;
+          for (int t = 0; t < nt; ++t) {
+            // issue order: k chunk outer, M block inner (the tiles are stored M block outer)
+            int kc = 0, mb = 0;
+            for (int w = 0; w < (int)n; ++w) {
+              const int ti = interleave ? mb * k_chunks + kc : w;
+              if (++mb == m_blocks) { mb = 0; ++kc; }
               mbar_wait(bar_empty + 8 * stage, phase ^ 1);
               mbar_expect_tx(bar_full + 8 * stage, TILE_HALF_BYTES);
-              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_HALF_BYTES), src + w * TILE_BYTES, TILE_HALF_BYTES,
+              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_HALF_BYTES), src + (size_t)ti * TILE_BYTES, TILE_HALF_BYTES,
                        bar_full + 8 * stage);
               if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
             }
+          }
         }
       }
     }
@@ -715,6 +734,47 @@ mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __re
           mbar_wait(bar_act + 8 * t, act_phase[t]);      // tile t: B operand staged, its accumulators drained
           act_phase[t] ^= 1;
           tc_fence_after();
+          if (interleave) {
+            // Consecutive MMAs go to DIFFERENT accumulators (the M blocks of one k chunk): a chain on one
+            // accumulator pays ~44 cycles of fixed latency per MMA on top of the N/2 cycles of math
+            // (tools/umma_bench.cu); rotating over the M blocks hides it.
+            for (int kc = 0; kc < k_chunks; ++kc) {
+              uint32_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;
+#pragma unroll
+              for (int mb = 0; mb < 4; ++mb) {
+                if (mb < m_blocks) {
+                  mbar_wait(bar_full + 8 * stage, phase);
+                  if (mb == 0) st0 = stage; else if (mb == 1) st1 = stage; else if (mb == 2) st2 = stage; else st3 = stage;
+                  if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
+                }
+              }
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t db = desc_b_base[t] + (uint64_t)((kc * (KC / 8) * CB_CHUNK) >> 4);
+                const uint32_t d = tm + (uint32_t)(t * 256);
+#pragma unroll
+                for (int j = 0; j < KC / 16; ++j) {
+#pragma unroll
+                  for (int mb = 0; mb < 4; ++mb) {
+                    if (mb < m_blocks) {
+                      const uint32_t st = mb == 0 ? st0 : mb == 1 ? st1 : mb == 2 ? st2 : st3;
+                      const uint64_t da = desc_a_base + (uint64_t)((st * TILE_HALF_BYTES) >> 4);
+                      umma_f16(d + (uint32_t)(mb * 64), da + (uint64_t)((j * 2 * A_LBO) >> 4),
+                               db + (uint64_t)((j * 2 * CB_CHUNK) >> 4), kIdesc64, (kc | j) ? 1u : 0u);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) {
+                  if (mb < m_blocks) {
+                    const uint32_t st = mb == 0 ? st0 : mb == 1 ? st1 : mb == 2 ? st2 : st3;
+                    umma_commit(bar_empty + 8 * st);
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          } else {
           for (int mb = 0; mb < m_blocks; ++mb) {
             const uint32_t d = tm + (uint32_t)(t * 256 + mb * 64);
             for (int kc = 0; kc < k_chunks; ++kc) {
@@ -732,6 +792,7 @@ mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __re
               __syncwarp();
               if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
             }
+          }
           }
           if (elect_one()) umma_commit(bar_acc + 8 * t);
           __syncwarp();
@@ -877,6 +938,459 @@ mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __re
   if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Coarse lattice pass, wide-tile version.
+//
+// Measured on B200 (tools/umma_issue_bench.cu, profiles/r01_issue_loop.md): the issuing warp spends
+// ~170 cycles per iteration of the weight-stage ring (mbarrier wait, fence, commit) whatever it issues,
+// and a tcgen05.mma with M=128, K=16 takes max(N/2, ~52) cycles.  Two N=64 MMAs per stage therefore run
+// at 90 cycles per MMA (36 % of the tensor peak), four N=128 MMAs per stage at 65 (98 %).  So this
+// kernel makes the point tile as wide as one CTA can hold - up to 128 points (N = 128, B operand
+// 128 KB, the four M-block accumulators fill the 512 TMEM columns) - and a weight stage two k-chunks
+// deep (four MMAs per ring iteration).
+//
+// That leaves no room for a second resident tile (as the ping-pong kernel above has), so the epilogue
+// (16 warps) is overlapped with the MMAs at M-block granularity instead:
+//   * accumulator mb is committed on its own mbarrier; M blocks 0 and 1 are turned into packed fp16
+//     rows held in registers while the MMAs of the later M blocks still run (the rows cannot be
+//     stored yet: they overwrite the B operand those MMAs read);
+//   * once the last MMA of the pass has completed, the rows are stored M block by M block, each
+//     followed by its own "rows ready" mbarrier; the next pass starts with its M block 0, whose
+//     k-chunks 4q..4q+3 only need the rows of M block q, so its MMAs run under the epilogue of
+//     M blocks 2 and 3.
+// The tile width is chosen on the host so that the last round of tiles is as full as the others
+// (112 points for the 40^3 lattice on 148 SMs).
+// ---------------------------------------------------------------------------------------------
+__device__ unsigned long long g_wide_timing[32];   // SDFR_TC_WIDE_DBG bit 4: CTA 0's issuer loop in cycles and in ns
+constexpr int W_THREADS = 576;           // 16 epilogue warps + weight producer + MMA issuer
+constexpr int W_NEPI = 512;
+
+struct WidePlan {
+  uint32_t stages, b, inp, bars, tmem_slot, total;
+};
+template <int W_GROUP>
+__host__ __device__ inline WidePlan make_wide_plan(int in0, int npt) {
+  constexpr int W_STAGES = W_GROUP == 2 ? 5 : 3, W_STAGE_BYTES = W_GROUP * TILE_HALF_BYTES;
+  WidePlan p;
+  uint32_t o = 0;
+  p.stages = o; o += W_STAGES * W_STAGE_BYTES;
+  p.b = o; o += 64 * (uint32_t)npt * 16;                 // 64 chunks of 8 k x (npt/8 point groups x 128 B)
+  const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
+  p.inp = o; o += in_pad * (uint32_t)npt * 4;
+  p.bars = o; o += 32 * 8;
+  p.tmem_slot = o; o += 16;
+  p.total = o;
+  return p;
+}
+
+template <int W_GROUP>      // weight tiles (k-chunks of 32) per ring stage: 2 -> 4 MMAs per iteration, 4 -> 8
+__global__ void __launch_bounds__(W_THREADS, 1)
+mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
+                          float* __restrict__ sdf_out, int npt, int dbg) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (in.count_dev && *in.count_dev <= 0) return;
+  const TcTable& T = *tabp;
+  const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
+  constexpr int W_STAGES = W_GROUP == 2 ? 5 : 3, W_STAGE_BYTES = W_GROUP * TILE_HALF_BYTES;
+  const WidePlan P = make_wide_plan<W_GROUP>(in0, npt);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t bars = smem_u32(smem + P.bars);
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * W_STAGES, bar_acc = bars + 8 * (2 * W_STAGES),
+                 bar_rows = bars + 8 * (2 * W_STAGES + 4);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
+  const int in_pad = (in0 + 7) & ~7;
+  const int ch = npt * 16;                 // bytes per 8-k chunk of the B operand
+  const int ngroups = npt >> 3;            // 8-point groups per tile
+  const long long n_rows = mlp_rows(in);
+  const long long num_point_tiles = (n_rows + npt - 1) / npt;
+
+  if (tid == 0) {
+    for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int m = 0; m < 4; ++m) { mbar_init(bar_acc + 8 * m, 1); mbar_init(bar_rows + 8 * m, W_NEPI / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  long long my_tiles = 0;
+  for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) ++my_tiles;
+
+  if (warp == 16) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < num_layers; ++p) {
+          const int m_blocks = T.pass[p].m_blocks, k_chunks = T.pass[p].k_chunks;
+          const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
+          auto load_stage = [&](int mb, int kc, int cnt) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            if (dbg & 2) {                                // timing experiment: no weight traffic
+              mbar_arrive(bar_full + 8 * stage);
+            } else {
+              mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * TILE_HALF_BYTES);
+              for (int i = 0; i < cnt; ++i)
+                bulk_g2s(smem_u32(smem + P.stages + stage * W_STAGE_BYTES + i * TILE_HALF_BYTES),
+                         src + (size_t)(mb * k_chunks + kc + i) * TILE_BYTES, TILE_HALF_BYTES, bar_full + 8 * stage);
+            }
+            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          };
+          if (W_GROUP == 4 && k_chunks == 16 && m_blocks == 4) {
+            // same order as the issuer: M blocks 0 and 1 interleaved by k quarter, then M blocks 2 and 3
+            for (int qd = 0; qd < 4; ++qd)
+              for (int mb = 0; mb < 2; ++mb) load_stage(mb, qd * 4, 4);
+            for (int mb = 2; mb < 4; ++mb)
+              for (int qd = 0; qd < 4; ++qd) load_stage(mb, qd * 4, 4);
+          } else {
+            for (int mb = 0; mb < m_blocks; ++mb)
+              for (int kc = 0; kc < k_chunks; kc += W_GROUP) load_stage(mb, kc, min(W_GROUP, k_chunks - kc));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane) =====================
+    // The loop must stay SHORTER than the MMAs it feeds (4 x N/2 cycles per iteration): a first version with
+    // run-time k-chunk counts, predicated groups, 64-bit descriptor arithmetic and debug branches took ~380
+    // cycles per iteration of four N=112 MMAs (248 cycles of tensor work) and the tensor pipe idled a third of
+    // the time.  Passes with the full 16 k-chunks (every 512-wide layer) therefore take the unrolled path
+    // below: compile-time operand offsets, no predicates, descriptor arithmetic on the low word only (the
+    // 14-bit start-address field cannot carry: every operand lies below 256 KB); the rows-ready waits only
+    // exist in the M block 0 instance.
+    uint32_t stage = 0, phase = 0, rows_phase = 0;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc_a_base = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);
+    const uint64_t desc_b_base = make_desc(smem_u32(smem + P.b), (uint32_t)ch, B_SBO);
+    const uint32_t da_hi = (uint32_t)(desc_a_base >> 32), da_lo0 = (uint32_t)desc_a_base;
+    const uint32_t db_hi = (uint32_t)(desc_b_base >> 32), db_lo0 = (uint32_t)desc_b_base;
+    const uint32_t idesc = idesc_for(npt);
+    const uint32_t chq = (uint32_t)(ch >> 4);            // descriptor units per 8-k chunk of B
+    long long t_c0 = 0;
+    unsigned long long t_n0 = 0;
+    if (dbg & 16) { t_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_n0)); }
+    auto desc64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
+    // Everything the unrolled path needs is computed ONCE and pinned in registers (the empty asm keeps the
+    // compiler from re-deriving the descriptors from the shared-memory base in every iteration: that
+    // re-materialised chain of ~25 dependent uniform-datapath instructions was the ~390 cycles per iteration).
+    uint32_t db_it[16 / W_GROUP], db_off[W_GROUP * (KC / 16)];
+#pragma unroll
+    for (int itq = 0; itq < 16 / W_GROUP; ++itq) {
+      db_it[itq] = db_lo0 + (uint32_t)(itq * W_GROUP * (KC / 8)) * chq;
+      asm volatile("" : "+r"(db_it[itq]));
+    }
+#pragma unroll
+    for (int i = 0; i < W_GROUP; ++i)
+#pragma unroll
+      for (int j = 0; j < KC / 16; ++j) {
+        db_off[i * (KC / 16) + j] = (uint32_t)(i * (KC / 8) + j * 2) * chq;
+        asm volatile("" : "+r"(db_off[i * (KC / 16) + j]));
+      }
+    uint32_t da_hi_r = da_hi, db_hi_r = db_hi, da_lo0_r = da_lo0, idesc_r = idesc, bar_full_r = bar_full, bar_empty_r = bar_empty;
+    asm volatile("" : "+r"(da_hi_r), "+r"(db_hi_r), "+r"(da_lo0_r), "+r"(idesc_r), "+r"(bar_full_r), "+r"(bar_empty_r));
+    // one ring iteration: W_GROUP weight tiles x 2 MMAs on accumulator d, B rows starting at descriptor word db_lo
+    auto ring_iteration = [&](const uint32_t d, const uint32_t db_lo, const bool first) {
+      mbar_wait(bar_full_r + 8 * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t da_lo = da_lo0_r + stage * (uint32_t)(W_STAGE_BYTES >> 4);
+#pragma unroll
+        for (int i = 0; i < W_GROUP; ++i)
+#pragma unroll
+          for (int j = 0; j < KC / 16; ++j)
+            umma_f16(d, desc64(da_hi_r, da_lo + (uint32_t)((i * TILE_HALF_BYTES + j * 2 * A_LBO) >> 4)),
+                     desc64(db_hi_r, db_lo + db_off[i * (KC / 16) + j]), idesc_r, (first && i == 0 && j == 0) ? 0u : 1u);
+        umma_commit(bar_empty_r + 8 * stage);
+      }
+      __syncwarp();
+      if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+    };
+    auto issue_full_block = [&](const uint32_t d, const bool first_block) {
+#pragma unroll
+      for (int itq = 0; itq < 16 / W_GROUP; ++itq) {
+        constexpr int kGroupsPerQuarter = 4 / W_GROUP;   // iterations per 4 k-chunks (rows of one M block)
+        if (first_block && (itq % kGroupsPerQuarter) == 0 && !(dbg & 8))
+          mbar_wait(bar_rows + 8 * (itq / kGroupsPerQuarter), rows_phase);
+        ring_iteration(d, db_it[itq], itq == 0);
+      }
+    };
+    for (long long it = 0; it < my_tiles; ++it) {
+      for (int p = 0; p < num_layers; ++p) {
+        const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
+        if (W_GROUP == 4 && k_chunks == 16 && m_blocks == 4) {
+          // Full pass.  The k-chunks 4q..4q+3 are the rows M block q of the previous pass produced, and its
+          // epilogue publishes them in that order (rows_ready[q]) while this pass already runs: M blocks 0 and 1
+          // (whose accumulators the epilogue drained first) advance together, one k quarter at a time, so
+          // that 2 x 16 MMAs are issued before the last rows are needed.
+          if ((dbg & 16) && it == 1 && (p == 4 || p == 5) && blockIdx.x == 0 && lane == 0)
+            g_wide_timing[4 + (p - 4) * 4] = (unsigned long long)clock64();
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            if (!(dbg & 8)) mbar_wait(bar_rows + 8 * qd, rows_phase);
+            if ((dbg & 16) && it == 1 && p == 5 && blockIdx.x == 0 && lane == 0) g_wide_timing[12 + qd] = (unsigned long long)clock64();
+            ring_iteration(tm, db_it[qd], qd == 0);
+            ring_iteration(tm + 128u, db_it[qd], qd == 0);
+          }
+          rows_phase ^= 1;
+          if (elect_one()) { umma_commit(bar_acc); umma_commit(bar_acc + 8); }
+          __syncwarp();
+          for (int mb = 2; mb < 4; ++mb) {
+            if ((dbg & 16) && it == 1 && (p == 4 || p == 5) && blockIdx.x == 0 && lane == 0)
+              g_wide_timing[4 + (p - 4) * 4 + mb] = (unsigned long long)clock64();
+            issue_full_block(tm + (uint32_t)(mb * 128), false);
+            if (elect_one()) umma_commit(bar_acc + 8 * mb);
+            __syncwarp();
+          }
+          continue;
+        }
+        for (int mb = 0; mb < m_blocks; ++mb) {
+          const uint32_t d = tm + (uint32_t)(mb * 128);
+          if (k_chunks == 16) {
+            if (mb == 0) issue_full_block(d, true); else issue_full_block(d, false);
+          } else {
+            for (int kc = 0; kc < k_chunks; kc += W_GROUP) {
+              // k-chunks 4q..4q+3 are the rows the previous pass's M block q produced (for the first pass: the
+              // staged inputs); rows_ready[q] also says that accumulator q of the previous pass has been drained
+              if (mb == 0 && (kc & 3) == 0 && !(dbg & 8)) mbar_wait(bar_rows + 8 * (kc >> 2), rows_phase);
+              const int cnt = min(W_GROUP, k_chunks - kc);
+              mbar_wait(bar_full + 8 * stage, phase);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint32_t da_lo = da_lo0 + ((stage * W_STAGE_BYTES) >> 4);
+                const uint32_t db_lo = db_lo0 + (uint32_t)(kc * (KC / 8)) * chq;
+#pragma unroll
+                for (int i = 0; i < W_GROUP; ++i) {
+                  if (i < cnt) {
+#pragma unroll
+                    for (int j = 0; j < KC / 16; ++j)
+                      umma_f16(d, desc64(da_hi, da_lo + (uint32_t)((i * TILE_HALF_BYTES + j * 2 * A_LBO) >> 4)),
+                               desc64(db_hi, db_lo + (uint32_t)(i * (KC / 8) + j * 2) * chq), idesc, (kc | i | j) ? 1u : 0u);
+                  }
+                }
+                umma_commit(bar_empty + 8 * stage);
+              }
+              __syncwarp();
+              if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          if (mb == 0) {                                   // quarters this pass has no k-chunks for
+            if (!(dbg & 8)) for (int qq = (k_chunks + 3) >> 2; qq < 4; ++qq) mbar_wait(bar_rows + 8 * qq, rows_phase);
+            rows_phase ^= 1;
+          }
+          if (elect_one()) umma_commit(bar_acc + 8 * mb);   // this M block's accumulator is complete
+          __syncwarp();
+        }
+      }
+    }
+    if ((dbg & 16) && blockIdx.x == 0 && lane == 0) {
+      unsigned long long t_n1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_n1));
+      g_wide_timing[0] = (unsigned long long)(clock64() - t_c0);
+      g_wide_timing[1] = t_n1 - t_n0;
+      g_wide_timing[2] = 0;
+      g_wide_timing[3] = 0;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3, slot = warp >> 2;          // TMEM lane quadrant; point groups g = slot, slot+4, ...
+    const int tl = q * 32 + lane;                      // TMEM lane = feature within the M block
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* inp = reinterpret_cast<float*>(smem + P.inp);
+    unsigned char* bop = smem + P.b;
+    uint32_t acc_phase = 0;                            // bit mb = phase of bar_acc[mb]
+    for (long long it = 0; it < ((dbg & 64) ? 0 : my_tiles); ++it) {
+      const long long pt = it * gridDim.x + blockIdx.x;
+      const long long base = pt * npt;
+      for (int i = tid; i < in_pad * npt; i += W_NEPI) {
+        const int c = i / npt, n = i - c * npt;
+        const long long gi = base + n;
+        float v = 0.f;
+        if (gi < n_rows && c < in0) {
+          const long long src = in.index ? (long long)in.index[gi] : gi;
+          if (in.inputs) {
+            v = in.inputs[src * in0 + c];
+          } else {
+            const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
+            if (c < latent) {
+              v = in.latent_unit[b * latent + c];
+            } else {
+              float x, y, z;
+              lattice_point(in.lattice, k, x, y, z);
+              v = (c - latent) == 0 ? x : (c - latent) == 1 ? y : z;
+            }
+          }
+        }
+        inp[i] = v;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (q == 0) {                                    // B operand of layer 0: k = input column
+        const int k = lane;
+        unsigned char* row = bop + (k >> 3) * ch + (k & 7) * 16;
+#pragma unroll
+        for (int gi = 0; gi < 4; ++gi) {
+          const int g = slot + 4 * gi;
+          if (g < ngroups) {
+            float h[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * npt + g * 8 + e] * ACT_SCALE : 0.f;
+            pack8_store_hi(row, g, h);
+          }
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int m2 = 0; m2 < 4; ++m2) mbar_arrive(bar_rows + 8 * m2);
+      }
+
+      for (int p = 0; p < num_layers; ++p) {
+        const TcPassDev Ps = T.pass[p];
+        if (Ps.kind == 1) {                            // last Linear: row 0 is the pre-activation of the sdf
+          if (dbg & 4) mbar_wait_sleep(bar_acc, acc_phase & 1u); else mbar_wait(bar_acc, acc_phase & 1u);
+          acc_phase ^= 1u;
+          tc_fence_after();
+          if (q == 0 && !(dbg & 1)) {
+            const float bias0 = __ldg(Ps.bias);
+#pragma unroll
+            for (int gi = 0; gi < 4; ++gi) {
+              const int g = slot + 4 * gi;
+              if (g < ngroups) {
+                uint32_t v[8];
+                tmem_ld8(lane_base + (uint32_t)(g * 8), v);
+                tmem_ld_wait();
+                if (lane == 0) {
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int n = g * 8 + e;
+                    float y = __uint_as_float(v[e]) * Ps.inv_scale + bias0;
+                    if (use_tanh) y = tanhf(y);
+                    y = tanhf(y);
+                    if (base + n < n_rows) sdf_out[base + n] = y;
+                  }
+                }
+                __syncwarp();
+              }
+            }
+          }
+          tc_fence_before();
+          continue;
+        }
+        if (dbg & 1) {                                 // timing experiment: barrier protocol only
+          for (int m2 = 0; m2 < Ps.m_blocks; ++m2) {
+            if (dbg & 4) mbar_wait_sleep(bar_acc + 8 * m2, (acc_phase >> m2) & 1u); else mbar_wait(bar_acc + 8 * m2, (acc_phase >> m2) & 1u);
+            acc_phase ^= 1u << m2;
+          }
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) for (int m2 = 0; m2 < 4; ++m2) mbar_arrive(bar_rows + 8 * m2);
+          continue;
+        }
+        // M blocks 0 and 1 become packed rows (held in registers) while the MMAs of the later M blocks run.
+        // The scales are powers of two, so max(acc * (inv_scale * out_scale) + bias * out_scale, 0) is bit-identical
+        // to relu(acc * inv_scale + bias) * out_scale: two instructions per value instead of four.
+        const float k_scale = Ps.inv_scale * Ps.out_scale;
+        auto process_block = [&](const int mb, uint4 (&cur)[4]) {
+          const int f = mb * 128 + tl;
+          if ((dbg & 16) && it == 1 && p == 4 && blockIdx.x == 0 && tid == 0) g_wide_timing[16 + mb] = (unsigned long long)clock64();
+          // the TMEM loads are warp-collective (.sync.aligned): every lane issues them, whatever its row class
+          const bool regular = f < Ps.rows;             // all but the concat / padding rows
+          const bool cat = !regular && f < Ps.rows + Ps.cat_dim;
+          const float bias_s = regular ? __ldg(Ps.bias + f) * Ps.out_scale : 0.f;
+          const int cat_row = (Ps.cat_off + f - Ps.rows) * npt;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[2][8];
+#pragma unroll
+            for (int gj = 0; gj < 2; ++gj)
+              if (slot + 4 * (2 * half + gj) < ngroups)
+                tmem_ld8(lane_base + (uint32_t)(mb * 128 + (slot + 4 * (2 * half + gj)) * 8), v[gj]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int gj = 0; gj < 2; ++gj) {
+              const int g = slot + 4 * (2 * half + gj);
+              if (g < ngroups) {
+                uint32_t* hw = reinterpret_cast<uint32_t*>(&cur[2 * half + gj]);
+                if (regular) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float h0 = fmaxf(fmaf(__uint_as_float(v[gj][2 * i]), k_scale, bias_s), 0.f);
+                    const float h1 = fmaxf(fmaf(__uint_as_float(v[gj][2 * i + 1]), k_scale, bias_s), 0.f);
+                    const __half2 a = __floats2half2_rn(h0, h1);
+                    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float h0 = 0.f, h1 = 0.f;
+                    if (cat) { h0 = inp[cat_row + g * 8 + 2 * i] * Ps.out_scale; h1 = inp[cat_row + g * 8 + 2 * i + 1] * Ps.out_scale; }
+                    const __half2 a = __floats2half2_rn(h0, h1);
+                    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
+                  }
+                }
+              }
+            }
+          }
+        };
+        auto publish_block = [&](const int mb, const uint4 (&rowsv)[4]) {
+          const int f = mb * 128 + tl;
+          unsigned char* row = bop + (f >> 3) * ch + (f & 7) * 16;
+#pragma unroll
+          for (int gi = 0; gi < 4; ++gi)
+            if (slot + 4 * gi < ngroups) *reinterpret_cast<uint4*>(row + (slot + 4 * gi) * 128) = rowsv[gi];
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_rows + 8 * mb);
+          if ((dbg & 16) && it == 1 && p == 4 && blockIdx.x == 0 && tid == 0) g_wide_timing[20 + mb] = (unsigned long long)clock64();
+        };
+        uint4 packed[2][4];
+        const int hold = Ps.m_blocks >= 3 ? 2 : 0;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          if (mb < Ps.m_blocks) {
+            if (mb < hold) {
+              mbar_wait(bar_acc + 8 * mb, (acc_phase >> mb) & 1u);
+            } else if (mb == hold) {                   // wait for every remaining accumulator of the pass
+#pragma unroll
+              for (int m2 = 0; m2 < 4; ++m2)
+                if (m2 >= hold && m2 < Ps.m_blocks) mbar_wait(bar_acc + 8 * m2, (acc_phase >> m2) & 1u);
+            }
+            acc_phase ^= 1u << mb;
+            tc_fence_after();
+            if (mb < hold) {
+              if (mb < 2) process_block(mb, packed[mb < 2 ? mb : 0]);
+            } else {
+              // every MMA of this pass has completed: the B operand may be overwritten in place.  Rows are
+              // published M block by M block so that the next pass can start on the first ones.
+              if (mb == hold) {
+#pragma unroll
+                for (int m2 = 0; m2 < 2; ++m2)
+                  if (m2 < hold) publish_block(m2, packed[m2]);
+              }
+              uint4 cur[4];
+              process_block(mb, cur);
+              publish_block(mb, cur);
+            }
+          }
+        }
+        if (lane == 0) for (int m2 = Ps.m_blocks; m2 < 4; ++m2) mbar_arrive(bar_rows + 8 * m2);
+      }
+      // the inputs (concatenated rows) are dead once every epilogue thread is past the last pass
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1018,6 +1532,8 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
   if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)make_plan<16>(NL, in0).total));
+  if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)make_plan<32>(NL, in0).total));
 #undef TC_CUDA
   if (rc != SDFR_OK) { delete st; return rc; }
   st->smem_bytes = plan.total;
@@ -1027,6 +1543,10 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   dec->tc.tiles = reinterpret_cast<const uint4*>(st->tiles_dev);
   dec->tc_ptr = reinterpret_cast<DecoderTc*>(st);   // opaque host state (freed with the decoder)
   return SDFR_OK;
+}
+
+extern "C" int sdfr_debug_wide_timing(unsigned long long* out4) {
+  return cudaMemcpyFromSymbol(out4, g_wide_timing, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : 1;
 }
 
 #ifdef SDFR_TC_PROFILE
@@ -1067,8 +1587,42 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
   if (pingpong < 0) { const char* e = getenv("SDFR_TC_PINGPONG"); pingpong = e ? atoi(e) : 1; }
   if (!pingpong) return launch_mlp_tc_impl(dec, in, sdf, nullptr, 1, s);
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
-  const long long point_tiles = (in.n + NPTS - 1) / NPTS;
   const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  static int wide = -1;
+  if (wide < 0) { const char* e = getenv("SDFR_TC_WIDE"); wide = e ? atoi(e) : 1; }
+  if (wide) {
+    static int wide_dbg = -1;
+    if (wide_dbg < 0) { const char* d = getenv("SDFR_TC_WIDE_DBG"); wide_dbg = d ? atoi(d) : 0; }
+    static int wide_group = -1;
+    if (wide_group < 0) { const char* g = getenv("SDFR_TC_WIDE_GROUP"); wide_group = (g && atoi(g) == 2) ? 2 : 4; }
+    // tile width: as wide as the CTA can hold next to the weight ring (112 points with 32 KB stages, 128 with
+    // 16 KB stages), shrunk so that all rounds of tiles are equally full
+    const int max_npt = wide_group == 4 ? 112 : 128;
+    const long long rounds = ((in.n + max_npt - 1) / max_npt + sms - 1) / sms;
+    long long w = (in.n + rounds * sms - 1) / (rounds * sms);
+    int npt = (int)std::min<long long>(max_npt, ((w + 15) / 16) * 16);
+    const char* e = getenv("SDFR_TC_WIDE_NPT");
+    if (e && atoi(e) >= 16 && atoi(e) <= max_npt && atoi(e) % 16 == 0) npt = atoi(e);
+    const long long tiles_n = (in.n + npt - 1) / npt;
+    const int grid = (int)std::min<long long>(tiles_n, sms);
+    static bool wide_attr_set = false;
+    if (!wide_attr_set) {
+      SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)make_wide_plan<2>(dec->dev.in0, 128).total));
+      SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)make_wide_plan<4>(dec->dev.in0, 112).total));
+      wide_attr_set = true;
+    }
+    if (wide_group == 4 && npt <= 112)
+      mlp_tc_coarse_wide_kernel<4><<<grid, W_THREADS, make_wide_plan<4>(dec->dev.in0, npt).total, s>>>(
+          st->table_dev, st->tiles_dev, in, sdf, npt, wide_dbg);
+    else
+      mlp_tc_coarse_wide_kernel<2><<<grid, W_THREADS, make_wide_plan<2>(dec->dev.in0, npt).total, s>>>(
+          st->table_dev, st->tiles_dev, in, sdf, npt, wide_dbg);
+    SDFR_LAUNCH_CHECK();
+    return SDFR_OK;
+  }
+  const long long point_tiles = (in.n + NPTS - 1) / NPTS;
   const int grid = (int)std::min<long long>((point_tiles + 1) / 2, sms);
   const CoarsePlan plan = make_coarse_plan(dec->dev.in0);
   static bool attr_set = false;
@@ -1076,7 +1630,9 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
     SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
     attr_set = true;
   }
-  mlp_tc_coarse_kernel<<<grid, NTHREADS, plan.total, s>>>(st->table_dev, st->tiles_dev, in, sdf, point_tiles);
+  static int interleave = -1;
+  if (interleave < 0) { const char* e = getenv("SDFR_TC_INTERLEAVE"); interleave = e ? atoi(e) : 0; }
+  mlp_tc_coarse_kernel<<<grid, NTHREADS, plan.total, s>>>(st->table_dev, st->tiles_dev, in, sdf, point_tiles, interleave);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
@@ -1090,18 +1646,27 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
   // 16-point tiles when the caller expects a short row list (MlpInputs::small_tiles: the band pass of a
   // few detections), so that ~2 000 rows still fill the machine; 64-point tiles otherwise.
-  const bool small = in.small_tiles && !coarse;
-  const int np = small ? 16 : 64;
+  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  static int small_np = -1;
+  if (small_np < 0) {
+    const char* e = getenv("SDFR_TC_SMALL_NP");
+    small_np = e ? atoi(e) : 16;
+    if (small_np != 16 && small_np != 32 && small_np != 64) small_np = 16;
+  }
+  const bool small = (in.small_tiles || (!in.count_dev && in.n <= 16LL * sms)) && !coarse && small_np != 64;
+  const int np = small ? small_np : 64;
   const long long point_tiles = (in.n + np - 1) / np;
-  static int cluster = -1;
+  static int cluster = -1, cluster_small = -1;
   if (cluster < 0) {
     const char* e = getenv("SDFR_TC_CLUSTER");
     cluster = e ? atoi(e) : 1;   // multicast measured slower than per-CTA streaming
     if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+    e = getenv("SDFR_TC_CLUSTER_SMALL");
+    cluster_small = e ? atoi(e) : 1;
+    if (cluster_small != 1 && cluster_small != 2 && cluster_small != 4) cluster_small = 1;
   }
-  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
   int grid = (int)std::min<long long>(point_tiles, sms);
-  int cl = small ? 1 : cluster;
+  int cl = small ? cluster_small : cluster;
   while (cl > 1 && (grid % cl != 0 || grid < cl)) {
     if (grid >= cl) grid -= grid % cl; else cl >>= 1;
   }
@@ -1109,7 +1674,9 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = small ? make_plan<16>(dec->dev.num_layers, dec->dev.in0).total : st->smem_bytes;
+  cfg.dynamicSmemBytes = !small ? st->smem_bytes
+                         : np == 16 ? make_plan<16>(dec->dev.num_layers, dec->dev.in0).total
+                                    : make_plan<32>(dec->dev.num_layers, dec->dev.in0).total;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1118,7 +1685,10 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (small) {
+  if (small && np == 32) {
+    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<32>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
+                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+  } else if (small) {
     SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<16>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
                                  in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
   } else {
