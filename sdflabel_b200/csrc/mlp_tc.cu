@@ -44,7 +44,8 @@ constexpr int NPTS = 64;                 // points per CTA tile
 constexpr int KC = 32;                   // k per weight stage (two K=16 MMA steps)
 constexpr int TILE_BYTES = 16384;        // 128 x 32 fp16 hi + the same lo
 constexpr int TILE_HALF_BYTES = 8192;
-constexpr int NSTAGE = 5;
+// weight-ring depth of mlp_tc_kernel<NP>: the smaller the point tile, the more shared memory is left for stages
+template <int NP> struct RingDepth { static constexpr int value = NP <= 16 ? 11 : NP <= 32 ? 9 : 5; };
 // B operand (activations), MN-major, no swizzle: core matrix = 8 k-rows x (8 points = 16 B).
 // Per 8-k chunk: 8 point groups of the hi halves (1024 B) followed by 8 point groups of the lo
 // halves (1024 B), so one descriptor with N = 128 covers [hi ; lo] and N = 64 covers hi only.
@@ -229,7 +230,7 @@ template <int NP>
 __host__ __device__ inline SmemPlan make_plan(int num_layers, int in0) {
   SmemPlan p;
   uint32_t o = 0;
-  p.stages = o; o += NSTAGE * TILE_BYTES;
+  p.stages = o; o += RingDepth<NP>::value * TILE_BYTES;
   p.b = o; o += 64 * (NP * 32);            // 64 k-chunks x (hi + lo) point groups
   const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
   p.inp = o; o += in_pad * NP * 4;
@@ -285,11 +286,12 @@ template <int NP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
-              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles, int coarse) {
+              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles, int coarse, int group) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (in.count_dev && *in.count_dev <= 0) return;   // nothing to evaluate (uniform over the whole grid)
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
+  constexpr int NSTAGE = RingDepth<NP>::value;
   constexpr int BCH = NP * 32;            // bytes per 8-k chunk of B: NP/8 hi groups then NP/8 lo groups
   constexpr int LO = NP * 16;             // offset of the lo groups inside a chunk
   constexpr int PT = NP / 2;              // points per epilogue thread (the two point halves)
@@ -389,6 +391,81 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         for (int mb = 0; mb < m_blocks; ++mb) {
           const uint32_t d_main = tm + (uint32_t)(mb * 2 * NP);  // columns [0,NP): hi*hi, [NP,2NP): cross terms
           const uint32_t d_cross = d_main + NP;
+          if (group == 2 && !coarse && CL == 1 && (k_chunks & 1) == 0) {
+            // two weight stages per loop iteration (a CTA that streams several 64-point tiles: 1.68 -> 1.57 ms for
+            // the 64 000-point forward+gradient sweep)
+            for (int kc = 0; kc < k_chunks; kc += 2) {
+              const uint32_t st0 = stage, st1 = stage + 1 == NSTAGE ? 0u : stage + 1;
+              const uint32_t ph1 = stage + 1 == NSTAGE ? phase ^ 1u : phase;
+              { PROF_T0(); mbar_wait(bar_full + 8 * st0, phase); mbar_wait(bar_full + 8 * st1, ph1); if (lane == 0) PROF_ADD(2); }
+              tc_fence_after();
+              if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const uint32_t st = i ? st1 : st0;
+                  const uint64_t da_hi = desc_a_base + (uint64_t)((st * TILE_BYTES) >> 4);
+                  const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
+                  const uint64_t db = desc_b_base + (uint64_t)(((kc + i) * (KC / 8) * BCH) >> 4);
+#pragma unroll
+                  for (int j = 0; j < KC / 16; ++j) {
+                    umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                             kIdMain, (kc | i | j) ? 1u : 0u);
+                    umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                             kIdCross, 1u);
+                  }
+                  umma_commit(bar_empty + 8 * st);
+                }
+              }
+              __syncwarp();
+              stage = st1 + 1 == NSTAGE ? 0u : st1 + 1;
+              if (stage <= st0) phase ^= 1;
+            }
+            continue;
+          }
+          if (group == 4 && !coarse && CL == 1 && (k_chunks & 3) == 0) {
+            constexpr int grp = 4;
+            // four weight stages per loop iteration (16-point tiles, 11-stage ring): the fixed cost of an iteration
+            // (barrier wait, fence, election, warp re-convergence: ~170 cycles, tools/umma_issue_bench.cu) is paid once
+            // per 16 MMAs - 210 -> 173 us for the band pass of one detection
+            for (int kc = 0; kc < k_chunks; kc += grp) {
+              uint32_t st[4];
+              {
+                PROF_T0();
+                uint32_t sg = stage, pg = phase;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (i < grp) {
+                    st[i] = sg;
+                    mbar_wait(bar_full + 8 * sg, pg);
+                    if (++sg == NSTAGE) { sg = 0; pg ^= 1; }
+                  }
+                }
+                stage = sg; phase = pg;
+                if (lane == 0) PROF_ADD(2);
+              }
+              tc_fence_after();
+              if (elect_one()) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (i < grp) {
+                    const uint64_t da_hi = desc_a_base + (uint64_t)((st[i] * TILE_BYTES) >> 4);
+                    const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
+                    const uint64_t db = desc_b_base + (uint64_t)(((kc + i) * (KC / 8) * BCH) >> 4);
+#pragma unroll
+                    for (int j = 0; j < KC / 16; ++j) {
+                      umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                               kIdMain, (kc | i | j) ? 1u : 0u);
+                      umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                               kIdCross, 1u);
+                    }
+                    umma_commit(bar_empty + 8 * st[i]);
+                  }
+                }
+              }
+              __syncwarp();
+            }
+            continue;
+          }
           for (int kc = 0; kc < k_chunks; ++kc) {
             { PROF_T0(); mbar_wait(bar_full + 8 * stage, phase); if (lane == 0) PROF_ADD(2); }
             tc_fence_after();
@@ -1670,6 +1747,13 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   while (cl > 1 && (grid % cl != 0 || grid < cl)) {
     if (grid >= cl) grid -= grid % cl; else cl >>= 1;
   }
+  // Weight stages per issuer iteration (SDFR_TC_GROUP=0 turns the grouping off).  16-point tiles: 4 (210 -> 173 us
+  // for ~1 850 rows).  64-point tiles: 2 when a CTA streams several tiles (1.68 -> 1.58 ms for the 64 000-point
+  // forward+gradient sweep); a CTA with a single 64-point tile waits on the weight stream and loses 10 % by
+  // waiting for two stages of its 5-stage ring.
+  static int grouping = -1;
+  if (grouping < 0) { const char* e = getenv("SDFR_TC_GROUP"); grouping = e ? atoi(e) : 1; }
+  const int group = !grouping || coarse || cl != 1 ? 1 : np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)grid);
@@ -1687,13 +1771,13 @@ static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, floa
   cfg.numAttrs = 1;
   if (small && np == 32) {
     SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<32>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
-                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse, group));
   } else if (small) {
     SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<16>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
-                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse, group));
   } else {
     SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<64>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
-                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse));
+                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse, group));
   }
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;

@@ -48,7 +48,7 @@ def coarse():
                                              _lib.stream_ptr()))
 
 
-t = timeit(coarse)
+t = timeit(coarse) if os.environ.get("PROBE_COARSE", "1") == "1" else 0.0
 err = float((sdf - sdf_ref).abs().max())
 extra = ""
 if int(os.environ.get("SDFR_TC_WIDE_DBG", "0")) & 16:
@@ -59,7 +59,8 @@ if int(os.environ.get("SDFR_TC_WIDE_DBG", "0")) & 16:
     extra = f" | CTA0 issuer loop: {buf[0]} cycles in {buf[1]} ns = {buf[0] / max(buf[1], 1):.3f} GHz, issuer pass4/5 [mb01, -, mb2, mb3]x2: {[int(buf[i]) - int(buf[4]) for i in range(4, 12)]}; issuer rows0-3 seen (pass 5): {[int(buf[i]) - int(buf[4]) for i in range(12, 16)]}; epilogue pass 4: acc seen mb0-3 {[int(buf[i]) - int(buf[4]) for i in range(16, 20)]}, rows arrived mb2,3 {[int(buf[i]) - int(buf[4]) for i in range(22, 24)]}"
 print(f"[{tag}] coarse lattice 40^3: {t * 1e3:.1f} us, max |sdf - ffma| {err:.2e}{extra}", flush=True)
 
-for n in (1850, 7400):
+ns = [int(v) for v in os.environ.get("PROBE_N", "1850,7400").split(",")]
+for n in ns:
     x = torch.cat([lat.cpu().expand(n, -1), torch.rand(n, 3) * 2 - 1], 1).contiguous().to(dev)
     outs = {}
     for name, impl in (("ffma", _lib.MLP_FFMA), ("tc", _lib.MLP_TCGEN05)):
