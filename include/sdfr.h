@@ -264,6 +264,27 @@ int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev, int64_t* c
 /* Asynchronous device-to-device copy of such a view into dst_dev (at most max_count elements). */
 int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_dev, int64_t max_count, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Initial-pose RANSAC
+ * replaces: the sklearn KD-tree queries of PoseEstimator.init_pose_3d
+ *           (utils/pose.py:133-134 build, 146 / 172 / 194 query) and, per RANSAC
+ *           hypothesis, pose.py:166-178 (transform of the scene cloud, 1-NN in the
+ *           model cloud, inlier test)
+ * ------------------------------------------------------------------------- */
+/* Exact 1-NN of queries [q,3] among refs [m,3] (float32 coordinates, distance in
+ * float64 like a KD-tree; the lowest index wins a tie): idx [q] int32, dist [q] double. */
+int sdfr_nn_query(const float* queries_dev, int64_t q, const float* refs_dev, int64_t m, int32_t* idx_dev,
+                  double* dist_dev, void* stream);
+/* All hypotheses of a RANSAC round in one launch.  transforms [h,12]: row-major 3x4
+ * float32 [R*scale | t] (pose.py:166-168).  For hypothesis i and scene point j:
+ * p = T_i * scene_pts[j] (float32), k = 1-NN of p in model_pts, inlier iff
+ * |p - model_pts[k]| < metric_thr and |scene_cls[j] - model_cls[k]| < nocs_thr
+ * (pose.py:170-178).  counts [h] int32 (zeroed here), masks [h,ns] uint8. */
+int sdfr_ransac_score(const float* scene_pts_dev, const float* scene_cls_dev, int64_t ns,
+                      const float* model_pts_dev, const float* model_cls_dev, int64_t m,
+                      const float* transforms_dev, int num_hypotheses, double metric_thr, float nocs_thr,
+                      int32_t* counts_dev, uint8_t* masks_dev, void* stream);
+
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t sdfr_launch_count(void);
 
