@@ -76,7 +76,9 @@ def num_ransac_iterations(p=0.99, outlier_prob=0.7, sample_size=4) -> int:
 
 
 def init_pose_3d(model_pts, model_cls, scene_pts, scene_cls, metric_distance_threshold=0.15,
-                 nocs_distance_threshold=0.15, type='procrustes', scale_model=1, return_trace=False):
+                 nocs_distance_threshold=0.15, type='procrustes', scale_model=1, return_trace=False, nn='brute'):
+    """``nn='kdtree'`` uses sklearn KD-trees like the reference (the timed CPU baseline of
+    tools/pose_bench.py); ``'brute'`` is the dependency-free exact search the parity tests use."""
     model_pts = np.array(model_pts, copy=True)
     model_cls = np.asarray(model_cls)
     scene_pts = np.asarray(scene_pts)
@@ -87,6 +89,18 @@ def init_pose_3d(model_pts, model_cls, scene_pts, scene_cls, metric_distance_thr
         model_pts *= scale_model                                                # pose.py:119-120
     total = scene_pts.shape[0]
     iters = num_ransac_iterations()
+    if nn == 'kdtree':
+        from sklearn.neighbors import KDTree
+        tree_c, tree_p = KDTree(model_cls), KDTree(model_pts)                   # pose.py:133-134
+
+        def _query(tree):
+            def q(x, _refs):
+                d, i = tree.query(x)
+                return d[:, 0], i[:, 0]
+            return q
+        nn_cls, nn_pts = _query(tree_c), _query(tree_p)
+    else:
+        nn_cls = nn_pts = nn_exact
     best = np.array([], dtype=np.int64)
     trace = {'valid': np.zeros(iters, bool), 'transforms': np.zeros((iters, 12), np.float32),
              'counts': np.zeros(iters, np.int64), 'samples': np.zeros((iters, 4), np.int64)}
@@ -94,7 +108,7 @@ def init_pose_3d(model_pts, model_cls, scene_pts, scene_cls, metric_distance_thr
         indices = np.random.choice(range(total), 4, replace=False)             # pose.py:139
         trace['samples'][it] = indices
         sel_pts, sel_cls = scene_pts[indices], scene_cls[indices]
-        dists, idxs_nocs = nn_exact(sel_cls, model_cls)                         # pose.py:146
+        dists, idxs_nocs = nn_cls(sel_cls, model_cls)                         # pose.py:146
         if (dists > nocs_distance_threshold).any():                             # pose.py:151
             continue
         sel_model = model_pts[idxs_nocs]
@@ -112,7 +126,7 @@ def init_pose_3d(model_pts, model_cls, scene_pts, scene_cls, metric_distance_thr
         trans[:3, :3] = rot * scale
         trans[:3, 3] = tra
         transformed = (trans[:, :3] @ scene_pts.T).T + trans[:, 3]              # pose.py:170
-        dists, idxs = nn_exact(transformed, model_pts)                          # pose.py:172
+        dists, idxs = nn_pts(transformed, model_pts)                          # pose.py:172
         dists_color = np.linalg.norm(scene_cls - model_cls[idxs], axis=1)
         inliers = np.where((dists < metric_distance_threshold) & (dists_color < nocs_distance_threshold))[0]
         trace['valid'][it] = True
@@ -124,7 +138,7 @@ def init_pose_3d(model_pts, model_cls, scene_pts, scene_cls, metric_distance_thr
     if len(best) < 5:                                                           # pose.py:196
         return (None, trace) if return_trace else None
     sel_pts, sel_cls = scene_pts[best], scene_cls[best]
-    _, idxs = nn_exact(sel_cls, model_cls)                                      # pose.py:202
+    _, idxs = nn_cls(sel_cls, model_cls)                                        # pose.py:202
     sel_model = model_pts[idxs]
     if type == 'procrustes':
         scale, rot, tra = procrustes(sel_model, sel_pts)

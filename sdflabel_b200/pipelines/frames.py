@@ -94,3 +94,83 @@ def refine_frames(frames: Sequence[Sequence[Dict]], frame_ids: Iterable[int], ds
         for d, r in enumerate(results):
             recs.append(make_record(fid, d, r, L))
     return np.stack(recs) if recs else np.zeros((0, record_width(L)), dtype=np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Per-frame autolabel dumps in the reference's format
+# ---------------------------------------------------------------------------------------------------
+NECESSARY_KEYS = ('alpha', 'bbox', 'dimensions', 'location', 'rotation_y', 'score')   # refine_css.py:241
+
+
+def frame_dump_path(path_autolabels: str, frame_idx: int) -> str:
+    import os
+    return os.path.join(path_autolabels, str(frame_idx) + '.pkl')
+
+
+def frame_done(path_autolabels: str, frame_idx: int) -> bool:
+    """The reference's resume rule: a frame whose dump exists is skipped (refine_css.py:68-70)."""
+    import os
+    return os.path.exists(frame_dump_path(path_autolabels, frame_idx))
+
+
+def collect_labels(annos: Sequence[Dict], labels: Sequence[Dict]):
+    """Lists of per-detection annotation / label dicts (``get_kitti_label`` output) -> the two dicts of
+    arrays one frame dump holds (refine_css.py:90,232,241-245)."""
+    from collections import defaultdict
+    frame_annos, frame_estimations = defaultdict(list), defaultdict(list)
+    for a in annos:
+        for key, value in a.items():
+            frame_annos[key].append(value)
+    for l in labels:
+        for key, value in l.items():
+            frame_estimations[key].append(value)
+    for key in NECESSARY_KEYS:
+        frame_annos[key] = np.asarray(frame_annos[key])
+        frame_estimations[key] = np.asarray(frame_estimations[key])
+    return frame_annos, frame_estimations
+
+
+def dump_frame_labels(path_autolabels: str, frame_idx: int, annos: Sequence[Dict], labels: Sequence[Dict]) -> str:
+    """Writes ``<frame_idx>.pkl`` = pickle of ``[frame_annos, frame_estimations]``, the file
+    ``pipelines/evaluate_dump.py:24-46`` parses and ``refine_css.py:68`` treats as "frame done"
+    (refine_css.py:248).  Frames without annotations are not dumped (refine_css.py:237-238)."""
+    import os
+    import pickle
+    if not annos:
+        return ''
+    os.makedirs(path_autolabels, exist_ok=True)
+    frame_annos, frame_estimations = collect_labels(annos, labels)
+    path = frame_dump_path(path_autolabels, frame_idx)
+    tmp = path + '.tmp'
+    with open(tmp, 'wb') as f:                       # atomic: a killed rank never leaves a half-written "done" marker
+        pickle.dump([frame_annos, frame_estimations], f)
+    os.replace(tmp, path)
+    return path
+
+
+def load_autolabels(path_autolabels: str):
+    """(gt_annotations, pred_annotations) ordered by file name, exactly what evaluate_dump.py:20-46 builds
+    for ``Detection3DEvaluator.evaluate_detection_3d``."""
+    import glob
+    import os
+    import pickle
+    from collections import OrderedDict
+    gt, pred = OrderedDict(), OrderedDict()
+    for f in sorted(glob.glob(os.path.join(path_autolabels, '*.pkl'))):
+        if 'skipped_frames' in f:
+            continue
+        with open(f, 'rb') as fh:
+            anno = pickle.load(fh)
+        frame_id = int(os.path.basename(f).split('.')[0])
+        estimations = anno[1]
+        if 'name' not in estimations:
+            estimations['name'] = []
+            estimations['location'] = np.zeros((0, 3))
+            estimations['dimensions'] = np.zeros((0, 3))
+            estimations['bbox'] = np.zeros((0, 4))
+            estimations['rotation_y'] = np.zeros((0,))
+            estimations['alpha'] = np.zeros((0,))
+            estimations['score'] = np.zeros((0,))
+        gt[frame_id] = anno[0]
+        pred[frame_id] = estimations
+    return gt, pred

@@ -119,24 +119,28 @@ class PoseEstimator:
         samples = np.stack([np.random.choice(total, 4, replace=False) for _ in range(iters)])
         compatible = ~(cdist[samples] > nocs_distance_threshold).any(axis=1)
 
+        cand = np.nonzero(compatible)[0]
         transforms = []
-        for it in np.nonzero(compatible)[0]:
-            sel_scene = scene_pts_h[samples[it]]
-            sel_model = model_pts_h[cidx[samples[it]]]
-            if type == 'procrustes':
-                result = procrustes(sel_scene, sel_model)
+        if type == 'kabsch' and len(cand):
+            # all 4-point fits in one batched LAPACK call (same gufunc as the per-sample calls: same bits)
+            rots, tras = kabsch_batch(scene_pts_h[samples[cand]], model_pts_h[cidx[samples[cand]]])
+            for rot, tra in zip(rots, tras):
+                trans = np.zeros((3, 4), dtype=np.float32)
+                trans[:3, :3] = rot * 1
+                trans[:3, 3] = tra
+                transforms.append(trans)
+        else:
+            for it in cand:
+                result = procrustes(scene_pts_h[samples[it]], model_pts_h[cidx[samples[it]]])
                 if result is None:
                     continue
                 scale, rot, tra = result
-            else:
-                rot, tra = kabsch(sel_scene, sel_model)
-                scale = 1
-            if scale > 3:
-                continue
-            trans = np.zeros((3, 4), dtype=np.float32)
-            trans[:3, :3] = rot * scale
-            trans[:3, 3] = tra
-            transforms.append(trans)
+                if scale > 3:
+                    continue
+                trans = np.zeros((3, 4), dtype=np.float32)
+                trans[:3, :3] = rot * scale
+                trans[:3, 3] = tra
+                transforms.append(trans)
         if not transforms:
             return None
 
@@ -194,6 +198,25 @@ def procrustes(from_points, to_points):
     r = u.dot(s).dot(vt)
     c = (d * s.diagonal()).sum() / var_f
     return c, r, mu_t - c * r.dot(mu_f)
+
+
+def kabsch_batch(canonical_points, predicted_points):
+    """``kabsch`` for stacks (h,4,3) of samples: the reductions, products and the SVD are numpy's batched
+    forms of the very same calls, the two matrix-vector products of the translation stay per sample."""
+    mu_c, mu_p = np.mean(canonical_points, axis=1), np.mean(predicted_points, axis=1)
+    c_c = canonical_points - mu_c[:, None, :]
+    p_c = predicted_points - mu_p[:, None, :]
+    u, _, vt = np.linalg.svd(np.matmul(p_c.transpose(0, 2, 1), c_c))
+    rot = np.matmul(u, vt)
+    neg = np.linalg.det(rot) < 0.0
+    if neg.any():
+        vt[neg, -1, :] *= -1.0
+        rot[neg] = np.matmul(u[neg], vt[neg])
+    tras = []
+    for r, c, p in zip(rot, mu_c, mu_p):
+        t = p - c
+        tras.append(np.dot(r, t) - np.dot(r, p) + p)
+    return rot, tras
 
 
 def kabsch(canonical_points, predicted_points):

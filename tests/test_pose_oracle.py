@@ -57,6 +57,13 @@ def test_product_fits_equal_the_oracle_fits():
         p0, p1 = PO.procrustes(a, b), prod.procrustes(a, b)
         assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(p0, p1))
     assert prod.procrustes(np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32)) is None
+    # the batched form is the same LAPACK / BLAS calls: same bits (reflections included)
+    a = rng.normal(size=(300, 4, 3)).astype(np.float32)
+    b = rng.normal(size=(300, 4, 3)).astype(np.float32)
+    rots, tras = prod.kabsch_batch(a, b)
+    for i in range(300):
+        r0, t0 = PO.kabsch(a[i], b[i])
+        assert np.array_equal(r0, rots[i]) and np.array_equal(t0, tras[i])
 
 
 def test_product_needs_a_gpu():
