@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
   const int tx1 = min(tx0 + TILE - 1, V.width - 1), ty1 = min(ty0 + TILE - 1, V.height - 1);
 
   __shared__ float s_v[CHUNK][3], s_m[CHUNK][3], s_c[CHUNK][3], s_a[CHUNK];
+  __shared__ int4 s_bb[CHUNK];
   __shared__ int s_warp_cnt[TILE * TILE / 32];
   __shared__ int s_total;
 
@@ -188,8 +189,9 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
       // cull this chunk of surfels against the tile, compact survivors into shared memory
       const int i = base + tid;
       bool take = false;
+      int4 bb = make_int4(0, 0, 0, 0);
       if (i < m) {
-        const int4 bb = *reinterpret_cast<const int4*>(V.bbox + i * 4);
+        bb = *reinterpret_cast<const int4*>(V.bbox + i * 4);
         take = bb.x <= tx1 && bb.z >= tx0 && bb.y <= ty1 && bb.w >= ty0;
       }
       const unsigned ballot = __ballot_sync(0xffffffffu, take);
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
         s_v[off][0] = V.cam_v[i * 3]; s_v[off][1] = V.cam_v[i * 3 + 1]; s_v[off][2] = V.cam_v[i * 3 + 2];
         s_m[off][0] = V.cam_m[i * 3]; s_m[off][1] = V.cam_m[i * 3 + 1]; s_m[off][2] = V.cam_m[i * 3 + 2];
         s_a[off] = V.plane_a[i];
+        s_bb[off] = bb;
         if (sweep == 1) {
           s_c[off][0] = V.cam_c[i * 3]; s_c[off][1] = V.cam_c[i * 3 + 1]; s_c[off][2] = V.cam_c[i * 3 + 2];
         }
@@ -214,6 +217,10 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
       const int cnt = s_total;
       if (live) {
         for (int k = 0; k < cnt; ++k) {
+          // every hit of a surfel lies inside its pixel box (project_kernel): four integer compares reject
+          // the ~85 % of the tile's surfels that cannot touch this pixel before the ray / disc test
+          const int4 b = s_bb[k];
+          if (x < b.x || x > b.z || y < b.y || y > b.w) continue;
           const Hit h = disc_test(rx, ry, rz, s_v[k][0], s_v[k][1], s_v[k][2], s_m[k][0], s_m[k][1], s_m[k][2], s_a[k]);
           if (!h.hit) continue;
           const float zeta = -h.z;                      // primitives.py:227
