@@ -285,6 +285,17 @@ int sdfr_ransac_score(const float* scene_pts_dev, const float* scene_cls_dev, in
                       const float* transforms_dev, int num_hypotheses, double metric_thr, float nocs_thr,
                       int32_t* counts_dev, uint8_t* masks_dev, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Rotated BEV box overlap of the KITTI evaluator
+ * replaces: rotate_iou_gpu_eval / rotate_iou_kernel_eval (pipelines/rotate_iou.py:257-325),
+ *           the reference's only hand-written GPU kernel (numba.cuda)
+ * ------------------------------------------------------------------------- */
+/* boxes [n,5], query [k,5] rows [cx, cy, w, h, angle]; iou [n,k] row-major.
+ * criterion -1: intersection / union, 0: / area of the QUERY box, 1: / area of the box,
+ * 2: raw intersection area (the argument order of rotate_iou.py:286 is kept). */
+int sdfr_rotate_iou(const float* boxes_dev, int64_t n, const float* query_dev, int64_t k, int criterion,
+                    float* iou_dev, void* stream);
+
 /* Kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t sdfr_launch_count(void);
 
