@@ -1468,6 +1468,416 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
   if (warp == 17) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Coarse lattice pass, CTA-pair version (tcgen05 cta_group::2).
+//
+// The wide-tile kernel above is bound by the shared-memory data pipe: every 4 KB of a streamed weight tile
+// is written once and read once for a single N = 112 MMA (92 wavefronts per 56 cycles of math,
+// profiles/r01_mlp_tc_coarse_wide_kernel_ncu.md).  Here the GEMM is issued the usual way round,
+//     D[point, feature] = H[point, k] * W^T[k, feature],
+// as ONE instruction over a pair of CTAs: M = 256 points (each CTA keeps the activations of its own 128
+// points as the K-major A operand), N = 256 features of which each CTA streams and holds only HALF (its
+// 128-feature weight tile is the B operand rows it contributes; the hardware shares both halves), and each
+// CTA accumulates [its 128 points x 256 features] in its own TMEM.  Per 128-cycle MMA a CTA's shared memory
+// now moves 32 (A) + 32 (own half of B) + 32 (bulk-copy write of that half) wavefronts: 75 % of the pipe.
+// Because every CTA produces complete feature rows for its OWN points, the next layer's A operand is
+// written locally: the only things crossing the pair are the operand halves inside the MMA, the commit
+// multicasts and a few mbarrier arrives.
+//
+//   warps 0-15  epilogue: TMEM lane quadrant (32 points) x 64-column slice of a 256-feature block
+//   warp 16     weight producer (bulk copies of this CTA's tiles: M block 2 j + rank of the pass table)
+//   warp 17     rank 0: MMA issuer for the pair; rank 1: relays "my stage is full" to rank 0
+//
+// Per pass the 512 output features are two 256-column blocks j = 0, 1 of the 512 TMEM columns.  Block j of
+// the next pass is issued over k-half 0 first (the features block 0 of this pass produced) while the
+// epilogue of block 1 is still running, so only the tail of a tile is exposed.
+// ---------------------------------------------------------------------------------------------
+constexpr int P_THREADS = 576;
+constexpr int P_NEPI = 512;
+constexpr int P_STAGES = 5;
+constexpr int P_STAGE_TILES = 2;                      // k-chunks (32 k) per ring stage
+constexpr int P_STAGE_BYTES = P_STAGE_TILES * TILE_HALF_BYTES;
+constexpr int P_PTS = 128;                            // points per CTA
+constexpr int P_A_KK = 2048;                          // bytes per 8-k group of the A operand: 16 point groups x 128 B
+
+struct PairPlan {
+  uint32_t stages, a, inp, bias, bars, tmem_slot, total;
+};
+__host__ __device__ inline PairPlan make_pair_plan(int in0) {
+  PairPlan p;
+  uint32_t o = 0;
+  p.stages = o; o += P_STAGES * P_STAGE_BYTES;
+  p.a = o; o += 64 * P_A_KK;
+  const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
+  p.inp = o; o += in_pad * P_PTS * 4;
+  p.bias = o; o += (P_NEPI / 32) * 128 * 4;           // per epilogue warp: the 2 x 64 scaled biases of its column slices
+  p.bars = o; o += 32 * 8;
+  p.tmem_slot = o; o += 16;
+  p.total = o;
+  return p;
+}
+
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONEC_%=;\n\t"
+      "bra WAITC_%=;\n\t"
+      "DONEC_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both] * B[smem of both], issued by one thread of the pair's rank-0 CTA
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of `mask` once the pair MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+// instruction descriptor: D fp32, A / B fp16, both K-major, M = 256 over the pair
+__host__ __device__ constexpr uint32_t idesc_pair(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
+                          float* __restrict__ sdf_out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (in.count_dev && *in.count_dev <= 0) return;     // uniform over the grid: before any cluster traffic
+  const TcTable& T = *tabp;
+  const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
+  const PairPlan P = make_pair_plan(in0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bars = smem_u32(smem + P.bars);
+  const uint32_t bar_full = bars, bar_peer = bars + 8 * P_STAGES, bar_empty = bars + 8 * (2 * P_STAGES),
+                 bar_acc = bars + 8 * (3 * P_STAGES), bar_a = bars + 8 * (3 * P_STAGES + 2);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
+  const int in_pad = (in0 + 7) & ~7;
+  const long long n_rows = mlp_rows(in);
+  const long long num_pair_tiles = (n_rows + 2 * P_PTS - 1) / (2 * P_PTS);
+  const long long num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_peer + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int j = 0; j < 2; ++j) { mbar_init(bar_acc + 8 * j, 1); mbar_init(bar_a + 8 * j, 2 * (P_NEPI / 32)); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 17) tmem_alloc_pair(smem_u32(smem + P.tmem_slot), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // the peer's barriers and TMEM exist before anything targets them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  long long my_tiles = 0;
+  for (long long pt = pair_id; pt < num_pair_tiles; pt += num_pairs) ++my_tiles;
+
+  if (warp == 16) {
+    // ===================== weight producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < num_layers; ++p) {
+          const int m_blocks = T.pass[p].m_blocks, k_chunks = T.pass[p].k_chunks;
+          const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
+          const int nblocks = T.pass[p].kind == 1 ? 1 : m_blocks >> 1;
+          for (int j = 0; j < nblocks; ++j) {
+            // hidden pass: this CTA holds features [256 j + 128 rank, + 128) = M block 2 j + rank of the table;
+            // last pass: both CTAs load the single tile row (8 of its rows each enter the N = 16 MMA)
+            const int mb = T.pass[p].kind == 1 ? 0 : 2 * j + (int)rank;
+            for (int kc = 0; kc < k_chunks; kc += P_STAGE_TILES) {
+              const int cnt = min(P_STAGE_TILES, k_chunks - kc);
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * TILE_HALF_BYTES);
+              for (int i = 0; i < cnt; ++i)
+                bulk_g2s(smem_u32(smem + P.stages + stage * P_STAGE_BYTES + i * TILE_HALF_BYTES),
+                         src + (size_t)(mb * k_chunks + kc + i) * TILE_BYTES, TILE_HALF_BYTES, bar_full + 8 * stage);
+              if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17 && rank == 1) {
+    // ===================== rank 1: tell the issuer that this CTA's half of a stage has landed ==============
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t peer_bar[P_STAGES];
+#pragma unroll
+      for (int s = 0; s < P_STAGES; ++s) peer_bar[s] = mapa_u32(bar_peer + 8 * s, 0u);
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < num_layers; ++p) {
+          const int nblocks = T.pass[p].kind == 1 ? 1 : T.pass[p].m_blocks >> 1;
+          const int steps = nblocks * ((T.pass[p].k_chunks + P_STAGE_TILES - 1) / P_STAGE_TILES);
+          for (int st = 0; st < steps; ++st) {
+            mbar_wait(bar_full + 8 * stage, phase);
+#pragma unroll
+            for (int s = 0; s < P_STAGES; ++s)
+              if (s == (int)stage) mbar_arrive_cluster(peer_bar[s]);
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 17) {
+    // ===================== rank 0: MMA issuer for the pair =====================
+    uint32_t stage = 0, phase = 0, a_phase = 0;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc_a0 = make_desc(smem_u32(smem + P.a), P_A_KK, 128);        // K-major: LBO = next 8 k, SBO = next 8 points
+    const uint64_t desc_b0 = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);  // a weight tile, K-major
+    constexpr uint32_t kIdHidden = idesc_pair(256), kIdLast = idesc_pair(16);
+    for (long long it = 0; it < my_tiles; ++it) {
+      for (int p = 0; p < num_layers; ++p) {
+        const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
+        const bool last = __ldg(&T.pass[p].kind) == 1;
+        const int nblocks = last ? 1 : m_blocks >> 1;
+        const uint32_t idesc = last ? kIdLast : kIdHidden;
+        // a_ready[h]: both CTAs have written k-half h of their A operand (and drained block h of their TMEM)
+        mbar_wait(bar_a, a_phase);
+        bool half1_ready = false;
+        tc_fence_after();
+        for (int j = 0; j < nblocks; ++j) {
+          const uint32_t d = tm + (uint32_t)(j * 256);
+          if (j == 1 && !half1_ready) { mbar_wait(bar_a + 8, a_phase); half1_ready = true; tc_fence_after(); }
+          for (int kc = 0; kc < k_chunks; kc += P_STAGE_TILES) {
+            // k-chunks 8 .. 15 are features 256 .. 511 of the previous pass: its block 1
+            if (kc >= 8 && !half1_ready) { mbar_wait(bar_a + 8, a_phase); half1_ready = true; }
+            const int cnt = min(P_STAGE_TILES, k_chunks - kc);
+            mbar_wait(bar_full + 8 * stage, phase);
+            mbar_wait(bar_peer + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < P_STAGE_TILES; ++i) {
+                if (i < cnt) {
+#pragma unroll
+                  for (int t = 0; t < KC / 16; ++t) {
+                    const uint64_t da = desc_a0 + (uint64_t)((((kc + i) * (KC / 8) + 2 * t) * P_A_KK) >> 4);
+                    const uint64_t db = desc_b0 + (uint64_t)((stage * P_STAGE_BYTES + i * TILE_HALF_BYTES + t * 2 * A_LBO) >> 4);
+                    umma_f16_pair(d, da, db, idesc, (kc | i | t) ? 1u : 0u);
+                  }
+                }
+              }
+              umma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);    // the stage is free in both CTAs
+            }
+            __syncwarp();
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (elect_one()) umma_commit_pair(bar_acc + 8 * j, (uint16_t)3);   // block j is complete in both CTAs
+          __syncwarp();
+        }
+        if (!half1_ready) mbar_wait(bar_a + 8, a_phase);      // keep the phases of both barriers in step
+        a_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int q = warp & 3, cs = warp >> 2;            // TMEM lane quadrant (32 points); 64-column slice of a block
+    const int pt_l = q * 32 + lane;                    // point of this thread = TMEM lane
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    float* inp = reinterpret_cast<float*>(smem + P.inp);           // [in_pad][128]
+    float* wbias = reinterpret_cast<float*>(smem + P.bias) + warp * 128;
+    unsigned char* aop = smem + P.a;
+    unsigned char* arow = aop + (pt_l >> 3) * 128 + (pt_l & 7) * 16;   // + kk * P_A_KK
+    const uint32_t a_ready0 = mapa_u32(bar_a, 0u), a_ready1 = mapa_u32(bar_a + 8, 0u);   // the issuer's CTA
+    uint32_t acc_phase = 0;                            // bit j = phase of bar_acc[j]
+    auto publish = [&](const uint32_t remote_bar) {
+      fence_async_smem();                              // generic-proxy stores -> tensor-core reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(remote_bar);
+    };
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long ptile = it * num_pairs + pair_id;
+      const long long base = ptile * (2 * P_PTS) + (long long)rank * P_PTS;
+      for (int i = tid; i < in_pad * P_PTS; i += P_NEPI) {
+        const int c = i / P_PTS, n = i - c * P_PTS;
+        const long long gi = base + n;
+        float v = 0.f;
+        if (gi < n_rows && c < in0) {
+          const long long src = in.index ? (long long)in.index[gi] : gi;
+          if (in.inputs) {
+            v = in.inputs[src * in0 + c];
+          } else {
+            const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
+            if (c < latent) {
+              v = in.latent_unit[b * latent + c];
+            } else {
+              float x, y, z;
+              lattice_point(in.lattice, k, x, y, z);
+              v = (c - latent) == 0 ? x : (c - latent) == 1 ? y : z;
+            }
+          }
+        }
+        inp[i] = v;
+      }
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (cs == 0) {                                   // A operand of layer 0: k = input column, one 32-k chunk
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint4 pk;
+          uint32_t* hw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k0 = kk * 8 + 2 * e;
+            const float h0 = k0 < in0 ? inp[k0 * P_PTS + pt_l] * ACT_SCALE : 0.f;
+            const float h1 = k0 + 1 < in0 ? inp[(k0 + 1) * P_PTS + pt_l] * ACT_SCALE : 0.f;
+            const __half2 a = __floats2half2_rn(h0, h1);
+            hw[e] = *reinterpret_cast<const uint32_t*>(&a);
+          }
+          *reinterpret_cast<uint4*>(arow + kk * P_A_KK) = pk;
+        }
+      }
+      publish(a_ready0);
+      if (lane == 0) mbar_arrive_cluster(a_ready1);
+
+      for (int p = 0; p < num_layers; ++p) {
+        const TcPassDev Ps = T.pass[p];
+        if (Ps.kind == 1) {                            // last Linear: column 0 is the pre-activation of the sdf
+          mbar_wait(bar_acc, acc_phase & 1u);
+          acc_phase ^= 1u;
+          tc_fence_after();
+          if (cs == 0) {
+            uint32_t v[8];
+            tmem_ld8(lane_base, v);
+            tmem_ld_wait();
+            float y = __uint_as_float(v[0]) * Ps.inv_scale + __ldg(Ps.bias);
+            if (use_tanh) y = tanhf(y);
+            y = tanhf(y);
+            if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
+          }
+          tc_fence_before();
+          continue;
+        }
+        const float k_scale = Ps.inv_scale * Ps.out_scale;
+        const int nblocks = Ps.m_blocks >> 1;
+        // this warp's scaled biases (features j * 256 + cs * 64 + 0..63, j = 0, 1), fetched under the MMAs
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int f = j * 256 + cs * 64 + 2 * lane + u;
+            wbias[j * 64 + 2 * lane + u] = f < Ps.rows ? __ldg(Ps.bias + f) * Ps.out_scale : 0.f;
+          }
+        }
+        __syncwarp();
+        // 64 features of this thread's point -> eight packed 16-byte rows of the next A operand
+        auto compute_block = [&](const int j, uint4 (&pk)[8]) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {             // 2 x 16 features per TMEM round trip
+            const int f0 = j * 256 + cs * 64 + hf * 32;
+            uint32_t v[32];
+            tmem_ld16(lane_base + (uint32_t)f0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld16(lane_base + (uint32_t)(f0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_wait();
+            const float* wb = wbias + j * 64 + hf * 32;
+            if (f0 + 32 <= Ps.rows) {                  // all regular rows (warp-uniform)
+#pragma unroll
+              for (int o = 0; o < 4; ++o) {
+                const float4 b0 = *reinterpret_cast<const float4*>(wb + o * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(wb + o * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t* hw = reinterpret_cast<uint32_t*>(&pk[4 * hf + o]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float h0 = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e]), k_scale, bb[2 * e]), 0.f);
+                  const float h1 = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e + 1]), k_scale, bb[2 * e + 1]), 0.f);
+                  const __half2 a = __floats2half2_rn(h0, h1);
+                  hw[e] = *reinterpret_cast<const uint32_t*>(&a);
+                }
+              }
+            } else {                                   // the slice that holds the concatenated / padding rows
+#pragma unroll
+              for (int o = 0; o < 4; ++o) {
+                uint32_t* hw = reinterpret_cast<uint32_t*>(&pk[4 * hf + o]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float h[2];
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const int f = f0 + o * 8 + 2 * e + u;
+                    float val;
+                    if (f < Ps.rows) {
+                      val = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e + u]), k_scale, wb[o * 8 + 2 * e + u]), 0.f);
+                    } else if (f < Ps.rows + Ps.cat_dim) {         // cat[x, input] feeds the next Linear
+                      val = inp[(Ps.cat_off + f - Ps.rows) * P_PTS + pt_l] * Ps.out_scale;
+                    } else {
+                      val = 0.f;
+                    }
+                    h[u] = val;
+                  }
+                  const __half2 a = __floats2half2_rn(h[0], h[1]);
+                  hw[e] = *reinterpret_cast<const uint32_t*>(&a);
+                }
+              }
+            }
+          }
+        };
+        auto store_block = [&](const int j, const uint4 (&pk)[8]) {
+          const int kk0 = (j * 256 + cs * 64) >> 3;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4*>(arow + (kk0 + r) * P_A_KK) = pk[r];
+        };
+        uint4 pk[8];
+        mbar_wait(bar_acc, acc_phase & 1u);
+        acc_phase ^= 1u;
+        tc_fence_after();
+        compute_block(0, pk);                          // under the MMAs of block 1, which still read all of A
+        if (nblocks == 2) {
+          mbar_wait(bar_acc + 8, (acc_phase >> 1) & 1u);   // every MMA of the pass has completed: A may be overwritten
+          acc_phase ^= 2u;
+          tc_fence_after();
+        }
+        store_block(0, pk);
+        publish(a_ready0);
+        if (nblocks == 2) {
+          compute_block(1, pk);
+          store_block(1, pk);
+        }
+        publish(a_ready1);
+      }
+      // inputs / A operand are rewritten by the next tile: every epilogue thread must be past the last pass
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // no CTA may exit (or free TMEM) while its peer can still reach it
+  if (warp == 17) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1665,6 +2075,59 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
   if (!pingpong) return launch_mlp_tc_impl(dec, in, sdf, nullptr, 1, s);
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
   const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  // CTA-pair kernel (tcgen05 cta_group::2): stock-like pass tables only (every hidden pass an even number of
+  // 128-feature blocks, last Linear a single row)
+  static int pair_mode = -1, pair_slots = 0;
+  if (pair_mode < 0) {
+    const char* e = getenv("SDFR_TC_PAIR");
+    pair_mode = e ? atoi(e) : 0;
+    if (pair_mode) {
+      const TcTable& T = st->table;
+      for (int p = 0; p < T.num_layers; ++p) {
+        const bool last = T.pass[p].kind == 1;
+        if (last ? T.pass[p].m_blocks != 1 : (T.pass[p].m_blocks != 2 && T.pass[p].m_blocks != 4)) pair_mode = 0;
+        if (T.pass[p].k_chunks != 1 && (T.pass[p].k_chunks & 1)) pair_mode = 0;
+      }
+    }
+    if (pair_mode) {
+      const PairPlan plan = make_pair_plan(dec->dev.in0);
+      if (cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
+        cudaGetLastError();
+        pair_mode = 0;
+      } else {
+        cudaLaunchConfig_t q;
+        memset(&q, 0, sizeof(q));
+        q.gridDim = dim3((unsigned)(2 * 64));
+        q.blockDim = dim3(P_THREADS);
+        q.dynamicSmemBytes = plan.total;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_coarse_pair_kernel, &q) != cudaSuccess || nc < 1) { cudaGetLastError(); pair_mode = 0; }
+        pair_slots = nc;
+      }
+    }
+  }
+  if (pair_mode) {
+    const long long pair_tiles = (in.n + 2 * P_PTS - 1) / (2 * P_PTS);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * std::min<long long>(pair_tiles, pair_slots)));
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = make_pair_plan(dec->dev.in0).total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_coarse_pair_kernel, (const TcTable*)st->table_dev,
+                                 (const unsigned char*)st->tiles_dev, in, sdf));
+    SDFR_LAUNCH_CHECK();
+    return SDFR_OK;
+  }
   static int wide = -1;
   if (wide < 0) { const char* e = getenv("SDFR_TC_WIDE"); wide = e ? atoi(e) : 1; }
   if (wide) {
