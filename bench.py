@@ -346,6 +346,8 @@ def _lattice_kernel_name(impl):
         return "mlp_ffma_kernel"
     if os.environ.get("SDFR_TC_PINGPONG", "1") == "0":
         return "mlp_tc_kernel"
+    if os.environ.get("SDFR_TC_PAIR", "1") != "0":
+        return "mlp_tc_coarse_pair_kernel"
     return "mlp_tc_coarse_wide_kernel" if os.environ.get("SDFR_TC_WIDE", "1") != "0" else "mlp_tc_coarse_kernel"
 
 

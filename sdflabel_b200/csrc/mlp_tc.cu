@@ -2080,7 +2080,7 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
   static int pair_mode = -1, pair_slots = 0;
   if (pair_mode < 0) {
     const char* e = getenv("SDFR_TC_PAIR");
-    pair_mode = e ? atoi(e) : 0;
+    pair_mode = e ? atoi(e) : 1;
     if (pair_mode) {
       const TcTable& T = st->table;
       for (int p = 0; p < T.num_layers; ++p) {
