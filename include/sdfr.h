@@ -246,11 +246,19 @@ int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_host, const 
 /* Enqueue `iters` iterations for all detections. */
 int sdfr_refine_run(sdfr_refine* r, int iters, void* stream);
 
-/* Synchronises `stream` and reads detection b back: params_host =
+/* Synchronises `stream` (once) and reads detection b back: params_host =
  * [yaw, tx, ty, tz, scale, latent(L)]; history_host (may be NULL): per executed
- * iteration [loss_2d, loss_3d, total, skipped] (4 floats), *n_history rows. */
+ * iteration [loss_2d, loss_3d, total, skipped] (4 floats), *n_history rows.
+ * Fails with SDFR_E_UNSUPPORTED when the tensor-core decoder flagged an activation outside the
+ * fp16 range since the last check (same condition as sdfr_decoder_check, read in the same sync). */
 int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_host, int* n_history,
                     void* stream);
+
+/* Writes the current parameters of detection b into caller-owned DEVICE buffers (yaw [1], trans [3],
+ * scale [1], latent [L]; any may be NULL) with one stream-ordered launch: the in-place update of the
+ * `params` tensors (optimizer.py:26-30, read back at refine_css.py:229-231) without a host round trip. */
+int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* trans_dev, float* scale_dev, float* latent_dev,
+                       void* stream);
 
 /* Device views of the last iteration's intermediates of detection b (for
  * parity tests and label dumps): kind 0 sdf [D^3], 1 d sdf/d[latent,x] of the band points of the

@@ -230,6 +230,8 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
 int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host);
 void free_tc_tables(sdfr_decoder* dec);
 int tc_overflow_flag(const sdfr_decoder* dec, int* flag);
+int tc_overflow_flag_enqueue(const sdfr_decoder* dec, int* flag_host, cudaStream_t s);
+int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s);
 
 // surface.cu
 int launch_lattice_points(int density, float* pts, cudaStream_t s);

@@ -2063,6 +2063,22 @@ int tc_overflow_flag(const sdfr_decoder* dec, int* flag) {
   return SDFR_OK;
 }
 
+// Stream-ordered variant for callers that synchronise the stream anyway: enqueues the copy of the flag
+// into *flag_host (0 when the decoder has no tensor-core tables); tc_overflow_reset clears it after a hit.
+int tc_overflow_flag_enqueue(const sdfr_decoder* dec, int* flag_host, cudaStream_t s) {
+  *flag_host = 0;
+  if (!dec->tc.ok || !dec->tc_ptr) return SDFR_OK;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  SDFR_CUDA(cudaMemcpyAsync(flag_host, st->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+  return SDFR_OK;
+}
+int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s) {
+  if (!dec->tc.ok || !dec->tc_ptr) return SDFR_OK;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  SDFR_CUDA(cudaMemsetAsync(st->overflow_dev, 0, sizeof(int), s));
+  return SDFR_OK;
+}
+
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
   return launch_mlp_tc_impl(dec, in, sdf, dinput, 0, s);
 }

@@ -429,6 +429,7 @@ struct sdfr_refine {
   cudaGraphExec_t graph_exec;
   cudaStream_t capture_stream;   // the caller's stream may be the legacy default stream, which cannot be captured
   int graph_w, graph_h, graph_nodes, runs;
+  std::vector<int> iters_enqueued;   // per detection: iterations launched since its last set_detection
 };
 
 namespace {
@@ -464,6 +465,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   r->cfg = *cfg;
   r->max_w_set = r->max_h_set = 0;
   r->graph_exec = nullptr; r->capture_stream = nullptr; r->graph_w = r->graph_h = 0; r->graph_nodes = 0; r->runs = 0;
+  r->iters_enqueued.assign((size_t)std::max(cfg->batch, 1), 0);
   EngineDev& E = r->E;
   const int B = cfg->batch, L = dec->dev.latent_size;
   E.batch = B; E.L = L; E.in0 = L + 3;
@@ -540,6 +542,7 @@ extern "C" int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_h
                "crop %dx%d exceeds the configured capacity of %d pixels", width, height, r->E.max_pixels);
   SDFR_REQUIRE(n_lidar >= 0 && n_lidar <= r->E.max_lidar, SDFR_E_CAPACITY, "%d lidar points exceed capacity %d",
                n_lidar, r->E.max_lidar);
+  r->iters_enqueued[b] = 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   EngineDev& E = r->E;
   DetState D;
@@ -641,6 +644,7 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   SDFR_REQUIRE(r && iters >= 0, SDFR_E_INVALID, "bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   SDFR_REQUIRE(r->max_w_set > 0 && r->max_h_set > 0, SDFR_E_INVALID, "no detection has been set");
+  for (int& c : r->iters_enqueued) c = (int)std::min<long long>((long long)c + iters, 1 << 30);
   static int use_graph = -1;
   if (use_graph < 0) { const char* e = getenv("SDFR_REFINE_GRAPH"); use_graph = e ? atoi(e) : 1; }
   int rc;
@@ -681,18 +685,52 @@ extern "C" int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float*
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   EngineDev& E = r->E;
   DetState D;
+  int overflow = 0;
+  // everything the caller reads back rides on ONE stream synchronisation: state, latent, the history rows
+  // the host knows were enqueued, and the fp16-range flag of the tensor-core decoder
+  const int nh_host = std::min(r->iters_enqueued[b], E.max_iters);
   SDFR_CUDA(cudaMemcpyAsync(&D, E.det + b, sizeof(D), cudaMemcpyDeviceToHost, s));
   SDFR_CUDA(cudaMemcpyAsync(params_host + 5, E.latent + (size_t)b * E.L, E.L * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (history_host && nh_host > 0)
+    SDFR_CUDA(cudaMemcpyAsync(history_host, E.history + (size_t)b * E.max_iters * 4, (size_t)nh_host * 4 * sizeof(float),
+                              cudaMemcpyDeviceToHost, s));
+  int rc = tc_overflow_flag_enqueue(r->dec, &overflow, s);
+  if (rc) return rc;
   SDFR_CUDA(cudaStreamSynchronize(s));
   params_host[0] = D.yaw; params_host[1] = D.trans[0]; params_host[2] = D.trans[1]; params_host[3] = D.trans[2];
   params_host[4] = D.scale;
   const int nh = std::min(D.iter, E.max_iters);
   if (n_history) *n_history = nh;
-  if (history_host && nh > 0) {
+  if (history_host && nh > nh_host) {      // iterations this handle did not count (not reachable through the ABI)
     SDFR_CUDA(cudaMemcpyAsync(history_host, E.history + (size_t)b * E.max_iters * 4, (size_t)nh * 4 * sizeof(float),
                               cudaMemcpyDeviceToHost, s));
     SDFR_CUDA(cudaStreamSynchronize(s));
   }
+  if (overflow) {
+    tc_overflow_reset(r->dec, s);
+    SDFR_REQUIRE(false, SDFR_E_UNSUPPORTED,
+                 "an activation left the fp16 range of the split-operand tensor-core kernel; use SDFR_MLP_FFMA for this network");
+  }
+  return SDFR_OK;
+}
+
+static __global__ void export_params_kernel(const DetState* __restrict__ det, const float* __restrict__ latent, int L,
+                                     float* __restrict__ yaw, float* __restrict__ trans, float* __restrict__ scale,
+                                     float* __restrict__ latent_out) {
+  const int t = threadIdx.x;
+  if (t == 0 && yaw) yaw[0] = det->yaw;
+  if (t < 3 && trans) trans[t] = det->trans[t];
+  if (t == 0 && scale) scale[0] = det->scale;
+  if (latent_out) for (int i = t; i < L; i += blockDim.x) latent_out[i] = latent[i];
+}
+
+extern "C" int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* trans_dev, float* scale_dev,
+                                  float* latent_dev, void* stream) {
+  SDFR_REQUIRE(r && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  EngineDev& E = r->E;
+  export_params_kernel<<<1, 32, 0, s>>>(E.det + b, E.latent + (size_t)b * E.L, E.L, yaw_dev, trans_dev, scale_dev, latent_dev);
+  SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
 

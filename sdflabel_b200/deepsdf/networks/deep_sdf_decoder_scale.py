@@ -148,7 +148,12 @@ class Decoder(nn.Module):
 
     # ---- native handle ---------------------------------------------------------------------
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        # (walking the module tree costs ~100 us per call; the Parameter objects never change after __init__,
+        #  .to() / load_state_dict() update them in place and bump data_ptr / _version)
+        plist = self.__dict__.get('_param_list')
+        if plist is None:
+            plist = self.__dict__['_param_list'] = list(self.parameters())
+        return tuple((p.data_ptr(), p._version) for p in plist)
 
     def native(self) -> _NativeDecoder:
         """Folds weight-norm on the host in fp32 (W = g v/||v||, exactly the tensor the

@@ -71,6 +71,7 @@ class _Engine:
         self._pinned: Dict = {}     # persistent pinned staging buffers, keyed by (name, detection)
         self._dirty = set()         # detections whose staging buffers may still be in flight
         self._kcache: Dict = {}
+        self._klast = None
 
     def __del__(self):
         try:
@@ -92,6 +93,8 @@ class _Engine:
         128-core host costs tens of milliseconds every few calls (measured)."""
         if isinstance(arr, torch.Tensor):
             src = arr.detach()
+            if src.device.type == 'cpu' and src.dtype == torch.float32 and src.is_contiguous() and src.is_pinned():
+                return src                       # already page-locked: DMA straight from the caller's buffer
             src = (src if src.device.type == 'cpu' else src.cpu()).numpy()
         else:
             src = np.asarray(arr)
@@ -107,6 +110,9 @@ class _Engine:
     def _intrinsics(self, K):
         """(K, K^-1) as contiguous fp32 host tensors; the inverse is torch's own K.float().inverse()
         (primitives.py:204), cached by value because a crop's K rarely changes between calls."""
+        fast = (K.data_ptr(), K._version) if isinstance(K, torch.Tensor) else None
+        if fast is not None and self._klast is not None and self._klast[0] == fast:
+            return self._klast[1]                # the very tensor of the previous call, untouched
         k32 = K.detach().float().cpu().contiguous()
         key = k32.numpy().tobytes()
         hit = self._kcache.get(key)
@@ -115,6 +121,7 @@ class _Engine:
                 self._kcache.clear()
             hit = (k32.clone(), k32.inverse().contiguous())
             self._kcache[key] = hit
+        self._klast = (fast, hit)
         return hit
 
     def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw, trans, scale, latent):
@@ -282,14 +289,22 @@ class Optimizer:
             eng.set_detection(0, K, width, height, nocs_pred, lidar, host['yaw'], host['trans'], host['scale'],
                               host['latent'])
             eng.run(iters_optim)
+            # the params tensors are updated in place on the device (one launch, no host round trip) ...
+            direct = all(p[k].is_cuda and p[k].dtype == torch.float32 and p[k].is_contiguous() and
+                         p[k].device == self.device for k in keys)
+            if direct:
+                _lib.check(_lib.load().sdfr_refine_export(eng.handle, 0, p['yaw'].data_ptr(), p['trans'].data_ptr(),
+                                                          p['scale'].data_ptr(), p['latent'].data_ptr(),
+                                                          _lib.stream_ptr()))
+            # ... and read back (one stream sync; it also carries the fp16-range guard of the TC kernel)
             out, hist = eng.get(0)
-            _lib.check(_lib.load().sdfr_decoder_check(eng.native_decoder.handle))   # fp16-range guard of the TC kernel
         self.engine = eng
         self.history = hist
         new = {'yaw': out[0:1].copy(), 'trans': out[1:4].copy(), 'scale': out[4:5].copy(), 'latent': out[5:].copy()}
-        with torch.no_grad():
-            for k, v in new.items():
-                p[k].copy_(torch.from_numpy(v), non_blocking=True)
+        if not direct:
+            with torch.no_grad():
+                for k, v in new.items():
+                    p[k].copy_(torch.from_numpy(v), non_blocking=True)
         self._host = (tuple((p[k].data_ptr(), p[k]._version) for k in ('yaw', 'trans', 'scale', 'latent')), new)
         if self.verbose:
             w2, w3 = self.weights['2d'], self.weights['3d']
