@@ -458,3 +458,40 @@ def test_coarse_lattice_pass_is_a_safe_preselection(stock_prior_path):
     assert err.max() < 2.5e-3, err.max()
     near = np.abs(ref) < 0.05
     assert err[near].max() < 2.5e-3
+
+
+def test_coarse_pass_ragged_rows_and_batches(stock_prior_path):
+    """The lattice-pass kernel (CTA pairs, 2 x 128 points per tile) on row counts around its tile sizes, through the
+    explicit-rows entry point and the batched lattice entry point, against the fp32 CUDA-core kernel."""
+    from sdflabel_b200 import _lib
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    nat = dec.native()
+    if not nat.tcgen05:
+        pytest.skip("coarse pass only exists for the tensor-core decoder")
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(4)
+    lat = torch.nn.functional.normalize(torch.tensor([0.5, 0.7, 0.5]), dim=0)
+    for n in (1, 127, 128, 129, 255, 256, 257, 1000, 20000):
+        x = torch.cat([lat.expand(n, -1), torch.rand(n, 3, generator=gen) * 2 - 1], 1).contiguous().to(cuda)
+        out = {}
+        for name, impl in (("ffma", _lib.MLP_FFMA), ("coarse", _lib.MLP_TCGEN05_COARSE)):
+            s = torch.full((n,), 7.0, device=cuda)
+            _lib.check(lib.sdfr_decoder_eval(nat.handle, x.data_ptr(), n, s.data_ptr(), 0, impl, _lib.stream_ptr()))
+            out[name] = s.cpu().numpy()
+        assert np.abs(out["coarse"] - out["ffma"]).max() < 2.5e-3, (n, np.abs(out["coarse"] - out["ffma"]).max())
+    # three detections with different latents in one launch (rows of one tile straddle two detections)
+    lats = torch.nn.functional.normalize(torch.tensor([[0.5, 0.7, 0.5], [0.6, 0.6, 0.5], [0.3, 0.8, 0.4]]), dim=1).to(cuda)
+    D = 20
+    ref = torch.empty(3 * D ** 3, device=cuda)
+    got = torch.empty(3 * D ** 3, device=cuda)
+    _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats.data_ptr(), 3, D, ref.data_ptr(), 0, _lib.MLP_FFMA, _lib.stream_ptr()))
+    _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats.data_ptr(), 3, D, got.data_ptr(), 0, _lib.MLP_TCGEN05_COARSE,
+                                             _lib.stream_ptr()))
+    assert float((got - ref).abs().max()) < 2.5e-3
+    # deterministic: the same launch twice gives the same bits
+    got2 = torch.empty_like(got)
+    _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats.data_ptr(), 3, D, got2.data_ptr(), 0, _lib.MLP_TCGEN05_COARSE,
+                                             _lib.stream_ptr()))
+    assert torch.equal(got, got2)
