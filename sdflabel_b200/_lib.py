@@ -10,7 +10,8 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsdfr.so")
+# SDFR_LIB points the binding at another build of the same ABI (a profiling build, a kernel variant under test)
+LIB_PATH = os.environ.get("SDFR_LIB") or os.path.join(HERE, "libsdfr.so")
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)

@@ -1588,7 +1588,8 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
       mbar_init(bar_peer + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int j = 0; j < 2; ++j) { mbar_init(bar_acc + 8 * j, 1); mbar_init(bar_a + 8 * j, 2 * (P_NEPI / 32)); }
+    for (int j = 0; j < 2; ++j) mbar_init(bar_acc + 8 * j, 1);
+    for (int qt = 0; qt < 4; ++qt) mbar_init(bar_a + 8 * qt, 2 * (P_NEPI / 32));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 17) tmem_alloc_pair(smem_u32(smem + P.tmem_slot), TMEM_COLS);
@@ -1663,16 +1664,23 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
         const bool last = __ldg(&T.pass[p].kind) == 1;
         const int nblocks = last ? 1 : m_blocks >> 1;
         const uint32_t idesc = last ? kIdLast : kIdHidden;
-        // a_ready[h]: both CTAs have written k-half h of their A operand (and drained block h of their TMEM)
-        mbar_wait(bar_a, a_phase);
-        bool half1_ready = false;
-        tc_fence_after();
+        // a_ready[qt]: both CTAs have written features [128 qt, 128 qt + 128) of their A operand = k-chunks
+        // 4 qt .. 4 qt + 3 of this pass.  The epilogue reads a whole 256-column TMEM block before it publishes the
+        // block's first quarter, so a_ready[0] also says "block 0 is drained" and a_ready[3] "block 1 is drained".
+        uint32_t waited = 0;                           // bit qt: a_ready[qt] of this pass has been consumed
+        auto need = [&](const int qt) {
+          if (!((waited >> qt) & 1u)) {
+            mbar_wait(bar_a + 8 * qt, a_phase);
+            waited |= 1u << qt;
+            tc_fence_after();
+          }
+        };
+        need(0);
         for (int j = 0; j < nblocks; ++j) {
           const uint32_t d = tm + (uint32_t)(j * 256);
-          if (j == 1 && !half1_ready) { mbar_wait(bar_a + 8, a_phase); half1_ready = true; tc_fence_after(); }
+          if (j == 1) { need(1); need(2); need(3); }
           for (int kc = 0; kc < k_chunks; kc += P_STAGE_TILES) {
-            // k-chunks 8 .. 15 are features 256 .. 511 of the previous pass: its block 1
-            if (kc >= 8 && !half1_ready) { mbar_wait(bar_a + 8, a_phase); half1_ready = true; }
+            need(kc >> 2);
             const int cnt = min(P_STAGE_TILES, k_chunks - kc);
             mbar_wait(bar_full + 8 * stage, phase);
             mbar_wait(bar_peer + 8 * stage, phase);
@@ -1697,7 +1705,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           if (elect_one()) umma_commit_pair(bar_acc + 8 * j, (uint16_t)3);   // block j is complete in both CTAs
           __syncwarp();
         }
-        if (!half1_ready) mbar_wait(bar_a + 8, a_phase);      // keep the phases of both barriers in step
+        need(1); need(2); need(3);                     // keep the phases of the four barriers in step
         a_phase ^= 1;
       }
     }
@@ -1710,7 +1718,9 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
     float* wbias = reinterpret_cast<float*>(smem + P.bias) + warp * 128;
     unsigned char* aop = smem + P.a;
     unsigned char* arow = aop + (pt_l >> 3) * 128 + (pt_l & 7) * 16;   // + kk * P_A_KK
-    const uint32_t a_ready0 = mapa_u32(bar_a, 0u), a_ready1 = mapa_u32(bar_a + 8, 0u);   // the issuer's CTA
+    uint32_t a_ready[4];                               // in the issuer's CTA
+#pragma unroll
+    for (int qt = 0; qt < 4; ++qt) a_ready[qt] = mapa_u32(bar_a + 8 * qt, 0u);
     uint32_t acc_phase = 0;                            // bit j = phase of bar_acc[j]
     auto publish = [&](const uint32_t remote_bar) {
       fence_async_smem();                              // generic-proxy stores -> tensor-core reads
@@ -1759,8 +1769,8 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           *reinterpret_cast<uint4*>(arow + kk * P_A_KK) = pk;
         }
       }
-      publish(a_ready0);
-      if (lane == 0) mbar_arrive_cluster(a_ready1);
+      publish(a_ready[0]);
+      if (lane == 0) { mbar_arrive_cluster(a_ready[1]); mbar_arrive_cluster(a_ready[2]); mbar_arrive_cluster(a_ready[3]); }
 
       for (int p = 0; p < num_layers; ++p) {
         const TcPassDev Ps = T.pass[p];
@@ -1782,91 +1792,95 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
         }
         const float k_scale = Ps.inv_scale * Ps.out_scale;
         const int nblocks = Ps.m_blocks >> 1;
-        // this warp's scaled biases (features j * 256 + cs * 64 + 0..63, j = 0, 1), fetched under the MMAs
+        // this warp's scaled biases (features 128 qt + 32 cs + 0..31 of the four quarters), fetched under the MMAs
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int f = j * 256 + cs * 64 + 2 * lane + u;
-            wbias[j * 64 + 2 * lane + u] = f < Ps.rows ? __ldg(Ps.bias + f) * Ps.out_scale : 0.f;
-          }
+        for (int qt = 0; qt < 4; ++qt) {
+          const int f = qt * 128 + cs * 32 + lane;
+          wbias[qt * 32 + lane] = f < Ps.rows ? __ldg(Ps.bias + f) * Ps.out_scale : 0.f;
         }
         __syncwarp();
-        // 64 features of this thread's point -> eight packed 16-byte rows of the next A operand
-        auto compute_block = [&](const int j, uint4 (&pk)[8]) {
+        // quarter qt of the pass output = features [128 qt, +128); this warp's 32-column slice of it for its
+        // 32 points -> four packed 16-byte rows of the next A operand per thread
+        auto compute_quarter = [&](const int qt, uint4 (&pk)[4]) {
+          const int f0 = qt * 128 + cs * 32;
+          uint32_t v[32];
+          tmem_ld16(lane_base + (uint32_t)f0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld16(lane_base + (uint32_t)(f0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+          tmem_ld_wait();
+          const float* wb = wbias + qt * 32;
+          if (f0 + 32 <= Ps.rows) {                    // all regular rows (warp-uniform)
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {             // 2 x 16 features per TMEM round trip
-            const int f0 = j * 256 + cs * 64 + hf * 32;
-            uint32_t v[32];
-            tmem_ld16(lane_base + (uint32_t)f0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-            tmem_ld16(lane_base + (uint32_t)(f0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-            tmem_ld_wait();
-            const float* wb = wbias + j * 64 + hf * 32;
-            if (f0 + 32 <= Ps.rows) {                  // all regular rows (warp-uniform)
+            for (int o = 0; o < 4; ++o) {
+              const float4 b0 = *reinterpret_cast<const float4*>(wb + o * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(wb + o * 8 + 4);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              uint32_t* hw = reinterpret_cast<uint32_t*>(&pk[o]);
 #pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                const float4 b0 = *reinterpret_cast<const float4*>(wb + o * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(wb + o * 8 + 4);
-                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                uint32_t* hw = reinterpret_cast<uint32_t*>(&pk[4 * hf + o]);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float h0 = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e]), k_scale, bb[2 * e]), 0.f);
-                  const float h1 = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e + 1]), k_scale, bb[2 * e + 1]), 0.f);
-                  const __half2 a = __floats2half2_rn(h0, h1);
-                  hw[e] = *reinterpret_cast<const uint32_t*>(&a);
-                }
+              for (int e = 0; e < 4; ++e) {
+                const float h0 = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e]), k_scale, bb[2 * e]), 0.f);
+                const float h1 = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e + 1]), k_scale, bb[2 * e + 1]), 0.f);
+                const __half2 a = __floats2half2_rn(h0, h1);
+                hw[e] = *reinterpret_cast<const uint32_t*>(&a);
               }
-            } else {                                   // the slice that holds the concatenated / padding rows
+            }
+          } else {                                     // the slice that holds the concatenated / padding rows
 #pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                uint32_t* hw = reinterpret_cast<uint32_t*>(&pk[4 * hf + o]);
+            for (int o = 0; o < 4; ++o) {
+              uint32_t* hw = reinterpret_cast<uint32_t*>(&pk[o]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  float h[2];
+              for (int e = 0; e < 4; ++e) {
+                float h[2];
 #pragma unroll
-                  for (int u = 0; u < 2; ++u) {
-                    const int f = f0 + o * 8 + 2 * e + u;
-                    float val;
-                    if (f < Ps.rows) {
-                      val = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e + u]), k_scale, wb[o * 8 + 2 * e + u]), 0.f);
-                    } else if (f < Ps.rows + Ps.cat_dim) {         // cat[x, input] feeds the next Linear
-                      val = inp[(Ps.cat_off + f - Ps.rows) * P_PTS + pt_l] * Ps.out_scale;
-                    } else {
-                      val = 0.f;
-                    }
-                    h[u] = val;
+                for (int u = 0; u < 2; ++u) {
+                  const int f = f0 + o * 8 + 2 * e + u;
+                  float val;
+                  if (f < Ps.rows) {
+                    val = fmaxf(fmaf(__uint_as_float(v[o * 8 + 2 * e + u]), k_scale, wb[o * 8 + 2 * e + u]), 0.f);
+                  } else if (f < Ps.rows + Ps.cat_dim) {           // cat[x, input] feeds the next Linear
+                    val = inp[(Ps.cat_off + f - Ps.rows) * P_PTS + pt_l] * Ps.out_scale;
+                  } else {
+                    val = 0.f;
                   }
-                  const __half2 a = __floats2half2_rn(h[0], h[1]);
-                  hw[e] = *reinterpret_cast<const uint32_t*>(&a);
+                  h[u] = val;
                 }
+                const __half2 a = __floats2half2_rn(h[0], h[1]);
+                hw[e] = *reinterpret_cast<const uint32_t*>(&a);
               }
             }
           }
         };
-        auto store_block = [&](const int j, const uint4 (&pk)[8]) {
-          const int kk0 = (j * 256 + cs * 64) >> 3;
+        auto store_quarter = [&](const int qt, const uint4 (&pk)[4]) {
+          const int kk0 = (qt * 128 + cs * 32) >> 3;
 #pragma unroll
-          for (int r = 0; r < 8; ++r) *reinterpret_cast<uint4*>(arow + (kk0 + r) * P_A_KK) = pk[r];
+          for (int r = 0; r < 4; ++r) *reinterpret_cast<uint4*>(arow + (kk0 + r) * P_A_KK) = pk[r];
         };
-        uint4 pk[8];
+        uint4 pk0[4], pk1[4];
         mbar_wait(bar_acc, acc_phase & 1u);
         acc_phase ^= 1u;
         tc_fence_after();
-        compute_block(0, pk);                          // under the MMAs of block 1, which still read all of A
+        compute_quarter(0, pk0);                       // under the MMAs of block 1, which still read all of A
+        compute_quarter(1, pk1);
         if (nblocks == 2) {
           mbar_wait(bar_acc + 8, (acc_phase >> 1) & 1u);   // every MMA of the pass has completed: A may be overwritten
           acc_phase ^= 2u;
           tc_fence_after();
         }
-        store_block(0, pk);
-        publish(a_ready0);
+        store_quarter(0, pk0);
+        publish(a_ready[0]);
+        store_quarter(1, pk1);
+        publish(a_ready[1]);
         if (nblocks == 2) {
-          compute_block(1, pk);
-          store_block(1, pk);
+          compute_quarter(2, pk0);
+          store_quarter(2, pk0);
+          publish(a_ready[2]);
+          compute_quarter(3, pk1);
+          store_quarter(3, pk1);
+          publish(a_ready[3]);
+        } else {
+          publish(a_ready[2]);
+          publish(a_ready[3]);
         }
-        publish(a_ready1);
       }
       // inputs / A operand are rewritten by the next tile: every epilogue thread must be past the last pass
       asm volatile("bar.sync 1, 512;" ::: "memory");
