@@ -190,6 +190,9 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # keep stdout to the one JSON line: NCCL_DEBUG=VERSION (some images export it) prints a banner there
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     sc = load_scene()
