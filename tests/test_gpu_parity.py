@@ -490,6 +490,16 @@ def test_coarse_pass_ragged_rows_and_batches(stock_prior_path):
     _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats.data_ptr(), 3, D, got.data_ptr(), 0, _lib.MLP_TCGEN05_COARSE,
                                              _lib.stream_ptr()))
     assert float((got - ref).abs().max()) < 2.5e-3
+    # many tiles per CTA pair (8 x 64 000 points = 2 000 pair tiles, 27 rounds): every point, every round
+    lats8 = torch.nn.functional.normalize(torch.rand(8, 3, generator=gen) + 0.2, dim=1).to(cuda)
+    big_ref = torch.empty(8 * 40 ** 3, device=cuda)
+    big = torch.empty(8 * 40 ** 3, device=cuda)
+    _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats8.data_ptr(), 8, 40, big_ref.data_ptr(), 0, _lib.MLP_FFMA, _lib.stream_ptr()))
+    for _ in range(2):
+        big.fill_(9.0)
+        _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats8.data_ptr(), 8, 40, big.data_ptr(), 0, _lib.MLP_TCGEN05_COARSE,
+                                                 _lib.stream_ptr()))
+        assert float((big - big_ref).abs().max()) < 2.5e-3
     # deterministic: the same launch twice gives the same bits
     got2 = torch.empty_like(got)
     _lib.check(lib.sdfr_decoder_eval_lattice(nat.handle, lats.data_ptr(), 3, D, got2.data_ptr(), 0, _lib.MLP_TCGEN05_COARSE,
