@@ -1581,6 +1581,13 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
   const long long n_rows = mlp_rows(in);
   const long long num_pair_tiles = (n_rows + 2 * P_PTS - 1) / (2 * P_PTS);
   const long long num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+  // The last Linear (hidden -> 1) is a dot product per point: when the layer before it is a plain hidden layer
+  // its epilogue computes it from the fp32 accumulators (no fp16 rounding of that layer's activations), and the
+  // 32 N = 16 MMAs, the operand stores and the barrier round of a separate pass disappear.
+  const bool fuse_last = num_layers >= 2 && T.pass[num_layers - 1].kind == 1 && T.pass[num_layers - 2].kind == 0 &&
+                         T.pass[num_layers - 2].cat_dim == 0 && T.pass[num_layers - 2].rows == T.last_k &&
+                         T.pass[num_layers - 2].m_blocks == 4;
+  const int num_passes = fuse_last ? num_layers - 1 : num_layers;
 
   if (tid == 0) {
     for (int s = 0; s < P_STAGES; ++s) {
@@ -1607,7 +1614,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (long long it = 0; it < my_tiles; ++it) {
-        for (int p = 0; p < num_layers; ++p) {
+        for (int p = 0; p < num_passes; ++p) {
           const int m_blocks = T.pass[p].m_blocks, k_chunks = T.pass[p].k_chunks;
           const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
           const int nblocks = T.pass[p].kind == 1 ? 1 : m_blocks >> 1;
@@ -1637,7 +1644,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
 #pragma unroll
       for (int s = 0; s < P_STAGES; ++s) peer_bar[s] = mapa_u32(bar_peer + 8 * s, 0u);
       for (long long it = 0; it < my_tiles; ++it) {
-        for (int p = 0; p < num_layers; ++p) {
+        for (int p = 0; p < num_passes; ++p) {
           const int nblocks = T.pass[p].kind == 1 ? 1 : T.pass[p].m_blocks >> 1;
           const int steps = nblocks * ((T.pass[p].k_chunks + P_STAGE_TILES - 1) / P_STAGE_TILES);
           for (int st = 0; st < steps; ++st) {
@@ -1659,7 +1666,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
     const uint64_t desc_b0 = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);  // a weight tile, K-major
     constexpr uint32_t kIdHidden = idesc_pair(256), kIdLast = idesc_pair(16);
     for (long long it = 0; it < my_tiles; ++it) {
-      for (int p = 0; p < num_layers; ++p) {
+      for (int p = 0; p < num_passes; ++p) {
         const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
         const bool last = __ldg(&T.pass[p].kind) == 1;
         const int nblocks = last ? 1 : m_blocks >> 1;
@@ -1772,7 +1779,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
       publish(a_ready[0]);
       if (lane == 0) { mbar_arrive_cluster(a_ready[1]); mbar_arrive_cluster(a_ready[2]); mbar_arrive_cluster(a_ready[3]); }
 
-      for (int p = 0; p < num_layers; ++p) {
+      for (int p = 0; p < num_passes; ++p) {
         const TcPassDev Ps = T.pass[p];
         if (Ps.kind == 1) {                            // last Linear: column 0 is the pre-activation of the sdf
           mbar_wait(bar_acc, acc_phase & 1u);
@@ -1788,6 +1795,56 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
             if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
           }
           tc_fence_before();
+          continue;
+        }
+        if (fuse_last && p == num_passes - 1) {
+          // ---- last hidden layer + last Linear: sdf = tanh(sum_f w_f relu(acc_f / scale + b_f) + b_last) ----
+          __syncwarp();
+#pragma unroll
+          for (int qt = 0; qt < 4; ++qt) {
+            const int f = qt * 128 + cs * 32 + lane;
+            wbias[qt * 32 + lane] = f < Ps.rows ? __ldg(Ps.bias + f) : 0.f;
+          }
+          __syncwarp();
+          float partial = 0.f;
+          auto dot_quarter = [&](const int qt) {
+            const int f0 = qt * 128 + cs * 32;
+            uint32_t v[32];
+            tmem_ld16(lane_base + (uint32_t)f0, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld16(lane_base + (uint32_t)(f0 + 16), *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_wait();
+            const float* wb = wbias + qt * 32;
+#pragma unroll
+            for (int o = 0; o < 8; ++o) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(T.last_w + f0) + o);
+              const float4 b4 = *reinterpret_cast<const float4*>(wb + o * 4);
+              partial = fmaf(w4.x, fmaxf(fmaf(__uint_as_float(v[4 * o]), Ps.inv_scale, b4.x), 0.f), partial);
+              partial = fmaf(w4.y, fmaxf(fmaf(__uint_as_float(v[4 * o + 1]), Ps.inv_scale, b4.y), 0.f), partial);
+              partial = fmaf(w4.z, fmaxf(fmaf(__uint_as_float(v[4 * o + 2]), Ps.inv_scale, b4.z), 0.f), partial);
+              partial = fmaf(w4.w, fmaxf(fmaf(__uint_as_float(v[4 * o + 3]), Ps.inv_scale, b4.w), 0.f), partial);
+            }
+          };
+          mbar_wait(bar_acc, acc_phase & 1u);
+          acc_phase ^= 1u;
+          tc_fence_after();
+          dot_quarter(0);
+          dot_quarter(1);
+          mbar_wait(bar_acc + 8, (acc_phase >> 1) & 1u);   // also: every MMA of the tile has completed
+          acc_phase ^= 2u;
+          tc_fence_after();
+          dot_quarter(2);
+          dot_quarter(3);
+          tc_fence_before();
+          // the inputs are dead by now (last used by the concat layer): their buffer carries the 4 partial sums
+          inp[cs * P_PTS + pt_l] = partial;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (cs == 0) {
+            float y = ((inp[pt_l] + inp[P_PTS + pt_l]) + (inp[2 * P_PTS + pt_l] + inp[3 * P_PTS + pt_l])) +
+                      __ldg(T.pass[num_layers - 1].bias);
+            if (use_tanh) y = tanhf(y);
+            y = tanhf(y);
+            if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
+          }
           continue;
         }
         const float k_scale = Ps.inv_scale * Ps.out_scale;
