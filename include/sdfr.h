@@ -283,6 +283,11 @@ int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_dev, int64_
  * float64 like a KD-tree; the lowest index wins a tie): idx [q] int32, dist [q] double. */
 int sdfr_nn_query(const float* queries_dev, int64_t q, const float* refs_dev, int64_t m, int32_t* idx_dev,
                   double* dist_dev, void* stream);
+/* HOST function (no kernel): `draws` times numpy's legacy `np.random.choice(range(n), 4, replace=False)`
+ * (pose.py:139) on the caller's MT19937 state - key [624] and position as `np.random.get_state()` returns
+ * them, updated in place so that `np.random.set_state()` continues the stream exactly where numpy would
+ * be.  samples [draws,4] int32. */
+int sdfr_np_choice4(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int32_t draws, int32_t* samples_out);
 /* All hypotheses of a RANSAC round in one launch.  transforms [h,12]: row-major 3x4
  * float32 [R*scale | t] (pose.py:166-168).  For hypothesis i and scene point j:
  * p = T_i * scene_pts[j] (float32), k = 1-NN of p in model_pts, inlier iff

@@ -86,6 +86,7 @@ SIGNATURES = {
     "sdfr_refine_view": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]),
     "sdfr_refine_copy_view": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64, vp]),
     "sdfr_rotate_iou": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp]),
+    "sdfr_np_choice4": (C.c_int, [vp, C.POINTER(C.c_int32), C.c_int64, C.c_int32, vp]),
     "sdfr_nn_query": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp, vp]),
     "sdfr_ransac_score": (C.c_int, [vp, vp, C.c_int64, vp, vp, C.c_int64, vp, C.c_int, C.c_double, C.c_float, vp, vp,
                                     vp]),

@@ -63,6 +63,22 @@ def ransac_score(scene_pts, scene_cls, model_pts, model_cls, transforms, metric_
     return counts, masks
 
 
+def legacy_choice4(n: int, draws: int) -> np.ndarray:
+    """``draws`` x ``np.random.choice(range(n), 4, replace=False)`` on numpy's global legacy generator, (draws, 4).
+    Same numbers, same generator state afterwards; the stream is consumed by ``sdfr_np_choice4`` (a host loop over
+    the MT19937 state) instead of 567 Python-level calls."""
+    import ctypes as C
+    state = np.random.get_state(legacy=True)
+    if state[0] != 'MT19937' or n < 4:
+        return np.stack([np.random.choice(n, 4, replace=False) for _ in range(draws)])
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = C.c_int32(int(state[2]))
+    out = np.empty((draws, 4), dtype=np.int32)
+    _lib.check(_lib.load().sdfr_np_choice4(key.ctypes.data, C.byref(pos), int(n), int(draws), out.ctypes.data))
+    np.random.set_state(('MT19937', key, pos.value, state[3], state[4]))
+    return out.astype(np.int64)
+
+
 class PoseEstimator:
     def __init__(self, type='kabsch', scale=2.2):
         self.scale = scale
@@ -116,7 +132,7 @@ class PoseEstimator:
         model_pts_h = model_pts_d.cpu().numpy()
 
         # the reference's sample sequence (one np.random.choice per iteration, whatever happens next)
-        samples = np.stack([np.random.choice(total, 4, replace=False) for _ in range(iters)])
+        samples = legacy_choice4(total, iters)
         compatible = ~(cdist[samples] > nocs_distance_threshold).any(axis=1)
 
         cand = np.nonzero(compatible)[0]

@@ -75,3 +75,28 @@ def test_product_needs_a_gpu():
     sc = PO.make_pose_scene(seed=1)
     with pytest.raises(_lib.SdfrError):
         PoseEstimator.init_pose_3d(sc["model_pts"], sc["model_cls"], sc["scene_pts"], sc["scene_cls"], type="kabsch")
+
+
+def test_legacy_choice_consumes_numpy_stream_exactly():
+    """sdfr_np_choice4 (host loop over numpy's MT19937 state) == the np.random.choice calls of pose.py:139,
+    numbers and generator state alike."""
+    from sdflabel_b200.utils.pose import legacy_choice4
+    for seed, n in ((1, 5), (2, 360), (3, 851), (4, 4), (5, 70000)):
+        draws = 567 if n < 10000 else 6
+        np.random.seed(seed)
+        np.random.rand(seed * 311)                       # somewhere inside the 624-word block
+        ref = np.stack([np.random.choice(range(n), 4, replace=False) for _ in range(draws)])
+        after_ref = np.random.randint(0, 2 ** 31 - 1, size=4)
+        np.random.seed(seed)
+        np.random.rand(seed * 311)
+        got = legacy_choice4(n, draws)
+        after = np.random.randint(0, 2 ** 31 - 1, size=4)
+        assert np.array_equal(ref, got) and np.array_equal(after_ref, after), (seed, n)
+    np.random.seed(9)
+    np.random.normal(size=3)                             # a cached gaussian in the state must survive the round trip
+    a = legacy_choice4(100, 3)
+    x = np.random.normal()
+    np.random.seed(9)
+    np.random.normal(size=3)
+    b = np.stack([np.random.choice(range(100), 4, replace=False) for _ in range(3)])
+    assert np.array_equal(a, b) and x == np.random.normal()
