@@ -154,6 +154,7 @@ __device__ __forceinline__ Hit disc_test(float rx, float ry, float rz, float vx,
 
 constexpr int TILE = 16;
 constexpr int CHUNK = 256;
+constexpr int LCAP = 512;      // surfels of one tile kept resident in shared memory for both sweeps
 
 __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatView* __restrict__ views) {
   const SplatView& V = views[blockIdx.z];
@@ -165,10 +166,9 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
   const bool live = x < V.width && y < V.height;
   const int tx1 = min(tx0 + TILE - 1, V.width - 1), ty1 = min(ty0 + TILE - 1, V.height - 1);
 
-  __shared__ float s_v[CHUNK][3], s_m[CHUNK][3], s_c[CHUNK][3], s_a[CHUNK];
-  __shared__ int4 s_bb[CHUNK];
+  __shared__ float s_v[LCAP][3], s_m[LCAP][3], s_c[LCAP][3], s_a[LCAP];
+  __shared__ int4 s_bb[LCAP];
   __shared__ int s_warp_cnt[TILE * TILE / 32];
-  __shared__ int s_total;
 
   const float fx = (float)x, fy = (float)y;
   const float rx = V.kinv[0] * fx + V.kinv[1] * fy + V.kinv[2];
@@ -180,68 +180,89 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
   float nu = 0.f, smax = 0.f, den = 0.f;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // colour3, mask, depth, normals3
 
-  for (int sweep = 0; sweep < 2; ++sweep) {
-    if (sweep == 1) {
+  // one candidate of the tile's list against this pixel; sweep 0: sum of squares / max / count of zeta,
+  // sweep 1: softmax-weighted accumulation (primitives.py:227-240, rasterer.py:113-144)
+  auto visit = [&](const int k, const int sweep) {
+    // every hit of a surfel lies inside its pixel box (project_kernel): four integer compares reject the
+    // ~85 % of the tile's surfels that cannot touch this pixel before the ray / disc test
+    const int4 b = s_bb[k];
+    if (x < b.x || x > b.z || y < b.y || y > b.w) return;
+    const Hit h = disc_test(rx, ry, rz, s_v[k][0], s_v[k][1], s_v[k][2], s_m[k][0], s_m[k][1], s_m[k][2], s_a[k]);
+    if (!h.hit) return;
+    const float zeta = -h.z;                      // primitives.py:227
+    if (sweep == 0) {
+      sumsq += zeta * zeta;                       // primitives.py:228
+      zeta_max = fmaxf(zeta_max, zeta);
+      ++hits;
+    } else {
+      const float sc = fmaxf(zeta / (nu + kEps32) + 1.f, 0.f) * kDepthGain;   // primitives.py:229-230
+      const float e = expf(sc - smax);            // softmax numerator (primitives.py:240)
+      den += e;
+      acc[0] += e * s_c[k][0]; acc[1] += e * s_c[k][1]; acc[2] += e * s_c[k][2];
+      acc[3] += e;
+      acc[4] += e * s_v[k][2];                    // rasterer.py:136 (surfel-centre z)
+      acc[5] += e * ((s_m[k][0] + 1.f) / 2.f);
+      acc[6] += e * ((s_m[k][1] + 1.f) / 2.f);
+      acc[7] += e * ((s_m[k][2] + 1.f) / 2.f);
+    }
+  };
+  // culls surfels [base, base + CHUNK) against the tile and appends the survivors (in index order) to the
+  // shared list at `start`; entries past `cap` are dropped.  Returns the number of survivors of the chunk.
+  auto cull_chunk = [&](const int base, const int start, const int cap) -> int {
+    const int i = base + tid;
+    bool take = false;
+    int4 bb = make_int4(0, 0, 0, 0);
+    if (i < m) {
+      bb = *reinterpret_cast<const int4*>(V.bbox + i * 4);
+      take = bb.x <= tx1 && bb.z >= tx0 && bb.y <= ty1 && bb.w >= ty0;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, take);
+    __syncthreads();                              // the previous chunk's readers of s_warp_cnt / the list are done
+    if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
+    __syncthreads();
+    int off = start + __popc(ballot & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+    for (int w = 0; w < TILE * TILE / 32; ++w) {
+      const int c = s_warp_cnt[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    if (take && off < cap) {
+      s_v[off][0] = V.cam_v[i * 3]; s_v[off][1] = V.cam_v[i * 3 + 1]; s_v[off][2] = V.cam_v[i * 3 + 2];
+      s_m[off][0] = V.cam_m[i * 3]; s_m[off][1] = V.cam_m[i * 3 + 1]; s_m[off][2] = V.cam_m[i * 3 + 2];
+      s_c[off][0] = V.cam_c[i * 3]; s_c[off][1] = V.cam_c[i * 3 + 1]; s_c[off][2] = V.cam_c[i * 3 + 2];
+      s_a[off] = V.plane_a[i];
+      s_bb[off] = bb;
+    }
+    return total;
+  };
+
+  // Pass 1: cull everything once.  If the tile's surfels fit the resident list (the usual case: a few hundred
+  // of the ~2 000 surfels of a detection touch a 16 x 16 tile) both sweeps run out of shared memory; the
+  // chunk-serial cull with its dependent global loads and block barriers is paid once instead of twice.
+  int total = 0;
+  for (int base = 0; base < m && total <= LCAP; base += CHUNK) total += cull_chunk(base, total, LCAP);
+  __syncthreads();
+  if (total <= LCAP) {
+    if (live) {
+      for (int k = 0; k < total; ++k) visit(k, 0);
       nu = sqrtf(sumsq);
       smax = fmaxf(zeta_max / (nu + kEps32) + 1.f, 0.f) * kDepthGain;
+      for (int k = 0; k < total; ++k) visit(k, 1);
     }
-    for (int base = 0; base < m; base += CHUNK) {
-      // cull this chunk of surfels against the tile, compact survivors into shared memory
-      const int i = base + tid;
-      bool take = false;
-      int4 bb = make_int4(0, 0, 0, 0);
-      if (i < m) {
-        bb = *reinterpret_cast<const int4*>(V.bbox + i * 4);
-        take = bb.x <= tx1 && bb.z >= tx0 && bb.y <= ty1 && bb.w >= ty0;
+  } else {
+    // more survivors than the list holds (small crops: every surfel touches every tile): chunk by chunk, per sweep
+    for (int sweep = 0; sweep < 2; ++sweep) {
+      if (sweep == 1) {
+        nu = sqrtf(sumsq);
+        smax = fmaxf(zeta_max / (nu + kEps32) + 1.f, 0.f) * kDepthGain;
       }
-      const unsigned ballot = __ballot_sync(0xffffffffu, take);
-      if (lane == 0) s_warp_cnt[warp] = __popc(ballot);
-      __syncthreads();
-      int off = __popc(ballot & ((1u << lane) - 1u));
-      for (int w = 0; w < warp; ++w) off += s_warp_cnt[w];
-      if (tid == 0) {
-        int t = 0;
-        for (int w = 0; w < TILE * TILE / 32; ++w) t += s_warp_cnt[w];
-        s_total = t;
+      for (int base = 0; base < m; base += CHUNK) {
+        const int cnt = cull_chunk(base, 0, CHUNK);
+        __syncthreads();
+        if (live)
+          for (int k = 0; k < cnt; ++k) visit(k, sweep);
       }
-      if (take) {
-        s_v[off][0] = V.cam_v[i * 3]; s_v[off][1] = V.cam_v[i * 3 + 1]; s_v[off][2] = V.cam_v[i * 3 + 2];
-        s_m[off][0] = V.cam_m[i * 3]; s_m[off][1] = V.cam_m[i * 3 + 1]; s_m[off][2] = V.cam_m[i * 3 + 2];
-        s_a[off] = V.plane_a[i];
-        s_bb[off] = bb;
-        if (sweep == 1) {
-          s_c[off][0] = V.cam_c[i * 3]; s_c[off][1] = V.cam_c[i * 3 + 1]; s_c[off][2] = V.cam_c[i * 3 + 2];
-        }
-      }
-      __syncthreads();
-      const int cnt = s_total;
-      if (live) {
-        for (int k = 0; k < cnt; ++k) {
-          // every hit of a surfel lies inside its pixel box (project_kernel): four integer compares reject
-          // the ~85 % of the tile's surfels that cannot touch this pixel before the ray / disc test
-          const int4 b = s_bb[k];
-          if (x < b.x || x > b.z || y < b.y || y > b.w) continue;
-          const Hit h = disc_test(rx, ry, rz, s_v[k][0], s_v[k][1], s_v[k][2], s_m[k][0], s_m[k][1], s_m[k][2], s_a[k]);
-          if (!h.hit) continue;
-          const float zeta = -h.z;                      // primitives.py:227
-          if (sweep == 0) {
-            sumsq += zeta * zeta;                       // primitives.py:228
-            zeta_max = fmaxf(zeta_max, zeta);
-            ++hits;
-          } else {
-            const float sc = fmaxf(zeta / (nu + kEps32) + 1.f, 0.f) * kDepthGain;   // primitives.py:229-230
-            const float e = expf(sc - smax);            // softmax numerator (primitives.py:240)
-            den += e;
-            acc[0] += e * s_c[k][0]; acc[1] += e * s_c[k][1]; acc[2] += e * s_c[k][2];
-            acc[3] += e;
-            acc[4] += e * s_v[k][2];                    // rasterer.py:136 (surfel-centre z)
-            acc[5] += e * ((s_m[k][0] + 1.f) / 2.f);
-            acc[6] += e * ((s_m[k][1] + 1.f) / 2.f);
-            acc[7] += e * ((s_m[k][2] + 1.f) / 2.f);
-          }
-        }
-      }
-      __syncthreads();
     }
   }
   if (!live) return;
