@@ -2164,21 +2164,18 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
   const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
   // CTA-pair kernel (tcgen05 cta_group::2): stock-like pass tables only (every hidden pass an even number of
   // 128-feature blocks, last Linear a single row)
-  static int pair_mode = -1, pair_slots = 0;
+  static int pair_mode = -1, pair_slots = 0, pair_smem_max = 0;
   if (pair_mode < 0) {
     const char* e = getenv("SDFR_TC_PAIR");
     pair_mode = e ? atoi(e) : 1;
     if (pair_mode) {
-      const TcTable& T = st->table;
-      for (int p = 0; p < T.num_layers; ++p) {
-        const bool last = T.pass[p].kind == 1;
-        if (last ? T.pass[p].m_blocks != 1 : (T.pass[p].m_blocks != 2 && T.pass[p].m_blocks != 4)) pair_mode = 0;
-        if (T.pass[p].k_chunks != 1 && (T.pass[p].k_chunks & 1)) pair_mode = 0;
-      }
-    }
-    if (pair_mode) {
-      const PairPlan plan = make_pair_plan(dec->dev.in0);
-      if (cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) != cudaSuccess) {
+      // opt in to the device maximum once: the plan grows with the decoder's input width
+      int devid = 0;
+      PairPlan plan = make_pair_plan(3 + 3);              // the stock input width, for the occupancy query
+      if (cudaGetDevice(&devid) != cudaSuccess ||
+          cudaDeviceGetAttribute(&pair_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) != cudaSuccess ||
+          (int)plan.total > pair_smem_max ||
+          cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_max) != cudaSuccess) {
         cudaGetLastError();
         pair_mode = 0;
       } else {
@@ -2197,7 +2194,15 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
       }
     }
   }
-  if (pair_mode) {
+  // per decoder (the switches above are per process): does this pass table fit the pair kernel?
+  bool pair_ok = pair_mode != 0 && (int)make_pair_plan(dec->dev.in0).total <= pair_smem_max;
+  for (int p = 0; pair_ok && p < st->table.num_layers; ++p) {
+    const TcPassDev& ps = st->table.pass[p];
+    const bool last = ps.kind == 1;
+    if (last ? ps.m_blocks != 1 : (ps.m_blocks != 2 && ps.m_blocks != 4)) pair_ok = false;
+    if (ps.k_chunks != 1 && (ps.k_chunks & 1)) pair_ok = false;
+  }
+  if (pair_ok) {
     const long long pair_tiles = (in.n + 2 * P_PTS - 1) / (2 * P_PTS);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
