@@ -66,3 +66,39 @@ def test_gather_handles_empty_rank(tmp_path):
     global NUM_FRAMES
     recs = F.gather_labels(_fake_records([]), L)
     assert recs.shape == (0, F.record_width(L))
+
+
+# ---- sharded per-frame dumps + the reference's resume rule (refine_css.py:68-70, 241-248) ----------------
+def _dump_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for f in F.shard_frames(NUM_FRAMES, rank, world):
+        if F.frame_done(out_dir, f):                 # resume: frame 2 was dumped by an earlier (interrupted) run
+            continue
+        n = f % 3 + 1
+        annos = [{'name': 'Car', 'bbox': np.array([f, d, f + 50, d + 40]), 'alpha': 0.1 * d, 'rotation_y': 0.2 * d,
+                  'dimensions': np.array([1.5, 1.6, 3.9]), 'location': np.array([1.0 * f, 1.5, 10.0 + d]), 'score': 1}
+                 for d in range(n)]
+        labels = [{'name': 'Car', 'bbox': a['bbox'], 'location': a['location'] + 0.1, 'dimensions': [1.4, 1.6, 3.8],
+                   'rotation_y': a['rotation_y'] + 0.01, 'alpha': a['alpha'] + 0.01, 'score': 1} for a in annos]
+        F.dump_frame_labels(out_dir, f, annos, labels)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_dumps_cover_every_frame_and_resume(tmp_path):
+    out = str(tmp_path / "labels")
+    marker = F.dump_frame_labels(out, 2, [{'name': 'Car', 'bbox': np.zeros(4), 'alpha': 0., 'rotation_y': 0.,
+                                          'dimensions': np.ones(3), 'location': np.zeros(3), 'score': 1}], [])
+    stamp = os.path.getmtime(marker)
+    world = 2
+    mp.spawn(_dump_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    gt, pred = F.load_autolabels(out)
+    assert sorted(gt) == list(range(NUM_FRAMES))                     # every frame exactly once, whoever owned it
+    assert os.path.getmtime(marker) == stamp and pred[2]['name'] == []      # the finished frame was not redone
+    for f in range(NUM_FRAMES):
+        if f != 2:
+            assert pred[f]['location'].shape == (f % 3 + 1, 3) and gt[f]['bbox'].shape == (f % 3 + 1, 4)
+    assert not [p for p in os.listdir(out) if p.endswith('.tmp')]     # atomic writes leave nothing behind
