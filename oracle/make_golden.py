@@ -142,6 +142,29 @@ def golden_raster(ref):
         np.savez_compressed(os.path.join(GOLDEN, f"raster_{tag}.npz"), **out)
 
 
+def golden_primitives(ref):
+    """The two circle primitives and background compositing (rasterer.py:93-126) on one small view: colour and
+    mask maps and the gradient with respect to the points, per (primitive, background) combination."""
+    prior = P.load_prior(STOCK_PRIOR)
+    sp, sn = _surfels(prior, 24)
+    w, h = 40, 30
+    K = scenes.intrinsics(max(w, h))
+    K[0, 2], K[1, 2] = w / 2.0, h / 2.0
+    pose = O.yaw_pose(torch.tensor([0.6]), torch.tensor([0.05, -0.02, 4.0])).detach()
+    bg = torch.rand(3, h, w, generator=torch.Generator().manual_seed(11))
+    ras = ref.Rasterer(K, (w, h))
+    out = {"K": _np(K), "width": w, "height": h, "coords": _np(sp), "normals": _np(sn), "pose": _np(pose), "bg": _np(bg)}
+    for prim in ("circle", "circle_opt", "disc"):
+        for use_bg in (False, True):
+            coords = sp.clone().requires_grad_(True)
+            r = ras(coords, sn, sn, pose, rot="dcm", primitives=prim, bg=(bg if use_bg else None), output_mask=True,
+                    output_nocs=True, output_points=False)
+            (g,) = torch.autograd.grad((r["color"] * bg).sum() + r["mask"].sum(), coords)
+            tag = f"{prim}_{'bg' if use_bg else 'nobg'}"
+            out[tag + "_color"], out[tag + "_mask"], out[tag + "_g_coords"] = _np(r["color"]), _np(r["mask"]), _np(g)
+    np.savez_compressed(os.path.join(GOLDEN, "raster_primitives.npz"), **out)
+
+
 def golden_losses(ref):
     prior = P.load_prior(STOCK_PRIOR)
     sc = scenes.make_scene(prior, size=32, density=20, n_lidar=150, seed=5)
@@ -200,6 +223,7 @@ def main():
     golden_decoders(ref)
     golden_stock(ref)
     golden_raster(ref)
+    golden_primitives(ref)
     golden_losses(ref)
     golden_refine(ref)
     for f in sorted(os.listdir(GOLDEN)):

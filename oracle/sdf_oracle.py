@@ -331,6 +331,93 @@ def render(K, width, height, points, normals, colors, pose, rot="dcm", output_no
 
 
 # ----------------------------------------------------------------------------
+# The other two primitives and background compositing (only the
+# demo CLI sdfrenderer/main.py reaches them, always with bg=None).  Oracle only in
+# round 1: the product raises NotImplementedError for them.
+# ----------------------------------------------------------------------------
+def _depth_scores(v, gain):
+    """primitives.py:52-56 / 143-146: per-point score from the camera depth alone."""
+    eps = torch.finfo(v.dtype).eps
+    z = -v[:, 2:]
+    nu = z.norm(p=2, dim=0).detach()
+    return (z / (nu.unsqueeze(0) + eps) + 1).clamp(min=0) * gain          # (M,1)
+
+
+def circle_weights(K, width, height, v, add_bg=False, diam=0.02, gain=100.0, soft=3.0):
+    """``inside_circle`` as ``Rasterer`` calls it (primitives.py:4-68, rasterer.py:93-96): the sigmoid "soft clamp" is
+    only tested for > 0, so a point covers every pixel the sigmoid does not underflow on; the softmax runs over
+    ALL points with uncovered ones scored 0 (``z * mask``, not a masked fill).  Returns (M [+1], P)."""
+    dtype = v.dtype
+    eps = torch.finfo(dtype).eps
+    yy, xx = torch.meshgrid(torch.arange(height), torch.arange(width), indexing="ij")
+    pix = torch.stack([xx.reshape(-1), yy.reshape(-1)], dim=1).to(dtype)          # rasterer.py:25-27
+    p2 = project_pixels(K, v, (width, height))
+    diff = p2.view(-1, 1, 2) - pix.unsqueeze(0)
+    radius = (K[0, 0] * diam / (v[:, 2] + eps)).abs().unsqueeze(-1)
+    cover = (torch.sigmoid((radius - diff.pow(2).sum(-1).sqrt()) * soft) > 0).detach().to(dtype)
+    z = _depth_scores(v, gain)
+    if add_bg:
+        z = torch.cat([z, (z.min() - 1).view(1, 1)])
+        cover = torch.cat([cover, torch.ones_like(cover[:1])])
+    return torch.softmax(z * cover, dim=0) * cover
+
+
+def circle_opt_weights(K, v, add_bg=True, diam=0.025, gain=10000.0, soft=5.0):
+    """``inside_circle_opt`` (primitives.py:71-162, rasterer.py:97-100).  Each point stamps its 15 x 15 pixel
+    neighbourhood (``Rasterer.grid_prim``, offsets -7..7) around its TRUNCATED pixel position, indices clamped
+    to the image, duplicates summed by the sparse -> dense conversion; the sigmoid never underflows inside that
+    window, so the mask is the clamped window itself.  The image size is taken from the principal point
+    (``x_px = int(K[0,2]) * 2``), as the reference does.  Returns (M [+1], P)."""
+    dtype = v.dtype
+    x_px, y_px = int(K[0, 2].int().item()) * 2, int(K[1, 2].int().item()) * 2
+    p2 = project_pixels(K, v, (x_px, y_px))
+    oy, ox = torch.meshgrid(torch.arange(-7, 8), torch.arange(-7, 8), indexing="ij")
+    offs = torch.stack([ox.reshape(-1), oy.reshape(-1)], dim=1)                    # rasterer.py:30-32
+    idx = (offs.to(dtype).unsqueeze(0) + p2.unsqueeze(1)).long()                   # truncation toward zero
+    idx = torch.max(torch.min(idx, torch.tensor([[x_px - 1, y_px - 1]])), torch.tensor([[0, 0]]))
+    cover = torch.zeros(v.shape[0], y_px * x_px, dtype=dtype)
+    flat = idx[..., 1] * x_px + idx[..., 0]
+    cover.scatter_(1, flat, torch.ones_like(flat, dtype=dtype))
+    z = _depth_scores(v, gain)
+    if add_bg:
+        z = torch.cat([z, (z.min() - 1).view(1, 1)])
+        cover = torch.cat([cover, torch.ones(1, y_px * x_px, dtype=dtype)])
+    score = z.expand(-1, cover.shape[1]).masked_fill(cover == 0, torch.finfo(dtype).min)
+    return torch.softmax(score, dim=0) * cover
+
+
+def disc_weights_bg(rays, v, m, radius=DISC_RADIUS, gain=DEPTH_GAIN):
+    """``inside_surfel`` with ``add_bg=True`` (primitives.py:232-237): one extra row that covers every pixel, scored
+    below the farthest surfel."""
+    dtype = v.dtype
+    eps = torch.finfo(dtype).eps
+    a = (m * v).sum(1, keepdim=True)
+    b = m @ rays.t()
+    b = torch.where(b.abs() < RAY_CUTOFF, torch.full_like(b, eps).detach(), b)
+    z = a / b
+    hit = rays.unsqueeze(0) * z.unsqueeze(-1)
+    gap = radius - (v.unsqueeze(1) - hit).pow(2).sum(-1).sqrt()
+    inside = (gap.clamp(min=0) > 0).detach()
+    zeta = -z * inside.to(dtype)
+    nu = zeta.norm(dim=0).detach()
+    score = (zeta / (nu.unsqueeze(0) + eps) + 1).clamp(min=0) * gain
+    bg = ((-v[:, 2:] * gain).min() - 1).expand(1, score.shape[1])
+    score = torch.cat([score, bg])
+    inside = torch.cat([inside, torch.ones_like(inside[:1])])
+    score = score.masked_fill(~inside, torch.finfo(dtype).min)
+    return torch.softmax(score, dim=0) * inside.to(dtype)
+
+
+def compose_bg(w, c, bg):
+    """rasterer.py:107-126 with a background image ``bg`` (3,H,W): only ``color`` and ``mask`` can be composed (the
+    reference's depth / normals lines mix M+1 weights with M values and fail to broadcast)."""
+    col = torch.cat([((c + 1) / 2).unsqueeze(-1).expand(-1, -1, w.shape[1]), bg.reshape(1, 3, -1)])
+    color = (w.unsqueeze(1) * col).sum(0).clamp(max=1)
+    mask = w.sum(0, keepdim=True).clamp(max=1)
+    return color, mask
+
+
+# ----------------------------------------------------------------------------
 # Losses  (pipelines/optimizer.py:166-198 and 200-237)
 # ----------------------------------------------------------------------------
 def nearest_neighbour(query: torch.Tensor, ref: torch.Tensor):

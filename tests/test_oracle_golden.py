@@ -115,3 +115,33 @@ def test_refine_trajectory(golden_dir, stock_prior_path):
         traj.append(np.concatenate([p[k].reshape(-1) for k in ("yaw", "trans", "scale", "latent")]))
     traj = np.stack(traj)
     assert np.abs(traj - g["traj"]).max() < 2e-5, np.abs(traj - g["traj"]).max(0)
+
+
+@pytest.mark.parametrize("prim", ["circle", "circle_opt", "disc"])
+@pytest.mark.parametrize("use_bg", [False, True])
+def test_other_primitives_and_background(golden_dir, prim, use_bg):
+    """SURVEY 8(f) row 3 (oracle only in round 1): circle / circle_opt primitives and bg compositing against the
+    reference Rasterer's colour and mask maps and point gradients."""
+    g = np.load(os.path.join(golden_dir, "raster_primitives.npz"))
+    w, h = int(g["width"]), int(g["height"])
+    K, pose, bg = torch.from_numpy(g["K"]), torch.from_numpy(g["pose"]), torch.from_numpy(g["bg"])
+    coords = torch.from_numpy(g["coords"]).requires_grad_(True)
+    normals = torch.from_numpy(g["normals"])
+    v, m, c, _ = O.to_camera(coords, normals, normals, pose, "dcm", True)
+    if prim == "circle":
+        wgt = O.circle_weights(K, w, h, v, add_bg=use_bg)
+    elif prim == "circle_opt":
+        wgt = O.circle_opt_weights(K, v, add_bg=use_bg)
+    else:
+        rays = O.pixel_rays(K, w, h)
+        wgt = O.disc_weights_bg(rays, v, m) if use_bg else O.disc_weights(rays, v, m)
+    if use_bg:
+        color, mask = O.compose_bg(wgt, c, bg)
+    else:
+        color, mask, _, _ = O.compose(wgt, v, m, c, True)
+    tag = f"{prim}_{'bg' if use_bg else 'nobg'}"
+    assert np.abs(color.view(3, h, w).detach().numpy() - g[tag + "_color"]).max() < 1e-6
+    assert np.abs(mask.view(1, h, w).detach().numpy() - g[tag + "_mask"]).max() < 1e-6
+    (gc,) = torch.autograd.grad((color.view(3, h, w) * bg).sum() + mask.sum(), coords)
+    ref = g[tag + "_g_coords"]
+    assert np.abs(gc.numpy() - ref).max() < 5e-5 * max(1.0, np.abs(ref).max())   # fp32 accumulation order of the M x P sums
