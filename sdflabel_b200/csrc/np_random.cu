@@ -67,11 +67,20 @@ extern "C" int sdfr_np_choice4(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int
   std::vector<int32_t> perm((size_t)n);
   for (int32_t d = 0; d < draws; ++d) {
     for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;          // permutation(n): arange, then shuffle
-    for (int64_t i = n - 1; i >= 1; --i) {
-      const uint32_t j = g.interval((uint32_t)i);
-      const int32_t t = perm[(size_t)i];
-      perm[(size_t)i] = perm[j];
+    // Fisher-Yates from the end with numpy's masked rejection, written without a data-dependent branch: a rejected
+    // candidate swaps position i with itself and leaves i where it is (the rejection branch of the textbook loop
+    // mispredicts on a third of the draws and was 2/3 of the time).
+    uint32_t i = (uint32_t)(n - 1);
+    while (i >= 1) {
+      uint32_t mask = i;
+      mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+      const uint32_t v = g.next32() & mask;
+      const uint32_t accept = v <= i ? 1u : 0u;
+      const uint32_t j = accept ? v : i;
+      const int32_t t = perm[i];
+      perm[i] = perm[j];
       perm[j] = t;
+      i -= accept;
     }
     for (int k = 0; k < 4; ++k) samples_out[(size_t)d * 4 + k] = perm[(size_t)k];   // [:size]
   }
