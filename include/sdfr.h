@@ -216,7 +216,7 @@ int sdfr_loss2d(const float* color_dev, const float* target_dev, int height, int
 typedef struct sdfr_refine sdfr_refine;
 
 typedef struct {
-  int32_t batch;        /* detections refined together */
+  int32_t batch;        /* detection slots (capacity); sdfr_refine_set_active picks how many a run covers */
   int32_t density;      /* Grid3D density D (config_refine.ini:11) */
   int32_t max_width;    /* crop capacity in pixels */
   int32_t max_height;
@@ -237,13 +237,36 @@ void sdfr_refine_destroy(sdfr_refine* r);
  * invert here; nocs_host: [3,th,tw] CSS NOCS
  * prediction (nearest-resized to the crop on the device, optimizer.py:135-137);
  * lidar_host: [n_lidar,3] un-scaled LIDAR crop (optimizer.py:84); the initial
- * parameters follow get_opt_params (optimizer.py:26-40). */
+ * parameters follow get_opt_params (optimizer.py:26-40) and may be NULL when
+ * sdfr_refine_import supplies them from device memory.  width / height must fit
+ * max_width / max_height (SDFR_E_CAPACITY otherwise).  The optimiser state of
+ * the slot (Adam moments, step count) is reset: a new Optimizer (optimizer.py:46-52). */
 int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_host, const float* kinv_host, int width,
                               int height, const float* nocs_host, int th, int tw, const float* lidar_host,
                               int n_lidar, const float* yaw_host, const float* trans_host,
                               const float* scale_host, const float* latent_host, void* stream);
 
-/* Enqueue `iters` iterations for all detections. */
+/* The engine is created for cfg.batch detection SLOTS; the next runs cover slots [0, count).  Frames with
+ * different numbers of detections share one engine: nothing is re-allocated, and one CUDA graph per
+ * (count, crop size class) is captured on first use and replayed afterwards. */
+int sdfr_refine_set_active(sdfr_refine* r, int count);
+
+/* Reads the initial parameters of slot b from caller-owned DEVICE buffers (yaw [1], trans [3], scale [1],
+ * latent [L]; any may be NULL) with one stream-ordered launch, after sdfr_refine_set_detection: the
+ * `params` tensors of optimizer.py:26-30 never travel through the host. */
+int sdfr_refine_import(sdfr_refine* r, int b, const float* yaw_dev, const float* trans_dev, const float* scale_dev,
+                       const float* latent_dev, void* stream);
+
+/* Adam state of slot b (moments of [yaw, tx, ty, tz] and the step count).  The reference builds its solver
+ * once per Optimizer (optimizer.py:46-52), so repeated optimize() calls on one Optimizer continue the same
+ * Adam state: the Python mirror reads it back after a run (get_..., valid after sdfr_refine_get /
+ * sdfr_refine_get_batch, no synchronisation of its own) and restores it after the next
+ * sdfr_refine_set_detection (set_..., stream-ordered). */
+int sdfr_refine_set_optimizer_state(sdfr_refine* r, int b, const float* adam_m_host, const float* adam_v_host,
+                                    int adam_t, void* stream);
+int sdfr_refine_get_optimizer_state(sdfr_refine* r, int b, float* adam_m_host, float* adam_v_host, int* adam_t);
+
+/* Enqueue `iters` iterations for the active detections. */
 int sdfr_refine_run(sdfr_refine* r, int iters, void* stream);
 
 /* Synchronises `stream` (once) and reads detection b back: params_host =
@@ -253,6 +276,21 @@ int sdfr_refine_run(sdfr_refine* r, int iters, void* stream);
  * fp16 range since the last check (same condition as sdfr_decoder_check, read in the same sync). */
 int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_host, int* n_history,
                     void* stream);
+
+/* The same for all active detections in ONE synchronisation: params_host [active, 5+L],
+ * history_host [active, max_iters, 4] (may be NULL), n_history [active] (may be NULL). */
+int sdfr_refine_get_batch(sdfr_refine* r, float* params_host, float* history_host, int* n_history, void* stream);
+
+/* Largest |coarse sdf - accurate sdf| the engine has measured on pre-selected rows since the last failure
+ * (tensor-core decoder only; 0 otherwise).  sdfr_refine_get fails with SDFR_E_UNSUPPORTED when it exceeds half
+ * the pre-selection margin of 5e-3: a band point could then have been missed by the fp16-operand lattice pass. */
+int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void* stream);
+
+/* Dump-time extents of get_kitti_label (utils/refinement.py:527-541) for all active detections: one more
+ * lattice evaluation with the CURRENT latent as it is (not normalised, refine_css.py:229), band extraction,
+ * min / max of the isosurface points.  extents_host [active, 8] = min xyz, max xyz (un-scaled object frame),
+ * point count, 0.  Overwrites the intermediates of the last iteration; synchronises `stream`. */
+int sdfr_refine_label_extents(sdfr_refine* r, float* extents_host, void* stream);
 
 /* Writes the current parameters of detection b into caller-owned DEVICE buffers (yaw [1], trans [3],
  * scale [1], latent [L]; any may be NULL) with one stream-ordered launch: the in-place update of the
@@ -267,7 +305,9 @@ int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* trans_dev, 
  * 6 normals map [3,H,W], 7 grads [dyaw,dt3,dscale,dlatent_unit(L),dlatent(L)],
  * 8 pre-selected point count m (int32; with the tensor-core decoder a superset of the band), 9 depth,
  * 10 camera-space surfel centres [m,3], 11 front-facing flags [m] (uint8), 12 band flags [m] (uint8: 1 =
- * inside the reference's band |sdf| < 0.03; rows with 0 are ignored by every stage).  Returns the device pointer and element count. */
+ * inside the reference's band |sdf| < 0.03; rows with 0 are ignored by every stage), 13 composited surfel
+ * colours [m,3] (points['rgb']), 14 lattice index of each pre-selected point [m] (int32).  Returns the device
+ * pointer and element count. */
 int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev, int64_t* count);
 /* Asynchronous device-to-device copy of such a view into dst_dev (at most max_count elements). */
 int sdfr_refine_copy_view(sdfr_refine* r, int b, int kind, void* dst_dev, int64_t max_count, void* stream);

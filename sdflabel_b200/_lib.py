@@ -80,7 +80,14 @@ SIGNATURES = {
     "sdfr_refine_destroy": (None, [vp]),
     "sdfr_refine_set_detection": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, vp, C.c_int, C.c_int,
                                             vp, C.c_int, c_float_p, c_float_p, c_float_p, c_float_p, vp]),
+    "sdfr_refine_set_active": (C.c_int, [vp, C.c_int]),
+    "sdfr_refine_import": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "sdfr_refine_set_optimizer_state": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.c_int, vp]),
+    "sdfr_refine_get_optimizer_state": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.POINTER(C.c_int)]),
     "sdfr_refine_run": (C.c_int, [vp, C.c_int, vp]),
+    "sdfr_refine_get_batch": (C.c_int, [vp, c_float_p, c_float_p, C.POINTER(C.c_int), vp]),
+    "sdfr_refine_preselect_error": (C.c_int, [vp, c_float_p, vp]),
+    "sdfr_refine_label_extents": (C.c_int, [vp, c_float_p, vp]),
     "sdfr_refine_get": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.POINTER(C.c_int), vp]),
     "sdfr_refine_export": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "sdfr_refine_view": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]),

@@ -58,6 +58,10 @@ constexpr float kEps32 = 1.1920928955078125e-07f;  // torch.finfo(float32).eps
 constexpr float kWinRadius = 5.0f;     // optimizer.py:200
 constexpr float kNocsThr = 1.0f;       // optimizer.py:200
 constexpr int kMaxWidthFFMA = 512;     // widest layer the kernels accept
+// Margin added to the band threshold (grid.py:43, 0.03) when the lattice pass runs at fp16 operand precision:
+// the accurate second pass sees every true band point as long as the coarse error stays below it.  The engine
+// measures that error on every pre-selected row and refuses results when it exceeds half the margin.
+constexpr float kPreselectMargin = 0.005f;
 
 // ---------------------------------------------------------------------------
 // Decoder (device resident)
@@ -281,6 +285,7 @@ struct BandArgs {
   unsigned char* out_valid; // [batch, cap] 1 where |band_sdf| < final_threshold (the true band)
   float final_threshold;
   long long cap;
+  int* presel_err;          // optional [1]: running max of |sdf[src] - band_sdf| (float bits, atomicMax)
 };
 int launch_band_select(const BandArgs& a, cudaStream_t s);
 int launch_band_surface(const BandArgs& a, cudaStream_t s);

@@ -16,6 +16,8 @@
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <tuple>
 
 #include "loss.cuh"
 
@@ -70,6 +72,8 @@ struct EngineDev {          // passed by value to the engine kernels
   float* partc;             // [B,nbc,16+L]
   float* history;           // [B,max_iters,4]
   float* grads;             // [B,5+2L]
+  int* presel_err;          // [1] max |coarse sdf - accurate sdf| over the pre-selected rows since the last read (float bits)
+  float* extents;           // [B,8] label extents: min xyz, max xyz, surfel count, pad
   SplatView* views;         // [B]
 };
 
@@ -148,8 +152,10 @@ __global__ void __launch_bounds__(LB) loss2d_batch_kernel(EngineDev E) {
     double ts = 0.0, th = 0.0;
     int tc = 0;
     for (int w = 0; w < LB / 32; ++w) { ts += s_sum[w]; th += s_hw[w]; tc += s_cnt[w]; }
-    double* o = E.part2 + ((size_t)b * E.nb2 + blockIdx.x) * 3;
-    o[0] = ts; o[1] = (double)tc; o[2] = th;
+    if ((int)blockIdx.x < E.nb2) {
+      double* o = E.part2 + ((size_t)b * E.nb2 + blockIdx.x) * 3;
+      o[0] = ts; o[1] = (double)tc; o[2] = th;
+    }
   }
 }
 
@@ -406,6 +412,76 @@ __global__ void __launch_bounds__(LB) update_kernel(EngineDev E) {
   for (int k = 0; k < L; ++k) E.latent[b * L + k] = E.latent[b * L + k] - 0.00003f * g[5 + L + k];
 }
 
+// ---- parameters straight from / to the caller's device tensors (optimizer.py:26-30) ---------------
+__global__ void import_params_kernel(DetState* __restrict__ det, float* __restrict__ latent, int L,
+                                     const float* __restrict__ yaw, const float* __restrict__ trans,
+                                     const float* __restrict__ scale, const float* __restrict__ latent_in) {
+  const int t = threadIdx.x;
+  if (t == 0 && yaw) det->yaw = yaw[0];
+  if (t < 3 && trans) det->trans[t] = trans[t];
+  if (t == 0 && scale) det->scale = scale[0];
+  if (latent_in) for (int i = t; i < L; i += blockDim.x) latent[i] = latent_in[i];
+}
+
+__global__ void export_params_kernel(const DetState* __restrict__ det, const float* __restrict__ latent, int L,
+                                     float* __restrict__ yaw, float* __restrict__ trans, float* __restrict__ scale,
+                                     float* __restrict__ latent_out) {
+  const int t = threadIdx.x;
+  if (t == 0 && yaw) yaw[0] = det->yaw;
+  if (t < 3 && trans) trans[t] = det->trans[t];
+  if (t == 0 && scale) scale[0] = det->scale;
+  if (latent_out) for (int i = t; i < L; i += blockDim.x) latent_out[i] = latent[i];
+}
+
+// ---- dump-time label extents (utils/refinement.py:527-541) ------------------------------------------
+// get_kitti_label evaluates the decoder with the refined latent AS IS (not normalised, refine_css.py:229)
+__global__ void raw_latent_kernel(EngineDev E) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < E.batch * E.L) E.latent_unit[i] = E.latent[i];
+}
+
+// min / max of the band's isosurface points of one detection (exact: min and max commute with the
+// reference's later multiplication by the positive scale)
+__global__ void __launch_bounds__(LB) extent_kernel(EngineDev E) {
+  __shared__ float s_lo[3][LB / 32], s_hi[3][LB / 32];
+  __shared__ int s_n[LB / 32];
+  const int b = blockIdx.x;
+  const int m = min(E.surf_count[b], (int)E.cap);
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int n = 0;
+  for (int i = threadIdx.x; i < m; i += LB) {
+    if (!E.surf_valid[(size_t)b * E.cap + i]) continue;
+    const float* p = E.surf_pts + ((size_t)b * E.cap + i) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], p[c]); hi[c] = fmaxf(hi[c], p[c]); }
+    ++n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int c = 0; c < 3; ++c) { s_lo[c][threadIdx.x >> 5] = lo[c]; s_hi[c][threadIdx.x >> 5] = hi[c]; }
+    s_n[threadIdx.x >> 5] = n;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tn = 0;
+    for (int w = 0; w < LB / 32; ++w) {
+      for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], s_lo[c][w]); hi[c] = fmaxf(hi[c], s_hi[c][w]); }
+      tn += s_n[w];
+    }
+    float* o = E.extents + (size_t)b * 8;
+    for (int c = 0; c < 3; ++c) { o[c] = lo[c]; o[3 + c] = hi[c]; }
+    o[6] = (float)tn; o[7] = 0.f;
+  }
+}
+
 }  // namespace
 
 }  // namespace sdfr
@@ -423,13 +499,17 @@ struct sdfr_refine {
   std::vector<SplatView> views_host;
   std::vector<float*> nocs_dev;       // per-detection staging of the un-resized NOCS prediction
   std::vector<size_t> nocs_cap;
-  int max_w_set, max_h_set;
-  // one refine iteration captured as a CUDA graph (16 kernel nodes, all arguments are device-resident
-  // state, so the same executable graph is replayed every iteration)
-  cudaGraphExec_t graph_exec;
+  std::vector<int> det_w, det_h;      // crop of each slot (0 = never set)
+  int active;                         // detections the next run covers: slots [0, active)
+  // One refine iteration captured as a CUDA graph (all arguments are device-resident state, so the same
+  // executable graph is replayed every iteration).  The launch shapes depend on the number of active
+  // detections and on the largest active crop, rounded up to a power of two: one graph per such key is kept, so
+  // a sequence of frames with 1-8 detections and ragged crops captures a handful of graphs once.
+  std::map<std::tuple<int, int, int>, std::pair<cudaGraphExec_t, int>> graphs;
   cudaStream_t capture_stream;   // the caller's stream may be the legacy default stream, which cannot be captured
-  int graph_w, graph_h, graph_nodes, runs;
+  int runs;
   std::vector<int> iters_enqueued;   // per detection: iterations launched since its last set_detection
+  std::vector<DetState> host_state;  // what the last sdfr_refine_get / get_batch read back
 };
 
 namespace {
@@ -452,6 +532,21 @@ void invert3x3(const float* k, float* o) {
   o[6] = (float)((d * h - e * g) / det); o[7] = (float)((b * g - a * h) / det); o[8] = (float)((a * e - b * d) / det);
 }
 
+int pow2_ceil(int v, int lo) {
+  int q = lo;
+  while (q < v) q <<= 1;
+  return q;
+}
+
+// launch shape of the per-pixel kernels: the largest crop among the active detections, rounded up to a power
+// of two (>= 32) and clamped to the capacity; kernels exit early outside each detection's own crop
+void active_shape(const sdfr_refine* r, int* qw, int* qh) {
+  int mw = 0, mh = 0;
+  for (int b = 0; b < r->active; ++b) { mw = std::max(mw, r->det_w[b]); mh = std::max(mh, r->det_h[b]); }
+  *qw = std::min(pow2_ceil(mw, 32), std::max(r->cfg.max_width, mw));
+  *qh = std::min(pow2_ceil(mh, 32), std::max(r->cfg.max_height, mh));
+}
+
 }  // namespace
 
 extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg, sdfr_refine** out) {
@@ -463,9 +558,13 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   sdfr_refine* r = new sdfr_refine();
   r->dec = dec;
   r->cfg = *cfg;
-  r->max_w_set = r->max_h_set = 0;
-  r->graph_exec = nullptr; r->capture_stream = nullptr; r->graph_w = r->graph_h = 0; r->graph_nodes = 0; r->runs = 0;
-  r->iters_enqueued.assign((size_t)std::max(cfg->batch, 1), 0);
+  r->capture_stream = nullptr; r->runs = 0;
+  r->active = cfg->batch;
+  r->iters_enqueued.assign((size_t)cfg->batch, 0);
+  r->det_w.assign((size_t)cfg->batch, 0);
+  r->det_h.assign((size_t)cfg->batch, 0);
+  r->host_state.resize((size_t)cfg->batch);
+  memset(r->host_state.data(), 0, sizeof(DetState) * (size_t)cfg->batch);
   EngineDev& E = r->E;
   const int B = cfg->batch, L = dec->dev.latent_size;
   E.batch = B; E.L = L; E.in0 = L + 3;
@@ -491,6 +590,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.l3rec, B * E.cap * 4); A(E.l3dot, B * E.cap); A(E.l2rec, (size_t)B * E.max_pixels * 4);
   A(E.part2, (size_t)B * E.nb2 * 3); A(E.part3, (size_t)B * E.nb3 * 3); A(E.partc, (size_t)B * E.nbc * (16 + L));
   A(E.history, (size_t)B * E.max_iters * 4); A(E.grads, (size_t)B * (5 + 2 * L));
+  A(E.presel_err, 4); A(E.extents, (size_t)B * 8);
   A(E.views, B);
   r->views_host.resize(B);
   r->nocs_dev.assign(B, nullptr);
@@ -523,11 +623,18 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
 
 extern "C" void sdfr_refine_destroy(sdfr_refine* r) {
   if (!r) return;
-  if (r->graph_exec) cudaGraphExecDestroy(r->graph_exec);
+  for (auto& g : r->graphs) if (g.second.first) cudaGraphExecDestroy(g.second.first);
   if (r->capture_stream) cudaStreamDestroy(r->capture_stream);
   for (void* p : r->allocs) cudaFree(p);
   for (float* p : r->nocs_dev) if (p) cudaFree(p);
   delete r;
+}
+
+extern "C" int sdfr_refine_set_active(sdfr_refine* r, int count) {
+  SDFR_REQUIRE(r && count >= 1 && count <= r->cfg.batch, SDFR_E_INVALID, "active count %d outside [1, %d]", count,
+               r ? r->cfg.batch : 0);
+  r->active = count;
+  return SDFR_OK;
 }
 
 extern "C" int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_host, const float* kinv_host,
@@ -535,24 +642,25 @@ extern "C" int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_h
                                          const float* lidar_host, int n_lidar, const float* yaw_host,
                                          const float* trans_host, const float* scale_host,
                                          const float* latent_host, void* stream) {
-  SDFR_REQUIRE(r && k_host && nocs_host && yaw_host && trans_host && scale_host && latent_host, SDFR_E_INVALID,
-               "null argument");
+  SDFR_REQUIRE(r && k_host && nocs_host, SDFR_E_INVALID, "null argument");
   SDFR_REQUIRE(b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "detection index %d out of range", b);
-  SDFR_REQUIRE(width > 0 && height > 0 && width * height <= r->E.max_pixels, SDFR_E_CAPACITY,
-               "crop %dx%d exceeds the configured capacity of %d pixels", width, height, r->E.max_pixels);
+  SDFR_REQUIRE(width > 0 && height > 0 && width <= r->cfg.max_width && height <= r->cfg.max_height, SDFR_E_CAPACITY,
+               "crop %dx%d exceeds the configured capacity %dx%d", width, height, r->cfg.max_width, r->cfg.max_height);
   SDFR_REQUIRE(n_lidar >= 0 && n_lidar <= r->E.max_lidar, SDFR_E_CAPACITY, "%d lidar points exceed capacity %d",
                n_lidar, r->E.max_lidar);
+  SDFR_REQUIRE(n_lidar == 0 || lidar_host, SDFR_E_INVALID, "null lidar array");
   r->iters_enqueued[b] = 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   EngineDev& E = r->E;
   DetState D;
-  memset(&D, 0, sizeof(D));
+  memset(&D, 0, sizeof(D));     // fresh optimiser state: a new Optimizer (optimizer.py:46-52)
   D.width = width; D.height = height; D.n_lidar = n_lidar; D.target_ready = 1;
-  D.yaw = yaw_host[0];
-  D.trans[0] = trans_host[0]; D.trans[1] = trans_host[1]; D.trans[2] = trans_host[2];
-  D.scale = scale_host[0];
+  if (yaw_host) D.yaw = yaw_host[0];
+  if (trans_host) { D.trans[0] = trans_host[0]; D.trans[1] = trans_host[1]; D.trans[2] = trans_host[2]; }
+  if (scale_host) D.scale = scale_host[0];
   SDFR_CUDA(cudaMemcpyAsync(E.det + b, &D, sizeof(D), cudaMemcpyHostToDevice, s));
-  SDFR_CUDA(cudaMemcpyAsync(E.latent + (size_t)b * E.L, latent_host, E.L * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (latent_host)
+    SDFR_CUDA(cudaMemcpyAsync(E.latent + (size_t)b * E.L, latent_host, E.L * sizeof(float), cudaMemcpyHostToDevice, s));
   if (n_lidar > 0)
     SDFR_CUDA(cudaMemcpyAsync(E.lidar + (size_t)b * E.max_lidar * 3, lidar_host, (size_t)n_lidar * 3 * sizeof(float),
                               cudaMemcpyHostToDevice, s));
@@ -575,16 +683,59 @@ extern "C" int sdfr_refine_set_detection(sdfr_refine* r, int b, const float* k_h
   if (kinv_host) for (int i = 0; i < 9; ++i) V.kinv[i] = kinv_host[i];
   else invert3x3(k_host, V.kinv);
   SDFR_CUDA(cudaMemcpyAsync(E.views + b, &V, sizeof(V), cudaMemcpyHostToDevice, s));
-  r->max_w_set = std::max(r->max_w_set, width);
-  r->max_h_set = std::max(r->max_h_set, height);
+  r->det_w[b] = width;
+  r->det_h[b] = height;
   return SDFR_OK;
 }
 
-// enqueues the kernels of ONE refine iteration on `s`
-static int enqueue_iteration(sdfr_refine* r, cudaStream_t s) {
+extern "C" int sdfr_refine_import(sdfr_refine* r, int b, const float* yaw_dev, const float* trans_dev,
+                                  const float* scale_dev, const float* latent_dev, void* stream) {
+  SDFR_REQUIRE(r && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
   EngineDev& E = r->E;
-  const int B = E.batch;
-  MlpInputs in;
+  import_params_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(E.det + b, E.latent + (size_t)b * E.L, E.L,
+                                                                             yaw_dev, trans_dev, scale_dev, latent_dev);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_set_optimizer_state(sdfr_refine* r, int b, const float* adam_m_host,
+                                               const float* adam_v_host, int adam_t, void* stream) {
+  SDFR_REQUIRE(r && adam_m_host && adam_v_host && b >= 0 && b < r->cfg.batch && adam_t >= 0, SDFR_E_INVALID,
+               "bad argument");
+  struct { float m[4], v[4]; int t; } st;
+  static_assert(offsetof(DetState, adam_v) == offsetof(DetState, adam_m) + 16 &&
+                offsetof(DetState, adam_t) == offsetof(DetState, adam_m) + 32, "Adam fields must be contiguous");
+  memcpy(st.m, adam_m_host, sizeof(st.m));
+  memcpy(st.v, adam_v_host, sizeof(st.v));
+  st.t = adam_t;
+  SDFR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(r->E.det + b) + offsetof(DetState, adam_m), &st, 36,
+                            cudaMemcpyHostToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_get_optimizer_state(sdfr_refine* r, int b, float* adam_m_host, float* adam_v_host,
+                                               int* adam_t) {
+  SDFR_REQUIRE(r && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
+  const DetState& D = r->host_state[b];
+  if (adam_m_host) memcpy(adam_m_host, D.adam_m, sizeof(D.adam_m));
+  if (adam_v_host) memcpy(adam_v_host, D.adam_v, sizeof(D.adam_v));
+  if (adam_t) *adam_t = D.adam_t;
+  return SDFR_OK;
+}
+
+namespace {
+
+struct IterPlan {
+  MlpInputs in, in_band;
+  BandArgs ba;
+  bool coarse;
+  int impl;
+};
+
+IterPlan make_iter_plan(sdfr_refine* r, int B) {
+  EngineDev& E = r->E;
+  IterPlan p;
+  MlpInputs& in = p.in;
   in.inputs = nullptr;
   in.latent_unit = E.latent_unit;
   in.lattice = make_lattice(r->cfg.density);
@@ -593,58 +744,78 @@ static int enqueue_iteration(sdfr_refine* r, cudaStream_t s) {
   in.index = nullptr;
   in.count_dev = nullptr;
   in.small_tiles = 0;
-  MlpInputs in_band = in;               // same lattice / latents, rows gathered through band_src
-  in_band.index = E.band_src;
-  in_band.count_dev = E.band_total;
-  in_band.small_tiles = B <= 4;         // a few detections: ~2 000 rows each, spread them over all SMs
+  p.in_band = in;                       // same lattice / latents, rows gathered through band_src
+  p.in_band.index = E.band_src;
+  p.in_band.count_dev = E.band_total;
+  p.in_band.small_tiles = B <= 4;       // a few detections: ~2 000 rows each, spread them over all SMs
   int impl = r->cfg.mlp_impl;
   if (impl == SDFR_MLP_AUTO) impl = r->dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
-  BandArgs ba;
+  p.impl = impl;
   // Pre-selection threshold = band (grid.py:43) + margin.  With the tensor-core decoder the lattice pass runs
-  // at fp16 operand precision (error ~3e-4, checked in tests to stay below half the margin); the accurate
-  // second pass then decides the real band, so the result is the same set the accurate kernel alone gives.
-  const bool coarse = impl == SDFR_MLP_TCGEN05;
-  ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B; ba.threshold = 0.03f + (coarse ? 0.005f : 0.f);
+  // at fp16 operand precision (error ~3e-4); the accurate second pass then decides the real band, so the result
+  // is the same set the accurate kernel alone gives as long as the coarse error stays inside the margin.  The
+  // error is MEASURED on every pre-selected row (band_surface_kernel) and checked by sdfr_refine_get.
+  p.coarse = impl == SDFR_MLP_TCGEN05;
+  BandArgs& ba = p.ba;
+  ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B;
+  ba.threshold = 0.03f + (p.coarse ? kPreselectMargin : 0.f);
   ba.out_valid = E.surf_valid; ba.final_threshold = 0.03f;
   ba.block_counts = E.band_block_counts; ba.block_prefix = E.band_block_prefix; ba.det_start = E.band_det_start;
   ba.det_count = E.surf_count; ba.total = E.band_total; ba.band_src = E.band_src;
   ba.band_sdf = E.band_sdf; ba.band_dinput = E.dinput; ba.in0 = E.in0; ba.latent = E.L;
   ba.out_pts = E.surf_pts; ba.out_nrm = E.surf_nrm; ba.out_idx = E.surf_idx; ba.out_glat = E.surf_glat; ba.cap = E.cap;
-  const int maxw = r->max_w_set, maxh = r->max_h_set;
+  ba.presel_err = p.coarse ? E.presel_err : nullptr;
+  return p;
+}
+
+// lattice pass -> band select -> accurate pass on the selected rows -> isosurface projection
+int enqueue_surface(sdfr_refine* r, const IterPlan& p, cudaStream_t s) {
+  EngineDev& E = r->E;
+  int rc = p.coarse ? launch_mlp_tc_coarse(r->dec, p.in, E.sdf, s) : launch_mlp_ffma(r->dec, p.in, E.sdf, nullptr, s);
+  if (rc) return rc;
+  if ((rc = launch_band_select(p.ba, s))) return rc;
+  rc = p.impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, p.in_band, E.band_sdf, E.dinput, s)
+                                  : launch_mlp_ffma(r->dec, p.in_band, E.band_sdf, E.dinput, s);
+  if (rc) return rc;
+  return launch_band_surface(p.ba, s);
+}
+
+// enqueues the kernels of ONE refine iteration of detections [0, B) on `s`
+int enqueue_iteration(sdfr_refine* r, int B, int qw, int qh, cudaStream_t s) {
+  EngineDev E = r->E;
+  E.batch = B;
+  const IterPlan p = make_iter_plan(r, B);
   int rc;
-  {
-    iter_begin_kernel<<<B, 32, 0, s>>>(E);
-    SDFR_LAUNCH_CHECK();
-    // sdf over the whole lattice (forward only), then sdf + input gradient for the band points
-    rc = coarse ? launch_mlp_tc_coarse(r->dec, in, E.sdf, s) : launch_mlp_ffma(r->dec, in, E.sdf, nullptr, s);
-    if (rc) return rc;
-    if ((rc = launch_band_select(ba, s))) return rc;
-    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, in_band, E.band_sdf, E.dinput, s)
-                                  : launch_mlp_ffma(r->dec, in_band, E.band_sdf, E.dinput, s);
-    if (rc) return rc;
-    if ((rc = launch_band_surface(ba, s))) return rc;
-    if ((rc = launch_project(E.views, B, (int)E.cap, s))) return rc;
-    if ((rc = launch_splat_forward(E.views, B, maxw, maxh, s))) return rc;
-    loss2d_batch_kernel<<<dim3((maxw * maxh + LB - 1) / LB, B), LB, 0, s>>>(E);
-    SDFR_LAUNCH_CHECK();
-    loss3d_batch_kernel<<<dim3(E.nb3, B), LB, 0, s>>>(E);
-    SDFR_LAUNCH_CHECK();
-    grad_prep_kernel<<<dim3((maxw * maxh + LB - 1) / LB, B), LB, 0, s>>>(E);
-    SDFR_LAUNCH_CHECK();
-    if ((rc = launch_splat_backward(E.views, B, (int)E.cap, s))) return rc;
-    chain_kernel<<<dim3(E.nbc, B), LB, 0, s>>>(E);
-    SDFR_LAUNCH_CHECK();
-    update_kernel<<<B, LB, 0, s>>>(E);
-    SDFR_LAUNCH_CHECK();
-  }
+  iter_begin_kernel<<<B, 32, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  if ((rc = enqueue_surface(r, p, s))) return rc;
+  if ((rc = launch_project(E.views, B, (int)E.cap, s))) return rc;
+  if ((rc = launch_splat_forward(E.views, B, qw, qh, s))) return rc;
+  loss2d_batch_kernel<<<dim3((qw * qh + LB - 1) / LB, B), LB, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  loss3d_batch_kernel<<<dim3(E.nb3, B), LB, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  grad_prep_kernel<<<dim3((qw * qh + LB - 1) / LB, B), LB, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  if ((rc = launch_splat_backward(E.views, B, (int)E.cap, s))) return rc;
+  chain_kernel<<<dim3(E.nbc, B), LB, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  update_kernel<<<B, LB, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
+
+}  // namespace
 
 extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   SDFR_REQUIRE(r && iters >= 0, SDFR_E_INVALID, "bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  SDFR_REQUIRE(r->max_w_set > 0 && r->max_h_set > 0, SDFR_E_INVALID, "no detection has been set");
-  for (int& c : r->iters_enqueued) c = (int)std::min<long long>((long long)c + iters, 1 << 30);
+  const int B = r->active;
+  for (int b = 0; b < B; ++b)
+    SDFR_REQUIRE(r->det_w[b] > 0, SDFR_E_INVALID, "detection %d of the %d active ones has not been set", b, B);
+  int qw, qh;
+  active_shape(r, &qw, &qh);
+  for (int b = 0; b < B; ++b) r->iters_enqueued[b] = (int)std::min<long long>((long long)r->iters_enqueued[b] + iters, 1 << 30);
   static int use_graph = -1;
   if (use_graph < 0) { const char* e = getenv("SDFR_REFINE_GRAPH"); use_graph = e ? atoi(e) : 1; }
   int rc;
@@ -652,48 +823,74 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   // The first call runs un-captured (lazy attribute setup inside the launchers must not happen during capture).
   if (!use_graph || r->runs == 0) {
     for (; done < (use_graph ? std::min(iters, 1) : iters); ++done)
-      if ((rc = enqueue_iteration(r, s))) return rc;
+      if ((rc = enqueue_iteration(r, B, qw, qh, s))) return rc;
   }
   r->runs += 1;
   if (done == iters) return SDFR_OK;
-  if (!r->graph_exec || r->graph_w != r->max_w_set || r->graph_h != r->max_h_set) {
-    if (r->graph_exec) { cudaGraphExecDestroy(r->graph_exec); r->graph_exec = nullptr; }
+  const auto key = std::make_tuple(B, qw, qh);
+  auto it = r->graphs.find(key);
+  if (it == r->graphs.end()) {
     cudaGraph_t graph = nullptr;
     const long long before = sdfr_launch_count();
     if (!r->capture_stream) SDFR_CUDA(cudaStreamCreateWithFlags(&r->capture_stream, cudaStreamNonBlocking));
     SDFR_CUDA(cudaStreamBeginCapture(r->capture_stream, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_iteration(r, r->capture_stream);
+    rc = enqueue_iteration(r, B, qw, qh, r->capture_stream);
     cudaError_t ce = cudaStreamEndCapture(r->capture_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     SDFR_CUDA(ce);
-    r->graph_nodes = (int)(sdfr_launch_count() - before);
-    count_launch(-r->graph_nodes);            // capturing launched nothing
-    SDFR_CUDA(cudaGraphInstantiate(&r->graph_exec, graph, 0));
+    const int nodes = (int)(sdfr_launch_count() - before);
+    count_launch(-nodes);                     // capturing launched nothing
+    cudaGraphExec_t exec = nullptr;
+    SDFR_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
-    r->graph_w = r->max_w_set; r->graph_h = r->max_h_set;
+    it = r->graphs.emplace(key, std::make_pair(exec, nodes)).first;
   }
   for (; done < iters; ++done) {
-    SDFR_CUDA(cudaGraphLaunch(r->graph_exec, s));
-    count_launch(r->graph_nodes);
+    SDFR_CUDA(cudaGraphLaunch(it->second.first, s));
+    count_launch(it->second.second);
   }
   return SDFR_OK;
 }
+
+namespace {
+
+// Checks riding on the read-back synchronisation: the fp16-range flag of the tensor-core decoder and the
+// measured error of its fp16-operand pre-selection pass.
+int check_decoder_flags(sdfr_refine* r, int overflow, int presel_bits, cudaStream_t s) {
+  float presel = 0.f;
+  memcpy(&presel, &presel_bits, sizeof(float));
+  if (overflow) {
+    tc_overflow_reset(r->dec, s);
+    SDFR_REQUIRE(false, SDFR_E_UNSUPPORTED,
+                 "an activation left the fp16 range of the split-operand tensor-core kernel; use SDFR_MLP_FFMA for this network");
+  }
+  if (!(presel <= kPreselectMargin * 0.5f)) {     // also catches a NaN sdf
+    cudaMemsetAsync(r->E.presel_err, 0, sizeof(int), s);
+    SDFR_REQUIRE(false, SDFR_E_UNSUPPORTED,
+                 "the fp16-operand lattice pass is off by %.2e near the band (limit %.2e): band points may have been "
+                 "missed by the pre-selection; use SDFR_MLP_FFMA for this network", presel, kPreselectMargin * 0.5f);
+  }
+  return SDFR_OK;
+}
+
+}  // namespace
 
 extern "C" int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float* history_host, int* n_history,
                                void* stream) {
   SDFR_REQUIRE(r && params_host && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   EngineDev& E = r->E;
-  DetState D;
-  int overflow = 0;
+  DetState& D = r->host_state[b];
+  int overflow = 0, presel_bits = 0;
   // everything the caller reads back rides on ONE stream synchronisation: state, latent, the history rows
-  // the host knows were enqueued, and the fp16-range flag of the tensor-core decoder
+  // the host knows were enqueued, and the two decoder flags
   const int nh_host = std::min(r->iters_enqueued[b], E.max_iters);
   SDFR_CUDA(cudaMemcpyAsync(&D, E.det + b, sizeof(D), cudaMemcpyDeviceToHost, s));
   SDFR_CUDA(cudaMemcpyAsync(params_host + 5, E.latent + (size_t)b * E.L, E.L * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (history_host && nh_host > 0)
     SDFR_CUDA(cudaMemcpyAsync(history_host, E.history + (size_t)b * E.max_iters * 4, (size_t)nh_host * 4 * sizeof(float),
                               cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(&presel_bits, E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
   int rc = tc_overflow_flag_enqueue(r->dec, &overflow, s);
   if (rc) return rc;
   SDFR_CUDA(cudaStreamSynchronize(s));
@@ -706,22 +903,43 @@ extern "C" int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float*
                               cudaMemcpyDeviceToHost, s));
     SDFR_CUDA(cudaStreamSynchronize(s));
   }
-  if (overflow) {
-    tc_overflow_reset(r->dec, s);
-    SDFR_REQUIRE(false, SDFR_E_UNSUPPORTED,
-                 "an activation left the fp16 range of the split-operand tensor-core kernel; use SDFR_MLP_FFMA for this network");
-  }
-  return SDFR_OK;
+  return check_decoder_flags(r, overflow, presel_bits, s);
 }
 
-static __global__ void export_params_kernel(const DetState* __restrict__ det, const float* __restrict__ latent, int L,
-                                     float* __restrict__ yaw, float* __restrict__ trans, float* __restrict__ scale,
-                                     float* __restrict__ latent_out) {
-  const int t = threadIdx.x;
-  if (t == 0 && yaw) yaw[0] = det->yaw;
-  if (t < 3 && trans) trans[t] = det->trans[t];
-  if (t == 0 && scale) scale[0] = det->scale;
-  if (latent_out) for (int i = t; i < L; i += blockDim.x) latent_out[i] = latent[i];
+extern "C" int sdfr_refine_get_batch(sdfr_refine* r, float* params_host, float* history_host, int* n_history,
+                                     void* stream) {
+  SDFR_REQUIRE(r && params_host, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  EngineDev& E = r->E;
+  const int B = r->active, L = E.L, W = 5 + L;
+  int overflow = 0, presel_bits = 0;
+  std::vector<float> lat((size_t)B * L);
+  SDFR_CUDA(cudaMemcpyAsync(r->host_state.data(), E.det, sizeof(DetState) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(lat.data(), E.latent, sizeof(float) * (size_t)B * L, cudaMemcpyDeviceToHost, s));
+  if (history_host)
+    SDFR_CUDA(cudaMemcpyAsync(history_host, E.history, sizeof(float) * (size_t)B * E.max_iters * 4, cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(&presel_bits, E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int rc = tc_overflow_flag_enqueue(r->dec, &overflow, s);
+  if (rc) return rc;
+  SDFR_CUDA(cudaStreamSynchronize(s));
+  for (int b = 0; b < B; ++b) {
+    const DetState& D = r->host_state[b];
+    float* p = params_host + (size_t)b * W;
+    p[0] = D.yaw; p[1] = D.trans[0]; p[2] = D.trans[1]; p[3] = D.trans[2]; p[4] = D.scale;
+    memcpy(p + 5, lat.data() + (size_t)b * L, sizeof(float) * L);
+    if (n_history) n_history[b] = std::min(D.iter, E.max_iters);
+  }
+  return check_decoder_flags(r, overflow, presel_bits, s);
+}
+
+extern "C" int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void* stream) {
+  SDFR_REQUIRE(r && err_host, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int bits = 0;
+  SDFR_CUDA(cudaMemcpyAsync(&bits, r->E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaStreamSynchronize(s));
+  memcpy(err_host, &bits, sizeof(float));
+  return SDFR_OK;
 }
 
 extern "C" int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* trans_dev, float* scale_dev,
@@ -731,6 +949,24 @@ extern "C" int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* 
   EngineDev& E = r->E;
   export_params_kernel<<<1, 32, 0, s>>>(E.det + b, E.latent + (size_t)b * E.L, E.L, yaw_dev, trans_dev, scale_dev, latent_dev);
   SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_label_extents(sdfr_refine* r, float* extents_host, void* stream) {
+  SDFR_REQUIRE(r && extents_host, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int B = r->active;
+  EngineDev E = r->E;
+  E.batch = B;
+  const IterPlan p = make_iter_plan(r, B);
+  raw_latent_kernel<<<(B * E.L + 127) / 128, 128, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  int rc = enqueue_surface(r, p, s);
+  if (rc) return rc;
+  extent_kernel<<<B, LB, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  SDFR_CUDA(cudaMemcpyAsync(extents_host, E.extents, sizeof(float) * 8 * (size_t)B, cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaStreamSynchronize(s));
   return SDFR_OK;
 }
 
@@ -753,6 +989,8 @@ extern "C" int sdfr_refine_view(sdfr_refine* r, int b, int kind, void** ptr_dev,
     case 10: *ptr_dev = V.cam_v; *count = E.cap * 3; break;
     case 11: *ptr_dev = V.front; *count = E.cap; break;
     case 12: *ptr_dev = E.surf_valid + (size_t)b * E.cap; *count = E.cap; break;
+    case 13: *ptr_dev = V.cam_c; *count = E.cap * 3; break;
+    case 14: *ptr_dev = E.surf_idx + (size_t)b * E.cap; *count = E.cap; break;
     default: SDFR_REQUIRE(false, SDFR_E_INVALID, "unknown view kind %d", kind);
   }
   return SDFR_OK;

@@ -185,6 +185,13 @@ __global__ void __launch_bounds__(256) band_surface_kernel(BandArgs a) {
   if (a.out_glat)
     for (int c = 0; c < a.latent; ++c) a.out_glat[o * a.latent + c] = g[c];
   if (a.out_valid) a.out_valid[o] = in_band(f, a.final_threshold) ? 1 : 0;
+  if (a.presel_err) {
+    // measured error of the coarse lattice pass on the rows it pre-selected (all of them lie near the band,
+    // the only place where that error can change the result); non-negative floats order like their bit patterns
+    const unsigned live = __activemask();         // the warp's threads past `total` have returned
+    const unsigned bits = __reduce_max_sync(live, __float_as_uint(fabsf(a.sdf[src] - f)));
+    if ((threadIdx.x & 31) == (__ffs(live) - 1) && bits) atomicMax(a.presel_err, (int)bits);
+  }
 }
 
 }  // namespace

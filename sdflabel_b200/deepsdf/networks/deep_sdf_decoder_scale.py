@@ -147,9 +147,26 @@ class Decoder(nn.Module):
         self._native_key = None
 
     # ---- native handle ---------------------------------------------------------------------
+    # The folded weights live in libsdfr's device memory; the handle is rebuilt whenever the parameters may
+    # have changed: load_state_dict / .to() / .float() / ... invalidate it explicitly, in-place edits through
+    # autograd-visible ops are caught by the tensors' version counters.  Raw ``.data`` writes bypass both
+    # (PyTorch does not count them): call ``invalidate_native()`` after such an edit.
+    def invalidate_native(self):
+        self._native = None
+        self._native_key = None
+        self.__dict__.pop('_param_list', None)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_native()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_native()
+        return super().load_state_dict(*args, **kwargs)
+
     def _param_key(self):
-        # (walking the module tree costs ~100 us per call; the Parameter objects never change after __init__,
-        #  .to() / load_state_dict() update them in place and bump data_ptr / _version)
+        # (walking the module tree costs ~100 us per call; the module keeps its Parameter objects alive, so a
+        #  data_ptr cannot be recycled by another tensor while it is part of the key)
         plist = self.__dict__.get('_param_list')
         if plist is None:
             plist = self.__dict__['_param_list'] = list(self.parameters())

@@ -55,8 +55,16 @@ def get_opt_params(params, device):
     return params, optim_params
 
 
+def _pow2_ceil(v: int, lo: int) -> int:
+    v = max(int(v), 1)
+    return max(lo, 1 << (v - 1).bit_length())
+
+
 class _Engine:
-    """One sdfr_refine handle (fixed capacities); cached on the decoder object."""
+    """One sdfr_refine handle: ``batch`` detection slots with fixed crop / LIDAR / history capacities,
+    of which a run covers the first ``active``.  Cached on the decoder object and only ever re-created
+    to GROW a capacity, so a sequence of frames with different detection counts and crop sizes
+    allocates (and captures its CUDA graphs) once."""
 
     def __init__(self, native_decoder, batch, density, max_w, max_h, max_lidar, max_iters, w2d, w3d, impl):
         lib = _lib.load()
@@ -68,10 +76,10 @@ class _Engine:
         h = _lib.vp()
         _lib.check(lib.sdfr_refine_create(native_decoder.handle, C.byref(self.cfg), C.byref(h)))
         self.handle = h
+        self.active = batch
         self._pinned: Dict = {}     # persistent pinned staging buffers, keyed by (name, detection)
         self._dirty = set()         # detections whose staging buffers may still be in flight
         self._kcache: Dict = {}
-        self._klast = None
 
     def __del__(self):
         try:
@@ -81,10 +89,9 @@ class _Engine:
         except Exception:
             pass
 
-    def key(self):
+    def capacity(self):
         c = self.cfg
-        return (c.batch, c.density, c.max_width, c.max_height, c.max_lidar, c.max_iters, c.weight_2d, c.weight_3d,
-                c.mlp_impl)
+        return (c.batch, c.max_width, c.max_height, c.max_lidar, c.max_iters)
 
     def _pin(self, key, arr) -> torch.Tensor:
         """float32 host copy in a persistent pinned buffer, so the H2D copy is a true async DMA and
@@ -109,11 +116,10 @@ class _Engine:
 
     def _intrinsics(self, K):
         """(K, K^-1) as contiguous fp32 host tensors; the inverse is torch's own K.float().inverse()
-        (primitives.py:204), cached by value because a crop's K rarely changes between calls."""
-        fast = (K.data_ptr(), K._version) if isinstance(K, torch.Tensor) else None
-        if fast is not None and self._klast is not None and self._klast[0] == fast:
-            return self._klast[1]                # the very tensor of the previous call, untouched
-        k32 = K.detach().float().cpu().contiguous()
+        (primitives.py:204).  Cached by VALUE (the 36 bytes of K): a fresh K tensor per detection usually
+        lands in the allocation the previous one just freed, so nothing about the tensor object identifies it."""
+        k32 = K.detach().float().cpu().contiguous() if isinstance(K, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(np.asarray(K, dtype=np.float32)))
         key = k32.numpy().tobytes()
         hit = self._kcache.get(key)
         if hit is None:
@@ -121,27 +127,54 @@ class _Engine:
                 self._kcache.clear()
             hit = (k32.clone(), k32.inverse().contiguous())
             self._kcache[key] = hit
-        self._klast = (fast, hit)
         return hit
 
-    def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw, trans, scale, latent):
+    def set_detection(self, b, K, width, height, nocs_pred, lidar_np, yaw=None, trans=None, scale=None, latent=None):
+        """Inputs of slot b.  The parameters are host arrays, or all None when ``import_params`` follows."""
         lib = _lib.load()
         k32, kinv = self._intrinsics(K)
         # the previous use of these staging buffers must have been consumed by the device
-        torch.cuda.current_stream().synchronize() if self._pinned_dirty(b) else None
+        if b in self._dirty:
+            torch.cuda.current_stream().synchronize()
+            self._dirty.clear()
         nocs = self._pin(('nocs', b), nocs_pred)
         lidar = self._pin(('lidar', b), np.asarray(lidar_np, dtype=np.float32).reshape(-1, 3))
-        par = [self._pin((n, b), np.asarray(v, dtype=np.float32).reshape(-1))
+        fp = lambda t: C.cast(t.data_ptr(), _lib.c_float_p)
+        par = [None if v is None else fp(self._pin((n, b), np.asarray(v, dtype=np.float32).reshape(-1)))
                for n, v in (('yaw', yaw), ('trans', trans), ('scale', scale), ('latent', latent))]
         self._dirty.add(b)
-        fp = lambda t: C.cast(t.data_ptr(), _lib.c_float_p)
         _lib.check(lib.sdfr_refine_set_detection(
             self.handle, b, fp(k32), fp(kinv), int(width), int(height), nocs.data_ptr(), int(nocs.shape[1]),
-            int(nocs.shape[2]), lidar.data_ptr(), int(lidar.shape[0]), fp(par[0]), fp(par[1]), fp(par[2]), fp(par[3]),
+            int(nocs.shape[2]), lidar.data_ptr(), int(lidar.shape[0]), par[0], par[1], par[2], par[3],
             _lib.stream_ptr()))
 
-    def _pinned_dirty(self, b) -> bool:
-        return b in self._dirty
+    def import_params(self, b, p):
+        """Initial parameters of slot b straight from the caller's device tensors (no host round trip)."""
+        _lib.check(_lib.load().sdfr_refine_import(self.handle, b, p['yaw'].data_ptr(), p['trans'].data_ptr(),
+                                                  p['scale'].data_ptr(), p['latent'].data_ptr(), _lib.stream_ptr()))
+
+    def export_params(self, b, p):
+        _lib.check(_lib.load().sdfr_refine_export(self.handle, b, p['yaw'].data_ptr(), p['trans'].data_ptr(),
+                                                  p['scale'].data_ptr(), p['latent'].data_ptr(), _lib.stream_ptr()))
+
+    def set_active(self, n):
+        _lib.check(_lib.load().sdfr_refine_set_active(self.handle, int(n)))
+        self.active = int(n)
+
+    def set_optimizer_state(self, b, state):
+        m, v, t = state
+        m = np.ascontiguousarray(m, dtype=np.float32)
+        v = np.ascontiguousarray(v, dtype=np.float32)
+        _lib.check(_lib.load().sdfr_refine_set_optimizer_state(self.handle, b, _lib.fptr(m), _lib.fptr(v), int(t),
+                                                               _lib.stream_ptr()))
+
+    def get_optimizer_state(self, b):
+        """(adam_m[4], adam_v[4], adam_t) of slot b as of the last ``get`` / ``get_batch``."""
+        m = np.zeros(4, dtype=np.float32)
+        v = np.zeros(4, dtype=np.float32)
+        t = C.c_int(0)
+        _lib.check(_lib.load().sdfr_refine_get_optimizer_state(self.handle, b, _lib.fptr(m), _lib.fptr(v), C.byref(t)))
+        return m, v, t.value
 
     def run(self, iters):
         _lib.check(_lib.load().sdfr_refine_run(self.handle, int(iters), _lib.stream_ptr()))
@@ -151,13 +184,41 @@ class _Engine:
         params = np.zeros(5 + L, dtype=np.float32)
         hist = np.zeros((self.cfg.max_iters, 4), dtype=np.float32)
         nh = C.c_int(0)
-        _lib.check(_lib.load().sdfr_refine_get(self.handle, b, _lib.fptr(params), _lib.fptr(hist), C.byref(nh),
-                                               _lib.stream_ptr()))
-        self._dirty.clear()         # sdfr_refine_get synchronised the stream: all staged copies are done
+        try:
+            _lib.check(_lib.load().sdfr_refine_get(self.handle, b, _lib.fptr(params), _lib.fptr(hist), C.byref(nh),
+                                                   _lib.stream_ptr()))
+        finally:
+            self._dirty.clear()     # sdfr_refine_get synchronised the stream: all staged copies are done
         return params, hist[:nh.value]
 
+    def get_batch(self):
+        """(params [active, 5+L], [history rows of each active detection]) in one synchronisation."""
+        L, B = self.latent_size, self.active
+        params = np.zeros((B, 5 + L), dtype=np.float32)
+        hist = np.zeros((B, self.cfg.max_iters, 4), dtype=np.float32)
+        nh = (C.c_int * B)()
+        try:
+            _lib.check(_lib.load().sdfr_refine_get_batch(self.handle, _lib.fptr(params), _lib.fptr(hist), nh,
+                                                         _lib.stream_ptr()))
+        finally:
+            self._dirty.clear()
+        return params, [hist[b, :nh[b]] for b in range(B)]
+
+    def preselect_error(self) -> float:
+        e = np.zeros(1, dtype=np.float32)
+        _lib.check(_lib.load().sdfr_refine_preselect_error(self.handle, _lib.fptr(e), _lib.stream_ptr()))
+        return float(e[0])
+
+    def label_extents(self):
+        """[active, 8]: min xyz, max xyz of the isosurface points of the CURRENT raw latent, count, 0
+        (the extents ``get_kitti_label`` derives, utils/refinement.py:527-541)."""
+        out = np.zeros((self.active, 8), dtype=np.float32)
+        _lib.check(_lib.load().sdfr_refine_label_extents(self.handle, _lib.fptr(out), _lib.stream_ptr()))
+        return out
+
     VIEW_KINDS = {'sdf': 0, 'dinput': 1, 'surf_pts': 2, 'surf_nrm': 3, 'color': 4, 'mask': 5, 'normals': 6,
-                  'grads': 7, 'surf_count': 8, 'depth': 9, 'cam_pts': 10, 'front': 11, 'surf_valid': 12}
+                  'grads': 7, 'surf_count': 8, 'depth': 9, 'cam_pts': 10, 'front': 11, 'surf_valid': 12, 'cam_rgb': 13,
+                  'surf_idx': 14}
 
     def view(self, b, kind):
         """Device copy of an intermediate of the last iteration (tests, label dumps)."""
@@ -166,7 +227,7 @@ class _Engine:
         p = _lib.vp()
         n = C.c_int64(0)
         _lib.check(lib.sdfr_refine_view(self.handle, b, kind, C.byref(p), C.byref(n)))
-        dtype = torch.int32 if kind == 8 else torch.uint8 if kind in (11, 12) else torch.float32
+        dtype = torch.int32 if kind in (8, 14) else torch.uint8 if kind in (11, 12) else torch.float32
         out = torch.empty((n.value,), device='cuda', dtype=dtype)
         _lib.check(lib.sdfr_refine_copy_view(self.handle, b, kind, out.data_ptr(), n.value, _lib.stream_ptr()))
         return out
@@ -177,21 +238,31 @@ class _Engine:
         keep = self.view(b, 'surf_valid')[:m].bool()
         return self.view(b, 'surf_pts')[:m * 3].view(-1, 3)[keep], self.view(b, 'surf_nrm')[:m * 3].view(-1, 3)[keep]
 
+    def front_points(self, b):
+        """points['xyzf'] / points['rgbf'] of the last iteration (projection.py:61-70, rasterer.py:151-152)."""
+        m = int(self.view(b, 'surf_count').item())
+        keep = self.view(b, 'front')[:m].bool()
+        return self.view(b, 'cam_pts')[:m * 3].view(-1, 3)[keep], self.view(b, 'cam_rgb')[:m * 3].view(-1, 3)[keep]
+
 
 def _engine_for(dsdf, batch, density, w, h, n_lidar, iters, weights, impl) -> _Engine:
+    """The decoder's engine for this (density, loss weights, MLP kernel), grown when a request exceeds a
+    capacity.  Capacities are rounded up to powers of two, so growth happens a handful of times at most;
+    nothing is re-created when a frame simply has fewer detections or a smaller crop than the last one."""
     native = dsdf.native()
     cache = dsdf.__dict__.setdefault('_sdfr_engines', {})
-    # round capacities up so a sequence of slightly different crops reuses one engine
-    cap_w = max(32, 1 << (int(w) - 1).bit_length())
-    cap_h = max(32, 1 << (int(h) - 1).bit_length())
-    cap_l = max(1024, 1 << (int(max(n_lidar, 1)) - 1).bit_length())
-    cap_i = max(64, int(iters))
-    key = (id(native), batch, density, cap_w, cap_h, cap_l, cap_i, float(weights['2d']), float(weights['3d']), impl)
+    for k in [k for k, e in cache.items() if e.native_decoder is not native]:
+        del cache[k]           # engines of a decoder handle that has been rebuilt (weights changed)
+    need = (_pow2_ceil(batch, 1), _pow2_ceil(w, 32), _pow2_ceil(h, 32), _pow2_ceil(max(n_lidar, 1), 1024),
+            max(64, int(iters)))
+    key = (int(density), float(weights['2d']), float(weights['3d']), int(impl))
     eng = cache.get(key)
-    if eng is None:
-        eng = _Engine(native, batch, density, cap_w, cap_h, cap_l, cap_i, float(weights['2d']), float(weights['3d']),
-                      impl)
-        cache.clear()          # one live engine per decoder keeps the memory footprint bounded
+    if eng is None or any(n > c for n, c in zip(need, eng.capacity())):
+        cap = need if eng is None else tuple(max(n, c) for n, c in zip(need, eng.capacity()))
+        if eng is not None:
+            del cache[key]
+            eng = None         # frees the smaller engine's device memory before the larger one allocates
+        eng = _Engine(native, cap[0], int(density), cap[1], cap[2], cap[3], cap[4], key[1], key[2], key[3])
         cache[key] = eng
     return eng
 
@@ -252,7 +323,9 @@ class Optimizer:
         self.rot = rot
         self.verbose = False
         self.history = None
-        self._host = None           # (versions, host copies) of the parameter tensors after the last optimize()
+        # Adam moments / step count of (yaw, trans): the reference builds its solver once per Optimizer
+        # (optimizer.py:46-52), so n calls of optimize(k) continue one state exactly like optimize(n*k)
+        self._adam = None
 
     def optimize(self, iters_optim, nocs_pred, pcd_frustum_np, dsdf, grid, K, crop_size, viz_type=None,
                  frame_vis=None):
@@ -276,36 +349,39 @@ class Optimizer:
         self.precision = grid.points.dtype
         height, width = int(crop_size[0]), int(crop_size[1])
         lidar = np.asarray(pcd_frustum_np, dtype=np.float32).reshape(-1, 3)
+        p = self.params
+        keys = ('yaw', 'trans', 'scale', 'latent')
         with torch.cuda.device(self.device):
             eng = _engine_for(dsdf, 1, int(grid.density), width, height, lidar.shape[0], iters_optim, self.weights,
                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
-            p = self.params
-            keys = ('yaw', 'trans', 'scale', 'latent')
-            versions = tuple((p[k].data_ptr(), p[k]._version) for k in keys)
-            if self._host is not None and self._host[0] == versions:
-                host = self._host[1]        # nobody touched the tensors since we wrote them: skip four D2H syncs
-            else:
-                host = {k: p[k].detach().cpu().numpy() for k in keys}
-            eng.set_detection(0, K, width, height, nocs_pred, lidar, host['yaw'], host['trans'], host['scale'],
-                              host['latent'])
-            eng.run(iters_optim)
-            # the params tensors are updated in place on the device (one launch, no host round trip) ...
+            # the params tensors are read and updated in place ON THE DEVICE (one launch each way): whatever
+            # the caller did to them since the last call (in-place edits included) is what the loop starts from
             direct = all(p[k].is_cuda and p[k].dtype == torch.float32 and p[k].is_contiguous() and
                          p[k].device == self.device for k in keys)
+            if eng.active != 1:
+                eng.set_active(1)
             if direct:
-                _lib.check(_lib.load().sdfr_refine_export(eng.handle, 0, p['yaw'].data_ptr(), p['trans'].data_ptr(),
-                                                          p['scale'].data_ptr(), p['latent'].data_ptr(),
-                                                          _lib.stream_ptr()))
-            # ... and read back (one stream sync; it also carries the fp16-range guard of the TC kernel)
+                eng.set_detection(0, K, width, height, nocs_pred, lidar)
+                eng.import_params(0, p)
+            else:
+                host = {k: p[k].detach().cpu().numpy() for k in keys}
+                eng.set_detection(0, K, width, height, nocs_pred, lidar, host['yaw'], host['trans'], host['scale'],
+                                  host['latent'])
+            if self._adam is not None:
+                eng.set_optimizer_state(0, self._adam)
+            eng.run(iters_optim)
+            if direct:
+                eng.export_params(0, p)
+            # read back (one stream sync; it also carries the decoder's fp16-range and pre-selection guards)
             out, hist = eng.get(0)
+            self._adam = eng.get_optimizer_state(0)
         self.engine = eng
         self.history = hist
-        new = {'yaw': out[0:1].copy(), 'trans': out[1:4].copy(), 'scale': out[4:5].copy(), 'latent': out[5:].copy()}
         if not direct:
+            new = {'yaw': out[0:1], 'trans': out[1:4], 'scale': out[4:5], 'latent': out[5:]}
             with torch.no_grad():
                 for k, v in new.items():
-                    p[k].copy_(torch.from_numpy(v), non_blocking=True)
-        self._host = (tuple((p[k].data_ptr(), p[k]._version) for k in ('yaw', 'trans', 'scale', 'latent')), new)
+                    p[k].copy_(torch.from_numpy(v.copy()).to(p[k].dtype))
         if self.verbose:
             w2, w3 = self.weights['2d'], self.weights['3d']
             for e, (l2, l3, tot, skip) in enumerate(hist):
@@ -313,7 +389,6 @@ class Optimizer:
                     print('Skip frame')
                 else:
                     print('ITER {} | Losses: 2D - {}, 3D - {}, Total - {}'.format(e, w2 * l2, w3 * l3, tot))
-
 
     # ---- stand-alone losses with the reference's signatures (optimizer.py:166-237) -------------------
     def compute_loss_3d(self, pcd_dsdf_trans, pcd_frustum, threshold=0.2):
@@ -338,13 +413,22 @@ class BatchOptimizer:
     ``detections`` is a sequence of dicts with the arguments ``Optimizer`` takes
     per detection: ``params`` (yaw/trans/scale/latent), ``nocs_pred``, ``lidar``,
     ``K``, ``crop_size``.  This is the per-GPU unit of the multi-GPU pipeline
-    (frames are sharded across ranks)."""
+    (frames are sharded across ranks).  Every detection starts
+    from a fresh optimiser state, like the ``Optimizer`` the reference constructs per
+    annotation (refine_css.py:203)."""
 
     def __init__(self, weights, device='cuda'):
         self.weights = weights
         self.device = torch.device(device)
 
-    def optimize(self, iters_optim, detections: Sequence[Dict], dsdf, grid):
+    def reserve(self, dsdf, grid, max_batch, max_crop, max_lidar=1024, iters=64):
+        """Allocates the engine for the largest batch / crop / LIDAR crop up front."""
+        with torch.cuda.device(self.device):
+            self.engine = _engine_for(dsdf, max_batch, int(grid.density), max_crop[1], max_crop[0], max_lidar, iters,
+                                      self.weights, getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
+        return self.engine
+
+    def optimize(self, iters_optim, detections: Sequence[Dict], dsdf, grid, extents=False):
         B = len(detections)
         if B == 0:
             return []
@@ -354,15 +438,21 @@ class BatchOptimizer:
         with torch.cuda.device(self.device):
             eng = _engine_for(dsdf, B, int(grid.density), max_w, max_h, max_l, iters_optim, self.weights,
                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
+            if eng.active != B:
+                eng.set_active(B)
             for b, d in enumerate(detections):
                 p = d['params']
                 eng.set_detection(b, d['K'], int(d['crop_size'][1]), int(d['crop_size'][0]), d['nocs_pred'],
                                   d['lidar'], p['yaw'], p['trans'], p['scale'], p['latent'])
             eng.run(iters_optim)
-            results = []
-            for b in range(B):
-                out, hist = eng.get(b)
-                results.append({'yaw': out[0:1].copy(), 'trans': out[1:4].copy(), 'scale': out[4:5].copy(),
-                                'latent': out[5:].copy(), 'history': hist.copy()})
+            out, hists = eng.get_batch()
+            ext = eng.label_extents() if extents else None
+        results = []
+        for b in range(B):
+            res = {'yaw': out[b, 0:1].copy(), 'trans': out[b, 1:4].copy(), 'scale': out[b, 4:5].copy(),
+                   'latent': out[b, 5:].copy(), 'history': hists[b].copy()}
+            if ext is not None:
+                res['extent_min'], res['extent_max'], res['extent_count'] = ext[b, 0:3].copy(), ext[b, 3:6].copy(), int(ext[b, 6])
+            results.append(res)
         self.engine = eng
         return results

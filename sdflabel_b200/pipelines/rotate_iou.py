@@ -27,12 +27,12 @@ def rotate_iou_gpu_eval(boxes, query_boxes, criterion=-1, device_id=0):
         query_boxes (np.ndarray [K, 5])
         criterion: -1 IoU, 0 intersection / query-box area, 1 intersection / box area, 2 intersection
         device_id: CUDA device
-    Returns: np.ndarray [N, K] of ``boxes.dtype``
+    Returns: np.ndarray [N, K], always float32: the reference rebinds ``boxes`` to its float32 copy before
+        ``iou.astype(boxes.dtype)`` (rotate_iou.py:304-305,325), so float64 inputs come back as float32 too
     """
-    box_dtype = boxes.dtype
     n, k = boxes.shape[0], query_boxes.shape[0]
     if n == 0 or k == 0:
-        return np.zeros((n, k), dtype=np.float32)         # (the reference returns float32 on this path)
+        return np.zeros((n, k), dtype=np.float32)
     if not torch.cuda.is_available():
         raise _lib.SdfrError("rotate_iou_gpu_eval needs a CUDA device (there is no CPU path)")
     dev = torch.device('cuda', int(device_id))
@@ -42,7 +42,7 @@ def rotate_iou_gpu_eval(boxes, query_boxes, criterion=-1, device_id=0):
         iou = torch.empty((n, k), device=dev, dtype=torch.float32)
         _lib.check(_lib.load().sdfr_rotate_iou(b.data_ptr(), n, q.data_ptr(), k, int(criterion), iou.data_ptr(),
                                                _lib.stream_ptr()))
-        return iou.cpu().numpy().astype(box_dtype)
+        return iou.cpu().numpy()
 
 
 def d3_box_overlap_kernel(boxes, qboxes, rinc, criterion=-1, camera_coordinate=False):

@@ -68,3 +68,29 @@ def get_kitti_label(dsdf, grid, latent, scale, trans, yaw, p_WC, bbox):
     label['alpha'] = alpha_in_bev(global_T, label['rotation_y'])
     label['score'] = 1
     return label, scaled_points, cam_T
+
+
+def kitti_label_from_extents(ext_min, ext_max, latent, scale, trans, yaw, p_WC, bbox):
+    """``get_kitti_label`` with the extents already known: ``ext_min`` / ``ext_max`` are the bounds of the
+    un-scaled isosurface points of the raw latent (``sdfr_refine_label_extents``, evaluated for all detections of
+    a batch in one pass).  min / max commute with the multiplication by the positive float32 scale, so
+    ``ext * scale`` is bit for bit what the reference gets from ``(points * scale).min()`` (refinement.py:536-541).
+    Returns (label, cam_T) - the scaled point cloud itself only feeds the reference's visualiser."""
+    scale32 = np.asarray(scale, dtype=np.float32).reshape(-1)[:1]
+    yaw_f = float(np.asarray(yaw, dtype=np.float32).reshape(-1)[0])
+    trans32 = np.asarray(trans, dtype=np.float32).reshape(3)
+    cam_T = np.eye(4)
+    cam_T[:3, :3] = rot_from_yaw(yaw_f).numpy() @ np.diag([1, -1, 1])
+    cam_T[:3, 3] = trans32 * scale32
+    global_T = np.linalg.inv(p_WC) @ cam_T
+    mins = np.asarray(ext_min, dtype=np.float32) * scale32
+    maxs = np.asarray(ext_max, dtype=np.float32) * scale32
+    width, height, length = (maxs - mins).tolist()
+    bottom_center = np.asarray([0, mins[1], 0])
+    label = {'name': 'Car', 'bbox': bbox}
+    label['location'] = (global_T[:3, :3] @ bottom_center.T).T + global_T[:3, 3]
+    label['dimensions'] = [height, width, length]
+    label['rotation_y'] = roty_in_bev(global_T)
+    label['alpha'] = alpha_in_bev(global_T, label['rotation_y'])
+    label['score'] = 1
+    return label, cam_T

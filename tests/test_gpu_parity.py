@@ -51,10 +51,13 @@ def test_lattice_bit_exact(d):
 # ------------------------------------------------------------------------------------------
 # T2/T3 decoder variants (golden = reference outputs)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["wn_skip", "layernorm", "xyz_in_all", "use_tanh", "latent8"])
+@pytest.mark.parametrize("name", ["wn_skip", "layernorm", "xyz_in_all", "use_tanh", "latent8", "latent256"])
 def test_decoder_variants_vs_reference(golden_dir, name):
+    """T2 / T3: sdf and the input gradient against the reference's Decoder for each spec variant
+    (latent 3 / 8 / 256; weight-norm + skip, LayerNorm, xyz_in_all, use_tanh)."""
     g, spec, sd = H.golden_decoder(golden_dir, name)
     dec = H.our_decoder_from_state(spec, sd)
+    params = O.params_from_state_dict(spec, sd)
     for tag, impl in _impls(dec):
         dec.mlp_impl = impl
         inp = torch.from_numpy(g["inputs"]).to(cuda).requires_grad_(True)
@@ -62,9 +65,9 @@ def test_decoder_variants_vs_reference(golden_dir, name):
         (grad,) = torch.autograd.grad(sdf.sum(), inp)
         err = np.abs(sdf.detach().cpu().numpy() - g["sdf"]).max()
         assert err < SDF_TOL[tag], (tag, err)
-        gmax = np.abs(g["dinput"]).max()
-        frac = H.frac_within(grad.cpu().numpy(), g["dinput"], 1e-4, atol=1e-5 * gmax)
-        assert frac >= 0.995, (tag, frac)
+        nbad = H.assert_grad_rows_close(grad.cpu().numpy(), g["dinput"], params, torch.from_numpy(g["inputs"]),
+                                        f"{name}/{tag}")
+        print(f"decoder {name}/{tag}: sdf err {err:.2e}, {nbad} gradient rows at a ReLU kink")
 
 
 def test_decoder_ragged_sizes(golden_dir):
@@ -101,9 +104,9 @@ def test_stock_decoder_full_lattice(stock_prior_path):
         err = np.abs(sdf.cpu().numpy() - sdf_ref.detach().numpy().ravel()).max()
         assert err < SDF_TOL[tag], (tag, err)
         gx = dinp[:, 3:].cpu().numpy()
-        gmax = np.abs(g_ref.numpy()).max()
-        frac = H.frac_within(gx, g_ref.numpy(), 1e-4, atol=1e-5 * gmax)
-        assert frac >= 0.999, (tag, frac)
+        full_in = torch.cat([lat.expand(pts.shape[0], -1), pts], 1)
+        nbad = H.assert_grad_rows_close(gx, g_ref.numpy(), prior, full_in, f"stock lattice/{tag}")
+        print(f"stock lattice/{tag}: sdf err {err:.2e}, {nbad} of 64000 gradient rows at a ReLU kink")
         # latent gradient of sdf against autograd
         latv = lat.clone().requires_grad_(True)
         sub = slice(0, 64000, 97)
@@ -144,8 +147,22 @@ def test_surface_vs_reference_golden(golden_dir, stock_prior_path):
 # ------------------------------------------------------------------------------------------
 # T5 rasteriser (maps, point lists, gradients) vs the reference's outputs
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("tag,rot", [("dcm_45x22", "dcm"), ("dcm_32x32", "dcm"), ("quat_40x30", "quat")])
+def _quat_to_pose(p7):
+    """4x4 [R|t] of the quaternion pose [qw,qx,qy,qz,t] with the reference's un-normalised qrot matrix."""
+    w, x, y, z = [float(v) for v in p7[:4]]
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    pose = np.eye(4)
+    pose[:3, :3], pose[:3, 3] = R, p7[4:]
+    return pose
+
+
+@pytest.mark.parametrize("tag,rot", [("dcm_45x22", "dcm"), ("dcm_32x32", "dcm"), ("quat_40x30", "quat"),
+                                     ("dcm_64x64", "dcm"), ("dcm_256x256", "dcm")])
 def test_rasterer_vs_reference_golden(golden_dir, tag, rot):
+    """T5: maps, point lists and gradients of Rasterer.forward fed with the reference's surfels.  Every pixel
+    within 1e-4 of the reference except pixels where a surfel sits on a hard threshold (counted, attributed)."""
     from sdflabel_b200.renderer.rasterer import Rasterer
     g = np.load(os.path.join(golden_dir, f"raster_{tag}.npz"))
     w, h = int(g["width"]), int(g["height"])
@@ -155,24 +172,31 @@ def test_rasterer_vs_reference_golden(golden_dir, tag, rot):
     ras = Rasterer(torch.from_numpy(g["K"]), (w, h)).to(cuda)
     rendering, points = ras(coords, normals, normals, pose, rot=rot, primitives='disc', bg=None, output_depth=True,
                             output_normals=True, output_nocs=True, output_mask=True, output_points=True)
+    v64, m64 = H.camera_space(g["coords"], g["normals"], g["pose"] if rot == "dcm" else _quat_to_pose(g["pose"]))
+    large = "cot_color" not in g.files          # the large goldens use recomputable cotangents
     scalar = 0
-    for k in ("color", "mask", "depth", "normals"):
-        ref = g["r_" + k]
-        ours = rendering[k].detach().cpu().numpy()
-        bad = np.abs(ours - ref) > 1e-4 * max(1.0, np.abs(ref).max())
-        assert bad.mean() < 2e-3, (k, bad.sum(), np.abs(ours - ref).max())
-        scalar = scalar + (rendering[k] * torch.from_numpy(g["cot_" + k]).to(cuda)).sum()
+    flips = 0
+    for i, k in enumerate(("color", "mask", "depth", "normals")):
+        flips = max(flips, H.assert_maps_close(rendering[k].detach().cpu().numpy(), g["r_" + k], g["K"], w, v64, m64,
+                                               f"{tag}/{k}"))
+        cot = H.pattern_cotangent(tuple(g["r_" + k].shape), i) if large else torch.from_numpy(g["cot_" + k])
+        scalar = scalar + (rendering[k] * cot.to(cuda)).sum()
     if rot == "dcm":
         assert np.abs(points["xyz"].detach().cpu().numpy() - g["p_xyz"]).max() < 2e-6
         assert points["xyzf"].shape == tuple(g["p_xyzf"].shape)
         assert np.abs(points["xyzf"].detach().cpu().numpy() - g["p_xyzf"]).max() < 2e-6
         assert np.abs(points["rgbf"].detach().cpu().numpy() - g["p_rgbf"]).max() < 2e-6
-        scalar = scalar + (points["xyzf"] * torch.from_numpy(g["cot_xyzf"]).to(cuda)).sum()
+        cot = H.pattern_cotangent(tuple(g["p_xyzf"].shape), 7) if large else torch.from_numpy(g["cot_xyzf"])
+        scalar = scalar + (points["xyzf"] * cot.to(cuda)).sum()
     gc, gn, gp = torch.autograd.grad(scalar, [coords, normals, pose])
+    # a pixel that flips membership of one surfel moves that surfel's gradient by O(1) of ITS value, so the
+    # per-surfel gradients are compared at 1e-4 only when no pixel flipped; the pose gradient (a sum over all
+    # surfels) always is, with one part in 1e-4 of slack per flipped pixel
     for name, ours, ref in (("coords", gc, g["g_coords"]), ("normals", gn, g["g_normals"]), ("pose", gp, g["g_pose"])):
-        tol = 1e-4 if name == "pose" else 1e-3
         err = np.abs(ours.cpu().numpy() - ref).max() / max(1.0, np.abs(ref).max())
-        assert err < tol, (name, err)
+        tol = 1e-4 * (1 + flips)
+        assert err < tol, (tag, name, err, flips)
+    print(f"raster {tag}: {flips} attributed pixels")
 
 
 def test_rasterer_empty_and_single():
@@ -275,56 +299,195 @@ def test_refine_trajectory_vs_reference_golden(golden_dir, stock_prior_path):
         assert err.max() < 2e-4 * n, (n, got, ref)
 
 
-@pytest.mark.parametrize("size,density", [(64, 40)])
-def test_refine_iteration_vs_oracle(stock_prior_path, size, density):
-    """cfg1: one full iteration (forward maps, both losses, every gradient, the update) vs the oracle."""
+def _check_iteration_vs_oracle(stock_prior_path, size, density, tile_rows):
+    """One full iteration (surfels, four maps, point lists, both losses, every gradient, the update) against the
+    oracle on the same inputs.  Tolerances: north_star's 1e-4 on maps and gradients, SURVEY T6's 1e-5 on the
+    losses; a pixel may exceed them only where a surfel sits on a hard threshold of the splat, and each such
+    pixel (there are `flips` of them, printed) loosens the loss / gradient bounds by its share 4/N of the
+    rendered pixels - the size of the jump a membership flip of one pixel causes."""
     prior = P.load_prior(stock_prior_path)
     sc = scenes.make_scene(prior, size=size, density=density)
     st = O.RefineState.create(**sc["init"])
-    out = O.refine_iteration(prior, O.lattice(density), torch.from_numpy(sc["K"]), size, size, st,
-                             torch.from_numpy(sc["nocs_pred"]), sc["lidar"], 0.3, 0.5)
+    K = torch.from_numpy(sc["K"])
+    out = O.refine_iteration(prior, O.lattice(density), K, size, size, st, torch.from_numpy(sc["nocs_pred"]),
+                             sc["lidar"], 0.3, 0.5, tile_rows=tile_rows)
     opt, params, dec = _run_engine(stock_prior_path, sc, 1)
     eng = opt.engine
+    # --- surfels (T4)
     surf_pts, surf_nrm = eng.surfels(0)
     assert surf_pts.shape[0] == out["surf_pts"].shape[0]
     assert np.abs(surf_pts.cpu().numpy() - out["surf_pts"].detach().numpy()).max() < 1e-5
-    col = eng.view(0, 'color').view(3, size, size).cpu().numpy()
-    ref = out["render"]["color"].detach().numpy()
-    bad = np.abs(col - ref) > 1e-4
-    assert bad.mean() < 1e-3, (bad.sum(), np.abs(col - ref).max())
+    # normals (unit vectors): within 1e-4 on >= 99.9 % of the surfels, every outlier at a ReLU kink (T3)
+    lat = torch.nn.functional.normalize(torch.from_numpy(sc["init"]["latent"]), dim=0)
+    band_pts = O.lattice(density)[out["keep"]]
+    kinks = H.assert_grad_rows_close(surf_nrm.cpu().numpy(), out["surf_nrm"].numpy(), prior,
+                                     torch.cat([lat.expand(band_pts.shape[0], -1), band_pts], 1), f"{size}/normals")
+    # --- maps (T5), with attribution of the out-of-tolerance pixels
+    pose = O.yaw_pose(torch.tensor(sc["init"]["yaw"]), torch.tensor(sc["init"]["trans"])).numpy()
+    v64, m64 = H.camera_space(out["surf_pts"].detach().numpy(), out["surf_nrm"].numpy(), pose)
+    flips = 0
+    for kind in ("color", "mask", "depth", "normals"):
+        ref = out["render"][kind].detach().numpy()
+        ours = eng.view(0, kind).cpu().numpy().reshape(ref.shape)
+        flips = max(flips, H.assert_maps_close(ours, ref, sc["K"], size, v64, m64, f"{size}/{kind}"))
+    # --- point lists
+    xyzf, rgbf = eng.front_points(0)
+    assert xyzf.shape[0] == out["render"]["xyzf"].shape[0]
+    assert np.abs(xyzf.cpu().numpy() - out["render"]["xyzf"].detach().numpy()).max() < 2e-6 * 8
+    assert np.abs(rgbf.cpu().numpy() - out["render"]["rgbf"].detach().numpy()).max() < 2e-6
+    # --- losses (T6) and gradients (T7)
+    n_rendered = max(1, int((out["render"]["mask"] > 0).sum()))
+    slack = flips * 4.0 / n_rendered
     l2, l3, tot, skip = opt.history[0]
     assert skip == 0
-    assert abs(l2 - float(out["loss_2d"])) < 1e-4 * abs(float(out["loss_2d"]))
-    assert abs(l3 - float(out["loss_3d"])) < 1e-4 * abs(float(out["loss_3d"]))
+    e2 = abs(l2 - float(out["loss_2d"])) / abs(float(out["loss_2d"]))
+    e3 = abs(l3 - float(out["loss_3d"])) / abs(float(out["loss_3d"]))
+    assert e2 < 1e-5 + slack and e3 < 1e-5, (e2, e3, flips)
     grads = eng.view(0, 'grads').cpu().numpy()
     gref = np.concatenate([out["grads"][k].numpy().reshape(-1) for k in ("yaw", "trans", "scale")])
-    assert np.abs(grads[:5] - gref).max() < 1e-3 * np.abs(gref).max(), (grads[:5], gref)
+    eg = np.abs(grads[:5] - gref).max() / np.abs(gref).max()
     glat = out["grads"]["latent"].numpy()
-    assert np.abs(grads[8:11] - glat).max() < 1e-3 * np.abs(glat).max(), (grads[8:11], glat)
+    el = np.abs(grads[8:11] - glat).max() / np.abs(glat).max()
+    assert eg < 1e-4 + slack and el < 1e-4 + slack, (eg, el, flips, grads[:5], gref)
+    # --- the update: parameters after the step
     got = np.concatenate([params[k].detach().cpu().numpy().reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
     want = np.concatenate([st.as_numpy()[k].reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
-    assert np.abs(got - want).max() < 1e-5, (got, want)
+    ep = np.abs(got - want).max()
+    assert ep < 1e-5, (got, want)
+    print(f"iteration {size}x{size} D={density}: {kinks} normals at a ReLU kink, {flips} threshold pixels of {n_rendered} rendered, loss2d rel {e2:.1e}, "
+          f"loss3d rel {e3:.1e}, pose/scale grads rel {eg:.1e}, latent grad rel {el:.1e}, params abs {ep:.1e}")
+
+
+def test_refine_iteration_vs_oracle(stock_prior_path):
+    """cfg1 (64x64, D=40)."""
+    _check_iteration_vs_oracle(stock_prior_path, 64, 40, None)
 
 
 def test_refine_256_forward_and_gradients(stock_prior_path):
-    """cfg2: 256x256 fwd+bwd of one latent; the oracle evaluates the pixels in row tiles."""
+    """cfg2, the headline configuration (256x256, D=40); the oracle evaluates the pixels in 16-row tiles."""
+    _check_iteration_vs_oracle(stock_prior_path, 256, 40, 16)
+
+
+def test_refine_trajectory50_vs_reference_golden(golden_dir, stock_prior_path):
+    """T8: the reference's own Optimizer stepped 50 times at cfg1 (64x64, D=40).  Parameters after every step
+    and the printed losses; the product is driven the same way (50 calls of optimize(1) on ONE Optimizer, so the
+    Adam state has to persist across calls as it does in the reference, optimizer.py:46-52)."""
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import Optimizer
+    g = np.load(os.path.join(golden_dir, "refine_traj50_64.npz"))
+    sc = H.scene_from_golden(g)
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    grid = Grid3D(sc["density"], device=cuda)
+    params = {k: v.copy() for k, v in sc["init"].items()}
+    opt = Optimizer(params, cuda, sc["weights"])
+    groups = {"yaw": slice(0, 1), "trans": slice(1, 4), "scale": slice(4, 5), "latent": slice(5, 8)}
+    worst = {k: 0.0 for k in groups}
+    for n in range(g["traj"].shape[0]):
+        opt.optimize(1, torch.from_numpy(sc["nocs_pred"]), sc["lidar"], dec, grid, torch.from_numpy(sc["K"]),
+                     sc["crop_size"], viz_type=None)
+        got = np.concatenate([params[k].detach().cpu().numpy().reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
+        ref = g["traj"][n]
+        for k, sl in groups.items():      # T8: rel <= 1e-3 per parameter group (vector-relative), at every step
+            err = float(np.abs(got[sl] - ref[sl]).max() / np.abs(ref[sl]).max())
+            worst[k] = max(worst[k], err)
+            assert err < 1e-3, (n, k, err, got, ref)
+        l2, l3, tot, skip = opt.history[0]
+        assert skip == 0 and abs(tot - g["losses"][n, 2]) < 1e-2 * g["losses"][n, 2], (n, tot, g["losses"][n])
+    # one call of optimize(50) on a fresh Optimizer gives the very same bits
+    params2 = {k: v.copy() for k, v in sc["init"].items()}
+    opt2 = Optimizer(params2, cuda, sc["weights"])
+    opt2.optimize(50, torch.from_numpy(sc["nocs_pred"]), sc["lidar"], dec, grid, torch.from_numpy(sc["K"]),
+                  sc["crop_size"], viz_type=None)
+    for k in ("yaw", "trans", "scale", "latent"):
+        assert torch.equal(params[k], params2[k]), k
+    print("50-step trajectory: worst relative error per group " + ", ".join(f"{k} {v:.1e}" for k, v in worst.items()))
+
+
+def test_refine_ragged_vs_reference_golden(golden_dir, stock_prior_path):
+    """cfg3 shape: three detections with different (non-square) crops and LIDAR counts, refined TOGETHER by the
+    batched engine, against the reference's Optimizer run on each of them alone (6 steps, D=20)."""
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import BatchOptimizer
+    g = np.load(os.path.join(golden_dir, "refine_ragged.npz"))
+    scs = [H.scene_from_golden(g, f"d{i}_") for i in range(int(g["count"]))]
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    grid = Grid3D(20, device=cuda)
+    bo = BatchOptimizer(scs[0]["weights"])
+    dets = [{"params": sc["init"], "nocs_pred": sc["nocs_pred"], "lidar": sc["lidar"], "K": torch.from_numpy(sc["K"]),
+             "crop_size": sc["crop_size"]} for sc in scs]
+    for n in (1, 3, 6):
+        res = bo.optimize(n, dets, dec, grid)
+        for i, r in enumerate(res):
+            got = np.concatenate([r[k].reshape(-1) for k in ("yaw", "trans", "scale", "latent")])
+            ref = g[f"d{i}_traj"][n - 1]
+            err = (np.abs(got - ref) / np.maximum(1e-2, np.abs(ref))).max()
+            assert err < 2e-4 * n, (i, n, err, got, ref)
+            want = g[f"d{i}_losses"][:n, 2]
+            assert np.allclose(r["history"][:, 2], want, rtol=1e-2, equal_nan=True), (i, r["history"][:, 2], want)
+
+
+def test_optimize_calls_continue_adam_state(stock_prior_path):
+    """optimize(5) twice on one Optimizer == optimize(10) (bit for bit); a NEW Optimizer starts a new Adam state."""
     prior = P.load_prior(stock_prior_path)
-    sc = scenes.make_scene(prior, size=256, density=40)
-    st = O.RefineState.create(**sc["init"])
-    out = O.refine_iteration(prior, O.lattice(40), torch.from_numpy(sc["K"]), 256, 256, st,
-                             torch.from_numpy(sc["nocs_pred"]), sc["lidar"], 0.3, 0.5, tile_rows=16)
-    opt, params, dec = _run_engine(stock_prior_path, sc, 1)
-    eng = opt.engine
-    for kind, key in (("color", "color"), ("mask", "mask"), ("normals", "normals")):
-        ours = eng.view(0, kind).cpu().numpy().reshape(out["render"][key].shape)
-        ref = out["render"][key].detach().numpy()
-        bad = np.abs(ours - ref) > 1e-4
-        assert bad.mean() < 1e-3, (kind, bad.sum(), np.abs(ours - ref).max())
-    grads = eng.view(0, 'grads').cpu().numpy()
-    gref = np.concatenate([out["grads"][k].numpy().reshape(-1) for k in ("yaw", "trans", "scale")])
-    assert np.abs(grads[:5] - gref).max() < 1e-3 * np.abs(gref).max(), (grads[:5], gref)
-    glat = out["grads"]["latent"].numpy()
-    assert np.abs(grads[8:11] - glat).max() < 1e-3 * np.abs(glat).max(), (grads[8:11], glat)
+    sc = scenes.make_scene(prior, size=32, density=20, n_lidar=150, seed=5)
+    a = _run_engine(stock_prior_path, sc, 10)
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import Optimizer
+    dec = a[2]
+    grid = Grid3D(sc["density"], device=cuda)
+    params = {k: v.copy() for k, v in sc["init"].items()}
+    opt = Optimizer(params, cuda, sc["weights"])
+    args = (torch.from_numpy(sc["nocs_pred"]), sc["lidar"], dec, grid, torch.from_numpy(sc["K"]), sc["crop_size"])
+    opt.optimize(5, *args, viz_type=None)
+    mid = {k: params[k].detach().clone() for k in params}
+    opt.optimize(5, *args, viz_type=None)
+    for k in ("yaw", "trans", "scale", "latent"):
+        assert torch.equal(params[k], a[1][k]), k
+    # a fresh Optimizer on the mid-way parameters restarts Adam (bias-corrected first step) and ends elsewhere
+    fresh = Optimizer({k: v.cpu().numpy() for k, v in mid.items()}, cuda, sc["weights"])
+    fresh.optimize(5, *args, viz_type=None)
+    assert not torch.equal(fresh.params["yaw"], params["yaw"])
+
+
+def test_params_are_read_from_the_tensors_every_call(stock_prior_path):
+    """In-place edits of the params tensors between two optimize() calls - including `.data` writes, which do not
+    bump the version counter - and a fresh K tensor in a recycled allocation are honoured (no stale host caches)."""
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import Optimizer
+    prior = P.load_prior(stock_prior_path)
+    sc = scenes.make_scene(prior, size=32, density=20, n_lidar=150, seed=5)
+    opt0, params0, dec = _run_engine(stock_prior_path, sc, 1)
+    grid = Grid3D(sc["density"], device=cuda)
+    params = {k: v.copy() for k, v in sc["init"].items()}
+    opt = Optimizer(params, cuda, sc["weights"])
+    nocs, lidar = torch.from_numpy(sc["nocs_pred"]), sc["lidar"]
+    opt.optimize(1, nocs, lidar, dec, grid, torch.from_numpy(sc["K"]), sc["crop_size"], viz_type=None)
+    # reset the parameters through .data and render with ANOTHER camera: both must take effect
+    for k in ("yaw", "trans", "scale", "latent"):
+        params[k].data.copy_(torch.from_numpy(np.asarray(sc["init"][k], dtype=np.float32)).to(cuda))
+    K2 = torch.from_numpy(sc["K"]).clone()
+    K2[0, 0] *= 1.25
+    K2[1, 1] *= 1.25
+    opt_b = Optimizer({k: v.copy() for k, v in sc["init"].items()}, cuda, sc["weights"])
+    opt_b.optimize(1, nocs, lidar, dec, grid, K2.clone(), sc["crop_size"], viz_type=None)
+    want = {k: opt_b.params[k].detach().clone() for k in opt_b.params}
+    for _ in range(3):          # fresh K tensors: their storage is recycled between calls
+        Kt = (K2 * 1.0).clone()
+        opt_c = Optimizer({k: v.copy() for k, v in sc["init"].items()}, cuda, sc["weights"])
+        opt_c.optimize(1, nocs, lidar, dec, grid, torch.from_numpy(sc["K"]).clone(), sc["crop_size"], viz_type=None)
+        for k in ("yaw", "trans", "scale", "latent"):
+            assert torch.equal(opt_c.params[k], params0[k]), k
+        opt_d = Optimizer({k: v.copy() for k, v in sc["init"].items()}, cuda, sc["weights"])
+        opt_d.optimize(1, nocs, lidar, dec, grid, Kt, sc["crop_size"], viz_type=None)
+        for k in ("yaw", "trans", "scale", "latent"):
+            assert torch.equal(opt_d.params[k], want[k]), k
+    # the .data reset above: a second step from the initial parameters with the continued Adam state
+    opt.optimize(1, nocs, lidar, dec, grid, torch.from_numpy(sc["K"]), sc["crop_size"], viz_type=None)
+    assert abs(float(params["yaw"][0]) - float(sc["init"]["yaw"][0])) < 0.011      # one Adam step of lr 0.01 from init
 
 
 def test_refine_is_deterministic_and_converges(stock_prior_path):
@@ -369,6 +532,46 @@ def test_batch_matches_single(stock_prior_path):
         opt, params, _ = _run_engine(stock_prior_path, d, 4)
         for k in ("yaw", "trans", "scale", "latent"):
             assert np.array_equal(params[k].detach().cpu().numpy().reshape(-1), r[k].reshape(-1)), k
+
+
+def test_cfg3_batch_of_32_matches_single(stock_prior_path):
+    """cfg3 at its stated size (BASELINE.json): 32 ragged synthetic crops x 50 optimizer steps on the 40^3
+    lattice, pose + latent.  The batched engine must give every detection bit for bit what it gets alone, a
+    smaller batch on the SAME engine (fewer active slots) too, and the frame-like sub-batches reuse the engine."""
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import BatchOptimizer, Optimizer
+    prior = P.load_prior(stock_prior_path)
+    scs = [scenes.random_detection(prior, s, density=20) for s in range(32)]    # scene synthesis at D=20 (CPU oracle)
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    grid = Grid3D(40, device=cuda)
+    w = {"2d": 0.3, "3d": 0.5}
+    dets = [{"params": d["init"], "nocs_pred": d["nocs_pred"], "lidar": d["lidar"], "K": torch.from_numpy(d["K"]),
+             "crop_size": d["crop_size"]} for d in scs]
+    bo = BatchOptimizer(w)
+    res = bo.optimize(50, dets, dec, grid)
+    eng = bo.engine
+    assert len(res) == 32 and all(r["history"].shape[0] == 50 for r in res)
+    moved = 0
+    for i, (d, r) in enumerate(zip(scs, res)):
+        params = {k: v.copy() for k, v in d["init"].items()}
+        opt = Optimizer(params, cuda, w)
+        opt.optimize(50, torch.from_numpy(d["nocs_pred"]), d["lidar"], dec, grid, torch.from_numpy(d["K"]),
+                     d["crop_size"], viz_type=None)
+        assert opt.engine is eng                                   # no re-allocation for a smaller batch
+        for k in ("yaw", "trans", "scale", "latent"):
+            assert np.array_equal(params[k].detach().cpu().numpy().reshape(-1), r[k].reshape(-1)), (i, k)
+        assert np.array_equal(opt.history, r["history"]), i
+        moved += int(np.isfinite(r["history"][:, 2]).all() and r["history"][-1, 2] < r["history"][0, 2])
+    assert moved >= 24, moved                                      # the loss goes down for (nearly) all of them
+    # frames of 1..8 detections on the same engine: same bits again, engine untouched
+    for lo, hi in ((0, 1), (1, 4), (4, 12), (12, 17)):
+        sub = bo.optimize(50, dets[lo:hi], dec, grid)
+        assert bo.engine is eng
+        for r, full in zip(sub, res[lo:hi]):
+            for k in ("yaw", "trans", "scale", "latent", "history"):
+                assert np.array_equal(r[k], full[k]), (lo, hi, k)
 
 
 # ------------------------------------------------------------------------------------------
@@ -422,42 +625,134 @@ def test_component_api_matches_fused_engine(stock_prior_path):
     assert np.abs(glat - g_fused[8:11]).max() < 1e-4 * np.abs(g_fused[8:11]).max(), (glat, g_fused[8:11])
 
 
-def test_get_kitti_label(stock_prior_path):
+def test_get_kitti_label_vs_reference_golden(golden_dir, stock_prior_path):
+    """a14: location / dimensions / rotation_y / alpha against the reference's get_kitti_label
+    (utils/refinement.py:501-562 with roty_in_bev 201-220 and alpha_in_bev 223-257), six refined states with
+    different LIDAR->camera matrices."""
     from sdflabel_b200.deepsdf.workspace import setup_dsdf
     from sdflabel_b200.grid import Grid3D
     from sdflabel_b200.utils.refinement import get_kitti_label
-    prior = P.load_prior(stock_prior_path)
+    g = np.load(os.path.join(golden_dir, "kitti_label.npz"))
     dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
     dec = dec.to(cuda)
     grid = Grid3D(30, device=cuda)
-    latent = torch.tensor([0.5, 0.7, 0.5], device=cuda)
-    label, pts, cam_T = get_kitti_label(dec, grid, latent, torch.tensor([2.0], device=cuda),
-                                        torch.tensor([0.1, 0.0, 4.0], device=cuda), torch.tensor([0.6], device=cuda),
-                                        np.eye(4), [0, 0, 10, 10])
-    sdf, nrm, _ = O.sdf_and_normals(prior, latent.cpu(), O.lattice(30))   # the un-normalised latent, as the reference does
-    sp, _, _, _ = O.surface_points(O.lattice(30), sdf.detach(), nrm)
-    ext = (sp.max(0)[0] - sp.min(0)[0]).numpy() * 2.0
-    assert np.allclose(label['dimensions'], [ext[1], ext[0], ext[2]], atol=1e-4)
-    assert label['name'] == 'Car' and abs(label['rotation_y']) <= np.pi
+    for i in range(int(g["count"])):
+        f = lambda k: g[f"c{i}_{k}"]
+        label, pts, cam_T = get_kitti_label(dec, grid, torch.from_numpy(f("latent")).to(cuda),
+                                            torch.from_numpy(f("scale")).to(cuda), torch.from_numpy(f("trans")).to(cuda),
+                                            torch.from_numpy(f("yaw")).to(cuda), f("p_WC"), list(f("bbox")))
+        assert label["name"] == "Car" and label["score"] == 1 and list(label["bbox"]) == list(f("bbox"))
+        assert abs(pts.shape[0] - int(f("n_points"))) <= 2, (i, pts.shape[0], int(f("n_points")))
+        assert np.abs(np.asarray(label["dimensions"]) - f("dimensions")).max() < 2e-5, i
+        assert np.abs(np.asarray(label["location"]) - f("location")).max() < 2e-5, i
+        assert abs(label["rotation_y"] - float(f("rotation_y"))) < 1e-6 and abs(label["alpha"] - float(f("alpha"))) < 1e-6
+        assert np.abs(cam_T - f("cam_T")).max() < 1e-6
 
 
-def test_coarse_lattice_pass_is_a_safe_preselection(stock_prior_path):
-    """The fp16-operand lattice pass only pre-selects band candidates with a 5e-3 margin; its error must
-    stay well inside that margin so that the accurate pass sees every true band point."""
+def test_batch_label_extents_match_get_kitti_label(stock_prior_path):
+    """The dump-time extents of a whole batch (sdfr_refine_label_extents) give the labels get_kitti_label computes
+    one detection at a time."""
     from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines.optimizer import BatchOptimizer
+    from sdflabel_b200.utils.refinement import get_kitti_label, kitti_label_from_extents
     prior = P.load_prior(stock_prior_path)
-    sc = scenes.make_scene(prior, size=32, density=40, n_lidar=100)
-    opt, params, dec = _run_engine(stock_prior_path, sc, 1)
-    if not dec.native().tcgen05:
-        pytest.skip("coarse pass only exists for the tensor-core decoder")
-    lat = torch.nn.functional.normalize(torch.from_numpy(sc["init"]["latent"]), dim=0)
+    scs = [scenes.random_detection(prior, s, density=20) for s in range(3)]
+    dec, L = setup_dsdf(stock_prior_path, precision=torch.float32)
+    dec = dec.to(cuda)
+    grid = Grid3D(30, device=cuda)
+    bo = BatchOptimizer({"2d": 0.3, "3d": 0.5})
+    res = bo.optimize(3, [{"params": d["init"], "nocs_pred": d["nocs_pred"], "lidar": d["lidar"],
+                           "K": torch.from_numpy(d["K"]), "crop_size": d["crop_size"]} for d in scs], dec, grid,
+                      extents=True)
+    p_WC = np.eye(4)
+    p_WC[:3, 3] = [0.1, -0.2, 0.3]
+    for r in res:
+        t = lambda k: torch.from_numpy(r[k]).to(cuda)
+        want, pts, cam_T = get_kitti_label(dec, grid, t("latent"), t("scale"), t("trans"), t("yaw"), p_WC, [0, 0, 9, 9])
+        got, cam_T2 = kitti_label_from_extents(r["extent_min"], r["extent_max"], r["latent"], r["scale"], r["trans"],
+                                               r["yaw"], p_WC, [0, 0, 9, 9])
+        assert r["extent_count"] == pts.shape[0]
+        assert np.array_equal(np.asarray(got["dimensions"]), np.asarray(want["dimensions"]))
+        assert np.array_equal(got["location"], want["location"]) and np.array_equal(cam_T, cam_T2)
+        assert got["rotation_y"] == want["rotation_y"] and got["alpha"] == want["alpha"]
+
+
+def _derived_prior(stock_prior_path, tmp_path, kind):
+    """Variants of the stock prior for the pre-selection tests: 'sharp' scales the last Linear (a steeper field
+    amplifies any error of the hidden layers), 'perturbed' is a different network of the same family (every
+    weight-norm gain multiplied by a seeded log-normal factor), 'steep' is sharp enough to break the margin."""
+    import json
+    ckpt = torch.load(stock_prior_path, map_location="cpu")["model_state_dict"]
+    sd = {k: v.clone() for k, v in ckpt.items()}
+    if kind in ("sharp", "steep"):
+        f = 2.5 if kind == "sharp" else 40.0
+        sd["module.lin8.weight"] = sd["module.lin8.weight"] * f
+        sd["module.lin8.bias"] = sd["module.lin8.bias"] * f
+    elif kind == "perturbed":
+        gen = torch.Generator().manual_seed(5)
+        for l in range(8):
+            k = f"module.lin{l}.weight_g"
+            sd[k] = sd[k] * torch.exp(0.08 * torch.randn(sd[k].shape, generator=gen))
+    path = os.path.join(str(tmp_path), f"prior_{kind}.pt")
+    spec = json.load(open(os.path.splitext(stock_prior_path)[0] + ".json"))
+    P.save_prior(path, O.DecoderSpec.from_json(spec), sd)
+    return path
+
+
+@pytest.mark.parametrize("kind", ["stock", "sharp", "perturbed"])
+def test_coarse_lattice_pass_is_a_safe_preselection(stock_prior_path, tmp_path, kind):
+    """The fp16-operand lattice pass only pre-selects band candidates with a 5e-3 margin.  On three priors and
+    three latents each: its error stays inside half the margin, the error the ENGINE measures on the selected
+    rows agrees with that, and the surfel set equals the one the fp32 CUDA-core decoder selects alone (up to
+    points within 1e-5 of the band edge)."""
+    from sdflabel_b200 import _lib
+    path = stock_prior_path if kind == "stock" else _derived_prior(stock_prior_path, tmp_path, kind)
+    prior = P.load_prior(path)
     pts = O.lattice(40)
-    ref = O.decoder_forward(prior, torch.cat([lat.expand(pts.shape[0], -1), pts], 1)).detach().numpy().ravel()
-    coarse = opt.engine.view(0, 'sdf').cpu().numpy()
-    err = np.abs(coarse - ref)
-    assert err.max() < 2.5e-3, err.max()
-    near = np.abs(ref) < 0.05
-    assert err[near].max() < 2.5e-3
+    for li, lat0 in enumerate(([0.6, 0.6, 0.5], [0.1, 0.9, 0.3], [-0.5, 0.4, 0.8])):
+        sc = scenes.make_scene(P.load_prior(stock_prior_path), size=32, density=20, n_lidar=100)
+        sc["density"] = 40
+        sc["init"]["latent"] = np.asarray(lat0, dtype=np.float32)
+        opt, params, dec = _run_engine(path, sc, 1)
+        if not dec.native().tcgen05:
+            pytest.skip("coarse pass only exists for the tensor-core decoder")
+        lat = torch.nn.functional.normalize(torch.from_numpy(sc["init"]["latent"]), dim=0)
+        ref = O.decoder_forward(prior, torch.cat([lat.expand(pts.shape[0], -1), pts], 1)).detach().numpy().ravel()
+        coarse = opt.engine.view(0, 'sdf').cpu().numpy()
+        err = np.abs(coarse - ref)
+        near = np.abs(ref) < 0.05
+        assert err[near].max() < 2.5e-3, (kind, li, err[near].max())
+        measured = opt.engine.preselect_error()
+        assert measured < 2.5e-3 and (not near.any() or measured > 0), (kind, li, measured)
+        m = int(opt.engine.view(0, 'surf_count').item())
+        keep = opt.engine.view(0, 'surf_valid')[:m].bool().cpu().numpy()
+        got = set(opt.engine.view(0, 'surf_idx')[:m].cpu().numpy()[keep].tolist())
+        want = set(np.nonzero(np.abs(ref) < 0.03)[0].tolist())
+        edge = set(np.nonzero(np.abs(np.abs(ref) - 0.03) < 1e-5)[0].tolist())
+        assert (got ^ want) <= edge, (kind, li, len(got ^ want))
+        ffma, _, _ = _run_engine(path, sc, 1, impl=_lib.MLP_FFMA)
+        m2 = int(ffma.engine.view(0, 'surf_count').item())
+        assert set(ffma.engine.view(0, 'surf_idx')[:m2].cpu().numpy().tolist()) ^ got <= edge
+        print(f"preselection {kind}/{li}: coarse err near band {err[near].max():.2e}, engine-measured {measured:.2e}, "
+              f"{len(got)} band points")
+
+
+def test_preselection_guard_trips_on_a_steep_field(stock_prior_path, tmp_path):
+    """A network whose last Linear is scaled by 40 makes the fp16-operand pass miss the margin: the engine must
+    say so (SDFR_E_UNSUPPORTED through the read-back) instead of silently dropping band points, and the fp32
+    CUDA-core decoder must still work for it."""
+    from sdflabel_b200 import _lib
+    path = _derived_prior(stock_prior_path, tmp_path, "steep")
+    sc = scenes.make_scene(P.load_prior(stock_prior_path), size=32, density=20, n_lidar=100)
+    sc["density"] = 40
+    probe = _run_engine(stock_prior_path, sc, 1)[2]
+    if not probe.native().tcgen05:
+        pytest.skip("coarse pass only exists for the tensor-core decoder")
+    with pytest.raises(_lib.SdfrError, match="pre-selection"):
+        _run_engine(path, sc, 1)
+    opt, params, dec = _run_engine(path, sc, 1, impl=_lib.MLP_FFMA)
+    assert opt.history.shape[0] == 1
 
 
 def test_coarse_pass_ragged_rows_and_batches(stock_prior_path):

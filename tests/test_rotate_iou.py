@@ -56,7 +56,10 @@ def test_cuda_kernel_vs_reference_and_oracle():
         assert got.dtype == np.float32 and np.abs(got - g[f"iou_crit{c}"]).max() < TOL * (10 if c == 2 else 1)
     assert np.abs(prod.rotate_iou_gpu_eval(g["special"], g["special"], -1) - g["special_iou"]).max() < TOL
     assert np.abs(prod.rotate_iou_gpu_eval(g["boxes_ragged"], g["query_ragged"], -1) - g["iou_ragged"]).max() < TOL
-    assert prod.rotate_iou_gpu_eval(g["boxes"].astype(np.float64), g["query"].astype(np.float64)).dtype == np.float64
+    # float64 boxes come back as float32: the reference casts `boxes` first, then `iou.astype(boxes.dtype)`
+    assert prod.rotate_iou_gpu_eval(g["boxes"].astype(np.float64), g["query"].astype(np.float64)).dtype == np.float32
+    # and the empty case keeps that dtype (rotate_iou.py:308-310)
+    assert prod.rotate_iou_gpu_eval(np.zeros((0, 5)), g["query"]).dtype == np.float32
     # seeded larger case against the oracle: several 64 x 64 tiles, ragged edges
     rng = np.random.RandomState(3)
     from oracle.make_golden_iou import random_boxes
