@@ -10,24 +10,38 @@ DeepSDF latent.  A *step* is one full refine iteration of the reference's
 input gradient -> band extraction -> surfel splat -> 2D + 3D losses -> every
 gradient -> Adam/SGD update.  rays/s = detections * W * H / step time.
 
-``value``  : device-resident inputs, CUDA-event timed, L2 flushed between steps.
-``e2e``    : the same step through the public API ``Optimizer.optimize(1, ...)`` with
-             host (pinned) inputs: H2D of the NOCS prediction, LIDAR crop, K and
-             parameters, D2H of parameters + loss history, every step.
-``roofline``: the dominant kernel (DeepSDF MLP forward + input-gradient) timed alone.
+``value``   : device-resident inputs, CUDA-event timed, L2 flushed between steps.
+``e2e``     : the same step through the public API ``Optimizer.optimize(1, ...)`` with
+              host (pinned) inputs: H2D of the NOCS prediction, LIDAR crop, K and
+              parameters, D2H of parameters + loss history, every step.
+``roofline``: the dominant kernel (the DeepSDF lattice pass) timed alone (burst peak).
+``kernels`` : every stage of one iteration timed with events (un-captured launches), each with the
+              roofline that bounds it (tensor pipe or HBM) and its fraction of the measured peak.
+``sustained``: the same step replayed back to back for >= 3 s (power-capped clocks), and the lattice
+              kernel alone for >= 1.5 s against the SUSTAINED bf16 peak.
+``cfg3``    : BASELINE.json configs[2]: 32 ragged synthetic crops x 50 optimizer steps in one batch.
+``frames``  : BASELINE.json configs[3]: the frame loop of refine_css.py (pose initialisation, 60
+              refinement steps, KITTI label, per-frame dump) over 512 synthetic frames of 1-8 detections,
+              frames sharded over the N ranks by detection count, labels all-gathered over NCCL at
+              dump time; frames/s over the whole loop (strong scaling), a checksum of all label records
+              (identical for every N) and a bit-exact re-refinement of a sample of frames on rank 0.
 ``cpu_baseline`` / ``--impl reference``: the oracle restatement of the reference's
-             algorithm (torch CPU fp32, all host threads, decoder weights left
-             requiring grad so the two wasted dW passes of the reference are paid).
-N > 1: frames are sharded, one process per GPU, no data-path collective (weak scaling);
-the label all-gather happens after the timed region (dump time).
+              algorithm (torch CPU fp32, all host threads, decoder weights left
+              requiring grad so the two wasted dW passes of the reference are paid).
+``torch_gpu_baseline``: the same restatement on device='cuda' (plain PyTorch on the B200) at cfg1.
+N > 1: one process per GPU, no data-path collective; the headline ``value`` is weak scaling
+(every rank refines its own detection), the ``frames`` block is strong scaling.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -35,11 +49,12 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 SIZE = 256
 DENSITY = 40
 PRIOR = os.path.join(ROOT, "assets", "deepsdf_synth.pt")
-FLOP_PER_POINT_FWD = None   # filled from the decoder spec
+REFINE_ITERS = 60            # the reference's iteration count per detection (config_refine.ini `iters`)
 
 
 def mlp_flops_per_point(spec_json):
@@ -77,7 +92,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def summary(self, t0=None, t1=None):
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, r in list(self.rows):
+            if (t0 is not None and t < t0) or (t1 is not None and t > t1):
+                continue
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
     def stop(self):
         if not self.proc:
@@ -87,21 +121,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return self.summary()
 
 
 def load_scene():
@@ -113,15 +133,24 @@ def load_scene():
 
 
 def load_oracle_prior():
-    """Only the cpu_baseline / --impl reference legs touch the oracle."""
+    """Only the cpu_baseline / torch_gpu_baseline / --impl reference legs touch the oracle."""
     from oracle import prior as P
     return P.load_prior(PRIOR)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return {"tensor": p["bf16_tflops"], "tensor_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "hbm": p["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json)"}
+    return {"tensor": 1590.0, "tensor_sustained": 1590.0, "hbm": 6500.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm
 # ------------------------------------------------------------------------------------------------
-def cpu_iteration_time(prior, sc, steps, warmup, threads=None):
+def cpu_iteration_time(prior, sc, steps, warmup, threads=None, size=SIZE, tile_rows=16):
     import torch
     from oracle import sdf_oracle as O
     threads = threads or os.cpu_count() or 1
@@ -135,13 +164,41 @@ def cpu_iteration_time(prior, sc, steps, warmup, threads=None):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.refine_iteration(prior, pts, K, SIZE, SIZE, st, nocs, sc["lidar"], sc["weights"]["2d"], sc["weights"]["3d"],
-                           tile_rows=16)
+        O.refine_iteration(prior, pts, K, size, size, st, nocs, sc["lidar"], sc["weights"]["2d"], sc["weights"]["3d"],
+                           tile_rows=tile_rows)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     for t in list(prior.weight) + list(prior.bias):
         t.requires_grad_(False)
     return float(np.mean(times)), threads
+
+
+def torch_gpu_iteration_time(dev, steps=5, warmup=2):
+    """The oracle restatement of the reference algorithm on device='cuda' (plain PyTorch ops on the B200) at
+    cfg1 (64x64, D=40: the largest crop whose M x P x 3 tensors the reference formulation holds comfortably)."""
+    import torch
+    from oracle import prior as P, scenes, sdf_oracle as O
+    prior_cpu = P.load_prior(PRIOR)
+    sc = scenes.make_scene(prior_cpu, size=64, density=DENSITY)
+    with torch.device(dev):
+        prior = O.DecoderParams(prior_cpu.spec, [w.to(dev).requires_grad_(True) for w in prior_cpu.weight],
+                                [b.to(dev).requires_grad_(True) for b in prior_cpu.bias])
+        pts = O.lattice(DENSITY).to(dev)
+        st = O.RefineState.create(**sc["init"])
+        st = O.RefineState(st.yaw.to(dev), st.trans.to(dev), st.scale.to(dev), st.latent.to(dev))
+        K = torch.from_numpy(sc["K"]).to(dev)
+        nocs = torch.from_numpy(sc["nocs_pred"]).to(dev)
+        times = []
+        for i in range(warmup + steps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = O.refine_iteration(prior, pts, K, 64, 64, st, nocs, sc["lidar"], sc["weights"]["2d"],
+                                     sc["weights"]["3d"])
+            float(out["loss"])                      # the reference's .item() prints (optimizer.py:153)
+            torch.cuda.synchronize()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), sc
 
 
 def run_reference(args, rank, world):
@@ -176,6 +233,157 @@ def workload_config(batch):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def stage_table(lib, eng, B, flop_pt, pk, band_rows_hint=None):
+    """Per-stage device times of one iteration with the roofline that bounds each stage."""
+    n = C.c_int(0)
+    ms = np.zeros(16, dtype=np.float32)
+    rows = C.c_int32(0)
+    from sdflabel_b200 import _lib
+    _lib.check(lib.sdfr_refine_profile(eng.handle, 5, _lib.fptr(ms), 16, C.byref(n), C.byref(rows), _lib.stream_ptr()))
+    ms = [float(v) for v in ms]
+    ng = DENSITY ** 3
+    P = SIZE * SIZE
+    m = int(rows.value)                       # rows of the band pass (pre-selected lattice points), whole batch
+    # algorithmic work per launch (DESIGN.md section 3): flops for the two decoder passes, bytes for the rest
+    alg = {
+        "lattice_pass": ("tensor", flop_pt * ng * B),
+        "band_pass": ("tensor", 2.0 * flop_pt * m),
+        "band_select": ("hbm", B * ng * 4 + m * 4),
+        "band_surface": ("hbm", m * (4 + 4 + 6 * 4) + m * (12 + 12 + 4 + 12 + 1)),
+        "project": ("hbm", m * (24 + 60)),
+        "splat_forward": ("hbm", m * 44 + B * P * (32 + 48)),
+        "loss2d": ("hbm", B * P * (12 + 12 + 16)),
+        "loss3d": ("hbm", m * (12 + 20)),
+        "grad_prep": ("hbm", B * P * (16 + 32 + 48)),
+        "splat_backward": ("hbm", m * (44 + 36)),
+        "chain": ("hbm", m * 100),
+    }
+    table = []
+    total = float(sum(ms[:n.value]))
+    for k in range(n.value):
+        name = lib.sdfr_refine_stage_name(k).decode()
+        row = {"kernel": name, "ms": float(ms[k]), "share": float(ms[k]) / total if total else None}
+        if name in alg:
+            bound, work = alg[name]
+            row["bound"] = bound
+            if ms[k] > 0:
+                if bound == "tensor":
+                    row["achieved"] = work / (ms[k] * 1e-3) / 1e12
+                    row["unit"] = "TFLOP/s"
+                    row["frac"] = row["achieved"] / pk["tensor"]
+                else:
+                    row["achieved"] = work / (ms[k] * 1e-3) / 1e9
+                    row["unit"] = "GB/s"
+                    row["frac"] = row["achieved"] / pk["hbm"]
+        else:
+            row["bound"] = "latency"
+        table.append(row)
+    return table, m, total
+
+
+def run_cfg3(dec, grid, weights, dev):
+    """configs[2]: 32 ragged synthetic crops x 50 optimizer steps, one batch, pose + latent."""
+    import torch
+    import synth_frames
+    from sdflabel_b200.pipelines.optimizer import BatchOptimizer
+    pool = synth_frames.load_pool()
+    g = np.load(synth_frames.POOL)
+    rng = np.random.RandomState(11)
+    dets = []
+    for i in range(32):
+        j = i % len(pool)
+        src = pool[j]
+        gt = {k: g[f"p{j}_gt_{k}"] for k in ("yaw", "trans", "scale", "latent")}
+        init = {"yaw": gt["yaw"] + rng.normal(0, 0.08, 1), "trans": gt["trans"] + rng.normal(0, 0.05, 3),
+                "scale": gt["scale"] + rng.normal(0, 0.03, 1), "latent": src["latent_pred"]}
+        dets.append({"params": {k: np.asarray(v, dtype=np.float32) for k, v in init.items()}, "nocs_pred": src["nocs_pred"],
+                     "lidar": src["lidar"], "K": torch.from_numpy(src["K"]), "crop_size": [int(v) for v in src["crop_size"]]})
+    bo = BatchOptimizer(weights, device=dev)
+    bo.optimize(2, dets, dec, grid)                      # allocation, graph capture
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = bo.optimize(50, dets, dec, grid)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    # device time of the 50 steps alone
+    eng = bo.engine
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.run(50)
+    b.record()
+    torch.cuda.synchronize()
+    dev_s = a.elapsed_time(b) * 1e-3
+    rays = sum(d["crop_size"][0] * d["crop_size"][1] for d in dets)
+    improved = sum(int(np.isfinite(r["history"][:, 2]).all() and r["history"][-1, 2] < r["history"][0, 2]) for r in res)
+    return {"workload": "cfg3: 32 ragged synthetic crops (33x43 .. 78x45 px, 84-786 LIDAR points) x 50 optimizer steps, "
+                        "pose + latent, one batch on one GPU, Grid3D(40)",
+            "device_ms_per_step": dev_s / 50 * 1e3, "detection_iterations_per_s": 32 * 50 / dev_s,
+            "rays_per_s": rays * 50 / dev_s, "e2e_s": wall, "e2e_detection_iterations_per_s": 32 * 50 / wall,
+            "losses_improved": improved}
+
+
+def run_frames(args, dec, grid, weights, dev, rank, world, dist):
+    """configs[3]: the frame loop, frames sharded by detection count, label all-gather at dump time."""
+    import torch
+    import synth_frames
+    from sdflabel_b200.pipelines import frames as F
+    from sdflabel_b200.pipelines.refine_frames import FrameRefiner, records_of
+    frames = synth_frames.make_frames(args.frames, seed=0)
+    counts = [len(f["detections"]) for f in frames]
+    mine = F.shard_frames(len(frames), rank, world, counts)
+    out_dir = tempfile.mkdtemp(prefix=f"sdfr_labels_r{rank}_")
+    fr = FrameRefiner(dec, grid, weights, iters=REFINE_ITERS, max_batch=args.frame_batch)
+    fr.refine(synth_frames.make_frames(2, seed=99), [0, 1])            # warm-up: allocations, graph capture
+    fr.timing = {k: 0 for k in fr.timing}
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t0 = time.perf_counter()
+    done = fr.refine(frames, mine, out_dir)
+    torch.cuda.synchronize()
+    local_s = time.perf_counter() - t0
+    recs = records_of(done, dec.latent_size)
+    tg = time.perf_counter()
+    allrec = F.gather_labels(recs, dec.latent_size, device=dev)       # the ONE exchange: label records over NCCL
+    torch.cuda.synchronize()
+    gather_s = time.perf_counter() - tg
+    total_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([total_s, local_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_s, slowest_local = float(t[0]), float(t[1])
+        t = torch.tensor([local_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        fastest_local = float(t[0])
+    else:
+        slowest_local = fastest_local = local_s
+    dumped = len(os.listdir(out_dir))
+    shutil.rmtree(out_dir, ignore_errors=True)
+    block = None
+    if rank == 0:
+        # T11 on a sample: frames refined by ANY rank, re-refined here alone, must give the same records bit for bit
+        sample = sorted(np.random.RandomState(5).choice(len(frames), size=min(8, len(frames)), replace=False).tolist())
+        again = records_of(FrameRefiner(dec, grid, weights, iters=REFINE_ITERS, max_batch=5).refine(frames, sample),
+                           dec.latent_size)
+        ref_rows = allrec[np.isin(allrec[:, 0], sample)]
+        n_det = int(sum(counts))
+        block = {
+            "workload": f"cfg4: {len(frames)} synthetic frames of 1-8 detections ({n_det} detections), per detection: model "
+                        f"cloud of the predicted latent + Kabsch RANSAC pose initialisation, {REFINE_ITERS} refinement steps "
+                        f"(Grid3D({DENSITY}), crops <= 96 px), KITTI label, per-frame .pkl dump; frames sharded over "
+                        f"{world} rank(s) by detection count, one all-gather of the label records",
+            "frames": len(frames), "detections": n_det, "labels": int(allrec.shape[0]),
+            "frames_per_s": len(frames) / total_s, "detections_per_s": n_det / total_s, "seconds": total_s,
+            "scaling": "strong", "n_gpus": world,
+            "slowest_rank_s": slowest_local, "fastest_rank_s": fastest_local, "gather_s": gather_s,
+            "checksum": F.checksum(allrec), "resample_bit_exact": bool(np.array_equal(again, ref_rows)),
+            "resampled_frames": len(sample), "dumped_frames_rank0": dumped,
+            "rank0_breakdown_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in fr.timing.items()},
+            "detections_per_batch": args.frame_batch,
+        }
+    return block
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from sdflabel_b200 import _lib
@@ -198,6 +406,7 @@ def run_ours(args, rank, world, local_rank):
     sc = load_scene()
     spec_json = json.load(open(os.path.splitext(PRIOR)[0] + ".json"))
     flop_pt = mlp_flops_per_point(spec_json)
+    pk = peaks()
     B = args.batch
 
     dec, L = setup_dsdf(PRIOR, precision=torch.float32)
@@ -213,6 +422,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident loop: engine iterations ------------------------------------------
     eng = _engine_for(dec, B, DENSITY, SIZE, SIZE, sc["lidar"].shape[0], 64, sc["weights"], dec.mlp_impl)
+    eng.set_active(B)
     for b in range(B):
         eng.set_detection(b, K, SIZE, SIZE, nocs, sc["lidar"], sc["init"]["yaw"], sc["init"]["trans"],
                           sc["init"]["scale"], sc["init"]["latent"])
@@ -224,6 +434,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
+    t_head0 = time.perf_counter()
     launches0 = lib.sdfr_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
@@ -265,6 +476,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * SIZE * SIZE / e2e_s
+    t_head1 = time.perf_counter()
 
     # ---- roofline of the dominant kernel: the DeepSDF MLP forward over the lattice ---------------
     # (the engine evaluates the input gradient only for the ~2.5 % of the lattice inside the band, so the
@@ -272,17 +484,19 @@ def run_ours(args, rank, world, local_rank):
     ng = DENSITY ** 3
     lat = torch.nn.functional.normalize(torch.from_numpy(sc["init"]["latent"]), dim=0).to(dev).repeat(B, 1).contiguous()
     sdf = torch.empty(B * ng, device=dev)
-    dinp = torch.empty(B * ng, L + 3, device=dev)
     impl = dec.mlp_impl if dec.mlp_impl else (_lib.MLP_TCGEN05 if dec.native().tcgen05 else _lib.MLP_FFMA)
     # the engine's lattice pass: fp16-operand (hi-only) forward when the tensor-core decoder is in use
     k_impl = _lib.MLP_TCGEN05_COARSE if impl == _lib.MLP_TCGEN05 else impl
+
+    def lattice_launch():
+        _lib.check(lib.sdfr_decoder_eval_lattice(dec.native().handle, lat.data_ptr(), B, DENSITY, sdf.data_ptr(),
+                                                 0, k_impl, _lib.stream_ptr()))
     kev = []
     for i in range(3 + args.steps):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        _lib.check(lib.sdfr_decoder_eval_lattice(dec.native().handle, lat.data_ptr(), B, DENSITY, sdf.data_ptr(),
-                                                 0, k_impl, _lib.stream_ptr()))
+        lattice_launch()
         b.record()
         if i >= 3:
             kev.append((a, b))
@@ -290,53 +504,136 @@ def run_ours(args, rank, world, local_rank):
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     alg_flops = 1.0 * flop_pt * ng * B          # forward over the lattice (F flop per point)
     achieved = alg_flops / (k_ms * 1e-3) / 1e12
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, peak_src = json.load(open(peaks_path))["bf16_tflops"], "measured (MEASURED_PEAKS.json bf16_tflops, burst)"
-    else:
-        peak, peak_src = 1590.0, "fallback (B200_PROFILING.md)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "mlp_dram_bytes.json")
     if os.path.isfile(tpath):
         traffic = json.load(open(tpath)).get("bytes_per_launch")
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": _lattice_kernel_name(impl),
-                "kernel_ms": k_ms, "share_of_step": k_ms / ms_per_step, "peak_source": peak_src,
-                "algorithmic_flops_per_launch": alg_flops,
-                "issued_over_algorithmic": 1.0,
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tensor"], "traffic": traffic, "kernel": _lattice_kernel_name(impl),
+                "kernel_ms": k_ms, "share_of_step": k_ms / ms_per_step,
+                "peak_source": pk["source"] + " bf16_tflops, burst (kernel timed alone)",
+                "algorithmic_flops_per_launch": alg_flops, "issued_over_algorithmic": 1.0,
                 "note": "lattice pass of the engine (forward, one fp16 MMA per product); the accurate 3-MMA "
                         "forward+gradient pass runs on the pre-selected band points only"}
 
-    clocks = sampler.stop() if rank == 0 else None
+    extras = {}
+    if rank == 0 and not args.quick:
+        # ---- per-stage table ----------------------------------------------------------------------
+        try:
+            table, band_rows, stage_total = stage_table(lib, eng, B, flop_pt, pk)
+            extras["kernels"] = {"per_stage": table, "band_rows": band_rows, "sum_ms": stage_total,
+                                 "note": "un-captured launches with an event after every stage, mean of 5 iterations; "
+                                         "algorithmic flops / bytes per stage as in DESIGN.md section 3; peaks: "
+                                         f"{pk['tensor']} TFLOP/s bf16, {pk['hbm']} GB/s ({pk['source']})"}
+        except Exception as e:   # noqa: BLE001
+            extras["kernels"] = {"error": str(e)}
+    if not args.quick:
+        # ---- sustained: the step replayed back to back for >= 3 s, the lattice kernel alone for >= 1.5 s ----
+        for b in range(B):
+            eng.set_detection(b, K, SIZE, SIZE, nocs, sc["lidar"], sc["init"]["yaw"], sc["init"]["trans"],
+                              sc["init"]["scale"], sc["init"]["latent"])
+        torch.cuda.synchronize()
+        ts0 = time.perf_counter()
+        chunks = []
+        while time.perf_counter() - ts0 < args.sustain:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.run(200)
+            b.record()
+            torch.cuda.synchronize()
+            chunks.append(a.elapsed_time(b) / 200)
+        ts1 = time.perf_counter()
+        kchunks = []
+        tk0 = time.perf_counter()
+        while time.perf_counter() - tk0 < args.sustain / 2:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(200):
+                lattice_launch()
+            b.record()
+            torch.cuda.synchronize()
+            kchunks.append(a.elapsed_time(b) / 200)
+        tk1 = time.perf_counter()
+        sus_ms = float(np.mean(chunks[len(chunks) // 2:]))          # second half: clocks have settled
+        sus_k_ms = float(np.mean(kchunks[len(kchunks) // 2:]))
+        if dist:
+            t = torch.tensor([sus_ms, sus_k_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sus_ms, sus_k_ms = float(t[0]), float(t[1])
+        if rank == 0:
+            sus_ach = alg_flops / (sus_k_ms * 1e-3) / 1e12
+            extras["sustained"] = {
+                "seconds": ts1 - ts0, "ms_per_step": sus_ms, "value": world * B * SIZE * SIZE / (sus_ms * 1e-3),
+                "unit": "rays/s", "l2": "not flushed (graph replays back to back)",
+                "clocks": sampler.summary(ts0, ts1),
+                "lattice_kernel": {"seconds": tk1 - tk0, "kernel_ms": sus_k_ms, "achieved": sus_ach,
+                                   "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                                   "frac": sus_ach / pk["tensor_sustained"],
+                                   "peak_source": pk["source"] + " bf16_tflops_sustained",
+                                   "clocks": sampler.summary(tk0, tk1)}}
+    head_clocks = sampler.summary(t_head0, t_head1) if rank == 0 else None
 
-    # ---- dump-time exchange (N > 1): all-gather of the label records ---------------------------------
-    if dist:
-        rec = torch.tensor(np.concatenate([[rank], params_after]).astype(np.float32), device=dev)
-        out = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(out, rec)
+    # ---- cfg3 (rank 0) and cfg4 (all ranks) ---------------------------------------------------------
+    if rank == 0 and not args.quick:
+        try:
+            extras["cfg3"] = run_cfg3(dec, grid, sc["weights"], dev)
+        except Exception as e:   # noqa: BLE001
+            extras["cfg3"] = {"error": repr(e)}
+    frames_block = None
+    if args.frames > 0 and not args.quick:
+        frames_block = run_frames(args, dec, grid, sc["weights"], dev, rank, world, dist)
+
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
         cpu = None
+        tgb = None
         if world == 1 and not args.no_cpu:
             sec, threads = cpu_iteration_time(load_oracle_prior(), sc, 1, 0)
             cpu = {"value": SIZE * SIZE / sec, "unit": "rays/s", "cores": threads, "kind": "port",
                    "sample": f"1 full refine iteration at {SIZE}x{SIZE}, D={DENSITY} (oracle port, torch CPU fp32, "
                              f"16-row pixel tiles, decoder dW passes kept as in the reference), {sec:.1f} s"}
+            try:
+                tsec, sc64 = torch_gpu_iteration_time(dev)
+                # our engine on the very same cfg1 scene
+                p64 = {k: v.copy() for k, v in sc64["init"].items()}
+                o64 = Optimizer(p64, dev, sc64["weights"])
+                n64 = torch.from_numpy(sc64["nocs_pred"]).pin_memory()
+                K64 = torch.from_numpy(sc64["K"])
+                ours = []
+                for i in range(8):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    o64.optimize(1, n64, sc64["lidar"], dec, grid, K64, sc64["crop_size"], viz_type=None)
+                    torch.cuda.synchronize()
+                    if i >= 3:
+                        ours.append(time.perf_counter() - t0)
+                tgb = {"value": 64 * 64 / tsec, "unit": "rays/s", "ms_per_step": tsec * 1e3, "kind": "port",
+                       "ours_e2e_ms_same_config": float(np.mean(ours)) * 1e3, "speedup_e2e": tsec / float(np.mean(ours)),
+                       "sample": "cfg1 (64x64, D=40, 1 detection): the oracle restatement of the reference algorithm "
+                                 "run with plain PyTorch ops on this B200 (device='cuda', fp32, dW passes kept, one "
+                                 ".item() sync per iteration like the reference's loss print), mean of 5 iterations "
+                                 "after 2 warm-ups; 256x256 does not fit this formulation (M x P x 3 tensors)"}
+            except Exception as e:   # noqa: BLE001
+                tgb = {"unavailable": repr(e)[:300]}
         line = {
             "metric": "rays/s (fwd+bwd) 256x256 DeepSDF render", "value": value, "unit": "rays/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B),
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": head_clocks if head_clocks and head_clocks.get("samples") else clocks,
+            "clocks_whole_run": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3, "api": "sdflabel_b200.pipelines.optimizer.Optimizer.optimize(1, ...)"},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "frames_per_s": world * B / (ms_per_step * 1e-3) / 60.0,
-            "notes": {"frames_per_s": "detections/s assuming the reference's 60 iterations per detection",
+            "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": tgb,
+            "frames_per_s": frames_block["frames_per_s"] if frames_block else None,
+            "frames": frames_block,
+            "notes": {"frames_per_s": "measured over the whole frame loop of the `frames` block (strong scaling)",
                       "final_loss": float(hist[-1, 2]) if len(hist) else None,
                       "mlp_impl": "tcgen05" if impl == _lib.MLP_TCGEN05 else "ffma"},
         }
-        print(json.dumps(line), flush=True)
+        line.update(extras)
+        print(json.dumps(line, default=float), flush=True)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -345,13 +642,7 @@ def run_ours(args, rank, world, local_rank):
 def _lattice_kernel_name(impl):
     """Name of the kernel the lattice pass launches (the dispatch of csrc/mlp_tc.cu:launch_mlp_tc_coarse)."""
     from sdflabel_b200 import _lib
-    if impl != _lib.MLP_TCGEN05:
-        return "mlp_ffma_kernel"
-    if os.environ.get("SDFR_TC_PINGPONG", "1") == "0":
-        return "mlp_tc_kernel"
-    if os.environ.get("SDFR_TC_PAIR", "1") != "0":
-        return "mlp_tc_coarse_pair_kernel"
-    return "mlp_tc_coarse_wide_kernel" if os.environ.get("SDFR_TC_WIDE", "1") != "0" else "mlp_tc_coarse_kernel"
+    return "mlp_tc_coarse_pair_kernel" if impl == _lib.MLP_TCGEN05 else "mlp_ffma_kernel"
 
 
 def main():
@@ -362,7 +653,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="detections per GPU per step")
     ap.add_argument("--mlp", default="auto", choices=["auto", "ffma", "tcgen05"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / torch_gpu_baseline legs")
+    ap.add_argument("--quick", action="store_true", help="headline numbers only (profiling runs)")
+    ap.add_argument("--frames", type=int, default=512, help="frames of the cfg4 block (0 = skip)")
+    ap.add_argument("--frame-batch", type=int, default=32, help="detections refined together in the frame loop")
+    ap.add_argument("--sustain", type=float, default=3.0, help="seconds of the sustained block")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

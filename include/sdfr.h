@@ -50,6 +50,13 @@ enum {
 
 enum { SDFR_ROT_DCM = 0, SDFR_ROT_QUAT = 1 };
 
+/* Rasterer primitives (rasterer.py:93-105) */
+enum {
+  SDFR_PRIM_DISC = 0,       /* inside_surfel, diam 0.04: tangent discs (the refine loop's primitive) */
+  SDFR_PRIM_CIRCLE = 1,     /* inside_circle, diam 0.02: screen-space circles, sigmoid soft clamp */
+  SDFR_PRIM_CIRCLE_OPT = 2  /* inside_circle_opt, diam 0.025: 15 x 15 pixel stamps */
+};
+
 int sdfr_version(void);
 const char* sdfr_last_error(void);
 /* bit 0: a CUDA device is visible; bit 1: that device is sm_100 (tcgen05 path usable) */
@@ -122,10 +129,10 @@ int sdfr_surface_extract(const float* points_dev, int density, const float* sdf_
                          int32_t* scratch_dev, void* stream);
 
 /* ------------------------------------------------------------------------- *
- * Rasterer (disc / surfel primitive).
- * replaces: sdfrenderer/renderer/rasterer.py:49-155 (forward, primitives='disc'),
+ * Rasterer.
+ * replaces: sdfrenderer/renderer/rasterer.py:49-155 (forward: 'disc', 'circle', 'circle_opt', bg),
  *           renderer/projection.py:7-101 (dcm) and 104-199 (quat),
- *           renderer/primitives.py:165-243 (inside_surfel),
+ *           renderer/primitives.py:165-243 (inside_surfel), 4-68 (inside_circle), 71-162 (inside_circle_opt),
  *           renderer/utils_rasterer.py:6-24 (qrot)
  * ------------------------------------------------------------------------- */
 typedef struct {
@@ -136,6 +143,10 @@ typedef struct {
                               SDFR_ROT_QUAT: pose = [qw,qx,qy,qz,tx,ty,tz] */
   int32_t output_nocs;     /* 1: colours = object coords (x negated in the dcm path) shown as (c+1)/2;
                               0: colours = the given colour tensor, unscaled (rasterer.py:113-116) */
+  int32_t primitive;       /* SDFR_PRIM_* (rasterer.py:93-105) */
+  const float* bg_dev;     /* background image [3,H,W] or NULL (rasterer.py:107-111): composited into color
+                              and mask; with a background the depth / normals maps are not available (the
+                              reference fails to broadcast them) and colours are shown as (c+1)/2 */
 } sdfr_raster_cfg;
 
 /* Workspace sizes (bytes) for m surfels at the configured resolution. */
@@ -289,8 +300,20 @@ int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void* stream);
 /* Dump-time extents of get_kitti_label (utils/refinement.py:527-541) for all active detections: one more
  * lattice evaluation with the CURRENT latent as it is (not normalised, refine_css.py:229), band extraction,
  * min / max of the isosurface points.  extents_host [active, 8] = min xyz, max xyz (un-scaled object frame),
- * point count, 0.  Overwrites the intermediates of the last iteration; synchronises `stream`. */
+ * band point count, pre-selected row count (the length of views 2 / 3 / 12 / 14).  Overwrites the intermediates
+ * of the last iteration (the isosurface points themselves stay readable through sdfr_refine_view: this is
+ * also how the model clouds of the pose initialisation are produced, refine_css.py:143-151); synchronises. */
 int sdfr_refine_label_extents(sdfr_refine* r, float* extents_host, void* stream);
+/* Overwrites the latent of slot b (host -> device, stream-ordered) without touching anything else. */
+int sdfr_refine_set_latent(sdfr_refine* r, int b, const float* latent_host, void* stream);
+
+/* Measurement aid (bench.py's per-kernel table): runs `iters` iterations of the active detections WITHOUT the
+ * CUDA graph, with an event after every stage, and returns the mean device time of each stage in milliseconds
+ * (stage_ms_host [>= 13]; *n_stages = 13; names from sdfr_refine_stage_name) and the number of rows the band
+ * pass evaluated in the last iteration.  The iterations are real ones (the parameters move).  Synchronises. */
+int sdfr_refine_profile(sdfr_refine* r, int iters, float* stage_ms_host, int max_stages, int* n_stages,
+                        int32_t* band_rows_host, void* stream);
+const char* sdfr_refine_stage_name(int stage);
 
 /* Writes the current parameters of detection b into caller-owned DEVICE buffers (yaw [1], trans [3],
  * scale [1], latent [L]; any may be NULL) with one stream-ordered launch: the in-place update of the

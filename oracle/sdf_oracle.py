@@ -526,7 +526,7 @@ def iteration_losses(p: DecoderParams, pts, K, width, height, state: RefineState
     """Forward of one iteration with leaves (yaw, trans, scale, latent).  Returns
     a dict with both losses, the rendering and the surfels (graph attached)."""
     dt = pts.dtype
-    lidar_s = torch.as_tensor(lidar, dtype=torch.float32) / state.scale          # optimizer.py:84
+    lidar_s = torch.as_tensor(lidar, dtype=torch.float32).to(state.scale.device) / state.scale   # optimizer.py:84
     lidar_s = lidar_s.to(dt)
     pose = yaw_pose(state.yaw, state.trans)                                       # 87-90
     lat = torch.nn.functional.normalize(state.latent, p=2, dim=0)                 # 96

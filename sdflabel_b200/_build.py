@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libsdfr.so")
-SOURCES = ["api.cu", "mlp_ffma.cu", "mlp_tc.cu", "surface.cu", "splat.cu", "loss.cu", "refine.cu", "trace.cu", "pose.cu", "rotate_iou.cu", "np_random.cu"]
+SOURCES = ["api.cu", "mlp_ffma.cu", "mlp_tc.cu", "surface.cu", "splat.cu", "circle.cu", "loss.cu", "refine.cu", "trace.cu", "pose.cu", "rotate_iou.cu", "np_random.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC",

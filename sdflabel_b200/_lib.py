@@ -19,6 +19,7 @@ vp = C.c_void_p
 
 MLP_AUTO, MLP_FFMA, MLP_TCGEN05, MLP_TCGEN05_COARSE = 0, 1, 2, 3
 ROT_DCM, ROT_QUAT = 0, 1
+PRIM_DISC, PRIM_CIRCLE, PRIM_CIRCLE_OPT = 0, 1, 2
 
 
 class SdfrError(RuntimeError):
@@ -37,7 +38,7 @@ class RasterCfg(C.Structure):
     _fields_ = [
         ("width", C.c_int32), ("height", C.c_int32),
         ("kinv", C.c_float * 9), ("k", C.c_float * 9),
-        ("rot", C.c_int32), ("output_nocs", C.c_int32),
+        ("rot", C.c_int32), ("output_nocs", C.c_int32), ("primitive", C.c_int32), ("bg_dev", C.c_void_p),
     ]
 
 
@@ -88,6 +89,9 @@ SIGNATURES = {
     "sdfr_refine_get_batch": (C.c_int, [vp, c_float_p, c_float_p, C.POINTER(C.c_int), vp]),
     "sdfr_refine_preselect_error": (C.c_int, [vp, c_float_p, vp]),
     "sdfr_refine_label_extents": (C.c_int, [vp, c_float_p, vp]),
+    "sdfr_refine_set_latent": (C.c_int, [vp, C.c_int, c_float_p, vp]),
+    "sdfr_refine_profile": (C.c_int, [vp, C.c_int, c_float_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32), vp]),
+    "sdfr_refine_stage_name": (C.c_char_p, [C.c_int]),
     "sdfr_refine_get": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.POINTER(C.c_int), vp]),
     "sdfr_refine_export": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "sdfr_refine_view": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]),

@@ -38,7 +38,7 @@ int upload(sdfr_decoder* d, const std::vector<float>& host, const float** out) {
 // ---- stand-alone splat workspace ------------------------------------------------------------
 struct SplatWs {
   size_t off_view, off_count, off_v, off_m, off_c, off_a, off_bbox, off_front, off_dv, off_dm, off_dc, off_stat,
-      off_raw, off_grad, off_dpose, total;
+      off_raw, off_grad, off_dpose, off_score, off_p2, off_radius, off_scalars, off_dscore, total;
 };
 
 SplatWs splat_ws_layout(int64_t m, int64_t P) {
@@ -53,6 +53,8 @@ SplatWs splat_ws_layout(int64_t m, int64_t P) {
   w.off_dv = take(mm * 12); w.off_dm = take(mm * 12); w.off_dc = take(mm * 12);
   w.off_stat = take(pp * 16); w.off_raw = take(pp * 32); w.off_grad = take(pp * 48);
   w.off_dpose = take(64);
+  w.off_score = take(mm * 4); w.off_p2 = take(mm * 8); w.off_radius = take(mm * 4); w.off_scalars = take(64);
+  w.off_dscore = take(mm * 4);
   w.total = o;
   return w;
 }
@@ -65,6 +67,7 @@ SplatView make_view(const sdfr_raster_cfg* cfg, const float* coords, const float
   memcpy(V.kinv, cfg->kinv, sizeof(V.kinv));
   memcpy(V.k, cfg->k, sizeof(V.k));
   V.rot = cfg->rot; V.output_nocs = cfg->output_nocs;
+  V.primitive = cfg->primitive; V.bg = cfg->bg_dev; V.has_bg = cfg->bg_dev ? 1 : 0;
   V.coords = coords; V.normals = normals; V.colors = colors; V.pose = pose;
   V.count = nullptr; V.static_count = (int)m; V.capacity = (int)m;
   V.cam_v = reinterpret_cast<float*>(ws + L.off_v);
@@ -79,6 +82,11 @@ SplatView make_view(const sdfr_raster_cfg* cfg, const float* coords, const float
   V.pix_stat = reinterpret_cast<float*>(ws + L.off_stat);
   V.pix_raw = reinterpret_cast<float*>(ws + L.off_raw);
   V.pix_grad = reinterpret_cast<float*>(ws + L.off_grad);
+  V.score = reinterpret_cast<float*>(ws + L.off_score);
+  V.p2 = reinterpret_cast<float*>(ws + L.off_p2);
+  V.radius = reinterpret_cast<float*>(ws + L.off_radius);
+  V.prim_scalars = reinterpret_cast<float*>(ws + L.off_scalars);
+  V.d_score = reinterpret_cast<float*>(ws + L.off_dscore);
   return V;
 }
 
@@ -405,6 +413,16 @@ int sdfr_splat_forward(const sdfr_raster_cfg* cfg, const float* coords_dev, cons
   SDFR_REQUIRE(cfg->width > 0 && cfg->height > 0, SDFR_E_INVALID, "bad resolution");
   SDFR_REQUIRE(m == 0 || (coords_dev && normals_dev), SDFR_E_INVALID, "null surfel arrays");
   SDFR_REQUIRE(cfg->output_nocs || colors_dev || m == 0, SDFR_E_INVALID, "colors required when output_nocs == 0");
+  SDFR_REQUIRE(cfg->primitive >= SDFR_PRIM_DISC && cfg->primitive <= SDFR_PRIM_CIRCLE_OPT, SDFR_E_INVALID,
+               "unknown primitive %d", cfg->primitive);
+  SDFR_REQUIRE(!cfg->bg_dev || (!depth_dev && !nrm_map_dev), SDFR_E_UNSUPPORTED,
+               "with a background only the color and mask maps exist (rasterer.py:107-144 cannot broadcast the others)");
+  SDFR_REQUIRE(!cfg->bg_dev || cfg->output_nocs, SDFR_E_UNSUPPORTED,
+               "a background is composited with colours shown as (c+1)/2 (rasterer.py:107-111): output_nocs must be set");
+  SDFR_REQUIRE(cfg->primitive != SDFR_PRIM_CIRCLE_OPT ||
+                   ((int)cfg->k[2] * 2 == cfg->width && (int)cfg->k[5] * 2 == cfg->height),
+               SDFR_E_INVALID, "circle_opt takes the image size from the principal point (primitives.py:108-109): "
+               "int(K[0,2])*2 x int(K[1,2])*2 must equal the resolution %dx%d", cfg->width, cfg->height);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t P = (int64_t)cfg->width * cfg->height;
   const SplatWs L = splat_ws_layout(m, P);
@@ -416,7 +434,12 @@ int sdfr_splat_forward(const sdfr_raster_cfg* cfg, const float* coords_dev, cons
   const SplatView* vd = reinterpret_cast<const SplatView*>(ws + L.off_view);
   int rc;
   if ((rc = launch_project(vd, 1, (int)m, s))) return rc;
-  if ((rc = launch_splat_forward(vd, 1, cfg->width, cfg->height, s))) return rc;
+  if (cfg->primitive == SDFR_PRIM_DISC) {
+    if ((rc = launch_splat_forward(vd, 1, cfg->width, cfg->height, s))) return rc;
+    if (cfg->bg_dev && (rc = launch_disc_background(vd, 1, (int)P, s))) return rc;
+  } else {
+    if ((rc = launch_circle_forward(vd, 1, (int)P, s))) return rc;
+  }
   if (m > 0 && cam_pts_dev) SDFR_CUDA(cudaMemcpyAsync(cam_pts_dev, V.cam_v, (size_t)m * 12, cudaMemcpyDeviceToDevice, s));
   if (m > 0 && front_dev) SDFR_CUDA(cudaMemcpyAsync(front_dev, V.front, (size_t)m, cudaMemcpyDeviceToDevice, s));
   if (front_count_dev) {
@@ -451,7 +474,11 @@ int sdfr_splat_backward(const sdfr_raster_cfg* cfg, const float* coords_dev, con
   const SplatView* vd = reinterpret_cast<const SplatView*>(ws + L.off_view);
   int rc;
   if ((rc = launch_pixel_grad_prep(vd, 1, (int)P, g_color_dev, g_mask_dev, g_depth_dev, g_nrm_map_dev, s))) return rc;
-  if ((rc = launch_splat_backward(vd, 1, (int)m, s))) return rc;
+  if (cfg->primitive == SDFR_PRIM_DISC) {
+    if ((rc = launch_splat_backward(vd, 1, (int)m, s))) return rc;
+  } else {
+    if ((rc = launch_circle_backward(vd, 1, (int)m, cfg->bg_dev ? 1 : 0, s))) return rc;
+  }
   pose_chain_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(vd, g_cam_pts_dev, g_cam_rgb_dev, d_coords_dev,
                                                                 d_normals_dev, d_colors_dev, d_pose_dev);
   SDFR_LAUNCH_CHECK();

@@ -170,6 +170,9 @@ struct SplatView {
   float k[9];
   int rot;           // SDFR_ROT_*
   int output_nocs;
+  int primitive;     // SDFR_PRIM_*
+  int has_bg;
+  const float* bg;   // [3,P] background image or null
   // inputs
   const float* coords;    // [m,3] object-frame surfel centres
   const float* normals;   // [m,3]
@@ -187,6 +190,12 @@ struct SplatView {
   int* bbox;         // [cap,4] x0,y0,x1,y1 inclusive, clipped; x1<x0 -> empty
   unsigned char* front;  // [cap]
   float* cam_rgb;    // [cap,3] points['rgb'] (optional)
+  // circle primitives (circle.cu): per-point score / 2D position / pixel radius, scalars, score gradient
+  float* score;      // [cap]
+  float* p2;         // [cap,2]
+  float* radius;     // [cap]
+  float* prim_scalars;   // [4] nu, background score, arg-min point, d background score
+  float* d_score;    // [cap]
   // per-pixel outputs (unclamped sums are kept in ws_* for the backward)
   float* color;      // [3,P]
   float* mask;       // [1,P]
@@ -206,6 +215,10 @@ int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int m
 int launch_pixel_grad_prep(const SplatView* views_dev, int batch, int max_pixels, const float* g_color,
                            const float* g_mask, const float* g_depth, const float* g_nmap, cudaStream_t s);
 int launch_splat_backward(const SplatView* views_dev, int batch, int max_count, cudaStream_t s);
+// circle.cu
+int launch_circle_forward(const SplatView* views_dev, int batch, int max_pixels, cudaStream_t s);
+int launch_circle_backward(const SplatView* views_dev, int batch, int max_count, int has_bg, cudaStream_t s);
+int launch_disc_background(const SplatView* views_dev, int batch, int max_pixels, cudaStream_t s);
 
 // ---------------------------------------------------------------------------
 // MLP launchers (mlp_ffma.cu / mlp_tc.cu)
@@ -219,6 +232,9 @@ struct MlpInputs {
   const int* index;           // optional gather: row r evaluates source point index[r] (null = r)
   const int* count_dev;       // optional: number of rows, read on the device (no host sync)
   int small_tiles;            // hint: the row list is short, use 16-point tiles in the tensor-core kernel
+  // tensor-core kernel: ReLU sign scratch of this launch (null = the decoder's own).  Launches that may run
+  // concurrently on different streams (two engines on one decoder) must not share it.
+  unsigned long long* mask_scratch = nullptr;
 };
 
 __device__ __forceinline__ long long mlp_rows(const MlpInputs& in) {
@@ -231,6 +247,7 @@ int launch_mlp_ffma(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, fl
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s);
 // forward only, fp16 operand precision (hi halves only): the band pre-selection pass of the fused engine
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s);
+size_t mlp_tc_mask_scratch_bytes(const sdfr_decoder* dec);
 int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host);
 void free_tc_tables(sdfr_decoder* dec);
 int tc_overflow_flag(const sdfr_decoder* dec, int* flag);

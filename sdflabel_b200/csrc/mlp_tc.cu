@@ -45,7 +45,7 @@ constexpr int KC = 32;                   // k per weight stage (two K=16 MMA ste
 constexpr int TILE_BYTES = 16384;        // 128 x 32 fp16 hi + the same lo
 constexpr int TILE_HALF_BYTES = 8192;
 // weight-ring depth of mlp_tc_kernel<NP>: the smaller the point tile, the more shared memory is left for stages
-template <int NP> struct RingDepth { static constexpr int value = NP <= 16 ? 11 : NP <= 32 ? 9 : 5; };
+template <int NP> struct RingDepth { static constexpr int value = NP <= 16 ? 11 : 5; };
 // B operand (activations), MN-major, no swizzle: core matrix = 8 k-rows x (8 points = 16 B).
 // Per 8-k chunk: 8 point groups of the hi halves (1024 B) followed by 8 point groups of the lo
 // halves (1024 B), so one descriptor with N = 128 covers [hi ; lo] and N = 64 covers hi only.
@@ -99,19 +99,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-// wait with back-off: for warps that wait long (epilogue waiting for a whole MMA phase) and must not
-// compete for issue slots with the single MMA-issuing warp
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  for (;;) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    __nanosleep(64);
-  }
-}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -123,22 +110,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-// multicast variant: the slice lands at the same offset in every CTA of ctaMask and completes
-// tx bytes on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
-      : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t cluster_nctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -168,11 +142,6 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // arrives on the mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -286,7 +255,7 @@ template <int NP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
               float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
-              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles, int coarse, int group) {
+              unsigned long long* __restrict__ mask_scratch, long long num_point_tiles, int group) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (in.count_dev && *in.count_dev <= 0) return;   // nothing to evaluate (uniform over the whole grid)
   const TcTable& T = *tabp;
@@ -314,20 +283,13 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
                  bar_act = bars + 8 * (2 * NSTAGE + 1);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
   const int in_pad = (in0 + 7) & ~7;
-  // coarse: forward only with the hi halves alone (one MMA per K step, fp16 operand precision,
-  // ~3e-4 absolute on the sdf).  Used by the fused engine to pre-select a superset of the band.
-  const bool want_grad = dinput_out != nullptr && !coarse;
+  const bool want_grad = dinput_out != nullptr;
   const int npass = want_grad ? T.num_passes : num_layers;   // forward passes come first
-  const uint32_t tile_copy_bytes = coarse ? TILE_HALF_BYTES : TILE_BYTES;
-  // Thread-block cluster: every CTA of the cluster consumes the same weight-tile sequence, so each
-  // loads 1/CL of every tile and multicasts it to all of them (one L2 read per cluster instead of per CTA).
   const long long n_rows = mlp_rows(in);           // the row count may live on the device (band pass)
   if (in.count_dev) num_point_tiles = (n_rows + NP - 1) / NP;
-  const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
-  const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
 
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_acc, 1);
     mbar_init(bar_act, NEPI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -335,16 +297,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   if (warp == 9) tmem_alloc(smem_u32(smem + P.tmem_slot), TCOLS);
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // peers' barriers must exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Every CTA of a cluster runs the same number of iterations (it shares the weight ring with its
-  // peers); a CTA whose own point tile is past the end computes on masked (zero) points.
-  // Iteration `it` of cluster c covers point tiles (it * num_clusters + c) * CL + rank.
-  const long long num_clusters = gridDim.x / CL, cluster_id = blockIdx.x / CL;
+  // point tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   long long my_tiles = 0;
-  for (long long it = 0; (it * num_clusters + cluster_id) * CL < num_point_tiles; ++it) ++my_tiles;
+  for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) ++my_tiles;
 
   if (warp == 8) {
     // ===================== weight producer =====================
@@ -356,15 +314,8 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
           for (long long t = 0; t < n; ++t) {
             { PROF_T0(); mbar_wait(bar_empty + 8 * stage, phase ^ 1); PROF_ADD(0); }
-            mbar_expect_tx(bar_full + 8 * stage, tile_copy_bytes);
-            if (CL == 1) {
-              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, tile_copy_bytes,
-                       bar_full + 8 * stage);
-            } else {
-              const uint32_t slice = tile_copy_bytes / CL, off = crank * slice;
-              bulk_g2s_mcast(smem_u32(smem + P.stages + stage * TILE_BYTES) + off, src + t * TILE_BYTES + off, slice,
-                             bar_full + 8 * stage, cmask);
-            }
+            mbar_expect_tx(bar_full + 8 * stage, TILE_BYTES);
+            bulk_g2s(smem_u32(smem + P.stages + stage * TILE_BYTES), src + t * TILE_BYTES, TILE_BYTES, bar_full + 8 * stage);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
@@ -391,7 +342,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
         for (int mb = 0; mb < m_blocks; ++mb) {
           const uint32_t d_main = tm + (uint32_t)(mb * 2 * NP);  // columns [0,NP): hi*hi, [NP,2NP): cross terms
           const uint32_t d_cross = d_main + NP;
-          if (group == 2 && !coarse && CL == 1 && (k_chunks & 1) == 0) {
+          if (group == 2 && (k_chunks & 1) == 0) {
             // two weight stages per loop iteration (a CTA that streams several 64-point tiles: 1.68 -> 1.57 ms for
             // the 64 000-point forward+gradient sweep)
             for (int kc = 0; kc < k_chunks; kc += 2) {
@@ -422,7 +373,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             }
             continue;
           }
-          if (group == 4 && !coarse && CL == 1 && (k_chunks & 3) == 0) {
+          if (group == 4 && (k_chunks & 3) == 0) {
             constexpr int grp = 4;
             // four weight stages per loop iteration (16-point tiles, 11-stage ring): the fixed cost of an iteration
             // (barrier wait, fence, election, warp re-convergence: ~170 cycles, tools/umma_issue_bench.cu) is paid once
@@ -473,23 +424,14 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
               const uint64_t da_hi = desc_a_base + (uint64_t)((stage * TILE_BYTES) >> 4);
               const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
               const uint64_t db = desc_b_base + (uint64_t)((kc * (KC / 8) * BCH) >> 4);
-              if (coarse) {
 #pragma unroll
-                for (int j = 0; j < KC / 16; ++j)
-                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
-                           kIdCross, (kc | j) ? 1u : 0u);                                  // W_hi x H_hi only
-              } else {
-#pragma unroll
-                for (int j = 0; j < KC / 16; ++j) {
-                  umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
-                           kIdMain, (kc | j) ? 1u : 0u);                                    // W_hi x [H_hi ; H_lo]
-                  umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
-                           kIdCross, 1u);                                                    // W_lo x H_hi
-                }
+              for (int j = 0; j < KC / 16; ++j) {
+                umma_f16(d_main, da_hi + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                         kIdMain, (kc | j) ? 1u : 0u);                                      // W_hi x [H_hi ; H_lo]
+                umma_f16(d_cross, da_lo + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * BCH) >> 4),
+                         kIdCross, 1u);                                                      // W_lo x H_hi
               }
-              // frees the weight stage (in every CTA of the cluster: all of them write into it)
-              if (CL == 1) umma_commit(bar_empty + 8 * stage);
-              else umma_commit_mcast(bar_empty + 8 * stage, cmask);
+              umma_commit(bar_empty + 8 * stage);     // frees the weight stage
             }
             __syncwarp();
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -509,7 +451,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
     uint32_t acc_phase = 0;
     float amax = 0.f;
     for (long long it = 0; it < my_tiles; ++it) {
-      const long long pt = (it * num_clusters + cluster_id) * CL + crank;   // may be past the end: masked
+      const long long pt = it * gridDim.x + blockIdx.x;
       const long long base = pt * NP;
       // ---- stage inputs: inp[c][n] ----
       for (int i = et; i < in_pad * NP; i += NEPI) {
@@ -544,8 +486,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           float h[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NP + ph * PT + g * 8 + e] * ACT_SCALE : 0.f;
-          if (coarse) pack8_store_hi(row, ph * (PT / 8) + g, h);
-          else amax = fmaxf(amax, pack8_store_t<LO>(row, ph * (PT / 8) + g, h));
+          amax = fmaxf(amax, pack8_store_t<LO>(row, ph * (PT / 8) + g, h));
         }
       }
       fence_async_smem();
@@ -566,14 +507,13 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
             for (int g = 0; g < G; ++g) {
               uint32_t vm[GW], vc[GW];
               tmem_ldg(lane_base + ph * PT + g * GW, vm);
-              if (!coarse) tmem_ldg(lane_base + NP + ph * PT + g * GW, vc);
+              tmem_ldg(lane_base + NP + ph * PT + g * GW, vc);
               tmem_ld_wait();
               if (lane == 0) {
 #pragma unroll
                 for (int qq = 0; qq < GW; ++qq) {
                   const int n = ph * PT + g * GW + qq;
-                  const float cross = coarse ? 0.f : __uint_as_float(vc[qq]);
-                  float y = (__uint_as_float(vm[qq]) + cross) * Ps.inv_scale + bias0, gg = 1.f;
+                  float y = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale + bias0, gg = 1.f;
                   if (use_tanh) { y = tanhf(y); gg *= 1.f - y * y; }
                   y = tanhf(y);
                   gg *= 1.f - y * y;
@@ -623,12 +563,12 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
           for (int g = 0; g < G; ++g) {
             uint32_t vm[GW], vc[GW];
             tmem_ldg(tb + ph * PT + g * GW, vm);
-            if (!coarse) tmem_ldg(tb + NP + ph * PT + g * GW, vc);
+            tmem_ldg(tb + NP + ph * PT + g * GW, vc);
             tmem_ld_wait();
             float x[GW];
 #pragma unroll
             for (int qq = 0; qq < GW; ++qq)
-              x[qq] = (__uint_as_float(vm[qq]) + (coarse ? 0.f : __uint_as_float(vc[qq]))) * Ps.inv_scale;
+              x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
             if (Ps.kind == 3) {                                    // gradient with respect to the input row
               if (cls == 0) {
 #pragma unroll
@@ -672,8 +612,7 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
 #pragma unroll
               for (int e = 0; e < 8; ++e) h8[e] = h[pk * 8 + e];
               const int pgi = ph * (PT / 8) + g * PG + pk;
-              if (coarse) pack8_store_hi(row, pgi, h8);
-              else amax = fmaxf(amax, pack8_store_t<LO>(row, pgi, h8));
+              amax = fmaxf(amax, pack8_store_t<LO>(row, pgi, h8));
             }
           }
           if (fwd && want_grad) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;   // only the backward reads them
@@ -699,322 +638,8 @@ mlp_tc_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict_
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();      // no CTA may exit while a peer can still write into it
   if (warp == 9) tmem_dealloc(tmem_base, TCOLS);
 }
-
-// ---------------------------------------------------------------------------------------------
-// Coarse lattice pass, ping-pong version.
-//
-// Forward only, hi halves only (one MMA per product).  With the lo halves gone the B operand of a
-// 64-point tile is 64 KB and its accumulators 256 TMEM columns, so TWO point tiles (X, Y) are
-// resident per CTA and the epilogue of one overlaps the MMAs of the other:
-//     MMA  X(p)   Y(p)   X(p+1) Y(p+1) ...
-//     EPI         X(p)   Y(p)   X(p+1) ...
-// Each pass's weight tiles (hi halves, 8 KB) are streamed once per point tile (L2 has the headroom:
-// 31 % utilised before).  Same pass table, same layouts, same epilogue math as mlp_tc_kernel.
-// ---------------------------------------------------------------------------------------------
-constexpr int C_STAGES = 8;              // 8 KB stages (hi half of a weight tile)
-constexpr int CB_CHUNK = 1024;           // B (hi only): 8 point groups x 128 B per 8-k chunk
-constexpr int CB_BYTES = 64 * CB_CHUNK;  // 64 KB per point tile
-
-struct CoarsePlan {
-  uint32_t stages, b[2], inp[2], bars, tmem_slot, total;
-};
-__host__ __device__ inline CoarsePlan make_coarse_plan(int in0) {
-  CoarsePlan p;
-  uint32_t o = 0;
-  p.stages = o; o += C_STAGES * TILE_HALF_BYTES;
-  p.b[0] = o; o += CB_BYTES;
-  p.b[1] = o; o += CB_BYTES;
-  const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
-  p.inp[0] = o; o += in_pad * NPTS * 4;
-  p.inp[1] = o; o += in_pad * NPTS * 4;
-  p.bars = o; o += 32 * 8;
-  p.tmem_slot = o; o += 16;
-  p.total = o;
-  return p;
-}
-
-__global__ void __launch_bounds__(NTHREADS, 1)
-mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
-                     float* __restrict__ sdf_out, long long num_point_tiles, int interleave) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  if (in.count_dev && *in.count_dev <= 0) return;
-  const TcTable& T = *tabp;
-  const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
-  const CoarsePlan P = make_coarse_plan(in0);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t bars = smem_u32(smem + P.bars);
-  const uint32_t bar_full = bars, bar_empty = bars + 8 * C_STAGES, bar_acc = bars + 8 * (2 * C_STAGES),
-                 bar_act = bars + 8 * (2 * C_STAGES + 2);          // [2] each: one per resident point tile
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
-  const int in_pad = (in0 + 7) & ~7;
-  const long long n_rows = mlp_rows(in);
-  if (in.count_dev) num_point_tiles = (n_rows + NPTS - 1) / NPTS;
-
-  if (tid == 0) {
-    for (int s = 0; s < C_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < 2; ++t) { mbar_init(bar_acc + 8 * t, 1); mbar_init(bar_act + 8 * t, NEPI); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 9) tmem_alloc(smem_u32(smem + P.tmem_slot), TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // this CTA's point tiles: blockIdx.x, blockIdx.x + grid, ... processed two at a time
-  long long my_tiles = 0;
-  for (long long pt = blockIdx.x; pt < num_point_tiles; pt += gridDim.x) ++my_tiles;
-  const long long my_pairs = (my_tiles + 1) / 2;
-
-  if (warp == 8) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (long long pr = 0; pr < my_pairs; ++pr) {
-        const int nt = (2 * pr + 1 < my_tiles) ? 2 : 1;
-        for (int p = 0; p < num_layers; ++p) {
-          const long long n = (long long)T.pass[p].m_blocks * T.pass[p].k_chunks;
-          const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
-          const int m_blocks = T.pass[p].m_blocks, k_chunks = T.pass[p].k_chunks;
-          for (int t = 0; t < nt; ++t) {
-            // issue order: k chunk outer, M block inner (the tiles are stored M block outer)
-            int kc = 0, mb = 0;
-            for (int w = 0; w < (int)n; ++w) {
-              const int ti = interleave ? mb * k_chunks + kc : w;
-              if (++mb == m_blocks) { mb = 0; ++kc; }
-              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-              mbar_expect_tx(bar_full + 8 * stage, TILE_HALF_BYTES);
-              bulk_g2s(smem_u32(smem + P.stages + stage * TILE_HALF_BYTES), src + (size_t)ti * TILE_BYTES, TILE_HALF_BYTES,
-                       bar_full + 8 * stage);
-              if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
-            }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 9) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane) =====================
-    uint32_t stage = 0, phase = 0, act_phase[2] = {0, 0};
-    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-    const uint64_t desc_a_base = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);
-    const uint64_t desc_b_base[2] = {make_desc(smem_u32(smem + P.b[0]), CB_CHUNK, B_SBO),
-                                     make_desc(smem_u32(smem + P.b[1]), CB_CHUNK, B_SBO)};
-    for (long long pr = 0; pr < my_pairs; ++pr) {
-      const int nt = (2 * pr + 1 < my_tiles) ? 2 : 1;
-      for (int p = 0; p < num_layers; ++p) {
-        const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(bar_act + 8 * t, act_phase[t]);      // tile t: B operand staged, its accumulators drained
-          act_phase[t] ^= 1;
-          tc_fence_after();
-          if (interleave) {
-            // Consecutive MMAs go to DIFFERENT accumulators (the M blocks of one k chunk): a chain on one
-            // accumulator pays ~44 cycles of fixed latency per MMA on top of the N/2 cycles of math
-            // (tools/umma_bench.cu); rotating over the M blocks hides it.
-            for (int kc = 0; kc < k_chunks; ++kc) {
-              uint32_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;
-#pragma unroll
-              for (int mb = 0; mb < 4; ++mb) {
-                if (mb < m_blocks) {
-                  mbar_wait(bar_full + 8 * stage, phase);
-                  if (mb == 0) st0 = stage; else if (mb == 1) st1 = stage; else if (mb == 2) st2 = stage; else st3 = stage;
-                  if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
-                }
-              }
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t db = desc_b_base[t] + (uint64_t)((kc * (KC / 8) * CB_CHUNK) >> 4);
-                const uint32_t d = tm + (uint32_t)(t * 256);
-#pragma unroll
-                for (int j = 0; j < KC / 16; ++j) {
-#pragma unroll
-                  for (int mb = 0; mb < 4; ++mb) {
-                    if (mb < m_blocks) {
-                      const uint32_t st = mb == 0 ? st0 : mb == 1 ? st1 : mb == 2 ? st2 : st3;
-                      const uint64_t da = desc_a_base + (uint64_t)((st * TILE_HALF_BYTES) >> 4);
-                      umma_f16(d + (uint32_t)(mb * 64), da + (uint64_t)((j * 2 * A_LBO) >> 4),
-                               db + (uint64_t)((j * 2 * CB_CHUNK) >> 4), kIdesc64, (kc | j) ? 1u : 0u);
-                    }
-                  }
-                }
-#pragma unroll
-                for (int mb = 0; mb < 4; ++mb) {
-                  if (mb < m_blocks) {
-                    const uint32_t st = mb == 0 ? st0 : mb == 1 ? st1 : mb == 2 ? st2 : st3;
-                    umma_commit(bar_empty + 8 * st);
-                  }
-                }
-              }
-              __syncwarp();
-            }
-          } else {
-          for (int mb = 0; mb < m_blocks; ++mb) {
-            const uint32_t d = tm + (uint32_t)(t * 256 + mb * 64);
-            for (int kc = 0; kc < k_chunks; ++kc) {
-              mbar_wait(bar_full + 8 * stage, phase);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t da = desc_a_base + (uint64_t)((stage * TILE_HALF_BYTES) >> 4);
-                const uint64_t db = desc_b_base[t] + (uint64_t)((kc * (KC / 8) * CB_CHUNK) >> 4);
-#pragma unroll
-                for (int j = 0; j < KC / 16; ++j)
-                  umma_f16(d, da + (uint64_t)((j * 2 * A_LBO) >> 4), db + (uint64_t)((j * 2 * CB_CHUNK) >> 4), kIdesc64,
-                           (kc | j) ? 1u : 0u);
-                umma_commit(bar_empty + 8 * stage);
-              }
-              __syncwarp();
-              if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
-            }
-          }
-          }
-          if (elect_one()) umma_commit(bar_acc + 8 * t);
-          __syncwarp();
-        }
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3, ph = warp >> 2;
-    const int tl = q * 32 + lane;                      // TMEM lane = feature within the M block
-    const int et = tid;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t acc_phase[2] = {0, 0};
-    for (long long pr = 0; pr < my_pairs; ++pr) {
-      const int nt = (2 * pr + 1 < my_tiles) ? 2 : 1;
-      long long base[2];
-      for (int t = 0; t < nt; ++t) {
-        const long long pt = (2 * pr + t) * gridDim.x + blockIdx.x;
-        base[t] = pt * NPTS;
-        float* inp = reinterpret_cast<float*>(smem + P.inp[t]);
-        for (int i = et; i < in_pad * NPTS; i += NEPI) {
-          const int c = i / NPTS, n = i - c * NPTS;
-          const long long gi = base[t] + n;
-          float v = 0.f;
-          if (gi < n_rows && c < in0) {
-            const long long src = in.index ? (long long)in.index[gi] : gi;
-            if (in.inputs) {
-              v = in.inputs[src * in0 + c];
-            } else {
-              const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
-              if (c < latent) {
-                v = in.latent_unit[b * latent + c];
-              } else {
-                float x, y, z;
-                lattice_point(in.lattice, k, x, y, z);
-                v = (c - latent) == 0 ? x : (c - latent) == 1 ? y : z;
-              }
-            }
-          }
-          inp[i] = v;
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int t = 0; t < nt; ++t) {                    // B operand of layer 0 for both tiles
-        if (q == 0) {
-          const float* inp = reinterpret_cast<const float*>(smem + P.inp[t]);
-          const int k = lane;
-          unsigned char* row = smem + P.b[t] + (k >> 3) * CB_CHUNK + (k & 7) * 16;
-#pragma unroll
-          for (int pg = 0; pg < 4; ++pg) {
-            float h[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NPTS + ph * 32 + pg * 8 + e] * ACT_SCALE : 0.f;
-            pack8_store_hi(row, ph * 4 + pg, h);
-          }
-        }
-        fence_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_act + 8 * t);
-      }
-      for (int p = 0; p < num_layers; ++p) {
-        const TcPassDev Ps = T.pass[p];
-        for (int t = 0; t < nt; ++t) {
-          mbar_wait(bar_acc + 8 * t, acc_phase[t]);
-          acc_phase[t] ^= 1;
-          tc_fence_after();
-          const uint32_t tbuf = lane_base + (uint32_t)(t * 256);
-          const float* inp = reinterpret_cast<const float*>(smem + P.inp[t]);
-          unsigned char* bop = smem + P.b[t];
-          if (Ps.kind == 1) {                           // last Linear: row 0 is the pre-activation of the sdf
-            if (q == 0) {
-              const float bias0 = __ldg(Ps.bias);
-#pragma unroll
-              for (int g2 = 0; g2 < 2; ++g2) {
-                const int g4 = ph * 2 + g2;
-                uint32_t vm[16];
-                tmem_ld16(tbuf + g4 * 16, vm);
-                tmem_ld_wait();
-                if (lane == 0) {
-#pragma unroll
-                  for (int qq = 0; qq < 16; ++qq) {
-                    const int n = g4 * 16 + qq;
-                    float y = __uint_as_float(vm[qq]) * Ps.inv_scale + bias0;
-                    if (use_tanh) y = tanhf(y);
-                    y = tanhf(y);
-                    if (base[t] + n < n_rows) sdf_out[base[t] + n] = y;
-                  }
-                }
-                __syncwarp();
-              }
-            }
-            tc_fence_before();
-            // accumulators of tile t are drained: the next pair's first pass may overwrite them
-            continue;
-          }
-          for (int mb = 0; mb < Ps.m_blocks; ++mb) {
-            const int f = mb * 128 + tl;
-            const int cls = f < Ps.rows ? 0 : (f < Ps.rows + Ps.cat_dim ? 1 : 2);
-            const uint32_t tb = tbuf + (uint32_t)(mb * 64);
-            unsigned char* row = bop + (f >> 3) * CB_CHUNK + (f & 7) * 16;
-            const float bias = cls == 0 ? __ldg(Ps.bias + f) : 0.f;
-            const int cat_row = (Ps.cat_off + f - Ps.rows) * NPTS + ph * 32;
-#pragma unroll
-            for (int g2 = 0; g2 < 2; ++g2) {
-              const int g4 = ph * 2 + g2;
-              uint32_t vm[16];
-              tmem_ld16(tb + g4 * 16, vm);
-              tmem_ld_wait();
-              float h[16];
-              if (cls == 0) {
-#pragma unroll
-                for (int qq = 0; qq < 16; ++qq) {
-                  const float y = __uint_as_float(vm[qq]) * Ps.inv_scale + bias;
-                  h[qq] = y > 0.f ? y * Ps.out_scale : 0.f;
-                }
-              } else if (cls == 1) {
-#pragma unroll
-                for (int qq = 0; qq < 16; ++qq) h[qq] = inp[cat_row + g2 * 16 + qq] * Ps.out_scale;
-              } else {
-#pragma unroll
-                for (int qq = 0; qq < 16; ++qq) h[qq] = 0.f;
-              }
-              float h8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h8[e] = h[e];
-              pack8_store_hi(row, g4 * 2, h8);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h8[e] = h[8 + e];
-              pack8_store_hi(row, g4 * 2 + 1, h8);
-            }
-          }
-          fence_async_smem();
-          tc_fence_before();
-          mbar_arrive(bar_act + 8 * t);
-        }
-      }
-      // both tiles' inputs are dead once every epilogue thread is past the last pass
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Coarse lattice pass, wide-tile version.
@@ -1027,8 +652,8 @@ mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __re
 // 128 KB, the four M-block accumulators fill the 512 TMEM columns) - and a weight stage two k-chunks
 // deep (four MMAs per ring iteration).
 //
-// That leaves no room for a second resident tile (as the ping-pong kernel above has), so the epilogue
-// (16 warps) is overlapped with the MMAs at M-block granularity instead:
+// That leaves no room for a second resident tile, so the epilogue (16 warps) is overlapped with the MMAs at
+// M-block granularity:
 //   * accumulator mb is committed on its own mbarrier; M blocks 0 and 1 are turned into packed fp16
 //     rows held in registers while the MMAs of the later M blocks still run (the rows cannot be
 //     stored yet: they overwrite the B operand those MMAs read);
@@ -1039,7 +664,6 @@ mlp_tc_coarse_kernel(const TcTable* __restrict__ tabp, const unsigned char* __re
 // The tile width is chosen on the host so that the last round of tiles is as full as the others
 // (112 points for the 40^3 lattice on 148 SMs).
 // ---------------------------------------------------------------------------------------------
-__device__ unsigned long long g_wide_timing[32];   // SDFR_TC_WIDE_DBG bit 4: CTA 0's issuer loop in cycles and in ns
 constexpr int W_THREADS = 576;           // 16 epilogue warps + weight producer + MMA issuer
 constexpr int W_NEPI = 512;
 
@@ -1064,7 +688,7 @@ __host__ __device__ inline WidePlan make_wide_plan(int in0, int npt) {
 template <int W_GROUP>      // weight tiles (k-chunks of 32) per ring stage: 2 -> 4 MMAs per iteration, 4 -> 8
 __global__ void __launch_bounds__(W_THREADS, 1)
 mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
-                          float* __restrict__ sdf_out, int npt, int dbg) {
+                          float* __restrict__ sdf_out, int npt) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (in.count_dev && *in.count_dev <= 0) return;
   const TcTable& T = *tabp;
@@ -1106,14 +730,10 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
           auto load_stage = [&](int mb, int kc, int cnt) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (dbg & 2) {                                // timing experiment: no weight traffic
-              mbar_arrive(bar_full + 8 * stage);
-            } else {
-              mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * TILE_HALF_BYTES);
-              for (int i = 0; i < cnt; ++i)
-                bulk_g2s(smem_u32(smem + P.stages + stage * W_STAGE_BYTES + i * TILE_HALF_BYTES),
-                         src + (size_t)(mb * k_chunks + kc + i) * TILE_BYTES, TILE_HALF_BYTES, bar_full + 8 * stage);
-            }
+            mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * TILE_HALF_BYTES);
+            for (int i = 0; i < cnt; ++i)
+              bulk_g2s(smem_u32(smem + P.stages + stage * W_STAGE_BYTES + i * TILE_HALF_BYTES),
+                       src + (size_t)(mb * k_chunks + kc + i) * TILE_BYTES, TILE_HALF_BYTES, bar_full + 8 * stage);
             if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           };
           if (W_GROUP == 4 && k_chunks == 16 && m_blocks == 4) {
@@ -1147,9 +767,6 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
     const uint32_t db_hi = (uint32_t)(desc_b_base >> 32), db_lo0 = (uint32_t)desc_b_base;
     const uint32_t idesc = idesc_for(npt);
     const uint32_t chq = (uint32_t)(ch >> 4);            // descriptor units per 8-k chunk of B
-    long long t_c0 = 0;
-    unsigned long long t_n0 = 0;
-    if (dbg & 16) { t_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_n0)); }
     auto desc64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; };
     // Everything the unrolled path needs is computed ONCE and pinned in registers (the empty asm keeps the
     // compiler from re-deriving the descriptors from the shared-memory base in every iteration: that
@@ -1190,7 +807,7 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
 #pragma unroll
       for (int itq = 0; itq < 16 / W_GROUP; ++itq) {
         constexpr int kGroupsPerQuarter = 4 / W_GROUP;   // iterations per 4 k-chunks (rows of one M block)
-        if (first_block && (itq % kGroupsPerQuarter) == 0 && !(dbg & 8))
+        if (first_block && (itq % kGroupsPerQuarter) == 0)
           mbar_wait(bar_rows + 8 * (itq / kGroupsPerQuarter), rows_phase);
         ring_iteration(d, db_it[itq], itq == 0);
       }
@@ -1203,12 +820,9 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           // epilogue publishes them in that order (rows_ready[q]) while this pass already runs: M blocks 0 and 1
           // (whose accumulators the epilogue drained first) advance together, one k quarter at a time, so
           // that 2 x 16 MMAs are issued before the last rows are needed.
-          if ((dbg & 16) && it == 1 && (p == 4 || p == 5) && blockIdx.x == 0 && lane == 0)
-            g_wide_timing[4 + (p - 4) * 4] = (unsigned long long)clock64();
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
-            if (!(dbg & 8)) mbar_wait(bar_rows + 8 * qd, rows_phase);
-            if ((dbg & 16) && it == 1 && p == 5 && blockIdx.x == 0 && lane == 0) g_wide_timing[12 + qd] = (unsigned long long)clock64();
+            mbar_wait(bar_rows + 8 * qd, rows_phase);
             ring_iteration(tm, db_it[qd], qd == 0);
             ring_iteration(tm + 128u, db_it[qd], qd == 0);
           }
@@ -1216,8 +830,6 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           if (elect_one()) { umma_commit(bar_acc); umma_commit(bar_acc + 8); }
           __syncwarp();
           for (int mb = 2; mb < 4; ++mb) {
-            if ((dbg & 16) && it == 1 && (p == 4 || p == 5) && blockIdx.x == 0 && lane == 0)
-              g_wide_timing[4 + (p - 4) * 4 + mb] = (unsigned long long)clock64();
             issue_full_block(tm + (uint32_t)(mb * 128), false);
             if (elect_one()) umma_commit(bar_acc + 8 * mb);
             __syncwarp();
@@ -1232,7 +844,7 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
             for (int kc = 0; kc < k_chunks; kc += W_GROUP) {
               // k-chunks 4q..4q+3 are the rows the previous pass's M block q produced (for the first pass: the
               // staged inputs); rows_ready[q] also says that accumulator q of the previous pass has been drained
-              if (mb == 0 && (kc & 3) == 0 && !(dbg & 8)) mbar_wait(bar_rows + 8 * (kc >> 2), rows_phase);
+              if (mb == 0 && (kc & 3) == 0) mbar_wait(bar_rows + 8 * (kc >> 2), rows_phase);
               const int cnt = min(W_GROUP, k_chunks - kc);
               mbar_wait(bar_full + 8 * stage, phase);
               tc_fence_after();
@@ -1255,21 +867,13 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
             }
           }
           if (mb == 0) {                                   // quarters this pass has no k-chunks for
-            if (!(dbg & 8)) for (int qq = (k_chunks + 3) >> 2; qq < 4; ++qq) mbar_wait(bar_rows + 8 * qq, rows_phase);
+            for (int qq = (k_chunks + 3) >> 2; qq < 4; ++qq) mbar_wait(bar_rows + 8 * qq, rows_phase);
             rows_phase ^= 1;
           }
           if (elect_one()) umma_commit(bar_acc + 8 * mb);   // this M block's accumulator is complete
           __syncwarp();
         }
       }
-    }
-    if ((dbg & 16) && blockIdx.x == 0 && lane == 0) {
-      unsigned long long t_n1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_n1));
-      g_wide_timing[0] = (unsigned long long)(clock64() - t_c0);
-      g_wide_timing[1] = t_n1 - t_n0;
-      g_wide_timing[2] = 0;
-      g_wide_timing[3] = 0;
     }
   } else {
     // ===================== epilogue warps =====================
@@ -1279,7 +883,7 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
     float* inp = reinterpret_cast<float*>(smem + P.inp);
     unsigned char* bop = smem + P.b;
     uint32_t acc_phase = 0;                            // bit mb = phase of bar_acc[mb]
-    for (long long it = 0; it < ((dbg & 64) ? 0 : my_tiles); ++it) {
+    for (long long it = 0; it < my_tiles; ++it) {
       const long long pt = it * gridDim.x + blockIdx.x;
       const long long base = pt * npt;
       for (int i = tid; i < in_pad * npt; i += W_NEPI) {
@@ -1329,10 +933,10 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
       for (int p = 0; p < num_layers; ++p) {
         const TcPassDev Ps = T.pass[p];
         if (Ps.kind == 1) {                            // last Linear: row 0 is the pre-activation of the sdf
-          if (dbg & 4) mbar_wait_sleep(bar_acc, acc_phase & 1u); else mbar_wait(bar_acc, acc_phase & 1u);
+          mbar_wait(bar_acc, acc_phase & 1u);
           acc_phase ^= 1u;
           tc_fence_after();
-          if (q == 0 && !(dbg & 1)) {
+          if (q == 0) {
             const float bias0 = __ldg(Ps.bias);
 #pragma unroll
             for (int gi = 0; gi < 4; ++gi) {
@@ -1358,24 +962,12 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           tc_fence_before();
           continue;
         }
-        if (dbg & 1) {                                 // timing experiment: barrier protocol only
-          for (int m2 = 0; m2 < Ps.m_blocks; ++m2) {
-            if (dbg & 4) mbar_wait_sleep(bar_acc + 8 * m2, (acc_phase >> m2) & 1u); else mbar_wait(bar_acc + 8 * m2, (acc_phase >> m2) & 1u);
-            acc_phase ^= 1u << m2;
-          }
-          tc_fence_after();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) for (int m2 = 0; m2 < 4; ++m2) mbar_arrive(bar_rows + 8 * m2);
-          continue;
-        }
         // M blocks 0 and 1 become packed rows (held in registers) while the MMAs of the later M blocks run.
         // The scales are powers of two, so max(acc * (inv_scale * out_scale) + bias * out_scale, 0) is bit-identical
         // to relu(acc * inv_scale + bias) * out_scale: two instructions per value instead of four.
         const float k_scale = Ps.inv_scale * Ps.out_scale;
         auto process_block = [&](const int mb, uint4 (&cur)[4]) {
           const int f = mb * 128 + tl;
-          if ((dbg & 16) && it == 1 && p == 4 && blockIdx.x == 0 && tid == 0) g_wide_timing[16 + mb] = (unsigned long long)clock64();
           // the TMEM loads are warp-collective (.sync.aligned): every lane issues them, whatever its row class
           const bool regular = f < Ps.rows;             // all but the concat / padding rows
           const bool cat = !regular && f < Ps.rows + Ps.cat_dim;
@@ -1425,7 +1017,6 @@ mlp_tc_coarse_wide_kernel(const TcTable* __restrict__ tabp, const unsigned char*
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_rows + 8 * mb);
-          if ((dbg & 16) && it == 1 && p == 4 && blockIdx.x == 0 && tid == 0) g_wide_timing[20 + mb] = (unsigned long long)clock64();
         };
         uint4 packed[2][4];
         const int hold = Ps.m_blocks >= 3 ? 2 : 0;
@@ -2090,8 +1681,6 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
   if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                   (int)make_plan<16>(NL, in0).total));
-  if (rc == SDFR_OK) TC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)make_plan<32>(NL, in0).total));
 #undef TC_CUDA
   if (rc != SDFR_OK) { delete st; return rc; }
   st->smem_bytes = plan.total;
@@ -2103,10 +1692,6 @@ int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const floa
   return SDFR_OK;
 }
 
-extern "C" int sdfr_debug_wide_timing(unsigned long long* out4) {
-  return cudaMemcpyFromSymbol(out4, g_wide_timing, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : 1;
-}
-
 #ifdef SDFR_TC_PROFILE
 extern "C" int sdfr_debug_tc_prof(unsigned long long* out16, int reset) {
   if (out16) cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16);
@@ -2114,9 +1699,6 @@ extern "C" int sdfr_debug_tc_prof(unsigned long long* out16, int reset) {
   return 0;
 }
 #endif
-
-static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, int coarse,
-                              cudaStream_t s);
 
 void free_tc_tables(sdfr_decoder* dec) {
   if (dec->tc_ptr) delete reinterpret_cast<TcHostState*>(dec->tc_ptr);   // device memory is owned by dec->allocs
@@ -2150,52 +1732,74 @@ int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s) {
   return SDFR_OK;
 }
 
+// Forward + input gradient (or forward only when dinput is null) at full fp32-equivalent precision.
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
-  return launch_mlp_tc_impl(dec, in, sdf, dinput, 0, s);
+  SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,
+               "tcgen05 MLP kernel does not cover this decoder (needs sm_100, widths <= 512, no LayerNorm, "
+               "latent+3 <= 32, <= 9 layers)");
+  if (in.n <= 0) return SDFR_OK;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  // 16-point tiles when the caller expects a short row list (MlpInputs::small_tiles: the band pass of a
+  // few detections), so that ~2 000 rows still fill the machine; 64-point tiles otherwise.
+  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  const bool small = in.small_tiles || (!in.count_dev && in.n <= 16LL * sms);
+  const int np = small ? 16 : 64;
+  const long long point_tiles = (in.n + np - 1) / np;
+  const int grid = (int)std::min<long long>(point_tiles, sms);
+  // Weight stages per issuer iteration.  16-point tiles: 4 (210 -> 173 us for ~1 850 rows).  64-point tiles: 2 when
+  // a CTA streams several tiles (1.68 -> 1.58 ms for the 64 000-point forward+gradient sweep); a CTA with a single
+  // 64-point tile waits on the weight stream and loses 10 % by waiting for two stages of its 5-stage ring.
+  const int group = np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
+  unsigned long long* masks = in.mask_scratch ? in.mask_scratch : st->mask_dev;
+  if (small)
+    mlp_tc_kernel<16><<<grid, NTHREADS, make_plan<16>(dec->dev.num_layers, dec->dev.in0).total, s>>>(
+        st->table_dev, st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks, point_tiles, group);
+  else
+    mlp_tc_kernel<64><<<grid, NTHREADS, st->smem_bytes, s>>>(st->table_dev, st->tiles_dev, in, sdf, dinput,
+                                                             st->overflow_dev, masks, point_tiles, group);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
 }
 
+size_t mlp_tc_mask_scratch_bytes(const sdfr_decoder* dec) {
+  if (!dec->tc.ok) return 0;
+  return (size_t)(dec->sm_count > 0 ? dec->sm_count : 148) * (size_t)(dec->dev.num_layers - 1) * 512 * 8;
+}
+
+// Forward only at fp16 operand precision (hi halves): the lattice pass of the fused engine.  CTA-pair kernel for
+// stock-like pass tables (every hidden pass an even number of 128-feature blocks, last Linear a single row);
+// the wide-tile kernel for every other table the tensor-core path accepts.
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s) {
   SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED, "tcgen05 MLP kernel does not cover this decoder");
   if (in.n <= 0) return SDFR_OK;
-  static int pingpong = -1;
-  if (pingpong < 0) { const char* e = getenv("SDFR_TC_PINGPONG"); pingpong = e ? atoi(e) : 1; }
-  if (!pingpong) return launch_mlp_tc_impl(dec, in, sdf, nullptr, 1, s);
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
   const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
-  // CTA-pair kernel (tcgen05 cta_group::2): stock-like pass tables only (every hidden pass an even number of
-  // 128-feature blocks, last Linear a single row)
-  static int pair_mode = -1, pair_slots = 0, pair_smem_max = 0;
-  if (pair_mode < 0) {
-    const char* e = getenv("SDFR_TC_PAIR");
-    pair_mode = e ? atoi(e) : 1;
-    if (pair_mode) {
-      // opt in to the device maximum once: the plan grows with the decoder's input width
-      int devid = 0;
-      PairPlan plan = make_pair_plan(3 + 3);              // the stock input width, for the occupancy query
-      if (cudaGetDevice(&devid) != cudaSuccess ||
-          cudaDeviceGetAttribute(&pair_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) != cudaSuccess ||
-          (int)plan.total > pair_smem_max ||
-          cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_max) != cudaSuccess) {
-        cudaGetLastError();
-        pair_mode = 0;
-      } else {
-        cudaLaunchConfig_t q;
-        memset(&q, 0, sizeof(q));
-        q.gridDim = dim3((unsigned)(2 * 64));
-        q.blockDim = dim3(P_THREADS);
-        q.dynamicSmemBytes = plan.total;
-        cudaLaunchAttribute qa[1];
-        qa[0].id = cudaLaunchAttributeClusterDimension;
-        qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-        q.attrs = qa; q.numAttrs = 1;
-        int nc = 0;
-        if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_coarse_pair_kernel, &q) != cudaSuccess || nc < 1) { cudaGetLastError(); pair_mode = 0; }
-        pair_slots = nc;
-      }
+  static int pair_init = 0, pair_slots = 0, pair_smem_max = 0;
+  if (!pair_init) {
+    pair_init = 1;
+    // opt in to the device maximum once: the plan grows with the decoder's input width
+    int devid = 0;
+    PairPlan plan = make_pair_plan(3 + 3);              // the stock input width, for the occupancy query
+    if (cudaGetDevice(&devid) == cudaSuccess &&
+        cudaDeviceGetAttribute(&pair_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) == cudaSuccess &&
+        (int)plan.total <= pair_smem_max &&
+        cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_max) == cudaSuccess) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3((unsigned)(2 * 64));
+      q.blockDim = dim3(P_THREADS);
+      q.dynamicSmemBytes = plan.total;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_coarse_pair_kernel, &q) == cudaSuccess && nc >= 1) pair_slots = nc;
     }
+    cudaGetLastError();
   }
-  // per decoder (the switches above are per process): does this pass table fit the pair kernel?
-  bool pair_ok = pair_mode != 0 && (int)make_pair_plan(dec->dev.in0).total <= pair_smem_max;
+  // per decoder: does this pass table fit the pair kernel?
+  bool pair_ok = pair_slots > 0 && (int)make_pair_plan(dec->dev.in0).total <= pair_smem_max;
   for (int p = 0; pair_ok && p < st->table.num_layers; ++p) {
     const TcPassDev& ps = st->table.pass[p];
     const bool last = ps.kind == 1;
@@ -2220,120 +1824,22 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
     SDFR_LAUNCH_CHECK();
     return SDFR_OK;
   }
-  static int wide = -1;
-  if (wide < 0) { const char* e = getenv("SDFR_TC_WIDE"); wide = e ? atoi(e) : 1; }
-  if (wide) {
-    static int wide_dbg = -1;
-    if (wide_dbg < 0) { const char* d = getenv("SDFR_TC_WIDE_DBG"); wide_dbg = d ? atoi(d) : 0; }
-    static int wide_group = -1;
-    if (wide_group < 0) { const char* g = getenv("SDFR_TC_WIDE_GROUP"); wide_group = (g && atoi(g) == 2) ? 2 : 4; }
-    // tile width: as wide as the CTA can hold next to the weight ring (112 points with 32 KB stages, 128 with
-    // 16 KB stages), shrunk so that all rounds of tiles are equally full
-    const int max_npt = wide_group == 4 ? 112 : 128;
-    const long long rounds = ((in.n + max_npt - 1) / max_npt + sms - 1) / sms;
-    long long w = (in.n + rounds * sms - 1) / (rounds * sms);
-    int npt = (int)std::min<long long>(max_npt, ((w + 15) / 16) * 16);
-    const char* e = getenv("SDFR_TC_WIDE_NPT");
-    if (e && atoi(e) >= 16 && atoi(e) <= max_npt && atoi(e) % 16 == 0) npt = atoi(e);
-    const long long tiles_n = (in.n + npt - 1) / npt;
-    const int grid = (int)std::min<long long>(tiles_n, sms);
-    static bool wide_attr_set = false;
-    if (!wide_attr_set) {
-      SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)make_wide_plan<2>(dec->dev.in0, 128).total));
-      SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)make_wide_plan<4>(dec->dev.in0, 112).total));
-      wide_attr_set = true;
-    }
-    if (wide_group == 4 && npt <= 112)
-      mlp_tc_coarse_wide_kernel<4><<<grid, W_THREADS, make_wide_plan<4>(dec->dev.in0, npt).total, s>>>(
-          st->table_dev, st->tiles_dev, in, sdf, npt, wide_dbg);
-    else
-      mlp_tc_coarse_wide_kernel<2><<<grid, W_THREADS, make_wide_plan<2>(dec->dev.in0, npt).total, s>>>(
-          st->table_dev, st->tiles_dev, in, sdf, npt, wide_dbg);
-    SDFR_LAUNCH_CHECK();
-    return SDFR_OK;
+  // wide tiles: as wide as the CTA can hold next to the weight ring (112 points with 32 KB stages), shrunk so
+  // that all rounds of tiles are equally full
+  const int max_npt = 112;
+  const long long rounds = ((in.n + max_npt - 1) / max_npt + sms - 1) / sms;
+  const long long w = (in.n + rounds * sms - 1) / (rounds * sms);
+  const int npt = (int)std::min<long long>(max_npt, ((w + 15) / 16) * 16);
+  const long long tiles_n = (in.n + npt - 1) / npt;
+  const int grid = (int)std::min<long long>(tiles_n, sms);
+  static bool wide_attr_set = false;
+  if (!wide_attr_set) {
+    SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_wide_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)make_wide_plan<4>(KC, 112).total));
+    wide_attr_set = true;
   }
-  const long long point_tiles = (in.n + NPTS - 1) / NPTS;
-  const int grid = (int)std::min<long long>((point_tiles + 1) / 2, sms);
-  const CoarsePlan plan = make_coarse_plan(dec->dev.in0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    SDFR_CUDA(cudaFuncSetAttribute(mlp_tc_coarse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total));
-    attr_set = true;
-  }
-  static int interleave = -1;
-  if (interleave < 0) { const char* e = getenv("SDFR_TC_INTERLEAVE"); interleave = e ? atoi(e) : 0; }
-  mlp_tc_coarse_kernel<<<grid, NTHREADS, plan.total, s>>>(st->table_dev, st->tiles_dev, in, sdf, point_tiles, interleave);
-  SDFR_LAUNCH_CHECK();
-  return SDFR_OK;
-}
-
-static int launch_mlp_tc_impl(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, int coarse,
-                              cudaStream_t s) {
-  SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,
-               "tcgen05 MLP kernel does not cover this decoder (needs sm_100, widths <= 512, no LayerNorm, "
-               "latent+3 <= 32, <= 9 layers)");
-  if (in.n <= 0) return SDFR_OK;
-  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
-  // 16-point tiles when the caller expects a short row list (MlpInputs::small_tiles: the band pass of a
-  // few detections), so that ~2 000 rows still fill the machine; 64-point tiles otherwise.
-  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
-  static int small_np = -1;
-  if (small_np < 0) {
-    const char* e = getenv("SDFR_TC_SMALL_NP");
-    small_np = e ? atoi(e) : 16;
-    if (small_np != 16 && small_np != 32 && small_np != 64) small_np = 16;
-  }
-  const bool small = (in.small_tiles || (!in.count_dev && in.n <= 16LL * sms)) && !coarse && small_np != 64;
-  const int np = small ? small_np : 64;
-  const long long point_tiles = (in.n + np - 1) / np;
-  static int cluster = -1, cluster_small = -1;
-  if (cluster < 0) {
-    const char* e = getenv("SDFR_TC_CLUSTER");
-    cluster = e ? atoi(e) : 1;   // multicast measured slower than per-CTA streaming
-    if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
-    e = getenv("SDFR_TC_CLUSTER_SMALL");
-    cluster_small = e ? atoi(e) : 1;
-    if (cluster_small != 1 && cluster_small != 2 && cluster_small != 4) cluster_small = 1;
-  }
-  int grid = (int)std::min<long long>(point_tiles, sms);
-  int cl = small ? cluster_small : cluster;
-  while (cl > 1 && (grid % cl != 0 || grid < cl)) {
-    if (grid >= cl) grid -= grid % cl; else cl >>= 1;
-  }
-  // Weight stages per issuer iteration (SDFR_TC_GROUP=0 turns the grouping off).  16-point tiles: 4 (210 -> 173 us
-  // for ~1 850 rows).  64-point tiles: 2 when a CTA streams several tiles (1.68 -> 1.58 ms for the 64 000-point
-  // forward+gradient sweep); a CTA with a single 64-point tile waits on the weight stream and loses 10 % by
-  // waiting for two stages of its 5-stage ring.
-  static int grouping = -1;
-  if (grouping < 0) { const char* e = getenv("SDFR_TC_GROUP"); grouping = e ? atoi(e) : 1; }
-  const int group = !grouping || coarse || cl != 1 ? 1 : np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(NTHREADS);
-  cfg.dynamicSmemBytes = !small ? st->smem_bytes
-                         : np == 16 ? make_plan<16>(dec->dev.num_layers, dec->dev.in0).total
-                                    : make_plan<32>(dec->dev.num_layers, dec->dev.in0).total;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cl;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (small && np == 32) {
-    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<32>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
-                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse, group));
-  } else if (small) {
-    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<16>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
-                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse, group));
-  } else {
-    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<64>, (const TcTable*)st->table_dev, (const unsigned char*)st->tiles_dev,
-                                 in, sdf, dinput, st->overflow_dev, st->mask_dev, point_tiles, coarse, group));
-  }
+  mlp_tc_coarse_wide_kernel<4><<<grid, W_THREADS, make_wide_plan<4>(dec->dev.in0, npt).total, s>>>(
+      st->table_dev, st->tiles_dev, in, sdf, npt);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }

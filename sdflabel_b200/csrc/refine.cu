@@ -72,6 +72,7 @@ struct EngineDev {          // passed by value to the engine kernels
   float* partc;             // [B,nbc,16+L]
   float* history;           // [B,max_iters,4]
   float* grads;             // [B,5+2L]
+  unsigned long long* mask_scratch;   // ReLU sign words of the tensor-core band pass (per engine: engines may overlap)
   int* presel_err;          // [1] max |coarse sdf - accurate sdf| over the pre-selected rows since the last read (float bits)
   float* extents;           // [B,8] label extents: min xyz, max xyz, surfel count, pad
   SplatView* views;         // [B]
@@ -478,7 +479,7 @@ __global__ void __launch_bounds__(LB) extent_kernel(EngineDev E) {
     }
     float* o = E.extents + (size_t)b * 8;
     for (int c = 0; c < 3; ++c) { o[c] = lo[c]; o[3 + c] = hi[c]; }
-    o[6] = (float)tn; o[7] = 0.f;
+    o[6] = (float)tn; o[7] = (float)m;
   }
 }
 
@@ -591,6 +592,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.part2, (size_t)B * E.nb2 * 3); A(E.part3, (size_t)B * E.nb3 * 3); A(E.partc, (size_t)B * E.nbc * (16 + L));
   A(E.history, (size_t)B * E.max_iters * 4); A(E.grads, (size_t)B * (5 + 2 * L));
   A(E.presel_err, 4); A(E.extents, (size_t)B * 8);
+  A(E.mask_scratch, mlp_tc_mask_scratch_bytes(dec) / 8 + 1);
   A(E.views, B);
   r->views_host.resize(B);
   r->nocs_dev.assign(B, nullptr);
@@ -748,6 +750,7 @@ IterPlan make_iter_plan(sdfr_refine* r, int B) {
   p.in_band.index = E.band_src;
   p.in_band.count_dev = E.band_total;
   p.in_band.small_tiles = B <= 4;       // a few detections: ~2 000 rows each, spread them over all SMs
+  p.in_band.mask_scratch = E.mask_scratch;
   int impl = r->cfg.mlp_impl;
   if (impl == SDFR_MLP_AUTO) impl = r->dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
   p.impl = impl;
@@ -768,40 +771,72 @@ IterPlan make_iter_plan(sdfr_refine* r, int B) {
   return p;
 }
 
+// Optional per-stage timing of an un-captured iteration (sdfr_refine_profile): an event after every stage.
+struct StageClock {
+  std::vector<cudaEvent_t> ev;
+  cudaStream_t s;
+  void mark() {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+  }
+};
+#define STAGE_MARK(clk) do { if (clk) (clk)->mark(); } while (0)
+
+const char* const kStageNames[] = {"iter_begin", "lattice_pass", "band_select", "band_pass", "band_surface", "project",
+                                   "splat_forward", "loss2d", "loss3d", "grad_prep", "splat_backward", "chain", "update"};
+constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
+
 // lattice pass -> band select -> accurate pass on the selected rows -> isosurface projection
-int enqueue_surface(sdfr_refine* r, const IterPlan& p, cudaStream_t s) {
+int enqueue_surface(sdfr_refine* r, const IterPlan& p, cudaStream_t s, StageClock* clk = nullptr) {
   EngineDev& E = r->E;
   int rc = p.coarse ? launch_mlp_tc_coarse(r->dec, p.in, E.sdf, s) : launch_mlp_ffma(r->dec, p.in, E.sdf, nullptr, s);
   if (rc) return rc;
+  STAGE_MARK(clk);
   if ((rc = launch_band_select(p.ba, s))) return rc;
+  STAGE_MARK(clk);
   rc = p.impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, p.in_band, E.band_sdf, E.dinput, s)
                                   : launch_mlp_ffma(r->dec, p.in_band, E.band_sdf, E.dinput, s);
   if (rc) return rc;
-  return launch_band_surface(p.ba, s);
+  STAGE_MARK(clk);
+  rc = launch_band_surface(p.ba, s);
+  STAGE_MARK(clk);
+  return rc;
 }
 
 // enqueues the kernels of ONE refine iteration of detections [0, B) on `s`
-int enqueue_iteration(sdfr_refine* r, int B, int qw, int qh, cudaStream_t s) {
+int enqueue_iteration(sdfr_refine* r, int B, int qw, int qh, cudaStream_t s, StageClock* clk = nullptr) {
   EngineDev E = r->E;
   E.batch = B;
   const IterPlan p = make_iter_plan(r, B);
   int rc;
+  STAGE_MARK(clk);
   iter_begin_kernel<<<B, 32, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
-  if ((rc = enqueue_surface(r, p, s))) return rc;
+  STAGE_MARK(clk);
+  if ((rc = enqueue_surface(r, p, s, clk))) return rc;
   if ((rc = launch_project(E.views, B, (int)E.cap, s))) return rc;
+  STAGE_MARK(clk);
   if ((rc = launch_splat_forward(E.views, B, qw, qh, s))) return rc;
+  STAGE_MARK(clk);
   loss2d_batch_kernel<<<dim3((qw * qh + LB - 1) / LB, B), LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
+  STAGE_MARK(clk);
   loss3d_batch_kernel<<<dim3(E.nb3, B), LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
+  STAGE_MARK(clk);
   grad_prep_kernel<<<dim3((qw * qh + LB - 1) / LB, B), LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
+  STAGE_MARK(clk);
   if ((rc = launch_splat_backward(E.views, B, (int)E.cap, s))) return rc;
+  STAGE_MARK(clk);
   chain_kernel<<<dim3(E.nbc, B), LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
+  STAGE_MARK(clk);
   update_kernel<<<B, LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
+  STAGE_MARK(clk);
   return SDFR_OK;
 }
 
@@ -942,6 +977,43 @@ extern "C" int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void
   return SDFR_OK;
 }
 
+extern "C" int sdfr_refine_profile(sdfr_refine* r, int iters, float* stage_ms_host, int max_stages, int* n_stages,
+                                   int32_t* band_rows_host, void* stream) {
+  SDFR_REQUIRE(r && stage_ms_host && iters > 0 && max_stages >= kNumStages, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int B = r->active;
+  for (int b = 0; b < B; ++b)
+    SDFR_REQUIRE(r->det_w[b] > 0, SDFR_E_INVALID, "detection %d of the %d active ones has not been set", b, B);
+  int qw, qh;
+  active_shape(r, &qw, &qh);
+  std::vector<double> acc(kNumStages, 0.0);
+  int rc = SDFR_OK;
+  for (int it = 0; it < iters && rc == SDFR_OK; ++it) {
+    StageClock clk;
+    clk.s = s;
+    rc = enqueue_iteration(r, B, qw, qh, s, &clk);
+    r->iters_enqueued.assign(r->iters_enqueued.size(), 1 << 30);     // the history is read through D.iter
+    cudaStreamSynchronize(s);
+    if (rc == SDFR_OK && (int)clk.ev.size() == kNumStages + 1)
+      for (int k = 0; k < kNumStages; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, clk.ev[k], clk.ev[k + 1]);
+        acc[k] += ms;
+      }
+    for (cudaEvent_t e : clk.ev) cudaEventDestroy(e);
+  }
+  if (rc) return rc;
+  r->runs += 1;
+  for (int k = 0; k < kNumStages; ++k) stage_ms_host[k] = (float)(acc[k] / iters);
+  if (n_stages) *n_stages = kNumStages;
+  if (band_rows_host) SDFR_CUDA(cudaMemcpy(band_rows_host, r->E.band_total, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  return SDFR_OK;
+}
+
+extern "C" const char* sdfr_refine_stage_name(int stage) {
+  return stage >= 0 && stage < kNumStages ? kStageNames[stage] : "";
+}
+
 extern "C" int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* trans_dev, float* scale_dev,
                                   float* latent_dev, void* stream) {
   SDFR_REQUIRE(r && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
@@ -949,6 +1021,13 @@ extern "C" int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* 
   EngineDev& E = r->E;
   export_params_kernel<<<1, 32, 0, s>>>(E.det + b, E.latent + (size_t)b * E.L, E.L, yaw_dev, trans_dev, scale_dev, latent_dev);
   SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+extern "C" int sdfr_refine_set_latent(sdfr_refine* r, int b, const float* latent_host, void* stream) {
+  SDFR_REQUIRE(r && latent_host && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
+  SDFR_CUDA(cudaMemcpyAsync(r->E.latent + (size_t)b * r->E.L, latent_host, r->E.L * sizeof(float), cudaMemcpyHostToDevice,
+                            reinterpret_cast<cudaStream_t>(stream)));
   return SDFR_OK;
 }
 

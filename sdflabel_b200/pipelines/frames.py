@@ -9,7 +9,8 @@ only collective is one all-gather of fixed-width label records at dump time so t
 every rank (or rank 0) can run the evaluator (refine_css.py:253-263).  The payload is
 O(100 B) per detection: latency-bound, NVLink bandwidth is irrelevant.
 
-Record layout (float32): [frame, det, yaw, tx, ty, tz, scale, final_loss, latent(L)...].
+Record layout (float32): [frame, det, yaw, tx, ty, tz, scale, final_loss, latent(L)...,
+dimensions(3), location(3), rotation_y, alpha] - the refined parameters and the KITTI label built from them.
 """
 from __future__ import annotations
 
@@ -19,15 +20,35 @@ import numpy as np
 import torch
 
 
-def shard_frames(num_frames: int, rank: int, world: int) -> List[int]:
-    """Round-robin frame ownership (the natural unit: one dump file per frame)."""
+def shard_frames(num_frames: int, rank: int, world: int, detections_per_frame: Sequence[int] = None) -> List[int]:
+    """Frames owned by ``rank`` (the natural unit: one dump file per frame, refine_css.py:65-70).
+
+    Without ``detections_per_frame``: round robin.  With it (the annotation count of every frame is known before
+    any GPU work starts): longest-processing-time-first - frames in decreasing detection count, each to the rank
+    with the least work so far (ties: lowest rank) - because a frame costs time in proportion to its detections
+    and frames carry 1 to 8 of them.  Deterministic, so every rank computes the same partition on its own."""
     if not (0 <= rank < world):
         raise ValueError(f"rank {rank} outside world {world}")
-    return list(range(rank, num_frames, world))
+    if detections_per_frame is None:
+        return list(range(rank, num_frames, world))
+    if len(detections_per_frame) != num_frames:
+        raise ValueError("detections_per_frame must have one entry per frame")
+    load = [0] * world
+    mine: List[int] = []
+    order = sorted(range(num_frames), key=lambda i: (-int(detections_per_frame[i]), i))
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += max(int(detections_per_frame[i]), 1)
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+LABEL_FIELDS = 8     # dimensions(3), location(3), rotation_y, alpha
 
 
 def record_width(latent_size: int) -> int:
-    return 8 + latent_size
+    return 8 + latent_size + LABEL_FIELDS
 
 
 def make_record(frame: int, det: int, result: Dict, latent_size: int) -> np.ndarray:
@@ -39,7 +60,13 @@ def make_record(frame: int, det: int, result: Dict, latent_size: int) -> np.ndar
     rec[3:6] = result['trans']
     rec[6] = result['scale'][0]
     rec[7] = final
-    rec[8:] = result['latent']
+    rec[8:8 + latent_size] = result['latent']
+    label = result.get('label')
+    if label is not None:
+        o = 8 + latent_size
+        rec[o:o + 3] = label['dimensions']
+        rec[o + 3:o + 6] = label['location']
+        rec[o + 6], rec[o + 7] = label['rotation_y'], label['alpha']
     return rec
 
 
@@ -80,20 +107,14 @@ def checksum(records: np.ndarray) -> str:
     return hashlib.sha256(rec.tobytes()).hexdigest()
 
 
-def refine_frames(frames: Sequence[Sequence[Dict]], frame_ids: Iterable[int], dsdf, grid, weights, iters: int,
-                  device='cuda') -> np.ndarray:
-    """Refines the given frames (each a list of detection dicts, see BatchOptimizer) on this
-    rank's GPU and returns their label records."""
-    from .optimizer import BatchOptimizer
-    L = dsdf.latent_size
-    bo = BatchOptimizer(weights, device=device)
-    recs = []
-    for fid in frame_ids:
-        dets = frames[fid]
-        results = bo.optimize(iters, dets, dsdf, grid)
-        for d, r in enumerate(results):
-            recs.append(make_record(fid, d, r, L))
-    return np.stack(recs) if recs else np.zeros((0, record_width(L)), dtype=np.float32)
+def refine_frames(frames, frame_ids, dsdf, grid, weights, iters: int, device='cuda', path_autolabels=None,
+                  max_batch=32, **kw) -> np.ndarray:
+    """Refines the given frames (dicts with a ``detections`` list, see pipelines/refine_frames.py) on this
+    rank's GPU - pose initialisation, refinement, labels, optional per-frame dumps - and returns their label
+    records."""
+    from .refine_frames import FrameRefiner, records_of
+    fr = FrameRefiner(dsdf, grid, weights, iters, max_batch=max_batch, device=device, **kw)
+    return records_of(fr.refine(frames, frame_ids, path_autolabels), dsdf.latent_size)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -209,9 +209,29 @@ class _Engine:
         _lib.check(_lib.load().sdfr_refine_preselect_error(self.handle, _lib.fptr(e), _lib.stream_ptr()))
         return float(e[0])
 
+    def surface_clouds(self, latents):
+        """Isosurface points (device tensors (M_b, 3), object frame) of the raw latents [n, L]: the model clouds of
+        the pose initialisation (refine_css.py:143-151), all n in one lattice pass on slots [0, n)."""
+        lat = np.ascontiguousarray(latents, dtype=np.float32).reshape(-1, self.latent_size)
+        n = lat.shape[0]
+        lib = _lib.load()
+        pin = self._pin(('latents', 0), lat)
+        for b in range(n):
+            _lib.check(lib.sdfr_refine_set_latent(self.handle, b, C.cast(pin.data_ptr() + 4 * b * self.latent_size,
+                                                                       _lib.c_float_p), _lib.stream_ptr()))
+        if self.active != n:
+            self.set_active(n)
+        ext = self.label_extents()
+        clouds = []
+        for b in range(n):
+            m = int(ext[b, 7])
+            keep = self.view(b, 'surf_valid', m).bool()
+            clouds.append(self.view(b, 'surf_pts', 3 * m).view(-1, 3)[keep])
+        return clouds
+
     def label_extents(self):
-        """[active, 8]: min xyz, max xyz of the isosurface points of the CURRENT raw latent, count, 0
-        (the extents ``get_kitti_label`` derives, utils/refinement.py:527-541)."""
+        """[active, 8]: min xyz, max xyz of the isosurface points of the CURRENT raw latent, band point count,
+        pre-selected row count (the extents ``get_kitti_label`` derives, utils/refinement.py:527-541)."""
         out = np.zeros((self.active, 8), dtype=np.float32)
         _lib.check(_lib.load().sdfr_refine_label_extents(self.handle, _lib.fptr(out), _lib.stream_ptr()))
         return out
@@ -220,16 +240,18 @@ class _Engine:
                   'grads': 7, 'surf_count': 8, 'depth': 9, 'cam_pts': 10, 'front': 11, 'surf_valid': 12, 'cam_rgb': 13,
                   'surf_idx': 14}
 
-    def view(self, b, kind):
-        """Device copy of an intermediate of the last iteration (tests, label dumps)."""
+    def view(self, b, kind, count=None):
+        """Device copy of an intermediate of the last iteration (tests, label dumps); the first ``count``
+        elements when given."""
         lib = _lib.load()
         kind = self.VIEW_KINDS[kind] if isinstance(kind, str) else int(kind)
         p = _lib.vp()
         n = C.c_int64(0)
         _lib.check(lib.sdfr_refine_view(self.handle, b, kind, C.byref(p), C.byref(n)))
+        size = n.value if count is None else min(int(count), n.value)
         dtype = torch.int32 if kind in (8, 14) else torch.uint8 if kind in (11, 12) else torch.float32
-        out = torch.empty((n.value,), device='cuda', dtype=dtype)
-        _lib.check(lib.sdfr_refine_copy_view(self.handle, b, kind, out.data_ptr(), n.value, _lib.stream_ptr()))
+        out = torch.empty((size,), device='cuda', dtype=dtype)
+        _lib.check(lib.sdfr_refine_copy_view(self.handle, b, kind, out.data_ptr(), size, _lib.stream_ptr()))
         return out
 
     def surfels(self, b):

@@ -5,9 +5,11 @@ Mirror of ``Rasterer`` in the reference's sdfrenderer/renderer/rasterer.py:9-155
 dictionaries).  Projection (renderer/projection.py), the tangent-disc primitive
 (renderer/primitives.py:165-243) and the composition are one pair of CUDA
 launches behind ``sdfr_splat_forward``; the backward of the whole thing is
-``sdfr_splat_backward``.  Only ``primitives='disc'`` without background is on
-the refine path (optimizer.py:110-123); the circle primitives and ``bg`` are
-listed under "next" in SURVEY.md section 8(f).
+``sdfr_splat_backward``.  ``primitives='disc'`` without background is what the
+refine path uses (optimizer.py:110-123); the screen-space circle primitives
+(``'circle'``, ``'circle_opt'``, primitives.py:4-162) and background compositing
+(``bg``, rasterer.py:107-111) serve the stand-alone render API of
+sdfrenderer/main.py:62-121 and run through the same two entry points.
 """
 from __future__ import annotations
 
@@ -22,9 +24,11 @@ class _Splat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, coords, normals, colors, camera, cfg_tuple):
         lib = _lib.load()
-        width, height, kinv, kmat, rot, output_nocs = cfg_tuple
+        width, height, kinv, kmat, rot, output_nocs, primitive, bg = cfg_tuple
         dev = coords.device
-        cfg = _lib.RasterCfg(width=width, height=height, rot=rot, output_nocs=int(output_nocs))
+        bg32 = None if bg is None else bg.detach().to(dev, torch.float32).contiguous()
+        cfg = _lib.RasterCfg(width=width, height=height, rot=rot, output_nocs=int(output_nocs), primitive=primitive,
+                             bg_dev=_lib.ptr(bg32))
         cfg.kinv[:] = kinv
         cfg.k[:] = kmat
         c32 = coords.detach().contiguous().float()
@@ -39,8 +43,9 @@ class _Splat(torch.autograd.Function):
         f32 = dict(device=dev, dtype=torch.float32)
         color = torch.empty((3, height, width), **f32)
         mask = torch.empty((1, height, width), **f32)
-        depth = torch.empty((1, height, width), **f32)
-        nmap = torch.empty((3, height, width), **f32)
+        # with a background only colour and mask can be composed (rasterer.py:107-144)
+        depth = torch.empty((1, height, width), **f32) if bg32 is None else None
+        nmap = torch.empty((3, height, width), **f32) if bg32 is None else None
         cam_pts = torch.empty((m, 3), **f32)
         cam_rgb = torch.empty((m, 3), **f32)
         front = torch.empty((m,), device=dev, dtype=torch.uint8)
@@ -53,7 +58,7 @@ class _Splat(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.sdfr_splat_forward(
                 cfg, c32.data_ptr(), n32.data_ptr(), _lib.ptr(col32), pose32.data_ptr(), m,
-                color.data_ptr(), mask.data_ptr(), depth.data_ptr(), nmap.data_ptr(), cam_pts.data_ptr(),
+                color.data_ptr(), mask.data_ptr(), _lib.ptr(depth), _lib.ptr(nmap), cam_pts.data_ptr(),
                 cam_rgb.data_ptr(), front.data_ptr(), _lib.ptr(xyzf), _lib.ptr(rgbf), _lib.ptr(count),
                 ws.data_ptr(), _lib.stream_ptr()))
         if want_front:
@@ -64,7 +69,11 @@ class _Splat(torch.autograd.Function):
             xyzf = torch.empty((0, 3), **f32)
             rgbf = torch.empty((0, 3), **f32)
             front_idx = torch.empty((0,), device=dev, dtype=torch.long)
+        if bg32 is not None:
+            depth = torch.zeros((1, height, width), **f32)
+            nmap = torch.zeros((3, height, width), **f32)
         ctx.cfg = cfg
+        ctx.bg32 = bg32           # keeps the buffer cfg.bg_dev points at alive until the backward
         ctx.cfg_tuple = cfg_tuple
         ctx.ws = ws
         ctx.save_for_backward(c32, n32, col32 if col32 is not None else torch.empty(0, device=dev), pose32, front_idx)
@@ -80,7 +89,7 @@ class _Splat(torch.autograd.Function):
     def backward(ctx, g_color, g_mask, g_depth, g_nmap, g_pts, g_rgb, g_xyzf, g_rgbf):
         lib = _lib.load()
         c32, n32, col32, pose32, front_idx = ctx.saved_tensors
-        width, height, kinv, kmat, rot, output_nocs = ctx.cfg_tuple
+        width, height, kinv, kmat, rot, output_nocs, primitive, bg = ctx.cfg_tuple
         dev = c32.device
         m = c32.shape[0]
 
@@ -88,6 +97,8 @@ class _Splat(torch.autograd.Function):
             return None if g is None else g.contiguous().float()
 
         g_color, g_mask, g_depth, g_nmap = prep(g_color), prep(g_mask), prep(g_depth), prep(g_nmap)
+        if ctx.bg32 is not None:
+            g_depth = g_nmap = None
         g_pts, g_rgb = prep(g_pts), prep(g_rgb)
         if g_xyzf is not None and front_idx.numel():
             g_pts = (g_pts if g_pts is not None else torch.zeros((m, 3), device=dev)).index_add(
@@ -170,17 +181,24 @@ class Rasterer(torch.nn.Module):
         output_nocs=False,
         output_points=True
     ):
-        if primitives != 'disc':
-            raise NotImplementedError("only the 'disc' primitive (the one the refine loop uses) is implemented")
-        if bg is not None:
-            raise NotImplementedError("background compositing is not on the refine path")
+        prim = {'disc': _lib.PRIM_DISC, 'circle': _lib.PRIM_CIRCLE, 'circle_opt': _lib.PRIM_CIRCLE_OPT}.get(primitives)
+        if prim is None:
+            raise ValueError(f"unknown primitive {primitives!r}")      # (the reference dies with UnboundLocalError)
+        if bg is not None and (output_depth or output_normals):
+            # rasterer.py:133-144 multiplies M+1 weight rows with M depth / normal rows
+            raise RuntimeError("with a background only the color and mask maps can be composed "
+                               "(the reference fails to broadcast depth / normals, rasterer.py:133-144)")
+        if bg is not None and not output_nocs:
+            output_nocs_eff = True        # rasterer.py:107-111 shows (colors + 1) / 2 whatever output_nocs says
+        else:
+            output_nocs_eff = bool(output_nocs)
         if rot not in ('dcm', 'quat'):
             raise ValueError(rot)
         if not coords.is_cuda:
             raise _lib.SdfrError("sdflabel_b200.Rasterer runs on a CUDA device only (no CPU path)")
         kinv, kmat = self._intrinsics()
         cfg = (int(self.res_x_px), int(self.res_y_px), kinv, kmat,
-               _lib.ROT_DCM if rot == 'dcm' else _lib.ROT_QUAT, bool(output_nocs))
+               _lib.ROT_DCM if rot == 'dcm' else _lib.ROT_QUAT, output_nocs_eff, prim, bg)
         color, mask, depth, nmap, xyz, rgb, xyzf, rgbf = _Splat.apply(coords, normals, colors, camera_matrix, cfg)
         rendering = {'color': color}
         if output_mask:

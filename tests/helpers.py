@@ -89,17 +89,34 @@ def threshold_margin(K, width, v, m, pixels, chunk=256):
     return out
 
 
-def assert_maps_close(ours, ref, K, width, v, m, name, tol=1e-4, margin=2e-6):
+def ray_distance(K, width, v, pixels):
+    """(P,) distance from each pixel's ray to the nearest of the points ``v`` (camera frame)."""
+    kinv = np.linalg.inv(np.asarray(K, dtype=np.float32)).astype(np.float64)
+    px = np.asarray(pixels, dtype=np.int64).reshape(-1)
+    rays = np.stack([px % width, px // width, np.ones_like(px)], 1).astype(np.float64) @ kinv.T
+    rays /= np.linalg.norm(rays, axis=1, keepdims=True)
+    t = v @ rays.T                                               # (M,P) ray parameter of the closest approach
+    d = np.linalg.norm(v[:, None, :] - t[:, :, None] * rays[None], axis=-1)
+    return d.min(0)
+
+
+def assert_maps_close(ours, ref, K, width, v, m, name, tol=1e-4, margin=2e-6, kink_points=None):
     """Every pixel within ``tol`` (relative to the map's maximum, north_star 1e-4) except pixels at which a surfel
-    sits within ``margin`` of a hard threshold; returns the number of such attributed pixels."""
+    sits within ``margin`` of a hard threshold - or, when the two sides were given surfels of their OWN (the
+    engine-level tests), pixels whose ray passes one of ``kink_points``: surfels whose normal legitimately differs
+    between two fp32 evaluations of the decoder (a hidden unit on its ReLU kink), which tilts that
+    surfel's disc.  Returns the number of attributed pixels."""
     ours, ref = np.asarray(ours, np.float64), np.asarray(ref, np.float64)
     err = np.abs(ours - ref).reshape(ref.shape[0], -1).max(0)
     bad = np.nonzero(err > tol * max(1.0, np.abs(ref).max()))[0]
     if bad.size:
         mg = threshold_margin(K, width, v, m, bad)
-        worst = float(mg.max())
-        assert worst < margin, (f"{name}: {bad.size} pixels out of tolerance, one of them {worst:.2e} away from any "
-                                f"hard threshold (max err {err.max():.2e})")
+        explained = mg < margin
+        if kink_points is not None and len(kink_points):
+            explained |= ray_distance(K, width, np.asarray(kink_points, np.float64), bad) < 0.06   # disc radius 0.04
+        worst = float(mg[~explained].max()) if (~explained).any() else 0.0
+        assert explained.all(), (f"{name}: {bad.size} pixels out of tolerance, {int((~explained).sum())} of them "
+                                 f"unexplained (up to {worst:.2e} away from any hard threshold, max err {err.max():.2e})")
     return int(bad.size)
 
 

@@ -29,7 +29,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    mine = F.shard_frames(NUM_FRAMES, rank, world)
+    mine = F.shard_frames(NUM_FRAMES, rank, world, [f % 3 + 1 for f in range(NUM_FRAMES)])
     allrec = F.gather_labels(_fake_records(mine), L, device='cpu')
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), allrec)
     dist.barrier()
@@ -48,6 +48,34 @@ def test_shard_covers_all_frames_once():
     for world in (1, 2, 3, 8):
         seen = sorted(sum((F.shard_frames(NUM_FRAMES, r, world) for r in range(world)), []))
         assert seen == list(range(NUM_FRAMES))
+
+
+def test_shard_by_detection_count_is_balanced_and_deterministic():
+    """Longest-processing-time-first over the per-frame detection counts: every frame exactly once, the ranks'
+    detection totals within one frame's worth of each other, the same partition whoever computes it."""
+    rng = np.random.RandomState(0)
+    counts = rng.randint(1, 9, size=512).tolist()
+    for world in (1, 2, 4, 8):
+        parts = [F.shard_frames(512, r, world, counts) for r in range(world)]
+        assert sorted(sum(parts, [])) == list(range(512))
+        loads = [sum(counts[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= 8, (world, loads)
+        assert parts == [F.shard_frames(512, r, world, list(counts)) for r in range(world)]
+        rr = [sum(counts[i] for i in F.shard_frames(512, r, world)) for r in range(world)]
+        assert max(loads) <= max(rr)
+    # frames without detections still belong to somebody
+    parts = [F.shard_frames(5, r, 2, [0, 0, 3, 0, 1]) for r in range(2)]
+    assert sorted(sum(parts, [])) == [0, 1, 2, 3, 4]
+
+
+def test_record_layout_carries_the_label():
+    r = {'yaw': np.float32([0.5]), 'trans': np.float32([1, 2, 3]), 'scale': np.float32([2]), 'latent': np.float32([.1, .2, .3]),
+         'history': np.float32([[0, 0, 0.25, 0]]),
+         'label': {'dimensions': [1.5, 1.6, 4.0], 'location': np.array([1., 2., 30.]), 'rotation_y': -1.2, 'alpha': -1.1}}
+    rec = F.make_record(7, 2, r, 3)
+    assert rec.shape == (F.record_width(3),) == (19,)
+    assert rec[0] == 7 and rec[1] == 2 and rec[7] == 0.25 and np.allclose(rec[11:14], [1.5, 1.6, 4.0])
+    assert np.allclose(rec[14:17], [1, 2, 30]) and np.allclose(rec[17:], [-1.2, -1.1])
 
 
 def test_gather_world2_matches_single_process(tmp_path):

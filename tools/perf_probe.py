@@ -1,7 +1,6 @@
 """Times the two decoder launches of a refine iteration in isolation (coarse lattice pass, accurate
-forward+gradient on a band-sized row list) and checks them against the FFMA kernel.  The kernel
-variants are selected by environment variables read once per process, so run one process per
-variant:   SDFR_TC_INTERLEAVE=0 python tools/perf_probe.py"""
+forward+gradient on a band-sized row list) and checks them against the FFMA kernel.
+SDFR_LIB=<other build> python tools/perf_probe.py compares kernel variants (one process per build)."""
 import os
 import sys
 
@@ -51,12 +50,6 @@ def coarse():
 t = timeit(coarse) if os.environ.get("PROBE_COARSE", "1") == "1" else 0.0
 err = float((sdf - sdf_ref).abs().max())
 extra = ""
-if int(os.environ.get("SDFR_TC_WIDE_DBG", "0")) & 16:
-    import ctypes
-    buf = (ctypes.c_ulonglong * 32)()
-    lib.sdfr_debug_wide_timing.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
-    lib.sdfr_debug_wide_timing(buf)
-    extra = f" | CTA0 issuer loop: {buf[0]} cycles in {buf[1]} ns = {buf[0] / max(buf[1], 1):.3f} GHz, issuer pass4/5 [mb01, -, mb2, mb3]x2: {[int(buf[i]) - int(buf[4]) for i in range(4, 12)]}; issuer rows0-3 seen (pass 5): {[int(buf[i]) - int(buf[4]) for i in range(12, 16)]}; epilogue pass 4: acc seen mb0-3 {[int(buf[i]) - int(buf[4]) for i in range(16, 20)]}, rows arrived mb2,3 {[int(buf[i]) - int(buf[4]) for i in range(22, 24)]}"
 print(f"[{tag}] coarse lattice 40^3: {t * 1e3:.1f} us, max |sdf - ffma| {err:.2e}{extra}", flush=True)
 
 ns = [int(v) for v in os.environ.get("PROBE_N", "1850,7400").split(",")]

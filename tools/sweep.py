@@ -40,6 +40,7 @@ for size in (64, 256):
     K[:2] *= size / 256.0
     for B in (1, 4, 16, 32, 64):
         eng = _engine_for(dec, B, 40, size, size, sc["lidar"].shape[0], 64, sc["weights"], dec.mlp_impl)
+        eng.set_active(B)
         for b in range(B):
             eng.set_detection(b, K, size, size, nocs, sc["lidar"], sc["init"]["yaw"], sc["init"]["trans"],
                               sc["init"]["scale"], sc["init"]["latent"])
