@@ -152,23 +152,37 @@ __device__ __forceinline__ Hit disc_test(float rx, float ry, float rz, float vx,
   return h;
 }
 
-constexpr int TILE = 16;
-constexpr int CHUNK = 256;
-constexpr int LCAP = 512;      // surfels of one tile kept resident in shared memory for both sweeps
+constexpr int TILE = 16;       // pixels per tile side for crops above kSmallCropPixels
+constexpr int CHUNK = 256;     // = threads per block
+constexpr int LCAP_LARGE = 512;    // surfels of one tile kept resident in shared memory for both sweeps
+constexpr int LCAP_SMALL = 1024;
+// Crops up to this many pixels (the reference's default regime: rendering_area = 32..64, configs/config_refine.ini:12)
+// are split into 8 x 8 tiles with FOUR threads per pixel, each sweeping a quarter of the tile's surfel list: a
+// 32 x 32 crop is 16 CTAs instead of 4, and the ~1 600 surfels of a detection (all of them inside a few hundred
+// pixels) are ~300 per tile instead of overflowing the resident list.  The mode depends on the detection's OWN
+// crop only, so its bits do not depend on what else is in the batch.
+constexpr int kSmallCropPixels = 128 * 128;
 
-__global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatView* __restrict__ views) {
+__global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* __restrict__ views, int lcap) {
+  extern __shared__ __align__(16) float s_list[];
   const SplatView& V = views[blockIdx.z];
-  const int tx0 = blockIdx.x * TILE, ty0 = blockIdx.y * TILE;
+  const bool small = V.width * V.height <= kSmallCropPixels;
+  const int tile = small ? 8 : TILE, split = small ? 4 : 1;
+  const int tx0 = blockIdx.x * tile, ty0 = blockIdx.y * tile;
   if (tx0 >= V.width || ty0 >= V.height) return;
   const int m = min(V.count ? *V.count : V.static_count, V.capacity);
-  const int tid = threadIdx.y * TILE + threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pix = small ? tid >> 2 : tid, part = small ? tid & 3 : 0;
+  const int x = tx0 + (small ? pix & 7 : pix & 15), y = ty0 + (small ? pix >> 3 : pix >> 4);
   const bool live = x < V.width && y < V.height;
-  const int tx1 = min(tx0 + TILE - 1, V.width - 1), ty1 = min(ty0 + TILE - 1, V.height - 1);
+  const int tx1 = min(tx0 + tile - 1, V.width - 1), ty1 = min(ty0 + tile - 1, V.height - 1);
 
-  __shared__ float s_v[LCAP][3], s_m[LCAP][3], s_c[LCAP][3], s_a[LCAP];
-  __shared__ int4 s_bb[LCAP];
-  __shared__ int s_warp_cnt[TILE * TILE / 32];
+  float (*s_v)[3] = reinterpret_cast<float(*)[3]>(s_list);
+  float (*s_m)[3] = reinterpret_cast<float(*)[3]>(s_list + 3 * lcap);
+  float (*s_c)[3] = reinterpret_cast<float(*)[3]>(s_list + 6 * lcap);
+  float* s_a = s_list + 9 * lcap;
+  int4* s_bb = reinterpret_cast<int4*>(s_list + 10 * lcap);
+  __shared__ int s_warp_cnt[CHUNK / 32];
 
   const float fx = (float)x, fy = (float)y;
   const float rx = V.kinv[0] * fx + V.kinv[1] * fy + V.kinv[2];
@@ -206,6 +220,26 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
       acc[7] += e * ((s_m[k][2] + 1.f) / 2.f);
     }
   };
+  // the four threads of a pixel (small crops) hold partial results over their quarters of the list: combine them
+  // in a fixed order (lanes 4p .. 4p+3 of one warp)
+  auto combine_sweep0 = [&]() {
+    if (split == 1) return;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
+      zeta_max = fmaxf(zeta_max, __shfl_xor_sync(0xffffffffu, zeta_max, o));
+      hits += __shfl_xor_sync(0xffffffffu, hits, o);
+    }
+  };
+  auto combine_sweep1 = [&]() {
+    if (split == 1) return;
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+      den += __shfl_xor_sync(0xffffffffu, den, o);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+  };
   // culls surfels [base, base + CHUNK) against the tile and appends the survivors (in index order) to the
   // shared list at `start`; entries past `cap` are dropped.  Returns the number of survivors of the chunk.
   auto cull_chunk = [&](const int base, const int start, const int cap) -> int {
@@ -222,7 +256,7 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
     __syncthreads();
     int off = start + __popc(ballot & ((1u << lane) - 1u)), total = 0;
 #pragma unroll
-    for (int w = 0; w < TILE * TILE / 32; ++w) {
+    for (int w = 0; w < CHUNK / 32; ++w) {
       const int c = s_warp_cnt[w];
       if (w < warp) off += c;
       total += c;
@@ -237,23 +271,26 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
     return total;
   };
 
-  // Pass 1: cull everything once.  If the tile's surfels fit the resident list (the usual case: a few hundred
-  // of the ~2 000 surfels of a detection touch a 16 x 16 tile) both sweeps run out of shared memory; the
-  // chunk-serial cull with its dependent global loads and block barriers is paid once instead of twice.
+  // Pass 1: cull everything once.  If the tile's surfels fit the resident list (the usual case) both sweeps run
+  // out of shared memory; the chunk-serial cull with its dependent global loads and block barriers is paid once
+  // instead of twice.
   int total = 0;
-  for (int base = 0; base < m && total <= LCAP; base += CHUNK) total += cull_chunk(base, total, LCAP);
+  for (int base = 0; base < m && total <= lcap; base += CHUNK) total += cull_chunk(base, total, lcap);
   __syncthreads();
-  if (total <= LCAP) {
-    if (live) {
-      for (int k = 0; k < total; ++k) visit(k, 0);
-      nu = sqrtf(sumsq);
-      smax = fmaxf(zeta_max / (nu + kEps32) + 1.f, 0.f) * kDepthGain;
-      for (int k = 0; k < total; ++k) visit(k, 1);
-    }
+  if (total <= lcap) {
+    if (live)
+      for (int k = part; k < total; k += split) visit(k, 0);
+    combine_sweep0();
+    nu = sqrtf(sumsq);
+    smax = fmaxf(zeta_max / (nu + kEps32) + 1.f, 0.f) * kDepthGain;
+    if (live)
+      for (int k = part; k < total; k += split) visit(k, 1);
+    combine_sweep1();
   } else {
-    // more survivors than the list holds (small crops: every surfel touches every tile): chunk by chunk, per sweep
+    // more survivors than the list holds: chunk by chunk, per sweep
     for (int sweep = 0; sweep < 2; ++sweep) {
       if (sweep == 1) {
+        combine_sweep0();
         nu = sqrtf(sumsq);
         smax = fmaxf(zeta_max / (nu + kEps32) + 1.f, 0.f) * kDepthGain;
       }
@@ -261,11 +298,12 @@ __global__ void __launch_bounds__(TILE * TILE) splat_forward_kernel(const SplatV
         const int cnt = cull_chunk(base, 0, CHUNK);
         __syncthreads();
         if (live)
-          for (int k = 0; k < cnt; ++k) visit(k, sweep);
+          for (int k = part; k < cnt; k += split) visit(k, sweep);
       }
     }
+    combine_sweep1();
   }
-  if (!live) return;
+  if (!live || part != 0) return;
   const int P = V.width * V.height, j = y * V.width + x;
   const float inv_den = hits > 0 ? 1.f / den : 0.f;
 #pragma unroll
@@ -392,10 +430,19 @@ int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStr
   return SDFR_OK;
 }
 
-int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, cudaStream_t s) {
+int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, int any_small, cudaStream_t s) {
   if (max_w <= 0 || max_h <= 0 || batch <= 0) return SDFR_OK;
-  dim3 grid((max_w + TILE - 1) / TILE, (max_h + TILE - 1) / TILE, batch);
-  splat_forward_kernel<<<grid, dim3(TILE, TILE), 0, s>>>(views_dev);
+  // any_small: some detection of the batch is a small crop (8 x 8 tiles, longer resident list); the grid then
+  // covers the finer tiling and the blocks of large-crop detections beyond their 16 x 16 tiling exit at once
+  const int tile = any_small ? 8 : TILE;
+  const int lcap = any_small ? LCAP_SMALL : LCAP_LARGE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDFR_CUDA(cudaFuncSetAttribute(splat_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCAP_SMALL * 56));
+    attr_set = true;
+  }
+  dim3 grid((max_w + tile - 1) / tile, (max_h + tile - 1) / tile, batch);
+  splat_forward_kernel<<<grid, CHUNK, (size_t)lcap * 56, s>>>(views_dev, lcap);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
