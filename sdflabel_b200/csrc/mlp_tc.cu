@@ -1540,6 +1540,473 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
   if (warp == 17) tmem_dealloc_pair(tmem_base, TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Accurate forward + input gradient on CTA pairs (tcgen05 cta_group::2): the band pass.
+//
+// A short row list (the ~1 850 pre-selected lattice points of one detection) is spread over the machine in
+// small point tiles, and with 16 points per CTA every tcgen05.mma of mlp_tc_kernel<16> has N <= 32 and sits
+// on the ~52-cycle floor of an M = 128 instruction: each CTA sweeps all 932 weight tiles with four such MMAs
+// per tile (profiles/r01_launches.md).  Here one instruction covers M = 256 FEATURES over a pair of CTAs:
+//   A  = weight tiles, K-major; CTA `rank` streams M block 2 j + rank of the pass table (half of the tiles),
+//   B  = activations of the pair's 2 x NP points, MN-major; each CTA holds its OWN NP points, laid out per
+//        8-k chunk as [zeros | hi | lo] so that one descriptor starting at `hi` gives the N-rows [hi ; lo] and
+//        one starting at `zeros` gives [0 ; hi]:
+//            main  MMA  W_hi x [H_hi ; H_lo]   -> columns [hh | hl] of each CTA's half of D
+//            cross MMA  W_lo x [0 ; H_hi]      -> adds lo*hi onto the hl columns (and exact zeros onto hh),
+//        the same two accumulation chains per output as mlp_tc_kernel, so the results are bit-identical,
+//   D  = [128 features of this CTA] x [hh, cross of CTA 0's points | hh, cross of CTA 1's points] in TMEM.
+// Two MMAs per K step and 256 features instead of two per 128: half the instructions and half the weight
+// stream per CTA.  The epilogue thread that owns a feature writes the next layer's B rows for BOTH point
+// halves: its own CTA's with plain shared-memory stores, the peer's through distributed shared memory
+// (st.shared::cluster; 16 KB per CTA and pass at NP = 16).
+//
+//   warps 0-7  epilogue: TMEM lane quadrant (warp & 3) x point half (warp >> 2 = the CTA that owns the points)
+//   warp 8     weight producer (both CTAs, own tiles)
+//   warp 9     rank 0: MMA issuer for the pair; rank 1: relays "my stage has landed" to rank 0
+// ---------------------------------------------------------------------------------------------
+constexpr int Q_THREADS = 320;
+constexpr int Q_NEPI = 256;
+constexpr int Q_STAGE_TILES = 2;                       // k-chunks (32 k) per ring stage
+constexpr int Q_STAGE_BYTES = Q_STAGE_TILES * TILE_BYTES;
+template <int NP> struct BandRing { static constexpr int value = NP <= 16 ? 5 : 3; };
+
+struct BandPairPlan {
+  uint32_t stages, b, inp, dinp, g, bars, tmem_slot, total;
+};
+template <int NP>
+__host__ __device__ inline BandPairPlan make_band_pair_plan(int in0) {
+  BandPairPlan p;
+  uint32_t o = 0;
+  p.stages = o; o += BandRing<NP>::value * Q_STAGE_BYTES;
+  p.b = o; o += 64 * (3 * NP * 16);                    // 64 8-k chunks x [zeros | hi | lo] point groups
+  const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
+  p.inp = o; o += in_pad * 2 * NP * 4;                 // inputs of the whole pair tile
+  p.dinp = o; o += 2 * in_pad * 2 * NP * 4;            // input-gradient partials, double-buffered by tile parity
+  p.g = o; o += 2 * NP * 4;
+  p.bars = o; o += 32 * 8;
+  p.tmem_slot = o; o += 16;
+  p.total = o;
+  return p;
+}
+
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t remote_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// hi / lo split of 8 values -> two 16-byte rows at a shared::cluster address (own or peer CTA)
+__device__ __forceinline__ float pack8_store_cluster(uint32_t row_hi, uint32_t lo_off, int pg, const float (&h)[8]) {
+  uint4 hi, lo;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 a = __floats2half2_rn(h[2 * i], h[2 * i + 1]);
+    const float2 b = __half22float2(a);
+    const __half2 l = __floats2half2_rn(h[2 * i] - b.x, h[2 * i + 1] - b.y);
+    hw[i] = *reinterpret_cast<const uint32_t*>(&a);
+    lw[i] = *reinterpret_cast<const uint32_t*>(&l);
+    amax = fmaxf(amax, fmaxf(fabsf(h[2 * i]), fabsf(h[2 * i + 1])));
+  }
+  st_cluster_v4(row_hi + pg * 128, hi);
+  st_cluster_v4(row_hi + lo_off + pg * 128, lo);
+  return amax;
+}
+
+// instruction descriptor: D fp32, A / B fp16, A K-major, B MN-major, M = 256 over the pair
+__host__ __device__ constexpr uint32_t idesc_band_pair(int n) {
+  return (1u << 4) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int NP>
+__global__ void __launch_bounds__(Q_THREADS, 1)
+mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
+                        float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
+                        unsigned long long* __restrict__ mask_scratch) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  if (in.count_dev && *in.count_dev <= 0) return;     // uniform over the grid: before any cluster traffic
+  const TcTable& T = *tabp;
+  const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
+  constexpr int NSTAGE = BandRing<NP>::value;
+  constexpr int NPP = 2 * NP;                          // points of the pair tile
+  constexpr int BCH = 3 * NP * 16;                     // bytes per 8-k chunk of B: zeros, hi, lo point groups
+  constexpr int HI = NP * 16, LO = NP * 16;            // hi region inside a chunk; lo region relative to hi
+  constexpr int GW = 16;                               // points per TMEM load group
+  constexpr int G = NP / GW;
+  constexpr int PG = GW / 8;
+  constexpr int TCOLS = 8 * NP;                        // two 256-feature blocks x 4 NP columns
+  constexpr uint32_t kId = idesc_band_pair(4 * NP);
+  static_assert(NP == 16 || NP == 32, "pair tiles of 2 x 16 or 2 x 32 points");
+  const BandPairPlan P = make_band_pair_plan<NP>(in0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  unsigned char* bop = smem + P.b;
+  unsigned long long* masks = mask_scratch + (size_t)blockIdx.x * (size_t)(num_layers - 1) * 512;
+  float* inp = reinterpret_cast<float*>(smem + P.inp);         // [in_pad][2 NP]
+  float* gbuf = reinterpret_cast<float*>(smem + P.g);
+  const uint32_t bars = smem_u32(smem + P.bars);
+  const uint32_t bar_full = bars, bar_peer = bars + 8 * NSTAGE, bar_empty = bars + 8 * (2 * NSTAGE),
+                 bar_acc = bars + 8 * (3 * NSTAGE), bar_act = bars + 8 * (3 * NSTAGE + 1),
+                 bar_x = bars + 8 * (3 * NSTAGE + 2);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
+  const int in_pad = (in0 + 7) & ~7;
+  const bool want_grad = dinput_out != nullptr;
+  const int npass = want_grad ? T.num_passes : num_layers;
+  const long long n_rows = mlp_rows(in);
+  const long long num_pair_tiles = (n_rows + NPP - 1) / NPP;
+  const long long num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_peer + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_act, 2 * (Q_NEPI / 32));             // one arrival per epilogue warp of both CTAs (rank 0's copy is used)
+    mbar_init(bar_x, Q_NEPI / 32);                     // the peer's epilogue warps: "my input-gradient partials are final"
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // the zero point groups of every chunk are written once and never again
+  for (int i = tid; i < 64 * (HI / 16); i += Q_THREADS)
+    *reinterpret_cast<uint4*>(bop + (i / (HI / 16)) * BCH + (i % (HI / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  fence_async_smem();
+  if (warp == 9) tmem_alloc_pair(smem_u32(smem + P.tmem_slot), TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  long long my_tiles = 0;
+  for (long long pt = pair_id; pt < num_pair_tiles; pt += num_pairs) ++my_tiles;
+
+  if (warp == 8) {
+    // ===================== weight producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < npass; ++p) {
+          const int m_blocks = T.pass[p].m_blocks, k_chunks = T.pass[p].k_chunks;
+          const unsigned char* src = tiles + T.pass[p].tile0 * TILE_BYTES;
+          const int nblocks = m_blocks == 1 ? 1 : m_blocks >> 1;
+          for (int j = 0; j < nblocks; ++j) {
+            // a single-block pass (last Linear, gradient of the first) is computed by both CTAs on the same tile row
+            const int mb = m_blocks == 1 ? 0 : 2 * j + (int)rank;
+            for (int kc = 0; kc < k_chunks; kc += Q_STAGE_TILES) {
+              const int cnt = min(Q_STAGE_TILES, k_chunks - kc);
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+              mbar_expect_tx(bar_full + 8 * stage, (uint32_t)cnt * TILE_BYTES);
+              bulk_g2s(smem_u32(smem + P.stages + stage * Q_STAGE_BYTES), src + (size_t)(mb * k_chunks + kc) * TILE_BYTES,
+                       (uint32_t)cnt * TILE_BYTES, bar_full + 8 * stage);
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9 && rank == 1) {
+    // ===================== rank 1: tell the issuer that this CTA's half of a stage has landed ==============
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      uint32_t peer_bar[NSTAGE];
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) peer_bar[s] = mapa_u32(bar_peer + 8 * s, 0u);
+      for (long long it = 0; it < my_tiles; ++it) {
+        for (int p = 0; p < npass; ++p) {
+          const int m_blocks = T.pass[p].m_blocks;
+          const int nblocks = m_blocks == 1 ? 1 : m_blocks >> 1;
+          const int steps = nblocks * ((T.pass[p].k_chunks + Q_STAGE_TILES - 1) / Q_STAGE_TILES);
+          for (int st = 0; st < steps; ++st) {
+            mbar_wait(bar_full + 8 * stage, phase);
+#pragma unroll
+            for (int s = 0; s < NSTAGE; ++s)
+              if (s == (int)stage) mbar_arrive_cluster(peer_bar[s]);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================== rank 0: MMA issuer for the pair =====================
+    uint32_t stage = 0, phase = 0, act_phase = 0;
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t desc_a_base = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);
+    const uint64_t desc_b_main = make_desc(smem_u32(bop) + HI, BCH, B_SBO);     // N-rows of a CTA: [hi ; lo]
+    const uint64_t desc_b_cross = make_desc(smem_u32(bop), BCH, B_SBO);         //                  [0 ; hi]
+    for (long long it = 0; it < my_tiles; ++it) {
+      for (int p = 0; p < npass; ++p) {
+        const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
+        const int nblocks = m_blocks == 1 ? 1 : m_blocks >> 1;
+        mbar_wait_cluster(bar_act, act_phase);         // B operand of both CTAs staged, TMEM of both drained
+        act_phase ^= 1;
+        tc_fence_after();
+        for (int j = 0; j < nblocks; ++j) {
+          const uint32_t d = tm + (uint32_t)(j * 4 * NP);
+          for (int kc = 0; kc < k_chunks; kc += Q_STAGE_TILES) {
+            const int cnt = min(Q_STAGE_TILES, k_chunks - kc);
+            mbar_wait(bar_full + 8 * stage, phase);
+            mbar_wait(bar_peer + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int i = 0; i < Q_STAGE_TILES; ++i) {
+                if (i < cnt) {
+                  const uint64_t da_hi = desc_a_base + (uint64_t)((stage * Q_STAGE_BYTES + i * TILE_BYTES) >> 4);
+                  const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
+                  const uint64_t koff = (uint64_t)(((kc + i) * (KC / 8) * BCH) >> 4);
+#pragma unroll
+                  for (int t = 0; t < KC / 16; ++t) {
+                    const uint64_t ka = (uint64_t)((t * 2 * A_LBO) >> 4), kb = koff + (uint64_t)((t * 2 * BCH) >> 4);
+                    umma_f16_pair(d, da_hi + ka, desc_b_main + kb, kId, (kc | i | t) ? 1u : 0u);   // W_hi x [H_hi ; H_lo]
+                    umma_f16_pair(d, da_lo + ka, desc_b_cross + kb, kId, 1u);                     // W_lo x [0 ; H_hi]
+                  }
+                }
+              }
+              umma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);   // the stage is free in both CTAs
+            }
+            __syncwarp();
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (elect_one()) umma_commit_pair(bar_acc, (uint16_t)3);      // the accumulators of the pass are complete
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs) =====================
+    const int q = warp & 3, ph = warp >> 2;            // TMEM lane quadrant; point half = CTA that owns the points
+    const int t = q * 32 + lane;                       // TMEM lane = feature within this CTA's 128-feature block
+    const int et = tid;
+    const bool own = ph == (int)rank;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t b_dst = mapa_u32(smem_u32(bop), (uint32_t)ph) + HI;      // hi region of the owner's B operand
+    const uint32_t act_bar = mapa_u32(bar_act, 0u);
+    const uint32_t peer_x = mapa_u32(bar_x, rank ^ 1u);
+    uint32_t* masks32 = reinterpret_cast<uint32_t*>(masks);   // [layer][feature][point half]
+    uint32_t acc_phase = 0, x_phase = 0;
+    float amax = 0.f;
+    auto publish = [&]() {                             // this warp's operand rows (own and remote) are written, TMEM read
+      fence_async_all();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_release(act_bar);
+    };
+    for (long long it = 0; it < my_tiles; ++it) {
+      const long long ptile = it * num_pairs + pair_id;
+      const long long base = ptile * NPP;              // first row of the pair tile; this CTA owns [rank NP, rank NP + NP)
+      float* dinp = reinterpret_cast<float*>(smem + P.dinp) + (it & 1) * in_pad * NPP;
+      // ---- stage the inputs of the whole pair tile: inp[c][n] ----
+      for (int i = et; i < in_pad * NPP; i += Q_NEPI) {
+        const int c = i / NPP, n = i - c * NPP;
+        const long long gi = base + n;
+        float v = 0.f;
+        if (gi < n_rows && c < in0) {
+          const long long src = in.index ? (long long)in.index[gi] : gi;
+          if (in.inputs) {
+            v = in.inputs[src * in0 + c];
+          } else {
+            const long long b = src / in.points_per_batch, k = src - b * in.points_per_batch;
+            if (c < latent) {
+              v = in.latent_unit[b * latent + c];
+            } else {
+              float x, y, z;
+              lattice_point(in.lattice, k, x, y, z);
+              v = (c - latent) == 0 ? x : (c - latent) == 1 ? y : z;
+            }
+          }
+        }
+        inp[i] = v;
+        dinp[i] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // B operand of layer 0 (own points): k = input column, one 32-k chunk
+      if (q == 0 && own) {
+        const int k = lane;
+        unsigned char* row = bop + (k >> 3) * BCH + HI + (k & 7) * 16;
+#pragma unroll
+        for (int g = 0; g < NP / 8; ++g) {
+          float h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = k < in0 ? inp[k * NPP + ph * NP + g * 8 + e] * ACT_SCALE : 0.f;
+          amax = fmaxf(amax, pack8_store_t<LO>(row, g, h));
+        }
+      }
+      publish();
+
+      for (int p = 0; p < npass; ++p) {
+        const TcPassDev Ps = T.pass[p];
+        mbar_wait(bar_acc, acc_phase);
+        acc_phase ^= 1;
+        tc_fence_after();
+        if (Ps.kind == 1) {
+          // ---- last Linear (both CTAs hold row 0 for all 2 NP points): sdf and the tanh slope ----
+          if (q == 0) {
+            const float bias0 = __ldg(Ps.bias);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              uint32_t vm[GW], vc[GW];
+              tmem_ld16(lane_base + ph * 2 * NP + g * GW, vm);
+              tmem_ld16(lane_base + ph * 2 * NP + NP + g * GW, vc);
+              tmem_ld_wait();
+              if (lane == 0) {
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq) {
+                  const int n = ph * NP + g * GW + qq;
+                  float y = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale + bias0, gg = 1.f;
+                  if (use_tanh) { y = tanhf(y); gg *= 1.f - y * y; }
+                  y = tanhf(y);
+                  gg *= 1.f - y * y;
+                  if (own && base + n < n_rows) sdf_out[base + n] = y;
+                  gbuf[n] = gg;
+                }
+              }
+              __syncwarp();
+            }
+          }
+          tc_fence_before();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (want_grad) {
+            // backward of the last Linear is an outer product: delta[f][n] = W_last[f] * g[n] * mask[f][n]
+            const int hidden = T.last_k;
+            for (int j = 0; j < 2; ++j) {
+              const int f = (2 * j + (int)rank) * 128 + t;
+              const float w = f < hidden ? __ldg(T.last_w + f) * BWD_SCALE : 0.f;
+              const uint32_t mk = f < hidden ? masks32[((size_t)(num_layers - 2) * 512 + f) * 2 + ph] : 0u;
+              const uint32_t row = b_dst + (uint32_t)((f >> 3) * BCH + (f & 7) * 16);
+#pragma unroll
+              for (int g = 0; g < NP / 8; ++g) {
+                float h[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (g * 8 + e)) & 1u) ? w * gbuf[ph * NP + g * 8 + e] : 0.f;
+                amax = fmaxf(amax, pack8_store_cluster(row, LO, g, h));
+              }
+            }
+            publish();
+          }
+          continue;
+        }
+        if (Ps.kind == 3) {
+          // ---- gradient with respect to the input rows (single block, both CTAs hold it): own points only ----
+          if (q == 0 && own) {
+            const int f = t;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              uint32_t vm[GW], vc[GW];
+              tmem_ld16(lane_base + ph * 2 * NP + g * GW, vm);
+              tmem_ld16(lane_base + ph * 2 * NP + NP + g * GW, vc);
+              tmem_ld_wait();
+              if (f < in0) {
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq)
+                  dinp[f * NPP + ph * NP + g * GW + qq] += (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
+              }
+            }
+          }
+          tc_fence_before();
+          // the gradient of the concatenated input columns was accumulated by the CTA that owns those feature
+          // lanes, for both point halves: add the peer's partial for this CTA's points
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster_release(peer_x);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mbar_wait_cluster(bar_x, x_phase);
+          x_phase ^= 1;
+          const uint32_t peer_dinp = mapa_u32(smem_u32(dinp), rank ^ 1u);
+          for (int i = et; i < NP * in0; i += Q_NEPI) {
+            const int n = i / in0, c = i - n * in0;
+            const int np = (int)rank * NP + n;
+            const float v = dinp[c * NPP + np] + ld_cluster_f32(peer_dinp + (uint32_t)((c * NPP + np) * 4));
+            if (base + np < n_rows) dinput_out[(base + np) * in0 + c] = v;
+          }
+          continue;
+        }
+        const bool fwd = Ps.kind == 0;
+        const int split = fwd ? Ps.rows : Ps.prev_rows;       // rows below: regular outputs
+        const int nblocks = Ps.m_blocks >> 1;
+        for (int j = 0; j < nblocks; ++j) {
+          const int f = (2 * j + (int)rank) * 128 + t;
+          const int cls = f < split ? 0 : (f < split + Ps.cat_dim ? 1 : 2);
+          const uint32_t tb = lane_base + (uint32_t)(j * 4 * NP + ph * 2 * NP);
+          const uint32_t row = b_dst + (uint32_t)((f >> 3) * BCH + (f & 7) * 16);
+          const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
+          const uint32_t pmask = (!fwd && cls == 0) ? masks32[((size_t)(Ps.layer - 1) * 512 + f) * 2 + ph] : 0u;
+          const int cat_row = (Ps.cat_off + f - split) * NPP + ph * NP;
+          uint32_t mk = 0u;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            uint32_t vm[GW], vc[GW];
+            tmem_ld16(tb + g * GW, vm);
+            tmem_ld16(tb + NP + g * GW, vc);
+            tmem_ld_wait();
+            float x[GW];
+#pragma unroll
+            for (int qq = 0; qq < GW; ++qq)
+              x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
+            float h[GW];
+            if (fwd) {
+              if (cls == 0) {
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq) {
+                  const float y = x[qq] + bias;
+                  const bool on = y > 0.f;
+                  if (on) mk |= 1u << (g * GW + qq);
+                  h[qq] = on ? y * Ps.out_scale : 0.f;
+                }
+              } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq) h[qq] = inp[cat_row + g * GW + qq] * Ps.out_scale;
+              } else {
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
+              }
+            } else {
+              if (cls == 0) {
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq) h[qq] = ((pmask >> (g * GW + qq)) & 1u) ? x[qq] * Ps.out_scale : 0.f;
+              } else {
+                if (cls == 1) {                                    // gradient of the concatenated input columns
+#pragma unroll
+                  for (int qq = 0; qq < GW; ++qq) dinp[cat_row + g * GW + qq] += x[qq];
+                }
+#pragma unroll
+                for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
+              }
+            }
+#pragma unroll
+            for (int pk = 0; pk < PG; ++pk) {
+              float h8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h8[e] = h[pk * 8 + e];
+              amax = fmaxf(amax, pack8_store_cluster(row, LO, g * PG + pk, h8));
+            }
+          }
+          if (fwd && want_grad) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;   // only the backward reads them
+        }
+        publish();
+      }
+      // the next pair tile re-stages inp: every local epilogue thread must be past its last read
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    if (amax > 60000.f) atomicOr(overflow_flag, 1);   // a scaled operand left the fp16 range
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                 // no CTA may exit (or free TMEM) while its peer can still reach it
+  if (warp == 9) tmem_dealloc_pair(tmem_base, TCOLS);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -1732,6 +2199,50 @@ int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s) {
   return SDFR_OK;
 }
 
+// CTA pairs the band-pair kernel can keep resident (0: the kernel cannot run here), queried once per tile width.
+template <int NP>
+static int band_pair_slots(int in0) {
+  static int init = 0, slots = 0, smem_max = 0;
+  if (!init) {
+    init = 1;
+    int devid = 0;
+    const BandPairPlan plan = make_band_pair_plan<NP>(KC);   // the widest input the tensor-core path accepts
+    if (cudaGetDevice(&devid) == cudaSuccess &&
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) == cudaSuccess &&
+        (int)plan.total <= smem_max &&
+        cudaFuncSetAttribute(mlp_tc_band_pair_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) == cudaSuccess) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3((unsigned)(2 * 64));
+      q.blockDim = dim3(Q_THREADS);
+      q.dynamicSmemBytes = plan.total;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.attrs = qa; q.numAttrs = 1;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_band_pair_kernel<NP>, &q) == cudaSuccess && nc >= 1) slots = nc;
+    }
+    cudaGetLastError();
+  }
+  return in0 <= KC ? slots : 0;
+}
+
+// The band-pair kernel takes pass tables whose hidden passes are an even number of 128-feature blocks and whose
+// single-row passes (last Linear, gradient of the first) are one block; everything else stays on mlp_tc_kernel<16>.
+static bool band_pair_ok(const sdfr_decoder* dec, const TcHostState* st, bool want_grad) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("SDFR_BAND_PAIR"); enabled = e ? atoi(e) : 1; }   // 0: A/B runs of the single-CTA kernel
+  if (!enabled || band_pair_slots<16>(dec->dev.in0) <= 0) return false;
+  const int npass = want_grad ? st->table.num_passes : st->table.num_layers;
+  for (int p = 0; p < npass; ++p) {
+    const TcPassDev& ps = st->table.pass[p];
+    const bool single = ps.kind == 1 || ps.kind == 3;
+    if (single ? ps.m_blocks != 1 : (ps.m_blocks != 2 && ps.m_blocks != 4)) return false;
+  }
+  return true;
+}
+
 // Forward + input gradient (or forward only when dinput is null) at full fp32-equivalent precision.
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
   SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,
@@ -1751,6 +2262,26 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
   // 64-point tile waits on the weight stream and loses 10 % by waiting for two stages of its 5-stage ring.
   const int group = np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
   unsigned long long* masks = in.mask_scratch ? in.mask_scratch : st->mask_dev;
+  if (small && band_pair_ok(dec, st, dinput != nullptr)) {
+    // short row lists on CTA pairs: M = 256 features per instruction, 2 x 16 points per pair
+    constexpr int NP = 16;
+    const long long pair_tiles = (in.n + 2 * NP - 1) / (2 * NP);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * std::min<long long>(pair_tiles, band_pair_slots<NP>(dec->dev.in0))));
+    cfg.blockDim = dim3(Q_THREADS);
+    cfg.dynamicSmemBytes = make_band_pair_plan<NP>(dec->dev.in0).total;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_band_pair_kernel<NP>, (const TcTable*)st->table_dev,
+                                 (const unsigned char*)st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks));
+    SDFR_LAUNCH_CHECK();
+    return SDFR_OK;
+  }
   if (small)
     mlp_tc_kernel<16><<<grid, NTHREADS, make_plan<16>(dec->dev.num_layers, dec->dev.in0).total, s>>>(
         st->table_dev, st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks, point_tiles, group);
