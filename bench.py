@@ -249,14 +249,13 @@ def stage_table(lib, eng, B, flop_pt, pk, band_rows_hint=None):
         "lattice_pass": ("tensor", flop_pt * ng * B),
         "band_pass": ("tensor", 2.0 * flop_pt * m),
         "band_select": ("hbm", B * ng * 4 + m * 4),
-        "band_surface": ("hbm", m * (4 + 4 + 6 * 4) + m * (12 + 12 + 4 + 12 + 1)),
-        "project": ("hbm", m * (24 + 60)),
+        # isosurface projection (28 B + 4 L in, 41 B out per row) + camera projection (24 B in, 60 B out)
+        "surface_project": ("hbm", m * (4 + 4 + 6 * 4) + m * (12 + 12 + 4 + 12 + 1) + m * (24 + 60)),
         "splat_forward": ("hbm", m * 44 + B * P * (32 + 48)),
-        "loss2d": ("hbm", B * P * (12 + 12 + 16)),
-        "loss3d": ("hbm", m * (12 + 20)),
+        "losses": ("hbm", B * P * (12 + 12 + 16) + m * (12 + 20)),
         "grad_prep": ("hbm", B * P * (16 + 32 + 48)),
         "splat_backward": ("hbm", m * (44 + 36)),
-        "chain": ("hbm", m * 100),
+        "chain_update": ("hbm", m * 100),
     }
     table = []
     total = float(sum(ms[:n.value]))

@@ -309,7 +309,7 @@ int sdfr_refine_set_latent(sdfr_refine* r, int b, const float* latent_host, void
 
 /* Measurement aid (bench.py's per-kernel table): runs `iters` iterations of the active detections WITHOUT the
  * CUDA graph, with an event after every stage, and returns the mean device time of each stage in milliseconds
- * (stage_ms_host [>= 13]; *n_stages = 13; names from sdfr_refine_stage_name) and the number of rows the band
+ * (stage_ms_host [>= 9]; *n_stages = 9; names from sdfr_refine_stage_name) and the number of rows the band
  * pass evaluated in the last iteration.  The iterations are real ones (the parameters move).  Synchronises. */
 int sdfr_refine_profile(sdfr_refine* r, int iters, float* stage_ms_host, int max_stages, int* n_stages,
                         int32_t* band_rows_host, void* stream);

@@ -286,8 +286,8 @@ struct BandArgs {
   long long n;              // lattice points per detection
   int batch;
   float threshold;
-  int* block_counts;        // [batch, nblocks]
-  int* block_prefix;        // [batch, nblocks] exclusive, detection-major
+  unsigned long long* status;   // [batch * nblocks] chained-scan status words (epoch | state | value), zero-initialised
+  int* ctrl;                // [4] ticket, finished blocks, epoch, pad: zero-initialised, self-resetting
   int* det_start;           // [batch]
   int* det_count;           // [batch]  (also the surfel count the splat stages read)
   int* total;               // [1]
@@ -304,6 +304,7 @@ struct BandArgs {
   float final_threshold;
   long long cap;
   int* presel_err;          // optional [1]: running max of |sdf[src] - band_sdf| (float bits, atomicMax)
+  const SplatView* views;   // optional [batch]: the isosurface kernel also projects each surfel into its view
 };
 int launch_band_select(const BandArgs& a, cudaStream_t s);
 int launch_band_surface(const BandArgs& a, cudaStream_t s);

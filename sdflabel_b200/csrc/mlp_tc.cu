@@ -2243,6 +2243,27 @@ static bool band_pair_ok(const sdfr_decoder* dec, const TcHostState* st, bool wa
   return true;
 }
 
+template <int NP>
+static int launch_band_pair(const sdfr_decoder* dec, const TcHostState* st, const MlpInputs& in, float* sdf, float* dinput,
+                            unsigned long long* masks, cudaStream_t s) {
+  const long long pair_tiles = (in.n + 2 * NP - 1) / (2 * NP);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(2 * std::min<long long>(pair_tiles, band_pair_slots<NP>(dec->dev.in0))));
+  cfg.blockDim = dim3(Q_THREADS);
+  cfg.dynamicSmemBytes = make_band_pair_plan<NP>(dec->dev.in0).total;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_band_pair_kernel<NP>, (const TcTable*)st->table_dev,
+                               (const unsigned char*)st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks));
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
 // Forward + input gradient (or forward only when dinput is null) at full fp32-equivalent precision.
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s) {
   SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED,
@@ -2262,26 +2283,8 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
   // 64-point tile waits on the weight stream and loses 10 % by waiting for two stages of its 5-stage ring.
   const int group = np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
   unsigned long long* masks = in.mask_scratch ? in.mask_scratch : st->mask_dev;
-  if (small && band_pair_ok(dec, st, dinput != nullptr)) {
-    // short row lists on CTA pairs: M = 256 features per instruction, 2 x 16 points per pair
-    constexpr int NP = 16;
-    const long long pair_tiles = (in.n + 2 * NP - 1) / (2 * NP);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)(2 * std::min<long long>(pair_tiles, band_pair_slots<NP>(dec->dev.in0))));
-    cfg.blockDim = dim3(Q_THREADS);
-    cfg.dynamicSmemBytes = make_band_pair_plan<NP>(dec->dev.in0).total;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SDFR_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_band_pair_kernel<NP>, (const TcTable*)st->table_dev,
-                                 (const unsigned char*)st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks));
-    SDFR_LAUNCH_CHECK();
-    return SDFR_OK;
-  }
+  if (small && band_pair_ok(dec, st, dinput != nullptr))
+    return launch_band_pair<16>(dec, st, in, sdf, dinput, masks, s);   // short row lists: 2 x 16 points per CTA pair
   if (small)
     mlp_tc_kernel<16><<<grid, NTHREADS, make_plan<16>(dec->dev.num_layers, dec->dev.in0).total, s>>>(
         st->table_dev, st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks, point_tiles, group);

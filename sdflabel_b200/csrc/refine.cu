@@ -4,13 +4,13 @@
 //           SGD on scale/latent) and 56-164 (the loop body), with
 //           utils/refinement.py:108-125 (rot_from_yaw) folded into the pose kernel.
 //
-// One iteration = 16 launches, no host synchronisation, all detections of the
-// batch per launch (blockIdx.y / blockIdx.z = detection):
-//   begin -> MLP forward over the lattice -> band select (count / prefix / index) ->
-//   MLP forward + input-gradient over the band points only (the normals and d sdf/d latent
-//   are needed nowhere else: ~2.5 % of the lattice) -> isosurface projection -> project ->
-//   splat forward -> 2D loss pixels -> 3D loss pairs -> pixel-gradient records ->
-//   splat backward -> chain to (R, t, latent_unit, scale) partials -> update.
+// One iteration = 9 launches, no host synchronisation, all detections of the batch per launch
+// (blockIdx.y / blockIdx.z = detection):
+//   MLP forward over the lattice -> band select (one chained-scan kernel) -> MLP forward + input-gradient over
+//   the band points only (the normals and d sdf/d latent are needed nowhere else: ~2.5 % of the lattice) ->
+//   isosurface projection + camera projection -> splat forward -> 2D-loss pixels and 3D-loss pairs (one launch) ->
+//   pixel-gradient records -> splat backward -> chain to (R, t, latent_unit, scale) partials, whose last block
+//   per detection runs the update and the next iteration's pose.
 // Every reduction is an ordered two-level sum, so a run is bit-reproducible.
 #include <algorithm>
 #include <cstddef>
@@ -55,8 +55,9 @@ struct EngineDev {          // passed by value to the engine kernels
   float* surf_glat;         // [B,cap,L]
   int* surf_idx;            // [B,cap]
   int* surf_count;          // [B]  (= band count per detection)
-  int* band_block_counts;   // [B,nblk]
-  int* band_block_prefix;   // [B,nblk]
+  unsigned long long* band_status;   // [B*nblk] chained-scan status words of the band selection
+  int* band_ctrl;           // [4]  ticket / finished blocks / epoch of the band selection
+  int* chain_done;          // [B]  chain blocks that have published their partials (self-resetting)
   int* band_det_start;      // [B]
   int* band_total;          // [1]
   int* band_src;            // [B*ng] compact global source indices of the band points
@@ -79,23 +80,26 @@ struct EngineDev {          // passed by value to the engine kernels
 };
 
 // ---- iteration begin: pose + unit latent (optimizer.py:87-96) ----------------------
-__global__ void iter_begin_kernel(EngineDev E) {
-  const int b = blockIdx.x;
+// One thread per detection.  Runs once at the start of sdfr_refine_run (iter_begin_kernel) and then at the end of
+// every update (the parameters only change there), so an iteration does not pay a launch for it.
+__device__ __forceinline__ void begin_iteration(const EngineDev& E, int b) {
   DetState& D = E.det[b];
-  if (threadIdx.x == 0) {
-    const float c = cosf(D.yaw), s = sinf(D.yaw);
-    float* P = D.pose;
-    // rot_from_yaw (refinement.py:124) with row 1 negated (optimizer.py:89), then translation (:90)
-    P[0] = c;    P[1] = 0.f;   P[2] = s;   P[3] = D.trans[0];
-    P[4] = -0.f; P[5] = -1.f;  P[6] = -0.f; P[7] = D.trans[1];
-    P[8] = -s;   P[9] = 0.f;   P[10] = c;  P[11] = D.trans[2];
-    P[12] = 0.f; P[13] = 0.f;  P[14] = 0.f; P[15] = 1.f;
-    // F.normalize(latent, p=2, dim=0), eps 1e-12 (optimizer.py:96)
-    float n2 = 0.f;
-    for (int k = 0; k < E.L; ++k) n2 += E.latent[b * E.L + k] * E.latent[b * E.L + k];
-    const float nrm = fmaxf(sqrtf(n2), 1e-12f);
-    for (int k = 0; k < E.L; ++k) E.latent_unit[b * E.L + k] = E.latent[b * E.L + k] / nrm;
-  }
+  const float c = cosf(D.yaw), s = sinf(D.yaw);
+  float* P = D.pose;
+  // rot_from_yaw (refinement.py:124) with row 1 negated (optimizer.py:89), then translation (:90)
+  P[0] = c;    P[1] = 0.f;   P[2] = s;   P[3] = D.trans[0];
+  P[4] = -0.f; P[5] = -1.f;  P[6] = -0.f; P[7] = D.trans[1];
+  P[8] = -s;   P[9] = 0.f;   P[10] = c;  P[11] = D.trans[2];
+  P[12] = 0.f; P[13] = 0.f;  P[14] = 0.f; P[15] = 1.f;
+  // F.normalize(latent, p=2, dim=0), eps 1e-12 (optimizer.py:96)
+  float n2 = 0.f;
+  for (int k = 0; k < E.L; ++k) n2 += E.latent[b * E.L + k] * E.latent[b * E.L + k];
+  const float nrm = fmaxf(sqrtf(n2), 1e-12f);
+  for (int k = 0; k < E.L; ++k) E.latent_unit[b * E.L + k] = E.latent[b * E.L + k] / nrm;
+}
+
+__global__ void iter_begin_kernel(EngineDev E) {
+  if (threadIdx.x == 0) begin_iteration(E, blockIdx.x);
 }
 
 // ---- nearest resize of the CSS NOCS prediction to the crop (optimizer.py:135-137) ----
@@ -112,14 +116,13 @@ __global__ void resize_target_kernel(const float* __restrict__ src, int th, int 
 // ---- 2D loss: per rendered pixel (optimizer.py:200-237) --------------------------------
 constexpr int LB = 256;
 
-__global__ void __launch_bounds__(LB) loss2d_batch_kernel(EngineDev E) {
+__device__ __forceinline__ void loss2d_block(const EngineDev& E, const int b, const int block) {
   __shared__ double s_sum[LB / 32], s_hw[LB / 32];
   __shared__ int s_cnt[LB / 32];
-  const int b = blockIdx.y;
   const DetState& D = E.det[b];
   const SplatView& V = E.views[b];
   const int H = D.height, W = D.width, P = H * W;
-  const int j = blockIdx.x * LB + threadIdx.x;
+  const int j = block * LB + threadIdx.x;
   double sum = 0.0, hw = 0.0;
   int cnt = 0;
   if (j < P) {
@@ -153,8 +156,8 @@ __global__ void __launch_bounds__(LB) loss2d_batch_kernel(EngineDev E) {
     double ts = 0.0, th = 0.0;
     int tc = 0;
     for (int w = 0; w < LB / 32; ++w) { ts += s_sum[w]; th += s_hw[w]; tc += s_cnt[w]; }
-    if ((int)blockIdx.x < E.nb2) {
-      double* o = E.part2 + ((size_t)b * E.nb2 + blockIdx.x) * 3;
+    if (block < E.nb2) {
+      double* o = E.part2 + ((size_t)b * E.nb2 + block) * 3;
       o[0] = ts; o[1] = (double)tc; o[2] = th;
     }
   }
@@ -163,16 +166,15 @@ __global__ void __launch_bounds__(LB) loss2d_batch_kernel(EngineDev E) {
 // ---- 3D loss: exact NN of every front-facing surfel in lidar/scale (optimizer.py:84,166-198) ----
 constexpr int STAGE = 1024;
 
-__global__ void __launch_bounds__(LB) loss3d_batch_kernel(EngineDev E) {
+__device__ __forceinline__ void loss3d_block(const EngineDev& E, const int b, const int block) {
   __shared__ float s_pts[STAGE * 3];
   __shared__ double s_sum[LB / 32];
   __shared__ int s_cnt[LB / 32], s_front[LB / 32];
-  const int b = blockIdx.y;
   const DetState& D = E.det[b];
   const SplatView& V = E.views[b];
   const int m = min(E.surf_count[b], (int)E.cap);
-  if ((int)(blockIdx.x * LB) >= m) return;   // partials of these blocks are never read
-  const int i = blockIdx.x * LB + threadIdx.x;
+  if (block * LB >= m) return;   // partials of these blocks are never read
+  const int i = block * LB + threadIdx.x;
   const bool live = i < m && V.front[i];
   float qx = 0.f, qy = 0.f, qz = 0.f;
   if (live) { qx = V.cam_v[i * 3]; qy = V.cam_v[i * 3 + 1]; qz = V.cam_v[i * 3 + 2]; }
@@ -216,9 +218,16 @@ __global__ void __launch_bounds__(LB) loss3d_batch_kernel(EngineDev E) {
     double ts = 0.0;
     int tc = 0, tf = 0;
     for (int w = 0; w < LB / 32; ++w) { ts += s_sum[w]; tc += s_cnt[w]; tf += s_front[w]; }
-    double* o = E.part3 + ((size_t)b * E.nb3 + blockIdx.x) * 3;
+    double* o = E.part3 + ((size_t)b * E.nb3 + block) * 3;
     o[0] = ts; o[1] = (double)tc; o[2] = (double)tf;
   }
+}
+
+// Both losses in one launch: blocks [0, n2) take the 2D-loss pixels, blocks [n2, n2 + nb3) the 3D-loss surfels
+// (they are independent, so the two also overlap on the device).
+__global__ void __launch_bounds__(LB) losses_batch_kernel(EngineDev E, int n2) {
+  if ((int)blockIdx.x < n2) loss2d_block(E, blockIdx.y, blockIdx.x);
+  else loss3d_block(E, blockIdx.y, (int)blockIdx.x - n2);
 }
 
 // ---- per-pixel gradient records for the surfel gather -------------------------------------
@@ -279,9 +288,14 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
   return t;   // valid on thread 0
 }
 
-__global__ void __launch_bounds__(LB) chain_kernel(EngineDev E) {
+__device__ void update_detection(const EngineDev& E, int b);
+
+// The block that publishes a detection's last partial also runs its update (gradient assembly, Adam + SGD, the
+// next iteration's pose): chain and update are one launch.
+__global__ void __launch_bounds__(LB) chain_update_kernel(EngineDev E) {
   __shared__ float s_red[LB / 32];
-  __shared__ float s_l3scale;
+  __shared__ float s_l3scale, s_loss3d, s_n3;
+  __shared__ int s_front_count, s_last;
   const int b = blockIdx.y;
   DetState& D = E.det[b];
   const SplatView& V = E.views[b];
@@ -300,11 +314,9 @@ __global__ void __launch_bounds__(LB) chain_kernel(EngineDev E) {
     }
     if (threadIdx.x == 0) {
       s_l3scale = c > 0.0 ? E.w3d / (float)c : 0.f;
-      if (blockIdx.x == 0) {
-        D.loss3d = c > 0.0 ? (float)(s / c) : 0.f;                    // optimizer.py:192-197
-        D.n3 = (float)c;
-        D.front_count = (int)f;
-      }
+      s_loss3d = c > 0.0 ? (float)(s / c) : 0.f;                      // optimizer.py:192-197
+      s_n3 = (float)c;
+      s_front_count = (int)f;
     }
   }
   __syncthreads();
@@ -344,20 +356,33 @@ __global__ void __launch_bounds__(LB) chain_kernel(EngineDev E) {
     t = block_sum(g, s_red);
     if (threadIdx.x == 0) out[16 + k] = t;
   }
+  // ---- last block of the detection: update ----
+  if (threadIdx.x == 0) {
+    __threadfence();                                               // this block's partials before its ticket
+    const int nblk = max(1, (m + LB - 1) / LB);
+    s_last = atomicAdd(&E.chain_done[b], 1) == nblk - 1;
+    if (s_last) {
+      E.chain_done[b] = 0;
+      __threadfence();
+      // every block reduced the same 3D-loss partials in the same order: this block's copy is THE value
+      D.loss3d = s_loss3d; D.n3 = s_n3; D.front_count = s_front_count;
+    }
+  }
+  __syncthreads();
+  if (s_last) update_detection(E, b);
 }
 
 // ---- gradient assembly, skip logic, Adam + SGD (optimizer.py:34-38,49-52,146-157) ----------
-__global__ void __launch_bounds__(LB) update_kernel(EngineDev E) {
+__device__ void update_detection(const EngineDev& E, const int b) {
   __shared__ float s_tot[16 + kMaxLatent];
-  const int b = blockIdx.x;
   DetState& D = E.det[b];
   const int m = min(E.surf_count[b], (int)E.cap);
-  const int nb = (m + LB - 1) / LB;
+  const int nb = max(1, (m + LB - 1) / LB);                          // block 0 always writes a partial
   const int ncomp = 16 + E.L;
   for (int c = threadIdx.x; c < ncomp; c += LB) {
     float s = 0.f;
     const float* p = E.partc + (size_t)b * E.nbc * ncomp + c;
-    for (int k = 0; k < nb; ++k) s += p[(size_t)k * ncomp];
+    for (int k = 0; k < nb; ++k) s += __ldcg(p + (size_t)k * ncomp);  // other blocks' partials: not through L1
     s_tot[c] = s;
   }
   __syncthreads();
@@ -393,7 +418,7 @@ __global__ void __launch_bounds__(LB) update_kernel(EngineDev E) {
     h[0] = D.loss2d; h[1] = D.loss3d; h[2] = loss; h[3] = (float)skip;
   }
   D.iter += 1;
-  if (skip) return;
+  if (skip) return;                                                  // parameters, pose and unit latent stay as they are
   // Adam(lr 0.01, betas (0.9, 0.999), eps 1e-8) on yaw, trans
   D.adam_t += 1;
   const double b1 = 0.9, b2 = 0.999, lr = 0.01, eps = 1e-8;
@@ -411,6 +436,7 @@ __global__ void __launch_bounds__(LB) update_kernel(EngineDev E) {
   // SGD(momentum 0): scale lr 0.01, latent lr 3e-5
   D.scale = D.scale - 0.01f * dscale;
   for (int k = 0; k < L; ++k) E.latent[b * L + k] = E.latent[b * L + k] - 0.00003f * g[5 + L + k];
+  begin_iteration(E, b);                                             // pose and unit latent of the next iteration
 }
 
 // ---- parameters straight from / to the caller's device tensors (optimizer.py:26-30) ---------------
@@ -588,7 +614,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.sdf, B * E.ng); A(E.dinput, B * E.ng * E.in0);
   A(E.surf_pts, B * E.cap * 3); A(E.surf_nrm, B * E.cap * 3); A(E.surf_glat, B * E.cap * L);
   A(E.surf_idx, B * E.cap); A(E.surf_count, B);
-  A(E.band_block_counts, (size_t)B * (E.ng / 1024 + 2)); A(E.band_block_prefix, (size_t)B * (E.ng / 1024 + 2));
+  A(E.band_status, (size_t)B * (E.ng / 1024 + 2)); A(E.band_ctrl, 4); A(E.chain_done, B);
   A(E.band_det_start, B); A(E.band_total, 4); A(E.band_src, (size_t)B * E.ng); A(E.band_sdf, (size_t)B * E.ng);
   A(E.surf_valid, (size_t)B * E.cap);
   A(E.target, (size_t)B * 3 * E.max_pixels); A(E.lidar, (size_t)B * E.max_lidar * 3);
@@ -767,11 +793,12 @@ IterPlan make_iter_plan(sdfr_refine* r, int B) {
   ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B;
   ba.threshold = 0.03f + (p.coarse ? kPreselectMargin : 0.f);
   ba.out_valid = E.surf_valid; ba.final_threshold = 0.03f;
-  ba.block_counts = E.band_block_counts; ba.block_prefix = E.band_block_prefix; ba.det_start = E.band_det_start;
+  ba.status = E.band_status; ba.ctrl = E.band_ctrl; ba.det_start = E.band_det_start;
   ba.det_count = E.surf_count; ba.total = E.band_total; ba.band_src = E.band_src;
   ba.band_sdf = E.band_sdf; ba.band_dinput = E.dinput; ba.in0 = E.in0; ba.latent = E.L;
   ba.out_pts = E.surf_pts; ba.out_nrm = E.surf_nrm; ba.out_idx = E.surf_idx; ba.out_glat = E.surf_glat; ba.cap = E.cap;
   ba.presel_err = p.coarse ? E.presel_err : nullptr;
+  ba.views = E.views;
   return p;
 }
 
@@ -788,8 +815,8 @@ struct StageClock {
 };
 #define STAGE_MARK(clk) do { if (clk) (clk)->mark(); } while (0)
 
-const char* const kStageNames[] = {"iter_begin", "lattice_pass", "band_select", "band_pass", "band_surface", "project",
-                                   "splat_forward", "loss2d", "loss3d", "grad_prep", "splat_backward", "chain", "update"};
+const char* const kStageNames[] = {"lattice_pass", "band_select", "band_pass", "surface_project", "splat_forward",
+                                   "losses", "grad_prep", "splat_backward", "chain_update"};
 constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 
 // lattice pass -> band select -> accurate pass on the selected rows -> isosurface projection
@@ -809,36 +836,35 @@ int enqueue_surface(sdfr_refine* r, const IterPlan& p, cudaStream_t s, StageCloc
   return rc;
 }
 
-// enqueues the kernels of ONE refine iteration of detections [0, B) on `s`
+// pose and unit latent of detections [0, B) from their current parameters: once per run, the updates keep them current
+int enqueue_begin(sdfr_refine* r, int B, cudaStream_t s) {
+  EngineDev E = r->E;
+  E.batch = B;
+  iter_begin_kernel<<<B, 32, 0, s>>>(E);
+  SDFR_LAUNCH_CHECK();
+  return SDFR_OK;
+}
+
+// enqueues the NINE kernels of one refine iteration of detections [0, B) on `s`
 int enqueue_iteration(sdfr_refine* r, int B, int qw, int qh, int any_small, cudaStream_t s, StageClock* clk = nullptr) {
   EngineDev E = r->E;
   E.batch = B;
   const IterPlan p = make_iter_plan(r, B);
   int rc;
   STAGE_MARK(clk);
-  iter_begin_kernel<<<B, 32, 0, s>>>(E);
-  SDFR_LAUNCH_CHECK();
-  STAGE_MARK(clk);
-  if ((rc = enqueue_surface(r, p, s, clk))) return rc;
-  if ((rc = launch_project(E.views, B, (int)E.cap, s))) return rc;
-  STAGE_MARK(clk);
+  if ((rc = enqueue_surface(r, p, s, clk))) return rc;             // lattice, select, band pass, isosurface + projection
   if ((rc = launch_splat_forward(E.views, B, qw, qh, any_small, s))) return rc;
   STAGE_MARK(clk);
-  loss2d_batch_kernel<<<dim3((qw * qh + LB - 1) / LB, B), LB, 0, s>>>(E);
+  const int n2 = (qw * qh + LB - 1) / LB;
+  losses_batch_kernel<<<dim3(n2 + E.nb3, B), LB, 0, s>>>(E, n2);
   SDFR_LAUNCH_CHECK();
   STAGE_MARK(clk);
-  loss3d_batch_kernel<<<dim3(E.nb3, B), LB, 0, s>>>(E);
-  SDFR_LAUNCH_CHECK();
-  STAGE_MARK(clk);
-  grad_prep_kernel<<<dim3((qw * qh + LB - 1) / LB, B), LB, 0, s>>>(E);
+  grad_prep_kernel<<<dim3(n2, B), LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
   STAGE_MARK(clk);
   if ((rc = launch_splat_backward(E.views, B, (int)E.cap, s))) return rc;
   STAGE_MARK(clk);
-  chain_kernel<<<dim3(E.nbc, B), LB, 0, s>>>(E);
-  SDFR_LAUNCH_CHECK();
-  STAGE_MARK(clk);
-  update_kernel<<<B, LB, 0, s>>>(E);
+  chain_update_kernel<<<dim3(E.nbc, B), LB, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
   STAGE_MARK(clk);
   return SDFR_OK;
@@ -859,6 +885,7 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   if (use_graph < 0) { const char* e = getenv("SDFR_REFINE_GRAPH"); use_graph = e ? atoi(e) : 1; }
   int rc;
   int done = 0;
+  if (iters > 0 && (rc = enqueue_begin(r, B, s))) return rc;
   // The first call runs un-captured (lazy attribute setup inside the launchers must not happen during capture).
   if (!use_graph || r->runs == 0) {
     for (; done < (use_graph ? std::min(iters, 1) : iters); ++done)
@@ -995,6 +1022,7 @@ extern "C" int sdfr_refine_profile(sdfr_refine* r, int iters, float* stage_ms_ho
   for (int it = 0; it < iters && rc == SDFR_OK; ++it) {
     StageClock clk;
     clk.s = s;
+    if (it == 0 && (rc = enqueue_begin(r, B, s))) break;
     rc = enqueue_iteration(r, B, qw, qh, any_small, s, &clk);
     r->iters_enqueued.assign(r->iters_enqueued.size(), 1 << 30);     // the history is read through D.iter
     cudaStreamSynchronize(s);
@@ -1041,7 +1069,8 @@ extern "C" int sdfr_refine_label_extents(sdfr_refine* r, float* extents_host, vo
   const int B = r->active;
   EngineDev E = r->E;
   E.batch = B;
-  const IterPlan p = make_iter_plan(r, B);
+  IterPlan p = make_iter_plan(r, B);
+  p.ba.views = nullptr;                       // extents only: the slots need no crop / camera (they may never have been set)
   raw_latent_kernel<<<(B * E.L + 127) / 128, 128, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
   int rc = enqueue_surface(r, p, s);

@@ -9,6 +9,7 @@
 // reference's masked_select keeps ascending index order) is a two-launch
 // count/scatter with warp-ballot ranking inside the block.
 #include "common.cuh"
+#include "project.cuh"
 
 namespace sdfr {
 
@@ -89,74 +90,103 @@ __global__ void __launch_bounds__(SB) band_scatter_kernel(SurfaceArgs a, int nbl
 }
 
 // ---- band-restricted flow (fused engine) -------------------------------------------------------
-__global__ void __launch_bounds__(SB) band_count2_kernel(BandArgs a, int nblocks) {
-  const int b = blockIdx.y;
-  const long long i = (long long)blockIdx.x * SB + threadIdx.x;
-  const bool keep = i < a.n && in_band(a.sdf[(long long)b * a.n + i], a.threshold);
-  const int c = __syncthreads_count(keep);
-  if (threadIdx.x == 0) a.block_counts[(long long)b * nblocks + blockIdx.x] = c;
+// Order-preserving selection of |sdf| < thr over all detections in ONE launch: a chained scan with decoupled
+// look-back over 1024-point chunks (detection-major).  Chunks are handed out by an atomic ticket, so a block only
+// ever waits for chunks that started before it.  A chunk publishes its count as soon as it is known and its
+// inclusive prefix once its predecessors are summed; the status word carries the launch epoch, so nothing has to be
+// cleared between launches (the last block of a launch resets the ticket and advances the epoch).
+constexpr unsigned long long kStateAggregate = 1ull, kStateInclusive = 2ull;
+
+__device__ __forceinline__ unsigned long long status_word(unsigned epoch, unsigned long long state, int value) {
+  return ((unsigned long long)(epoch & 0x3fffffffu) << 34) | (state << 32) | (unsigned long long)(unsigned)value;
+}
+__device__ __forceinline__ unsigned long long status_load(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+__device__ __forceinline__ void status_store(unsigned long long* p, unsigned long long w) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+// spins until chunk j has published something for this epoch
+__device__ __forceinline__ unsigned long long status_wait(const unsigned long long* status, int j, unsigned epoch) {
+  unsigned long long w;
+  do { w = status_load(status + j); } while ((unsigned)(w >> 34) != (epoch & 0x3fffffffu));
+  return w;
 }
 
-// one block: exclusive scan of the batch*nblocks block counts (detection-major)
-__global__ void __launch_bounds__(1024) band_prefix_kernel(BandArgs a, int nblocks) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  const int total_blocks = a.batch * nblocks;
+__global__ void __launch_bounds__(SB) band_select_kernel(BandArgs a, int nblocks) {
+  __shared__ int warp_off[SB / 32];
+  __shared__ int s_chunk, s_base, s_total;
+  __shared__ unsigned s_epoch;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_carry = 0;
+  const int total_blocks = a.batch * nblocks;
+  if (tid == 0) {
+    s_chunk = atomicAdd(&a.ctrl[0], 1);
+    s_epoch = *reinterpret_cast<volatile unsigned*>(&a.ctrl[2]) + 1u;    // never 0: fresh status words match no launch
+  }
   __syncthreads();
-  for (int base = 0; base < total_blocks; base += 1024) {
-    const int i = base + tid;
-    const int v = i < total_blocks ? a.block_counts[i] : 0;
-    int incl = v;
+  const int chunk = s_chunk;
+  const unsigned epoch = s_epoch;
+  const int b = chunk / nblocks, blk = chunk - b * nblocks;
+  const long long i = (long long)blk * SB + tid;
+  const bool keep = i < a.n && in_band(a.sdf[(long long)b * a.n + i], a.threshold);
+  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) warp_off[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    const int c = warp_off[lane];
+    int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int w = s_warp[lane];
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    warp_off[lane] = incl - c;                                 // exclusive offset of each warp inside the chunk
+    if (lane == 0) status_store(a.status + chunk, status_word(epoch, chunk == 0 ? kStateInclusive : kStateAggregate, total));
+    int excl = 0;
+    if (chunk > 0) {
+      for (int pos = chunk - 1;; pos -= 32) {                  // 32 predecessors per round, nearest first
+        const int j = pos - lane;
+        unsigned long long w = status_word(epoch, kStateInclusive, 0);      // before the first chunk: prefix 0
+        if (j >= 0) w = status_wait(a.status, j, epoch);
+        const bool inclusive = ((w >> 32) & 3ull) == kStateInclusive;
+        const unsigned have = __ballot_sync(0xffffffffu, inclusive);
+        const int first = have ? __ffs(have) - 1 : 31;         // sum up to the nearest inclusive prefix
+        int v = lane <= first ? (int)(unsigned)w : 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += t;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (have) break;
       }
-      s_warp[lane] = w;   // inclusive over warps
+      if (lane == 0) status_store(a.status + chunk, status_word(epoch, kStateInclusive, excl + total));
     }
-    __syncthreads();
-    const int excl = s_carry + (warp ? s_warp[warp - 1] : 0) + incl - v;
-    if (i < total_blocks) {
-      a.block_prefix[i] = excl;
-      if (i % nblocks == 0) a.det_start[i / nblocks] = excl;
+    if (lane == 0) { s_base = excl; s_total = total; }
+  }
+  __syncthreads();
+  const int base = s_base;
+  if (keep) a.band_src[base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u))] = (int)((long long)b * a.n + i);
+  if (tid == 0) {
+    if (blk == nblocks - 1) {                                  // the detection's last chunk: its start and count
+      int start = 0;
+      if (b > 0) {                                             // inclusive prefix of the previous detection's last chunk
+        unsigned long long w;
+        do { w = status_wait(a.status, b * nblocks - 1, epoch); } while (((w >> 32) & 3ull) != kStateInclusive);
+        start = (int)(unsigned)w;
+      }
+      a.det_start[b] = start;
+      a.det_count[b] = base + s_total - start;
+      if (chunk == total_blocks - 1) *a.total = base + s_total;
     }
-    __syncthreads();
-    if (tid == 1023) s_carry = excl + v;
-    __syncthreads();
+    __threadfence();
+    if (atomicAdd(&a.ctrl[1], 1) == total_blocks - 1) {        // every block of the launch is past its look-back
+      a.ctrl[0] = 0;
+      a.ctrl[1] = 0;
+      a.ctrl[2] = (int)(epoch & 0x3fffffffu) == 0x3fffffff ? 0 : (int)(epoch & 0x3fffffffu);
+      __threadfence();
+    }
   }
-  if (tid == 0) *a.total = s_carry;
-  __syncthreads();
-  const int tot = s_carry;
-  for (int b = tid; b < a.batch; b += 1024) {
-    const int end = b + 1 < a.batch ? a.block_prefix[(b + 1) * nblocks] : tot;
-    a.det_count[b] = end - a.block_prefix[b * nblocks];
-  }
-}
-
-__global__ void __launch_bounds__(SB) band_index_kernel(BandArgs a, int nblocks) {
-  __shared__ int warp_cnt[SB / 32];
-  const int b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long i = (long long)blockIdx.x * SB + tid;
-  const bool keep = i < a.n && in_band(a.sdf[(long long)b * a.n + i], a.threshold);
-  const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-  if (lane == 0) warp_cnt[warp] = __popc(ballot);
-  __syncthreads();
-  if (!keep) return;
-  int off = a.block_prefix[(long long)b * nblocks + blockIdx.x] + __popc(ballot & ((1u << lane) - 1u));
-  for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-  a.band_src[off] = (int)((long long)b * a.n + i);
 }
 
 __global__ void __launch_bounds__(256) band_surface_kernel(BandArgs a) {
@@ -184,7 +214,12 @@ __global__ void __launch_bounds__(256) band_surface_kernel(BandArgs a) {
   if (a.out_idx) a.out_idx[o] = (int)k;
   if (a.out_glat)
     for (int c = 0; c < a.latent; ++c) a.out_glat[o * a.latent + c] = g[c];
-  if (a.out_valid) a.out_valid[o] = in_band(f, a.final_threshold) ? 1 : 0;
+  const bool is_surfel = in_band(f, a.final_threshold);
+  if (a.out_valid) a.out_valid[o] = is_surfel ? 1 : 0;
+  // camera-space surfel of the detection's view (the engine's next stage), from the values just stored
+  if (a.views)
+    project_surfel(a.views[b], local, __fsub_rn(px, __fmul_rn(f, nx)), __fsub_rn(py, __fmul_rn(f, ny)),
+                   __fsub_rn(pz, __fmul_rn(f, nz)), nx, ny, nz, is_surfel);
   if (a.presel_err) {
     // measured error of the coarse lattice pass on the rows it pre-selected (all of them lie near the band,
     // the only place where that error can change the result); non-negative floats order like their bit patterns
@@ -199,12 +234,7 @@ __global__ void __launch_bounds__(256) band_surface_kernel(BandArgs a) {
 int launch_band_select(const BandArgs& a, cudaStream_t s) {
   if (a.n <= 0 || a.batch <= 0) return SDFR_OK;
   const int nblocks = (int)((a.n + SB - 1) / SB);
-  dim3 grid(nblocks, a.batch);
-  band_count2_kernel<<<grid, SB, 0, s>>>(a, nblocks);
-  SDFR_LAUNCH_CHECK();
-  band_prefix_kernel<<<1, 1024, 0, s>>>(a, nblocks);
-  SDFR_LAUNCH_CHECK();
-  band_index_kernel<<<grid, SB, 0, s>>>(a, nblocks);
+  band_select_kernel<<<nblocks * a.batch, SB, 0, s>>>(a, nblocks);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
