@@ -281,7 +281,29 @@ def stage_table(lib, eng, B, flop_pt, pk, band_rows_hint=None):
 
 
 def run_cfg3(dec, grid, weights, dev):
-    """configs[2]: 32 ragged synthetic crops x 50 optimizer steps, one batch, pose + latent."""
+    """configs[2]: 32 ragged synthetic crops x 50 optimizer steps, one batch, pose + latent; with the temporal pruning
+    of the lattice pass (the product default) and with the whole lattice evaluated every iteration."""
+    from sdflabel_b200.pipelines import optimizer as OPT
+    out = None
+    for prune in (True, False):
+        OPT.TEMPORAL_PRUNING = prune
+        try:
+            blk = _run_cfg3_once(dec, grid, weights, dev)
+        finally:
+            OPT.TEMPORAL_PRUNING = True
+        if prune:
+            out = blk
+            out["temporal_pruning"] = True
+        else:
+            out["whole_lattice_every_iteration"] = {k: blk[k] for k in (
+                "device_ms_per_step", "detection_iterations_per_s", "rays_per_s", "e2e_s",
+                "e2e_detection_iterations_per_s")}
+            out["results_bit_identical_to_whole_lattice"] = bool(blk["digest"] == out["digest"])
+    return out
+
+
+def _run_cfg3_once(dec, grid, weights, dev):
+    import hashlib
     import torch
     import synth_frames
     from sdflabel_b200.pipelines.optimizer import BatchOptimizer
@@ -304,21 +326,30 @@ def run_cfg3(dec, grid, weights, dev):
     res = bo.optimize(50, dets, dec, grid)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    # device time of the 50 steps alone
+    digest = hashlib.sha256(b"".join(np.ascontiguousarray(r[k]).tobytes() for r in res
+                                     for k in ("yaw", "trans", "scale", "latent", "history"))).hexdigest()
+    # device time of 50 steps alone: the same detections from their initial parameters again
     eng = bo.engine
+    for b, d in enumerate(dets):
+        eng.set_detection(b, d["K"], int(d["crop_size"][1]), int(d["crop_size"][0]), d["nocs_pred"], d["lidar"],
+                          d["params"]["yaw"], d["params"]["trans"], d["params"]["scale"], d["params"]["latent"])
+    eng.lattice_rows(reset=True)
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     eng.run(50)
     b.record()
     torch.cuda.synchronize()
     dev_s = a.elapsed_time(b) * 1e-3
+    rows, its = eng.lattice_rows()
     rays = sum(d["crop_size"][0] * d["crop_size"][1] for d in dets)
     improved = sum(int(np.isfinite(r["history"][:, 2]).all() and r["history"][-1, 2] < r["history"][0, 2]) for r in res)
     return {"workload": "cfg3: 32 ragged synthetic crops (33x43 .. 78x45 px, 84-786 LIDAR points) x 50 optimizer steps, "
                         "pose + latent, one batch on one GPU, Grid3D(40)",
             "device_ms_per_step": dev_s / 50 * 1e3, "detection_iterations_per_s": 32 * 50 / dev_s,
             "rays_per_s": rays * 50 / dev_s, "e2e_s": wall, "e2e_detection_iterations_per_s": 32 * 50 / wall,
-            "losses_improved": improved}
+            "losses_improved": improved, "digest": digest,
+            "lattice_points_per_detection_iteration": (rows / its) if its else float(DENSITY ** 3)}
 
 
 def run_frames(args, dec, grid, weights, dev, rank, world, dist):
@@ -338,9 +369,11 @@ def run_frames(args, dec, grid, weights, dev, rank, world, dist):
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
+    fr.engine.lattice_rows(reset=True)
     done = fr.refine(frames, mine, out_dir)
     torch.cuda.synchronize()
     local_s = time.perf_counter() - t0
+    prune_rows, prune_its = fr.engine.lattice_rows()
     recs = records_of(done, dec.latent_size)
     tg = time.perf_counter()
     allrec = F.gather_labels(recs, dec.latent_size, device=dev)       # the ONE exchange: label records over NCCL
@@ -379,6 +412,8 @@ def run_frames(args, dec, grid, weights, dev, rank, world, dist):
             "resampled_frames": len(sample), "dumped_frames_rank0": dumped,
             "rank0_breakdown_s": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in fr.timing.items()},
             "detections_per_batch": args.frame_batch,
+            "temporal_pruning": True,
+            "lattice_points_per_detection_iteration": (prune_rows / prune_its) if prune_its else float(DENSITY ** 3),
         }
     return block
 
@@ -388,6 +423,7 @@ def run_ours(args, rank, world, local_rank):
     from sdflabel_b200 import _lib
     from sdflabel_b200.deepsdf.workspace import setup_dsdf
     from sdflabel_b200.grid import Grid3D
+    from sdflabel_b200.pipelines import optimizer as OPT
     from sdflabel_b200.pipelines.optimizer import Optimizer, _engine_for
 
     if not torch.cuda.is_available():
@@ -420,6 +456,10 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # ---- device-resident loop: engine iterations ------------------------------------------
+    # The headline numbers (value, e2e, roofline, kernels, sustained) evaluate the WHOLE lattice every iteration, as the
+    # reference does; the product default (temporal pruning of the lattice pass, same results) is reported beside them
+    # in the `pruned`, `cfg3` and `frames` blocks.
+    OPT.TEMPORAL_PRUNING = False
     eng = _engine_for(dec, B, DENSITY, SIZE, SIZE, sc["lidar"].shape[0], 64, sc["weights"], dec.mlp_impl)
     eng.set_active(B)
     for b in range(B):
@@ -571,6 +611,55 @@ def run_ours(args, rank, world, local_rank):
                                    "peak_source": pk["source"] + " bf16_tflops_sustained",
                                    "clocks": sampler.summary(tk0, tk1)}}
     head_clocks = sampler.summary(t_head0, t_head1) if rank == 0 else None
+    OPT.TEMPORAL_PRUNING = True
+    if rank == 0 and not args.quick:
+        # ---- the same cfg2 step with the product default: temporal pruning of the lattice pass ------------------
+        try:
+            peng = _engine_for(dec, B, DENSITY, SIZE, SIZE, sc["lidar"].shape[0], 64, sc["weights"], dec.mlp_impl)
+            peng.set_active(B)
+            for b in range(B):
+                peng.set_detection(b, K, SIZE, SIZE, nocs, sc["lidar"], sc["init"]["yaw"], sc["init"]["trans"],
+                                   sc["init"]["scale"], sc["init"]["latent"])
+            for _ in range(3):
+                peng.run(1)
+            peng.lattice_rows(reset=True)
+            pev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for s0, s1 in pev:
+                flush.fill_(1)
+                s0.record()
+                peng.run(1)
+                s1.record()
+            torch.cuda.synchronize()
+            rows, its = peng.lattice_rows()
+            p_ms = float(np.mean([a.elapsed_time(b) for a, b in pev]))
+            pp, _ = peng.get(0)
+            # the whole-lattice engine after the same 3 + steps iterations from the same start
+            for b in range(B):
+                eng.set_detection(b, K, SIZE, SIZE, nocs, sc["lidar"], sc["init"]["yaw"], sc["init"]["trans"],
+                                  sc["init"]["scale"], sc["init"]["latent"])
+            eng.run(3 + args.steps)
+            fp, _ = eng.get(0)
+            popt = Optimizer({k: v.copy() for k, v in sc["init"].items()}, dev, sc["weights"])
+            pe2e = []
+            for i in range(3 + args.steps):
+                flush.fill_(1)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                popt.optimize(1, nocs, sc["lidar"], dec, grid, K, sc["crop_size"], viz_type=None)
+                torch.cuda.synchronize()
+                if i >= 3:
+                    pe2e.append(time.perf_counter() - t0)
+            extras["pruned"] = {
+                "what": "the same cfg2 step with temporal pruning of the lattice pass (sdfr_refine_cfg.latent_lipschitz, the "
+                        "product default): an iteration evaluates only the lattice points the decoder's certified "
+                        "Lipschitz bound cannot exclude from the band; identical surfels and results",
+                "ms_per_step": p_ms, "value": B * SIZE * SIZE / (p_ms * 1e-3), "unit": "rays/s",
+                "e2e_ms_per_step": float(np.mean(pe2e)) * 1e3, "e2e_value": SIZE * SIZE / float(np.mean(pe2e)),
+                "lattice_points_per_iteration": rows / max(its, 1), "lattice_points_full": DENSITY ** 3,
+                "latent_lipschitz_bound": float(dec.native().latent_lipschitz),
+                "params_bit_identical_to_whole_lattice": bool(np.array_equal(pp, fp))}
+        except Exception as e:   # noqa: BLE001
+            extras["pruned"] = {"error": repr(e)[:300]}
 
     # ---- cfg3 (rank 0) and cfg4 (all ranks) ---------------------------------------------------------
     if rank == 0 and not args.quick:

@@ -236,6 +236,11 @@ typedef struct {
   float weight_2d;      /* config_refine.ini:26 */
   float weight_3d;      /* config_refine.ini:27 */
   int32_t mlp_impl;     /* SDFR_MLP_* */
+  float latent_lipschitz; /* certified upper bound of |d sdf / d latent| of the decoder (product of the spectral norms
+                           * along the latent's path): > 0 lets an iteration evaluate only the lattice points that the
+                           * bound cannot exclude from the band, given the sdf at an earlier latent of the same
+                           * detection (same surfels, same results); 0 evaluates the whole lattice every iteration
+                           * as the reference does (optimizer.py:99-101) */
 } sdfr_refine_cfg;
 
 int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg, sdfr_refine** out);
@@ -306,6 +311,12 @@ int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void* stream);
 int sdfr_refine_label_extents(sdfr_refine* r, float* extents_host, void* stream);
 /* Overwrites the latent of slot b (host -> device, stream-ordered) without touching anything else. */
 int sdfr_refine_set_latent(sdfr_refine* r, int b, const float* latent_host, void* stream);
+
+/* Temporal pruning (sdfr_refine_cfg.latent_lipschitz > 0): lattice points the pruned lattice passes have
+ * evaluated since the last reset, and the detection-iterations they served (without pruning every
+ * detection-iteration evaluates density^3 points; both are 0 for an engine created without the bound).  Synchronises. */
+int sdfr_refine_lattice_rows(sdfr_refine* r, int64_t* rows_host, int64_t* detection_iterations_host, int reset,
+                             void* stream);
 
 /* Measurement aid (bench.py's per-kernel table): runs `iters` iterations of the active detections WITHOUT the
  * CUDA graph, with an event after every stage, and returns the mean device time of each stage in milliseconds

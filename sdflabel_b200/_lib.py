@@ -46,7 +46,7 @@ class RefineCfg(C.Structure):
     _fields_ = [
         ("batch", C.c_int32), ("density", C.c_int32), ("max_width", C.c_int32), ("max_height", C.c_int32),
         ("max_lidar", C.c_int32), ("max_iters", C.c_int32), ("weight_2d", C.c_float), ("weight_3d", C.c_float),
-        ("mlp_impl", C.c_int32),
+        ("mlp_impl", C.c_int32), ("latent_lipschitz", C.c_float),
     ]
 
 
@@ -92,6 +92,7 @@ SIGNATURES = {
     "sdfr_refine_set_latent": (C.c_int, [vp, C.c_int, c_float_p, vp]),
     "sdfr_refine_profile": (C.c_int, [vp, C.c_int, c_float_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32), vp]),
     "sdfr_refine_stage_name": (C.c_char_p, [C.c_int]),
+    "sdfr_refine_lattice_rows": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, vp]),
     "sdfr_refine_get": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.POINTER(C.c_int), vp]),
     "sdfr_refine_export": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
     "sdfr_refine_view": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]),

@@ -280,14 +280,40 @@ int launch_surface_extract(const SurfaceArgs& a, cudaStream_t s);
 // Band-restricted flow of the fused engine: (1) select |sdf| < thr over all detections into one
 // compact source-index list, (2) evaluate the decoder with its input gradient on that list only,
 // (3) project the band points onto the zero isosurface.
+// Order-preserving selection |value| < threshold over the rows of every detection, ONE launch (chained scan with
+// decoupled look-back over 1024-row chunks, detection-major).  The rows of detection b are either the whole
+// lattice slice values[b n .. b n + n) or, with in_start / in_count / in_src, its slice of a compact list whose
+// entries carry their global lattice index.
+struct SelectArgs {
+  const float* values;
+  const int* in_src;        // optional: global source index of each compact row
+  const int* in_start;      // optional [batch]: first compact row of each detection
+  const int* in_count;      // optional [batch]: compact rows of each detection (<= n)
+  long long n;              // lattice points per detection (chunk layout: ceil(n / 1024) chunks per detection)
+  int batch;
+  float threshold;
+  const float* det_threshold;   // optional [batch]: per-detection threshold
+  const int* det_all;       // optional [batch]: != 0 selects every row of the detection
+  int* out_src;             // [batch * n] global source indices of the selected rows, ascending
+  int* det_start;           // [batch]
+  int* det_count;           // [batch]
+  int* total;               // [1]
+  unsigned long long* status;   // [batch * nblocks] status words (epoch | state | value), zero-initialised
+  int* ctrl;                // [4] ticket, finished blocks, epoch, pad: zero-initialised, self-resetting
+  float* scatter_values;    // optional: scatter_values[src] = value of every visited row
+  float* scatter_ref;       // optional: scatter_ref[src] = value for the detections with scatter_flag[b] != 0
+  const int* scatter_flag;
+  unsigned long long* total_accum;   // optional [2]: += selected rows, += batch (running totals over launches)
+  int* scatter_done;        // optional [batch]: set to 1 for the flagged detections (their scatter_ref slice is complete after the launch)
+};
+int launch_select(const SelectArgs& a, cudaStream_t s);
+
 struct BandArgs {
   LatticeParams lattice;
-  const float* sdf;         // [batch, n] from the forward-only lattice pass
+  const float* sdf;         // [batch, n] coarse sdf by global lattice index (valid at least at the selected rows)
   long long n;              // lattice points per detection
   int batch;
   float threshold;
-  unsigned long long* status;   // [batch * nblocks] chained-scan status words (epoch | state | value), zero-initialised
-  int* ctrl;                // [4] ticket, finished blocks, epoch, pad: zero-initialised, self-resetting
   int* det_start;           // [batch]
   int* det_count;           // [batch]  (also the surfel count the splat stages read)
   int* total;               // [1]
@@ -306,7 +332,6 @@ struct BandArgs {
   int* presel_err;          // optional [1]: running max of |sdf[src] - band_sdf| (float bits, atomicMax)
   const SplatView* views;   // optional [batch]: the isosurface kernel also projects each surfel into its view
 };
-int launch_band_select(const BandArgs& a, cudaStream_t s);
 int launch_band_surface(const BandArgs& a, cudaStream_t s);
 
 // loss.cu

@@ -26,6 +26,8 @@ namespace sdfr {
 namespace {
 
 constexpr int kMaxLatent = 256;
+constexpr float kPruneSlack = 0.005f;     // on top of the pre-selection threshold: twice the accepted fp16 lattice-pass error
+constexpr float kPruneMaxThr = 0.15f;     // candidate threshold beyond which the reference is renewed (~12 % of a car lattice)
 
 struct DetState {
   int width, height, n_lidar, target_ready;
@@ -58,6 +60,22 @@ struct EngineDev {          // passed by value to the engine kernels
   unsigned long long* band_status;   // [B*nblk] chained-scan status words of the band selection
   int* band_ctrl;           // [4]  ticket / finished blocks / epoch of the band selection
   int* chain_done;          // [B]  chain blocks that have published their partials (self-resetting)
+  // temporal pruning of the lattice pass (lip > 0): see begin_iteration
+  float lip;                // certified upper bound of |d sdf / d latent_unit| over the lattice
+  float pre_thr;            // pre-selection threshold of the lattice pass (band + fp16 margin)
+  float* sdf_ref;           // [B,ng] lattice-pass sdf at the reference latent of each detection
+  float* z_ref;             // [B,L]  that reference latent (unit)
+  int* ref_valid;           // [B]    sdf_ref / z_ref describe a completed full evaluation
+  float* cand_thr;          // [B]    candidate threshold of the coming iteration
+  int* cand_all;            // [B]    the coming iteration evaluates the whole lattice and renews the reference
+  int* cand_src;            // [B*ng] candidate rows (global lattice indices, ascending)
+  float* cand_sdf;          // [B*ng] their lattice-pass sdf (compact)
+  int* cand_start;          // [B]
+  int* cand_count;          // [B]
+  int* cand_total;          // [1]
+  unsigned long long* cand_status;   // chained-scan state of the candidate selection
+  int* cand_ctrl;           // [4]
+  unsigned long long* lattice_rows;  // [2] rows the pruned lattice passes evaluated; detection-iterations they served
   int* band_det_start;      // [B]
   int* band_total;          // [1]
   int* band_src;            // [B*ng] compact global source indices of the band points
@@ -96,6 +114,27 @@ __device__ __forceinline__ void begin_iteration(const EngineDev& E, int b) {
   for (int k = 0; k < E.L; ++k) n2 += E.latent[b * E.L + k] * E.latent[b * E.L + k];
   const float nrm = fmaxf(sqrtf(n2), 1e-12f);
   for (int k = 0; k < E.L; ++k) E.latent_unit[b * E.L + k] = E.latent[b * E.L + k] / nrm;
+  // Temporal pruning of the lattice pass.  The decoder is Lipschitz in its latent input with constant <= E.lip, so
+  //   |sdf(x; z)| >= |sdf(x; z_ref)| - lip |z - z_ref|
+  // and a lattice point whose reference value satisfies |sdf_ref| >= pre_thr + slack + lip |z - z_ref| cannot be
+  // pre-selected now: only the others ("candidates") are evaluated.  The slack covers the error of the fp16 lattice
+  // pass on both sides (measured on every pre-selected row, limit pre-selection margin / 2).  Once the candidate
+  // threshold has grown past kPruneMaxThr the whole lattice is evaluated again and becomes the new reference.
+  if (E.lip > 0.f) {
+    float d2 = 0.f;
+    for (int k = 0; k < E.L; ++k) {
+      const float d = E.latent_unit[b * E.L + k] - E.z_ref[b * E.L + k];
+      d2 += d * d;
+    }
+    const float thr = E.pre_thr + kPruneSlack + E.lip * sqrtf(d2) * 1.001f;
+    const bool renew = !E.ref_valid[b] || !(thr <= kPruneMaxThr);       // also a NaN latent
+    if (renew) {
+      for (int k = 0; k < E.L; ++k) E.z_ref[b * E.L + k] = E.latent_unit[b * E.L + k];
+      E.ref_valid[b] = 0;                                                // set again when the new reference is stored
+    }
+    E.cand_thr[b] = thr;
+    E.cand_all[b] = renew ? 1 : 0;
+  }
 }
 
 __global__ void iter_begin_kernel(EngineDev E) {
@@ -615,6 +654,17 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.surf_pts, B * E.cap * 3); A(E.surf_nrm, B * E.cap * 3); A(E.surf_glat, B * E.cap * L);
   A(E.surf_idx, B * E.cap); A(E.surf_count, B);
   A(E.band_status, (size_t)B * (E.ng / 1024 + 2)); A(E.band_ctrl, 4); A(E.chain_done, B);
+  E.lip = cfg->latent_lipschitz > 0.f ? cfg->latent_lipschitz : 0.f;
+  {
+    int impl = cfg->mlp_impl;
+    if (impl == SDFR_MLP_AUTO) impl = dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
+    E.pre_thr = 0.03f + (impl == SDFR_MLP_TCGEN05 ? kPreselectMargin : 0.f);
+  }
+  if (E.lip > 0.f) {
+    A(E.sdf_ref, B * E.ng); A(E.z_ref, B * L); A(E.ref_valid, B); A(E.cand_thr, B); A(E.cand_all, B);
+    A(E.cand_src, (size_t)B * E.ng); A(E.cand_sdf, (size_t)B * E.ng); A(E.cand_start, B); A(E.cand_count, B);
+    A(E.cand_total, 4); A(E.cand_status, (size_t)B * (E.ng / 1024 + 2)); A(E.cand_ctrl, 4); A(E.lattice_rows, 2);
+  }
   A(E.band_det_start, B); A(E.band_total, 4); A(E.band_src, (size_t)B * E.ng); A(E.band_sdf, (size_t)B * E.ng);
   A(E.surf_valid, (size_t)B * E.cap);
   A(E.target, (size_t)B * 3 * E.max_pixels); A(E.lidar, (size_t)B * E.max_lidar * 3);
@@ -758,9 +808,10 @@ extern "C" int sdfr_refine_get_optimizer_state(sdfr_refine* r, int b, float* ada
 namespace {
 
 struct IterPlan {
-  MlpInputs in, in_band;
+  MlpInputs in, in_band, in_cand;
   BandArgs ba;
-  bool coarse;
+  SelectArgs sel, sel_cand;   // band selection; candidate selection of the pruned lattice pass
+  bool coarse, prune;
   int impl;
 };
 
@@ -791,14 +842,35 @@ IterPlan make_iter_plan(sdfr_refine* r, int B) {
   p.coarse = impl == SDFR_MLP_TCGEN05;
   BandArgs& ba = p.ba;
   ba.lattice = in.lattice; ba.sdf = E.sdf; ba.n = E.ng; ba.batch = B;
-  ba.threshold = 0.03f + (p.coarse ? kPreselectMargin : 0.f);
+  ba.threshold = E.pre_thr;
   ba.out_valid = E.surf_valid; ba.final_threshold = 0.03f;
-  ba.status = E.band_status; ba.ctrl = E.band_ctrl; ba.det_start = E.band_det_start;
+  ba.det_start = E.band_det_start;
   ba.det_count = E.surf_count; ba.total = E.band_total; ba.band_src = E.band_src;
   ba.band_sdf = E.band_sdf; ba.band_dinput = E.dinput; ba.in0 = E.in0; ba.latent = E.L;
   ba.out_pts = E.surf_pts; ba.out_nrm = E.surf_nrm; ba.out_idx = E.surf_idx; ba.out_glat = E.surf_glat; ba.cap = E.cap;
   ba.presel_err = p.coarse ? E.presel_err : nullptr;
   ba.views = E.views;
+  // band selection over the whole lattice (no pruning) ...
+  SelectArgs& sel = p.sel;
+  memset(&sel, 0, sizeof(sel));
+  sel.values = E.sdf; sel.n = E.ng; sel.batch = B; sel.threshold = ba.threshold;
+  sel.out_src = E.band_src; sel.det_start = E.band_det_start; sel.det_count = E.surf_count; sel.total = E.band_total;
+  sel.status = E.band_status; sel.ctrl = E.band_ctrl;
+  p.prune = E.lip > 0.f;
+  if (p.prune) {
+    // ... or: candidates from the reference sdf, lattice pass on them only, band selection among the candidates
+    SelectArgs& sc = p.sel_cand;
+    memset(&sc, 0, sizeof(sc));
+    sc.values = E.sdf_ref; sc.n = E.ng; sc.batch = B; sc.det_threshold = E.cand_thr; sc.det_all = E.cand_all;
+    sc.out_src = E.cand_src; sc.det_start = E.cand_start; sc.det_count = E.cand_count; sc.total = E.cand_total;
+    sc.status = E.cand_status; sc.ctrl = E.cand_ctrl; sc.total_accum = E.lattice_rows;
+    p.in_cand = in;
+    p.in_cand.index = E.cand_src;
+    p.in_cand.count_dev = E.cand_total;
+    sel.values = E.cand_sdf; sel.in_src = E.cand_src; sel.in_start = E.cand_start; sel.in_count = E.cand_count;
+    sel.scatter_values = E.sdf;                      // the guard of the isosurface kernel reads the coarse sdf by lattice index
+    sel.scatter_ref = E.sdf_ref; sel.scatter_flag = E.cand_all; sel.scatter_done = E.ref_valid;
+  }
   return p;
 }
 
@@ -822,10 +894,16 @@ constexpr int kNumStages = sizeof(kStageNames) / sizeof(kStageNames[0]);
 // lattice pass -> band select -> accurate pass on the selected rows -> isosurface projection
 int enqueue_surface(sdfr_refine* r, const IterPlan& p, cudaStream_t s, StageClock* clk = nullptr) {
   EngineDev& E = r->E;
-  int rc = p.coarse ? launch_mlp_tc_coarse(r->dec, p.in, E.sdf, s) : launch_mlp_ffma(r->dec, p.in, E.sdf, nullptr, s);
+  int rc;
+  if (p.prune) {
+    if ((rc = launch_select(p.sel_cand, s))) return rc;
+    rc = p.coarse ? launch_mlp_tc_coarse(r->dec, p.in_cand, E.cand_sdf, s) : launch_mlp_ffma(r->dec, p.in_cand, E.cand_sdf, nullptr, s);
+  } else {
+    rc = p.coarse ? launch_mlp_tc_coarse(r->dec, p.in, E.sdf, s) : launch_mlp_ffma(r->dec, p.in, E.sdf, nullptr, s);
+  }
   if (rc) return rc;
   STAGE_MARK(clk);
-  if ((rc = launch_band_select(p.ba, s))) return rc;
+  if ((rc = launch_select(p.sel, s))) return rc;
   STAGE_MARK(clk);
   rc = p.impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(r->dec, p.in_band, E.band_sdf, E.dinput, s)
                                   : launch_mlp_ffma(r->dec, p.in_band, E.band_sdf, E.dinput, s);
@@ -1008,6 +1086,21 @@ extern "C" int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void
   return SDFR_OK;
 }
 
+extern "C" int sdfr_refine_lattice_rows(sdfr_refine* r, int64_t* rows_host, int64_t* detection_iterations_host,
+                                        int reset, void* stream) {
+  SDFR_REQUIRE(r && rows_host && detection_iterations_host, SDFR_E_INVALID, "null argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  unsigned long long v[2] = {0ull, 0ull};
+  if (r->E.lip > 0.f) {
+    SDFR_CUDA(cudaMemcpyAsync(v, r->E.lattice_rows, sizeof(v), cudaMemcpyDeviceToHost, s));
+    if (reset) SDFR_CUDA(cudaMemsetAsync(r->E.lattice_rows, 0, sizeof(v), s));
+    SDFR_CUDA(cudaStreamSynchronize(s));
+  }
+  *rows_host = (int64_t)v[0];
+  *detection_iterations_host = (int64_t)v[1];
+  return SDFR_OK;
+}
+
 extern "C" int sdfr_refine_profile(sdfr_refine* r, int iters, float* stage_ms_host, int max_stages, int* n_stages,
                                    int32_t* band_rows_host, void* stream) {
   SDFR_REQUIRE(r && stage_ms_host && iters > 0 && max_stages >= kNumStages, SDFR_E_INVALID, "bad argument");
@@ -1071,6 +1164,11 @@ extern "C" int sdfr_refine_label_extents(sdfr_refine* r, float* extents_host, vo
   E.batch = B;
   IterPlan p = make_iter_plan(r, B);
   p.ba.views = nullptr;                       // extents only: the slots need no crop / camera (they may never have been set)
+  if (p.prune) {                              // the raw latent is not the trajectory the pruning follows: whole lattice
+    p.prune = false;
+    p.sel.values = E.sdf; p.sel.in_src = nullptr; p.sel.in_start = nullptr; p.sel.in_count = nullptr;
+    p.sel.scatter_values = nullptr; p.sel.scatter_ref = nullptr; p.sel.scatter_flag = nullptr; p.sel.scatter_done = nullptr;
+  }
   raw_latent_kernel<<<(B * E.L + 127) / 128, 128, 0, s>>>(E);
   SDFR_LAUNCH_CHECK();
   int rc = enqueue_surface(r, p, s);

@@ -115,7 +115,7 @@ __device__ __forceinline__ unsigned long long status_wait(const unsigned long lo
   return w;
 }
 
-__global__ void __launch_bounds__(SB) band_select_kernel(BandArgs a, int nblocks) {
+__global__ void __launch_bounds__(SB) select_kernel(SelectArgs a, int nblocks) {
   __shared__ int warp_off[SB / 32];
   __shared__ int s_chunk, s_base, s_total;
   __shared__ unsigned s_epoch;
@@ -130,7 +130,20 @@ __global__ void __launch_bounds__(SB) band_select_kernel(BandArgs a, int nblocks
   const unsigned epoch = s_epoch;
   const int b = chunk / nblocks, blk = chunk - b * nblocks;
   const long long i = (long long)blk * SB + tid;
-  const bool keep = i < a.n && in_band(a.sdf[(long long)b * a.n + i], a.threshold);
+  // rows of detection b: the whole lattice [b n, b n + n), or its slice of a compact list
+  const long long rows = a.in_count ? (long long)a.in_count[b] : a.n;
+  const long long row0 = a.in_start ? (long long)a.in_start[b] : (long long)b * a.n;
+  const bool all = a.det_all && a.det_all[b];
+  const float thr = a.det_threshold ? a.det_threshold[b] : a.threshold;
+  bool keep = false;
+  int src = 0;
+  if (i < rows) {
+    const float v = a.values[row0 + i];
+    src = a.in_src ? a.in_src[row0 + i] : (int)(row0 + i);
+    keep = all || in_band(v, thr);
+    if (a.scatter_values) a.scatter_values[src] = v;
+    if (a.scatter_ref && a.scatter_flag[b]) a.scatter_ref[src] = v;
+  }
   const unsigned ballot = __ballot_sync(0xffffffffu, keep);
   if (lane == 0) warp_off[warp] = __popc(ballot);
   __syncthreads();
@@ -166,7 +179,7 @@ __global__ void __launch_bounds__(SB) band_select_kernel(BandArgs a, int nblocks
   }
   __syncthreads();
   const int base = s_base;
-  if (keep) a.band_src[base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u))] = (int)((long long)b * a.n + i);
+  if (keep) a.out_src[base + warp_off[warp] + __popc(ballot & ((1u << lane) - 1u))] = src;
   if (tid == 0) {
     if (blk == nblocks - 1) {                                  // the detection's last chunk: its start and count
       int start = 0;
@@ -177,7 +190,14 @@ __global__ void __launch_bounds__(SB) band_select_kernel(BandArgs a, int nblocks
       }
       a.det_start[b] = start;
       a.det_count[b] = base + s_total - start;
-      if (chunk == total_blocks - 1) *a.total = base + s_total;
+      if (a.scatter_done && a.scatter_flag[b]) a.scatter_done[b] = 1;
+      if (chunk == total_blocks - 1) {
+        *a.total = base + s_total;
+        if (a.total_accum) {
+          atomicAdd(a.total_accum, (unsigned long long)(base + s_total));
+          atomicAdd(a.total_accum + 1, (unsigned long long)a.batch);
+        }
+      }
     }
     __threadfence();
     if (atomicAdd(&a.ctrl[1], 1) == total_blocks - 1) {        // every block of the launch is past its look-back
@@ -231,10 +251,10 @@ __global__ void __launch_bounds__(256) band_surface_kernel(BandArgs a) {
 
 }  // namespace
 
-int launch_band_select(const BandArgs& a, cudaStream_t s) {
+int launch_select(const SelectArgs& a, cudaStream_t s) {
   if (a.n <= 0 || a.batch <= 0) return SDFR_OK;
   const int nblocks = (int)((a.n + SB - 1) / SB);
-  band_select_kernel<<<nblocks * a.batch, SB, 0, s>>>(a, nblocks);
+  select_kernel<<<nblocks * a.batch, SB, 0, s>>>(a, nblocks);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }

@@ -66,11 +66,12 @@ class _Engine:
     to GROW a capacity, so a sequence of frames with different detection counts and crop sizes
     allocates (and captures its CUDA graphs) once."""
 
-    def __init__(self, native_decoder, batch, density, max_w, max_h, max_lidar, max_iters, w2d, w3d, impl):
+    def __init__(self, native_decoder, batch, density, max_w, max_h, max_lidar, max_iters, w2d, w3d, impl,
+                 latent_lipschitz=0.0):
         lib = _lib.load()
         self.cfg = _lib.RefineCfg(batch=batch, density=density, max_width=max_w, max_height=max_h,
                                   max_lidar=max_lidar, max_iters=max_iters, weight_2d=w2d, weight_3d=w3d,
-                                  mlp_impl=impl)
+                                  mlp_impl=impl, latent_lipschitz=float(latent_lipschitz))
         self.native_decoder = native_decoder     # keeps the decoder handle alive
         self.latent_size = native_decoder.latent_size
         h = _lib.vp()
@@ -204,6 +205,14 @@ class _Engine:
             self._dirty.clear()
         return params, [hist[b, :nh[b]] for b in range(B)]
 
+    def lattice_rows(self, reset=False):
+        """(lattice points evaluated by the pruned lattice passes, detection-iterations served) since the last reset;
+        (0, 0) for an engine without temporal pruning."""
+        rows, its = C.c_int64(0), C.c_int64(0)
+        _lib.check(_lib.load().sdfr_refine_lattice_rows(self.handle, C.byref(rows), C.byref(its), int(bool(reset)),
+                                                        _lib.stream_ptr()))
+        return rows.value, its.value
+
     def preselect_error(self) -> float:
         e = np.zeros(1, dtype=np.float32)
         _lib.check(_lib.load().sdfr_refine_preselect_error(self.handle, _lib.fptr(e), _lib.stream_ptr()))
@@ -267,24 +276,32 @@ class _Engine:
         return self.view(b, 'cam_pts')[:m * 3].view(-1, 3)[keep], self.view(b, 'cam_rgb')[:m * 3].view(-1, 3)[keep]
 
 
-def _engine_for(dsdf, batch, density, w, h, n_lidar, iters, weights, impl) -> _Engine:
+# Temporal pruning of the lattice pass (sdfr_refine_cfg.latent_lipschitz): an iteration evaluates only the lattice
+# points the decoder's Lipschitz bound cannot exclude from the band.  Same surfels and results as evaluating the
+# whole lattice every iteration (tests/test_gpu_parity.py::test_temporal_pruning_is_exact); False restores that.
+TEMPORAL_PRUNING = True
+
+
+def _engine_for(dsdf, batch, density, w, h, n_lidar, iters, weights, impl, prune=None) -> _Engine:
     """The decoder's engine for this (density, loss weights, MLP kernel), grown when a request exceeds a
     capacity.  Capacities are rounded up to powers of two, so growth happens a handful of times at most;
     nothing is re-created when a frame simply has fewer detections or a smaller crop than the last one."""
     native = dsdf.native()
+    prune = TEMPORAL_PRUNING if prune is None else bool(prune)
+    lip = float(native.latent_lipschitz) if prune else 0.0
     cache = dsdf.__dict__.setdefault('_sdfr_engines', {})
     for k in [k for k, e in cache.items() if e.native_decoder is not native]:
         del cache[k]           # engines of a decoder handle that has been rebuilt (weights changed)
     need = (_pow2_ceil(batch, 1), _pow2_ceil(w, 32), _pow2_ceil(h, 32), _pow2_ceil(max(n_lidar, 1), 1024),
             max(64, int(iters)))
-    key = (int(density), float(weights['2d']), float(weights['3d']), int(impl))
+    key = (int(density), float(weights['2d']), float(weights['3d']), int(impl), lip)
     eng = cache.get(key)
     if eng is None or any(n > c for n, c in zip(need, eng.capacity())):
         cap = need if eng is None else tuple(max(n, c) for n, c in zip(need, eng.capacity()))
         if eng is not None:
             del cache[key]
             eng = None         # frees the smaller engine's device memory before the larger one allocates
-        eng = _Engine(native, cap[0], int(density), cap[1], cap[2], cap[3], cap[4], key[1], key[2], key[3])
+        eng = _Engine(native, cap[0], int(density), cap[1], cap[2], cap[3], cap[4], key[1], key[2], key[3], lip)
         cache[key] = eng
     return eng
 

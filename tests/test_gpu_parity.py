@@ -558,6 +558,50 @@ def test_refine_is_deterministic_and_converges(stock_prior_path):
     assert abs(yaw1 - yaw_gt) < abs(yaw0 - yaw_gt)
 
 
+def test_temporal_pruning_is_exact(stock_prior_path):
+    """sdfr_refine_cfg.latent_lipschitz: an iteration evaluates only the lattice points that the decoder's certified
+    Lipschitz bound cannot exclude from the band.  60 iterations with and without it must agree BIT FOR BIT
+    (parameters, loss history, the last surfel set), while the pruned engine evaluates a fraction of the lattice;
+    the bound itself must dominate the finite differences of the decoder in its latent."""
+    from sdflabel_b200.pipelines import optimizer as OPT
+    prior = P.load_prior(stock_prior_path)
+    sc = scenes.make_scene(prior, size=64, density=40)
+    runs = {}
+    for prune in (False, True):
+        OPT.TEMPORAL_PRUNING = prune
+        try:
+            opt, params, dec = _run_engine(stock_prior_path, sc, 60)
+            eng = opt.engine
+            m = int(eng.view(0, 'surf_count').item())
+            runs[prune] = ({k: params[k].detach().cpu().numpy().copy() for k in params}, opt.history.copy(),
+                           eng.view(0, 'surf_idx')[:m].cpu().numpy().copy(), eng.view(0, 'surf_valid')[:m].cpu().numpy().copy(),
+                           eng.lattice_rows(), float(dec.native().latent_lipschitz))
+        finally:
+            OPT.TEMPORAL_PRUNING = True
+    a, b = runs[False], runs[True]
+    for k in a[0]:
+        assert np.array_equal(a[0][k], b[0][k]), k
+    assert np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert a[4] == (0, 0)
+    rows, its = b[4]
+    assert its == 60 and rows < 0.5 * 60 * 40 ** 3, (rows, its)
+    print(f"temporal pruning: {rows / its:.0f} of {40 ** 3} lattice points per iteration "
+          f"({100.0 * rows / (its * 40 ** 3):.1f} %), Lipschitz bound {b[5]:.1f}")
+    # the bound against finite differences of the oracle decoder in the latent (float64)
+    p64 = prior.to(torch.float64)
+    pts = O.lattice(12).to(torch.float64)
+    gen = torch.Generator().manual_seed(3)
+    worst = 0.0
+    for _ in range(8):
+        z0 = torch.nn.functional.normalize(torch.randn(3, generator=gen, dtype=torch.float64), dim=0)
+        z1 = torch.nn.functional.normalize(z0 + 1e-3 * torch.randn(3, generator=gen, dtype=torch.float64), dim=0)
+        f0 = O.decoder_forward(p64, torch.cat([z0.expand(pts.shape[0], -1), pts], 1))
+        f1 = O.decoder_forward(p64, torch.cat([z1.expand(pts.shape[0], -1), pts], 1))
+        worst = max(worst, float((f1 - f0).abs().max() / (z1 - z0).norm()))
+    assert worst <= b[5], (worst, b[5])
+
+
 def test_refine_skip_paths(stock_prior_path):
     """Empty LIDAR crop: the reference prints 'Skip frame' and leaves the parameters untouched."""
     prior = P.load_prior(stock_prior_path)
