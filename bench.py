@@ -658,6 +658,17 @@ def run_ours(args, rank, world, local_rank):
                 "lattice_points_per_iteration": rows / max(its, 1), "lattice_points_full": DENSITY ** 3,
                 "latent_lipschitz_bound": float(dec.native().latent_lipschitz),
                 "params_bit_identical_to_whole_lattice": bool(np.array_equal(pp, fp))}
+            try:
+                ptable, prow, ptot = stage_table(lib, peng, B, flop_pt, pk)
+                for row in ptable:          # the lattice stage of a pruned iteration: candidate selection + lattice pass on them
+                    if row["kernel"] == "lattice_pass":
+                        for k in ("achieved", "frac", "unit", "bound"):
+                            row.pop(k, None)
+                        row["note"] = "candidate selection + lattice pass over the candidates only"
+                extras["pruned"]["per_stage"] = ptable
+                extras["pruned"]["per_stage_sum_ms"] = ptot
+            except Exception as e:   # noqa: BLE001
+                extras["pruned"]["per_stage"] = {"error": str(e)}
         except Exception as e:   # noqa: BLE001
             extras["pruned"] = {"error": repr(e)[:300]}
 

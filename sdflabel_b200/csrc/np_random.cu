@@ -64,25 +64,60 @@ extern "C" int sdfr_np_choice4(uint32_t* mt_key, int32_t* mt_pos, int64_t n, int
                (long long)n, draws);
   SDFR_REQUIRE(*mt_pos >= 0 && *mt_pos <= 624, SDFR_E_INVALID, "sdfr_np_choice4: bad generator position %d", *mt_pos);
   Mt19937 g{mt_key, *mt_pos};
-  std::vector<int32_t> perm((size_t)n);
+  // Only permutation(n)[:4] is used, so the array is never shuffled.  Pass 1 consumes the stream exactly as the
+  // Fisher-Yates loop does (j_i = random_interval(i) for i = n-1 .. 1; a rejected word leaves i where it is, written
+  // without a data-dependent branch) and records the j_i.  Pass 2 follows the four output positions back through the
+  // transpositions in reverse order of execution (i = 1 .. n-1): position c was fed by j_i when c == i and by i when
+  // c == j_i; once i > 3 a tracked position is always below i, so only the second case remains.
+  std::vector<uint32_t> jbuf((size_t)n);
+  uint32_t tempered[624];
+  int tpos = 624;                                        // next tempered word of the current block (624: none tempered yet)
+  auto refill_tempered = [&]() {
+    if (g.pos == 624) g.refill();
+    const int first = g.pos;
+    for (int k = first; k < 624; ++k) {
+      uint32_t y = g.key[k];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      tempered[k] = y;
+    }
+    tpos = first;
+  };
   for (int32_t d = 0; d < draws; ++d) {
-    for (int64_t i = 0; i < n; ++i) perm[(size_t)i] = (int32_t)i;          // permutation(n): arange, then shuffle
-    // Fisher-Yates from the end with numpy's masked rejection, written without a data-dependent branch: a rejected
-    // candidate swaps position i with itself and leaves i where it is (the rejection branch of the textbook loop
-    // mispredicts on a third of the draws and was 2/3 of the time).
     uint32_t i = (uint32_t)(n - 1);
     while (i >= 1) {
-      uint32_t mask = i;
-      mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-      const uint32_t v = g.next32() & mask;
-      const uint32_t accept = v <= i ? 1u : 0u;
-      const uint32_t j = accept ? v : i;
-      const int32_t t = perm[i];
-      perm[i] = perm[j];
-      perm[j] = t;
-      i -= accept;
+      if (tpos == 624) refill_tempered();              // g.pos == 624 here except before the very first word
+      // as many words as this block still has, or until the pass is done
+      int k = tpos;
+      // the mask only changes when i crosses a power of two: inside such a level the loop-carried work is one
+      // compare and one subtract per word
+      const uint32_t mask = 0xffffffffu >> __builtin_clz(i);
+      const uint32_t level = (mask >> 1) + 1u;           // smallest i with this mask
+      for (; k < 624 && i >= level; ++k) {
+        const uint32_t v = tempered[k] & mask;
+        jbuf[i] = v;                                     // overwritten by the next word when rejected
+        i -= v <= i ? 1u : 0u;
+      }
+      tpos = k;
+      g.pos = k;
     }
-    for (int k = 0; k < 4; ++k) samples_out[(size_t)d * 4 + k] = perm[(size_t)k];   // [:size]
+    uint32_t c[4] = {0u, 1u, 2u, 3u};
+    for (uint32_t s = 1; s <= 3 && s < (uint32_t)n; ++s) {
+      const uint32_t j = jbuf[s];
+      for (int q = 0; q < 4; ++q) c[q] = c[q] == s ? j : (c[q] == j ? s : c[q]);
+    }
+    uint32_t c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
+    for (uint32_t s = 4; s < (uint32_t)n; ++s) {
+      const uint32_t j = jbuf[s];
+      c0 = j == c0 ? s : c0;
+      c1 = j == c1 ? s : c1;
+      c2 = j == c2 ? s : c2;
+      c3 = j == c3 ? s : c3;
+    }
+    int32_t* o = samples_out + (size_t)d * 4;
+    o[0] = (int32_t)c0; o[1] = (int32_t)c1; o[2] = (int32_t)c2; o[3] = (int32_t)c3;
   }
   *mt_pos = g.pos;
   return SDFR_OK;

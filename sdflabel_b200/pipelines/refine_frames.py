@@ -27,6 +27,8 @@ which is what lets the multi-GPU driver shard frames freely (SURVEY.md section 8
 from __future__ import annotations
 
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -56,12 +58,13 @@ def compute_iou(box_a, box_b):
     return inter / float(area_a + area_b - inter)
 
 
-def initial_params(det: Dict, model_pts: torch.Tensor, estimator: PoseEstimator) -> Optional[Dict]:
+def initial_params(det: Dict, model_pts: torch.Tensor, estimator: PoseEstimator, rng=None) -> Optional[Dict]:
     """refine_css.py:150-199: RANSAC pose from the NOCS correspondences, rotation constrained to the
     azimuth, height re-estimated when the projected model misses the 2D box.  ``model_pts`` are the
-    isosurface points of the predicted latent (device tensor, object frame)."""
+    isosurface points of the predicted latent (device tensor, object frame); ``rng`` as in
+    ``PoseEstimator.estimate``."""
     nocs_dsdf = (model_pts + 1) / 2                                     # grid.py:67
-    init_pose = estimator.estimate(model_pts, nocs_dsdf, det['scene_pts'], det['scene_cls'], None, None)
+    init_pose = estimator.estimate(model_pts, nocs_dsdf, det['scene_pts'], det['scene_cls'], None, None, rng=rng)
     if init_pose is None:
         return None                                                     # 'NO RANSAC POSE FOUND!!!' (171-173)
     scale, rot, tra = init_pose['scale'], np.array(init_pose['rot'], dtype=np.float64), np.array(init_pose['tra'])
@@ -84,7 +87,7 @@ class FrameRefiner:
     """Refines frames on this process's GPU; see the module docstring."""
 
     def __init__(self, dsdf, grid, weights, iters, max_batch=32, max_crop=(96, 96), max_lidar=1024,
-                 pose_estimator='kabsch', init_scale=2.0, device='cuda', seed=0):
+                 pose_estimator='kabsch', init_scale=2.0, device='cuda', seed=0, init_threads=None):
         self.dsdf, self.grid, self.weights, self.iters = dsdf, grid, weights, int(iters)
         self.device = torch.device(device)
         self.max_batch = int(max_batch)
@@ -101,6 +104,13 @@ class FrameRefiner:
             #  per decoder, so with that kernel the two engines must not overlap: same stream)
             self.init_stream = torch.cuda.Stream(device=self.device) if dsdf.native().tcgen05 else \
                 torch.cuda.current_stream(self.device)
+        # the host part of the pose initialisation (sample draw, 4-point fits, read-backs) runs on a few threads:
+        # its C / LAPACK / CUDA calls release the GIL; every detection draws from a generator of its own
+        if init_threads is None:
+            local_ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+            init_threads = max(1, min(6, (os.cpu_count() or 2) // local_ranks - 1))
+        self.init_threads = int(init_threads)
+        self.pool = ThreadPoolExecutor(max_workers=self.init_threads) if self.init_threads > 1 else None
         self.timing = {'init_s': 0.0, 'refine_wait_s': 0.0, 'label_s': 0.0, 'detections': 0, 'batches': 0,
                        'no_pose': 0}
 
@@ -116,16 +126,21 @@ class FrameRefiner:
                 chunk = items[s:s + eng.cfg.batch]
                 lat = np.stack([np.asarray(d['latent_pred'], dtype=np.float32) for _, _, d in chunk])
                 clouds = eng.surface_clouds(lat)
-                for (fid, di, det), cloud in zip(chunk, clouds):
-                    if det.get('params') is not None:
-                        out.append((fid, di, det, det['params']))
-                        continue
-                    # the reference consumes numpy's global RNG in file order; a per-detection seed keeps a
-                    # detection's hypotheses independent of which rank / batch it lands in
-                    np.random.seed((self.seed * 1000003 + fid * 131 + di) % (2 ** 32))
-                    out.append((fid, di, det, initial_params(det, cloud, self.estimator)))
+                work = list(zip(chunk, clouds))
+                params = list(self.pool.map(self._initial, work)) if self.pool else [self._initial(w) for w in work]
+                out.extend((fid, di, det, p) for ((fid, di, det), _), p in zip(work, params))
         self.timing['init_s'] += time.perf_counter() - t0
         return out
+
+    def _initial(self, item):
+        (fid, di, det), cloud = item
+        if det.get('params') is not None:
+            return det['params']
+        # the reference consumes numpy's global RNG in file order; a generator seeded per detection keeps a
+        # detection's hypotheses independent of which rank / batch / thread it lands in
+        rng = np.random.RandomState((self.seed * 1000003 + fid * 131 + di) % (2 ** 32))
+        with torch.cuda.device(self.device), torch.cuda.stream(self.init_stream):
+            return initial_params(det, cloud, self.estimator, rng)
 
     # ---- stage 2: refinement of a prepared batch (main stream, asynchronous) ---------------------------
     def _launch(self, prepared):

@@ -63,19 +63,20 @@ def ransac_score(scene_pts, scene_cls, model_pts, model_cls, transforms, metric_
     return counts, masks
 
 
-def legacy_choice4(n: int, draws: int) -> np.ndarray:
-    """``draws`` x ``np.random.choice(range(n), 4, replace=False)`` on numpy's global legacy generator, (draws, 4).
-    Same numbers, same generator state afterwards; the stream is consumed by ``sdfr_np_choice4`` (a host loop over
-    the MT19937 state) instead of 567 Python-level calls."""
+def legacy_choice4(n: int, draws: int, rng=None) -> np.ndarray:
+    """``draws`` x ``np.random.choice(range(n), 4, replace=False)`` on numpy's global legacy generator (or on the
+    ``np.random.RandomState`` given as ``rng``), (draws, 4).  Same numbers, same generator state afterwards; the
+    stream is consumed by ``sdfr_np_choice4`` (a host loop over the MT19937 state) instead of 567 Python-level calls."""
     import ctypes as C
-    state = np.random.get_state(legacy=True)
+    rs = np.random if rng is None else rng
+    state = rs.get_state(legacy=True)
     if state[0] != 'MT19937' or n < 4:
-        return np.stack([np.random.choice(n, 4, replace=False) for _ in range(draws)])
+        return np.stack([rs.choice(n, 4, replace=False) for _ in range(draws)])
     key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
     pos = C.c_int32(int(state[2]))
     out = np.empty((draws, 4), dtype=np.int32)
     _lib.check(_lib.load().sdfr_np_choice4(key.ctypes.data, C.byref(pos), int(n), int(draws), out.ctypes.data))
-    np.random.set_state(('MT19937', key, pos.value, state[3], state[4]))
+    rs.set_state(('MT19937', key, pos.value, state[3], state[4]))
     return out.astype(np.int64)
 
 
@@ -84,11 +85,13 @@ class PoseEstimator:
         self.scale = scale
         self.type = type
 
-    def estimate(self, pcd_dsdf, nocs_dsdf, pcd_scene, nocs_scene, off_intrinsics, nocs_pred_resized):
-        """Pose dictionary (or None) for the configured estimator type, arguments as in the reference."""
+    def estimate(self, pcd_dsdf, nocs_dsdf, pcd_scene, nocs_scene, off_intrinsics, nocs_pred_resized, rng=None):
+        """Pose dictionary (or None) for the configured estimator type, arguments as in the reference.  ``rng``
+        (an ``np.random.RandomState``) replaces numpy's global generator as the source of the RANSAC samples, so
+        that detections can be initialised by several threads."""
         if self.type in ('kabsch', 'procrustes'):
             return self.init_pose_3d(pcd_dsdf, nocs_dsdf, pcd_scene, nocs_scene, type=self.type,
-                                     scale_model=self.scale)
+                                     scale_model=self.scale, rng=rng)
         if self.type == 'pnp':
             return self.init_pose_2d(off_intrinsics, nocs_pred_resized, scale_model=self.scale)
         raise ValueError(f"unknown pose estimator type {self.type!r}")
@@ -110,7 +113,7 @@ class PoseEstimator:
 
     @staticmethod
     def init_pose_3d(model_pts, model_cls, scene_pts, scene_cls, metric_distance_threshold=0.15,
-                     nocs_distance_threshold=0.15, type='procrustes', scale_model=1):
+                     nocs_distance_threshold=0.15, type='procrustes', scale_model=1, rng=None):
         """Kabsch / Procrustes RANSAC (reference 84-233): {'scale', 'rot', 'tra'} or None."""
         dev = _device()
         scene_pts_d, scene_cls_d = _f32_dev(scene_pts, dev), _f32_dev(scene_cls, dev)
@@ -127,25 +130,30 @@ class PoseEstimator:
 
         # NOCS correspondence of every scene point, once (the reference queries 4 per hypothesis)
         cdist_d, cidx_d = nn_query(scene_cls_d, model_cls_d)
-        cdist, cidx = cdist_d.cpu().numpy(), cidx_d.cpu().numpy().astype(np.int64)
-        scene_pts_h = scene_pts_d.cpu().numpy()
+        # host copies: the scene cloud usually IS a host array; distance, index and the model cloud ride on one
+        # synchronisation (the copies are enqueued in order, the last .cpu() waits for all of them)
+        scene_pts_h = scene_pts_d.cpu().numpy() if isinstance(scene_pts, torch.Tensor) else \
+            np.ascontiguousarray(np.asarray(scene_pts, dtype=np.float32))
+        cdist_t = cdist_d.to('cpu', non_blocking=True)
+        cidx_t = cidx_d.to('cpu', non_blocking=True)
         model_pts_h = model_pts_d.cpu().numpy()
+        torch.cuda.current_stream(dev).synchronize()
+        cdist, cidx = cdist_t.numpy(), cidx_t.numpy().astype(np.int64)
 
         # the reference's sample sequence (one np.random.choice per iteration, whatever happens next)
-        samples = legacy_choice4(total, iters)
+        samples = legacy_choice4(total, iters, rng)
         compatible = ~(cdist[samples] > nocs_distance_threshold).any(axis=1)
 
         cand = np.nonzero(compatible)[0]
-        transforms = []
+        transforms = None
         if type == 'kabsch' and len(cand):
             # all 4-point fits in one batched LAPACK call (same gufunc as the per-sample calls: same bits)
             rots, tras = kabsch_batch(scene_pts_h[samples[cand]], model_pts_h[cidx[samples[cand]]])
-            for rot, tra in zip(rots, tras):
-                trans = np.zeros((3, 4), dtype=np.float32)
-                trans[:3, :3] = rot * 1
-                trans[:3, 3] = tra
-                transforms.append(trans)
+            transforms = np.zeros((len(cand), 3, 4), dtype=np.float32)
+            transforms[:, :, :3] = rots
+            transforms[:, :, 3] = tras
         else:
+            rows = []
             for it in cand:
                 result = procrustes(scene_pts_h[samples[it]], model_pts_h[cidx[samples[it]]])
                 if result is None:
@@ -156,11 +164,13 @@ class PoseEstimator:
                 trans = np.zeros((3, 4), dtype=np.float32)
                 trans[:3, :3] = rot * scale
                 trans[:3, 3] = tra
-                transforms.append(trans)
-        if not transforms:
+                rows.append(trans)
+            if rows:
+                transforms = np.stack(rows)
+        if transforms is None or not len(transforms):
             return None
 
-        t_d = torch.from_numpy(np.stack(transforms)).to(dev)
+        t_d = torch.from_numpy(transforms).to(dev)
         counts_d, masks_d = ransac_score(scene_pts_d, scene_cls_d, model_pts_d, model_cls_d, t_d,
                                          metric_distance_threshold, np.float32(nocs_distance_threshold))
         counts = counts_d.cpu().numpy()
@@ -218,7 +228,7 @@ def procrustes(from_points, to_points):
 
 def kabsch_batch(canonical_points, predicted_points):
     """``kabsch`` for stacks (h,4,3) of samples: the reductions, products and the SVD are numpy's batched
-    forms of the very same calls, the two matrix-vector products of the translation stay per sample."""
+    forms of the very same calls."""
     mu_c, mu_p = np.mean(canonical_points, axis=1), np.mean(predicted_points, axis=1)
     c_c = canonical_points - mu_c[:, None, :]
     p_c = predicted_points - mu_p[:, None, :]
@@ -228,10 +238,10 @@ def kabsch_batch(canonical_points, predicted_points):
     if neg.any():
         vt[neg, -1, :] *= -1.0
         rot[neg] = np.matmul(u[neg], vt[neg])
-    tras = []
-    for r, c, p in zip(rot, mu_c, mu_p):
-        t = p - c
-        tras.append(np.dot(r, t) - np.dot(r, p) + p)
+    # the reference's translation, np.dot(R, p - c) - np.dot(R, p) + p, for the whole stack: matmul hands every
+    # 3x3 . 3 product to the same BLAS gemv as np.dot does (bit-identical, tests/test_pose_oracle.py)
+    t = mu_p - mu_c
+    tras = np.matmul(rot, t[:, :, None])[:, :, 0] - np.matmul(rot, mu_p[:, :, None])[:, :, 0] + mu_p
     return rot, tras
 
 
