@@ -13,8 +13,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ_DIR = os.path.join(HERE, "build")
-LIB_PATH = os.path.join(HERE, "libsdfr.so")
+# SDFR_BUILD_TAG=<tag> builds a variant (with SDFR_NVCC_FLAGS) next to the product library: libsdfr_<tag>.so, loaded
+# with SDFR_LIB for A/B measurements
+_TAG = os.environ.get("SDFR_BUILD_TAG", "")
+OBJ_DIR = os.path.join(HERE, "build", _TAG) if _TAG else os.path.join(HERE, "build")
+LIB_PATH = os.path.join(HERE, f"libsdfr_{_TAG}.so" if _TAG else "libsdfr.so")
 SOURCES = ["api.cu", "mlp_ffma.cu", "mlp_tc.cu", "surface.cu", "splat.cu", "circle.cu", "loss.cu", "refine.cu", "trace.cu", "pose.cu", "rotate_iou.cu", "np_random.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

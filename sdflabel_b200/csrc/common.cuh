@@ -211,8 +211,7 @@ struct SplatView {
 };
 
 int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStream_t s);
-int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, int any_small, cudaStream_t s);
-constexpr int kSmallCropPixelsHost = 128 * 128;   // = kSmallCropPixels of splat.cu
+int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, cudaStream_t s);
 int launch_pixel_grad_prep(const SplatView* views_dev, int batch, int max_pixels, const float* g_color,
                            const float* g_mask, const float* g_depth, const float* g_nmap, cudaStream_t s);
 int launch_splat_backward(const SplatView* views_dev, int batch, int max_count, cudaStream_t s);

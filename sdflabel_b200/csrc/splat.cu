@@ -51,28 +51,24 @@ __device__ __forceinline__ Hit disc_test(float rx, float ry, float rz, float vx,
   return h;
 }
 
-constexpr int TILE = 16;       // pixels per tile side for crops above kSmallCropPixels
-constexpr int CHUNK = 256;     // = threads per block
-constexpr int LCAP_LARGE = 512;    // surfels of one tile kept resident in shared memory for both sweeps
-constexpr int LCAP_SMALL = 1024;
-// Crops up to this many pixels (the reference's default regime: rendering_area = 32..64, configs/config_refine.ini:12)
-// are split into 8 x 8 tiles with FOUR threads per pixel, each sweeping a quarter of the tile's surfel list: a
-// 32 x 32 crop is 16 CTAs instead of 4, and the ~1 600 surfels of a detection (all of them inside a few hundred
-// pixels) are ~300 per tile instead of overflowing the resident list.  The mode depends on the detection's OWN
-// crop only, so its bits do not depend on what else is in the batch.
-constexpr int kSmallCropPixels = 128 * 128;
-
-__global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* __restrict__ views, int lcap) {
+constexpr int TILE = 8;        // pixels per tile side
+constexpr int SPLIT = 4;       // threads per pixel, each sweeping a quarter of the tile's surfel list
+constexpr int CHUNK = 256;     // = threads per block = TILE * TILE * SPLIT
+constexpr int LCAP = 1024;     // surfels of one tile kept resident in shared memory for both sweeps
+// 8 x 8 pixel tiles with FOUR threads per pixel at every crop size: a 32 x 32 crop (the reference's default regime,
+// configs/config_refine.ini:12) is 16 CTAs, a 256 x 256 crop 1024, and the ~1 600 surfels of a detection are a few
+// hundred per tile instead of overflowing the resident list; the critical path of a busy tile is a quarter of
+// what one thread per pixel on 16 x 16 tiles pays (256 x 256: 66 -> 30 us).
+__global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* __restrict__ views) {
   extern __shared__ __align__(16) float s_list[];
   const SplatView& V = views[blockIdx.z];
-  const bool small = V.width * V.height <= kSmallCropPixels;
-  const int tile = small ? 8 : TILE, split = small ? 4 : 1;
+  constexpr int tile = TILE, split = SPLIT, lcap = LCAP;
   const int tx0 = blockIdx.x * tile, ty0 = blockIdx.y * tile;
   if (tx0 >= V.width || ty0 >= V.height) return;
   const int m = min(V.count ? *V.count : V.static_count, V.capacity);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pix = small ? tid >> 2 : tid, part = small ? tid & 3 : 0;
-  const int x = tx0 + (small ? pix & 7 : pix & 15), y = ty0 + (small ? pix >> 3 : pix >> 4);
+  const int pix = tid >> 2, part = tid & 3;
+  const int x = tx0 + (pix & 7), y = ty0 + (pix >> 3);
   const bool live = x < V.width && y < V.height;
   const int tx1 = min(tx0 + tile - 1, V.width - 1), ty1 = min(ty0 + tile - 1, V.height - 1);
 
@@ -119,10 +115,9 @@ __global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* _
       acc[7] += e * ((s_m[k][2] + 1.f) / 2.f);
     }
   };
-  // the four threads of a pixel (small crops) hold partial results over their quarters of the list: combine them
-  // in a fixed order (lanes 4p .. 4p+3 of one warp)
+  // the four threads of a pixel hold partial results over their quarters of the list: combine them in a fixed
+  // order (lanes 4p .. 4p+3 of one warp)
   auto combine_sweep0 = [&]() {
-    if (split == 1) return;
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
       sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
@@ -131,7 +126,6 @@ __global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* _
     }
   };
   auto combine_sweep1 = [&]() {
-    if (split == 1) return;
 #pragma unroll
     for (int o = 1; o <= 2; o <<= 1) {
       den += __shfl_xor_sync(0xffffffffu, den, o);
@@ -329,19 +323,15 @@ int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStr
   return SDFR_OK;
 }
 
-int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, int any_small, cudaStream_t s) {
+int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, cudaStream_t s) {
   if (max_w <= 0 || max_h <= 0 || batch <= 0) return SDFR_OK;
-  // any_small: some detection of the batch is a small crop (8 x 8 tiles, longer resident list); the grid then
-  // covers the finer tiling and the blocks of large-crop detections beyond their 16 x 16 tiling exit at once
-  const int tile = any_small ? 8 : TILE;
-  const int lcap = any_small ? LCAP_SMALL : LCAP_LARGE;
   static bool attr_set = false;
   if (!attr_set) {
-    SDFR_CUDA(cudaFuncSetAttribute(splat_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCAP_SMALL * 56));
+    SDFR_CUDA(cudaFuncSetAttribute(splat_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCAP * 56));
     attr_set = true;
   }
-  dim3 grid((max_w + tile - 1) / tile, (max_h + tile - 1) / tile, batch);
-  splat_forward_kernel<<<grid, CHUNK, (size_t)lcap * 56, s>>>(views_dev, lcap);
+  dim3 grid((max_w + TILE - 1) / TILE, (max_h + TILE - 1) / TILE, batch);
+  splat_forward_kernel<<<grid, CHUNK, (size_t)LCAP * 56, s>>>(views_dev);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
 }
