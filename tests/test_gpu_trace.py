@@ -90,3 +90,64 @@ def test_trace_empty_view(stock_prior_path):
     assert float(r["mask"].sum()) == 0.0 and float(r["depth"].abs().sum()) == 0.0
     g = torch.autograd.grad(r["depth"].sum() + r["color"].sum(), [lat, pose], allow_unused=True)
     assert all(x is None or float(x.abs().sum()) == 0.0 for x in g)
+
+
+def _octahedron_decoder(radius, latent_size=3):
+    """A Decoder that IS a closed-form field: f(l, x) = tanh((|x|_1 - r) / sqrt(3)), the exact distance to the
+    faces of the octahedron |x|_1 <= r (a lower bound of the distance near its edges), as one hidden ReLU layer:
+    |x_i| = relu(x_i) + relu(-x_i).  The latent columns carry zero weights."""
+    from sdflabel_b200.deepsdf.networks.deep_sdf_decoder_scale import Decoder
+    dec = Decoder(latent_size, [8], dropout=None, dropout_prob=0.0, norm_layers=(), latent_in=(), weight_norm=False)
+    w0 = torch.zeros(8, latent_size + 3)
+    for a in range(3):
+        w0[2 * a, latent_size + a] = 1.0
+        w0[2 * a + 1, latent_size + a] = -1.0
+    w1 = torch.zeros(1, 8)
+    w1[0, :6] = 1.0 / np.sqrt(3.0)
+    sd = dec.state_dict()
+    sd["lin0.weight"], sd["lin0.bias"] = w0, torch.zeros(8)
+    sd["lin1.weight"], sd["lin1.bias"] = w1, torch.tensor([-radius / np.sqrt(3.0)])
+    dec.load_state_dict(sd)
+    return dec.to(cuda).eval()
+
+
+@pytest.mark.parametrize("impl", ["auto", "ffma"])
+def test_trace_closed_form_octahedron(impl):
+    """T9, closed form: the traced depth, NOCS and normals of an analytic field against the exact ray / octahedron
+    intersection (eight planes).  Sphere tracing stops at |f| < eps, i.e. within eps / cos(incidence) of the face."""
+    from sdflabel_b200 import _lib
+    from sdflabel_b200.renderer.tracer import SphereTracer
+    size, radius, eps = 64, 0.6, 1e-4
+    dec = _octahedron_decoder(radius)
+    if impl == "ffma":
+        dec.mlp_impl = _lib.MLP_FFMA
+    K = scenes.intrinsics(size)
+    pose = O.yaw_pose(torch.tensor([0.4]), torch.tensor([0.03, -0.05, 4.0]))
+    tracer = SphereTracer(K, (size, size), eps=eps).to(cuda)
+    r = tracer(dec, torch.tensor([0.5, 0.7, 0.5], device=cuda), pose.to(cuda))
+    # exact intersection in float64
+    o, d, rn = (t.double() for t in T.rays(K.double(), size, size, pose.double()))
+    signs = torch.tensor([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], dtype=torch.float64)
+    sd_, so_ = d @ signs.t(), (signs @ o)[None, :]                     # (P,8) s.d, (1,8) s.o
+    tt = (radius - so_) / sd_
+    t_in = torch.where(sd_ < 0, tt, torch.full_like(tt, -1e30)).max(dim=1)
+    t_out = torch.where(sd_ > 0, tt, torch.full_like(tt, 1e30)).min(dim=1)[0]
+    hit = (t_in[0] <= t_out) & (t_out > 0)
+    face = signs[t_in[1]] / np.sqrt(3.0)                               # outward normal of the entry face
+    cosi = (face * d).sum(1).abs()
+    got_hit = r["mask"][0].cpu().reshape(-1) > 0.5
+    # rays that pass the octahedron closer than the stopping band may legitimately count as hits
+    both = got_hit & hit
+    assert both.sum() >= 0.99 * (got_hit | hit).sum() and both.sum() > 200, (int(both.sum()), int(hit.sum()))
+    tau = (r["depth"][0].cpu().reshape(-1).double() / rn[:, 2])[both]
+    err = (tau - t_in[0][both]).abs()
+    bound = 2.0 * eps / cosi[both] + 2e-5
+    assert bool((err <= bound).all()), (float(err.max()), float((err / bound).max()))
+    x = o + t_in[0][both, None] * d[both]
+    interior = x.abs().min(dim=1)[0] > 5e-3                            # away from the edges, where the field has kinks
+    nocs = r["color"].cpu().reshape(3, -1).double()[:, both]
+    want = ((x * torch.tensor([-1.0, 1.0, 1.0], dtype=torch.float64) + 1) / 2).t()
+    assert float(((nocs - want).abs().max(dim=0)[0] - bound / 2).max()) <= 0.0
+    n_cam = face[both] @ pose[:3, :3].double().t()
+    got_n = r["normals"].cpu().reshape(3, -1).double()[:, both]
+    assert float(((got_n - ((n_cam + 1) / 2).t()).abs().max(dim=0)[0])[interior].max()) < 1e-5
