@@ -26,8 +26,10 @@ def rays(K, width, height, pose):
 
 
 def trace(params: O.DecoderParams, latent_unit, K, width, height, pose, max_steps=64, eps=1e-4):
-    """Returns dict(depth (1,H,W), normals (3,H,W), nocs (3,H,W), mask (1,H,W)); depth and nocs are
-    differentiable with respect to pose and latent_unit."""
+    """Returns dict(depth (1,H,W), normals (3,H,W), nocs (3,H,W), mask (1,H,W), slope (1,H,W)); depth and nocs
+    are differentiable with respect to pose and latent_unit.  The march stops anywhere inside |f| < eps, so the ray
+    parameter of a hit is only defined to eps / slope: an implementation that stops elsewhere in that band (or polishes
+    the root) is equally right, and the tests compare with that per-ray tolerance."""
     P = width * height
     with torch.no_grad():
         o, d, rn = rays(K, width, height, pose)
@@ -54,11 +56,20 @@ def trace(params: O.DecoderParams, latent_unit, K, width, height, pose, max_step
             if step == max_steps - 1:
                 active[:] = False
     hid = hit.nonzero().squeeze(1)
+    return render_hits(params, latent_unit, K, width, height, pose, tau, hid)
+
+
+def render_hits(params: O.DecoderParams, latent_unit, K, width, height, pose, tau, hid):
+    """The maps of `trace` for given hit pixels `hid` (flat indices) and ray parameters `tau` ((P,), constants):
+    values at o + tau d, gradients by one differentiable Newton step (= the implicit-function derivative).  Also the
+    way to evaluate the specification's gradients at the hit points ANOTHER march found."""
+    P = width * height
     o, d, rn = rays(K, width, height, pose)                      # with the graph this time
     depth = torch.zeros(P, dtype=K.dtype)
     nocs = torch.zeros(3, P, dtype=K.dtype)
     nmap = torch.zeros(3, P, dtype=K.dtype)
     mask = torch.zeros(P, dtype=K.dtype)
+    slope = torch.zeros(P, dtype=K.dtype)          # |grad f . d| at the hit: eps / slope is the width of the stopping band in tau
     if hid.numel():
         x0 = (o + tau[hid, None] * d[hid])
         xg = x0.detach().requires_grad_(True)
@@ -74,5 +85,7 @@ def trace(params: O.DecoderParams, latent_unit, K, width, height, pose, max_step
         n_cam = (G / G.norm(dim=1, keepdim=True)) @ pose[:3, :3].detach().t()
         nmap = nmap.index_put((torch.arange(3)[:, None], hid[None, :]), ((n_cam + 1) / 2).t())
         mask = mask.index_put((hid,), torch.ones(hid.numel(), dtype=K.dtype))
+        slope = slope.index_put((hid,), denom.abs())
     return {"depth": depth.view(1, height, width), "nocs": nocs.view(3, height, width),
-            "normals": nmap.view(3, height, width), "mask": mask.view(1, height, width), "hits": hid}
+            "normals": nmap.view(3, height, width), "mask": mask.view(1, height, width), "hits": hid,
+            "slope": slope.view(1, height, width)}

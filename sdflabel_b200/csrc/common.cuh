@@ -223,6 +223,8 @@ int launch_disc_background(const SplatView* views_dev, int batch, int max_pixels
 // ---------------------------------------------------------------------------
 // MLP launchers (mlp_ffma.cu / mlp_tc.cu)
 // ---------------------------------------------------------------------------
+struct RayMarch;   // trace.cuh
+
 struct MlpInputs {
   const float* inputs;        // explicit [n, L+3] or null
   const float* latent_unit;   // [batch, L] for lattice mode
@@ -235,6 +237,9 @@ struct MlpInputs {
   // tensor-core kernel: ReLU sign scratch of this launch (null = the decoder's own).  Launches that may run
   // concurrently on different streams (two engines on one decoder) must not share it.
   unsigned long long* mask_scratch = nullptr;
+  // lattice-pass kernel only: march mode (trace.cuh).  The rows are the rays of march->list (count_dev = march->count),
+  // and instead of writing sdf the epilogue advances every ray and sorts it into the next / near lists.
+  const RayMarch* march = nullptr;
 };
 
 __device__ __forceinline__ long long mlp_rows(const MlpInputs& in) {
@@ -247,6 +252,7 @@ int launch_mlp_ffma(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, fl
 int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, float* dinput, cudaStream_t s);
 // forward only, fp16 operand precision (hi halves only): the band pre-selection pass of the fused engine
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s);
+bool mlp_tc_march_ok(const sdfr_decoder* dec);   // the lattice-pass kernel can run trace mode's fused march for this decoder
 size_t mlp_tc_mask_scratch_bytes(const sdfr_decoder* dec);
 int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host);
 void free_tc_tables(sdfr_decoder* dec);

@@ -35,6 +35,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "trace.cuh"
 
 namespace sdfr {
 
@@ -1158,6 +1159,8 @@ __global__ void __launch_bounds__(P_THREADS, 1)
 mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* __restrict__ tiles, MlpInputs in,
                           float* __restrict__ sdf_out) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  // march mode: clear the counter the step after the next appends to (nobody touches it during this launch)
+  if (in.march && blockIdx.x == 0 && threadIdx.x == 0 && in.march->reset_count) *in.march->reset_count = 0;
   if (in.count_dev && *in.count_dev <= 0) return;     // uniform over the grid: before any cluster traffic
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
@@ -1333,7 +1336,9 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
         const int c = i / P_PTS, n = i - c * P_PTS;
         const long long gi = base + n;
         float v = 0.f;
-        if (gi < n_rows && c < in0) {
+        if (gi < n_rows && c < in0 && in.march) {
+          v = march_input(*in.march, gi, c);
+        } else if (gi < n_rows && c < in0) {
           const long long src = in.index ? (long long)in.index[gi] : gi;
           if (in.inputs) {
             v = in.inputs[src * in0 + c];
@@ -1383,7 +1388,8 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
             float y = __uint_as_float(v[0]) * Ps.inv_scale + __ldg(Ps.bias);
             if (use_tanh) y = tanhf(y);
             y = tanhf(y);
-            if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
+            if (in.march) march_advance(*in.march, base + pt_l < n_rows, base + pt_l, y);
+            else if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
           }
           tc_fence_before();
           continue;
@@ -1434,7 +1440,8 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
                       __ldg(T.pass[num_layers - 1].bias);
             if (use_tanh) y = tanhf(y);
             y = tanhf(y);
-            if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
+            if (in.march) march_advance(*in.march, base + pt_l < n_rows, base + pt_l, y);
+            else if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
           }
           continue;
         }
@@ -2303,21 +2310,19 @@ size_t mlp_tc_mask_scratch_bytes(const sdfr_decoder* dec) {
 // Forward only at fp16 operand precision (hi halves): the lattice pass of the fused engine.  CTA-pair kernel for
 // stock-like pass tables (every hidden pass an even number of 128-feature blocks, last Linear a single row);
 // the wide-tile kernel for every other table the tensor-core path accepts.
-int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s) {
-  SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED, "tcgen05 MLP kernel does not cover this decoder");
-  if (in.n <= 0) return SDFR_OK;
-  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
-  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
-  static int pair_init = 0, pair_slots = 0, pair_smem_max = 0;
-  if (!pair_init) {
-    pair_init = 1;
+static int g_pair_slots = -1, g_pair_smem_max = 0;
+
+// CTA pairs the lattice-pass kernel can keep resident, queried once (0: it cannot run here)
+static int coarse_pair_slots() {
+  if (g_pair_slots < 0) {
+    g_pair_slots = 0;
     // opt in to the device maximum once: the plan grows with the decoder's input width
     int devid = 0;
     PairPlan plan = make_pair_plan(3 + 3);              // the stock input width, for the occupancy query
     if (cudaGetDevice(&devid) == cudaSuccess &&
-        cudaDeviceGetAttribute(&pair_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) == cudaSuccess &&
-        (int)plan.total <= pair_smem_max &&
-        cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem_max) == cudaSuccess) {
+        cudaDeviceGetAttribute(&g_pair_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) == cudaSuccess &&
+        (int)plan.total <= g_pair_smem_max &&
+        cudaFuncSetAttribute(mlp_tc_coarse_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_pair_smem_max) == cudaSuccess) {
       cudaLaunchConfig_t q;
       memset(&q, 0, sizeof(q));
       q.gridDim = dim3((unsigned)(2 * 64));
@@ -2328,18 +2333,39 @@ int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sd
       qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_coarse_pair_kernel, &q) == cudaSuccess && nc >= 1) pair_slots = nc;
+      if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_coarse_pair_kernel, &q) == cudaSuccess && nc >= 1) g_pair_slots = nc;
     }
     cudaGetLastError();
   }
-  // per decoder: does this pass table fit the pair kernel?
-  bool pair_ok = pair_slots > 0 && (int)make_pair_plan(dec->dev.in0).total <= pair_smem_max;
-  for (int p = 0; pair_ok && p < st->table.num_layers; ++p) {
+  return g_pair_slots;
+}
+
+// per decoder: does its pass table fit the pair kernel (every hidden pass an even number of 128-feature blocks,
+// last Linear a single row)?
+static bool coarse_pair_ok(const sdfr_decoder* dec) {
+  if (!dec->tc.ok || !dec->tc_ptr) return false;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  bool ok = coarse_pair_slots() > 0 && (int)make_pair_plan(dec->dev.in0).total <= g_pair_smem_max;
+  for (int p = 0; ok && p < st->table.num_layers; ++p) {
     const TcPassDev& ps = st->table.pass[p];
     const bool last = ps.kind == 1;
-    if (last ? ps.m_blocks != 1 : (ps.m_blocks != 2 && ps.m_blocks != 4)) pair_ok = false;
-    if (ps.k_chunks != 1 && (ps.k_chunks & 1)) pair_ok = false;
+    if (last ? ps.m_blocks != 1 : (ps.m_blocks != 2 && ps.m_blocks != 4)) ok = false;
+    if (ps.k_chunks != 1 && (ps.k_chunks & 1)) ok = false;
   }
+  return ok;
+}
+
+// march mode of trace.cu lives in the pair kernel only
+bool mlp_tc_march_ok(const sdfr_decoder* dec) { return coarse_pair_ok(dec); }
+
+int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s) {
+  SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED, "tcgen05 MLP kernel does not cover this decoder");
+  if (in.n <= 0) return SDFR_OK;
+  const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);
+  const int sms = dec->sm_count > 0 ? dec->sm_count : 148;
+  const bool pair_ok = coarse_pair_ok(dec);
+  const int pair_slots = coarse_pair_slots();
+  SDFR_REQUIRE(pair_ok || !in.march, SDFR_E_UNSUPPORTED, "march mode needs the CTA-pair lattice kernel");
   if (pair_ok) {
     const long long pair_tiles = (in.n + 2 * P_PTS - 1) / (2 * P_PTS);
     cudaLaunchConfig_t cfg;

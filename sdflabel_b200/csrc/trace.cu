@@ -2,16 +2,24 @@
 // north_star describes; the reference itself only has the surfel splat).
 //
 // Not a replacement of a reference function - a new renderer behind the same decoder, validated
-// against its own torch restatement (oracle/trace_oracle.py) and, loosely, against splat mode.
+// against its own torch restatement (oracle/trace_oracle.py), a closed-form field and, loosely, splat mode.
 //
-// Structure: rays are "points" for the decoder kernels.  One march step = three launches with no
-// host synchronisation: trace_points (positions of the active rays -> decoder inputs), the decoder
-// forward over `count` rows read from device memory (tcgen05 kernel for the stock spec), and
-// trace_advance (tau += sdf, convergence / exit tests, warp-aggregated compaction of the surviving
-// rays into the next list).  A final decoder pass with the input gradient on the hit rays gives the
-// normals and d sdf / d latent; the backward is implicit differentiation of f(l, o + tau d) = 0 at the
-// hit: no storage of the march, one gradient evaluation per hit ray.
-#include "common.cuh"
+// Rays are "points" for the decoder kernels.  Two forms of the march, no host synchronisation in either:
+//
+//  * fused (tensor-core decoder with a CTA-pair pass table): ONE kernel per march step - the lattice-pass kernel
+//    (mlp_tc.cu, fp16 operands, 0.74 of the tensor roofline) in march mode generates its rows from the active rays
+//    (o + tau d), and its epilogue advances every ray (tau += sdf), drops it when it leaves the box, or - once
+//    |sdf| < near_thr - hands it to the `near` list (warp-ballot compaction, one atomic per warp and list).  Far from
+//    the surface the 3e-4 error of that pass only perturbs the step length.  The near rays are then finished at full
+//    precision by Newton steps along the ray, tau -= sdf / (grad sdf . d), using the accurate forward + input-gradient
+//    kernel whose last evaluation also yields the normals and d sdf / d latent: a hit is a root with |sdf| < eps.
+//  * stepwise (any decoder, SDFR_MLP_FFMA): three launches per step at full precision - trace_points, the decoder
+//    forward over `count` rows, trace_advance - and one gradient-carrying evaluation at the hits.
+//
+// The backward is implicit differentiation of f(l, o + tau d) = 0 at the hit: no storage
+// of the march, one gradient evaluation per hit ray.
+#include "trace.cuh"
+
 
 namespace sdfr {
 
@@ -21,45 +29,14 @@ struct TraceWs {
   float* tau;        // [P] current ray parameter (distance along the unit ray, camera units)
   float* tau_exit;   // [P]
   int* list[2];      // [P] active ray ids (ping-pong)
-  int* hits;         // [P] hit ray ids
-  int* counters;     // [4] active count (2, ping-pong), hit count, unused
+  int* hits;         // [P] rows of the final evaluation: the hit rays (stepwise) / the near rays (fused)
+  int* counters;     // [8] march counters (3, rotating), rows of the final evaluation [3], hits [4]
+  unsigned char* hit_flag;   // [P] per row of the final evaluation: 1 = hit
   float* inputs;     // [P, in0] decoder inputs of the rows being evaluated
   float* sdf;        // [P]
-  float* dinput;     // [P, in0] for the hit rows
+  float* dinput;     // [P, in0] for the rows of the final evaluation
+  RayMarch* march;   // [6] per-step descriptors of the fused march
 };
-
-struct TraceParams {
-  int width, height, in0, latent;
-  float kinv[9];
-  float R[9], t[3];       // camera pose: v_cam = R x_obj + t (R orthogonal)
-  float eps;
-  float lo, hi;           // lattice box [-1, hi]^3 the prior was trained on
-};
-
-__device__ __forceinline__ void ray_of_pixel(const TraceParams& p, int j, float (&o)[3], float (&d)[3], float (&rn)[3]) {
-  const int y = j / p.width, x = j - y * p.width;
-  const float fx = (float)x, fy = (float)y;
-  float r[3] = {p.kinv[0] * fx + p.kinv[1] * fy + p.kinv[2], p.kinv[3] * fx + p.kinv[4] * fy + p.kinv[5],
-                p.kinv[6] * fx + p.kinv[7] * fy + p.kinv[8]};
-  const float inv = rsqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-  for (int a = 0; a < 3; ++a) rn[a] = r[a] * inv;
-  for (int a = 0; a < 3; ++a) {
-    // x_obj = R^T (v_cam - t)
-    o[a] = -(p.R[0 * 3 + a] * p.t[0] + p.R[1 * 3 + a] * p.t[1] + p.R[2 * 3 + a] * p.t[2]);
-    d[a] = p.R[0 * 3 + a] * rn[0] + p.R[1 * 3 + a] * rn[1] + p.R[2 * 3 + a] * rn[2];
-  }
-}
-
-// warp-aggregated append: one atomic per warp
-__device__ __forceinline__ void append(bool pred, int value, int* list, int* counter) {
-  const unsigned ballot = __ballot_sync(0xffffffffu, pred);
-  if (!ballot) return;
-  const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == (__ffs(ballot) - 1)) base = atomicAdd(counter, __popc(ballot));
-  base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-  if (pred) list[base + __popc(ballot & ((1u << lane) - 1u))] = value;
-}
 
 __global__ void __launch_bounds__(256) trace_init_kernel(TraceParams p, TraceWs w) {
   const int P = p.width * p.height;
@@ -84,7 +61,7 @@ __global__ void __launch_bounds__(256) trace_init_kernel(TraceParams p, TraceWs 
     w.tau[j] = t0;
     w.tau_exit[j] = t1;
   }
-  append(active, j, w.list[0], w.counters + 0);
+  ray_append(active, j, w.list[0], w.counters + 0);
 }
 
 // decoder inputs [latent_unit, o + tau d] for the rows of `list` (also resets the next list's counter)
@@ -122,17 +99,47 @@ __global__ void __launch_bounds__(256) trace_advance_kernel(TraceParams p, Trace
       keep = tau <= w.tau_exit[j] && tau >= 0.f && !last_step;
     }
   }
-  append(keep, j, next_list, next_count);
-  append(hit, j, w.hits, w.counters + 2);
+  ray_append(keep, j, next_list, next_count);
+  ray_append(hit, j, w.hits, w.counters + 3);
+}
+
+// Newton step of the near rays along their ray, from the accurate evaluation (sdf, grad sdf) at o + tau d;
+// the LAST evaluation classifies: a hit is a root with |sdf| < eps inside the box.
+__global__ void __launch_bounds__(256) trace_newton_kernel(TraceParams p, TraceWs w, float max_step, int last) {
+  const int n = w.counters[3];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false;
+  if (i < n) {
+    const int j = w.hits[i];
+    const float f = w.sdf[i];
+    const float tau = w.tau[j];
+    if (last) {
+      hit = fabsf(f) < p.eps && tau >= 0.f && tau <= w.tau_exit[j];
+      w.hit_flag[i] = hit ? 1 : 0;
+    } else if (fabsf(f) >= 0.25f * p.eps) {     // already well inside the stopping band: stay
+      float o[3], d[3], rn[3];
+      ray_of_pixel(p, j, o, d, rn);
+      const float* G = w.dinput + (size_t)i * p.in0 + p.latent;
+      const float Gd = G[0] * d[0] + G[1] * d[1] + G[2] * d[2];
+      // f(tau + s) ~ f + s (G . d); a ray that runs (nearly) along the level set falls back to the sphere-tracing step
+      float step = fabsf(Gd) > 1e-3f ? -f / Gd : f;
+      step = fminf(fmaxf(step, -max_step), max_step);
+      if (step == step) w.tau[j] = tau + step;
+    }
+  }
+  if (last) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(w.counters + 4, __popc(ballot));
+  }
 }
 
 // maps of the hit rays from the gradient-carrying evaluation at the hit points
 __global__ void __launch_bounds__(256) trace_finalize_kernel(TraceParams p, TraceWs w, float* __restrict__ depth,
                                                              float* __restrict__ nmap, float* __restrict__ nocs,
                                                              float* __restrict__ mask) {
-  const int n = w.counters[2];
+  const int n = w.counters[3];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= n || !w.hit_flag[i]) return;
   const int P = p.width * p.height;
   const int j = w.hits[i];
   float o[3], d[3], rn[3];
@@ -160,14 +167,15 @@ __global__ void __launch_bounds__(256) trace_backward_kernel(TraceParams p, Trac
                                                              const float* __restrict__ g_nocs, float* __restrict__ d_pose,
                                                              float* __restrict__ d_latent) {
   __shared__ float s_red[8];
-  const int n = w.counters[2];
+  const int n = w.counters[3];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int P = p.width * p.height;
+  const bool live = i < n && w.hit_flag[i];
   float acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.f;
   float lam = 0.f;
-  if (i < n) {
+  if (live) {
     const int j = w.hits[i];
     float o[3], d[3], rn[3];
     ray_of_pixel(p, j, o, d, rn);
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(256) trace_backward_kernel(TraceParams p, Trac
   for (int k = 0; k < 12 + p.latent; ++k) {
     float v;
     if (k < 12) v = acc[k];
-    else v = i < n ? -lam * w.dinput[(size_t)i * p.in0 + (k - 12)] : 0.f;
+    else v = live ? -lam * w.dinput[(size_t)i * p.in0 + (k - 12)] : 0.f;
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o2);
     __syncthreads();
@@ -211,11 +219,13 @@ TraceWs carve(void* ws, int64_t P, int in0) {
   char* p = reinterpret_cast<char*>(ws);
   auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
   w.counters = reinterpret_cast<int*>(take(64));
+  w.march = reinterpret_cast<RayMarch*>(take(6 * sizeof(RayMarch)));
   w.tau = reinterpret_cast<float*>(take((size_t)P * 4));
   w.tau_exit = reinterpret_cast<float*>(take((size_t)P * 4));
   w.list[0] = reinterpret_cast<int*>(take((size_t)P * 4));
   w.list[1] = reinterpret_cast<int*>(take((size_t)P * 4));
   w.hits = reinterpret_cast<int*>(take((size_t)P * 4));
+  w.hit_flag = reinterpret_cast<unsigned char*>(take((size_t)P));
   w.inputs = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
   w.sdf = reinterpret_cast<float*>(take((size_t)P * 4));
   w.dinput = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
@@ -224,7 +234,7 @@ TraceWs carve(void* ws, int64_t P, int in0) {
 
 size_t ws_bytes(int64_t P, int in0) {
   auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  return r(64) + 6 * r((size_t)P * 4) + 2 * r((size_t)P * in0 * 4);
+  return r(64) + r(6 * sizeof(RayMarch)) + 6 * r((size_t)P * 4) + r((size_t)P) + 2 * r((size_t)P * in0 * 4);
 }
 
 int fill_params(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec, const float* pose_host, float eps, TraceParams* tp) {
@@ -276,26 +286,63 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
   in.inputs = w.inputs; in.latent_unit = nullptr; in.lattice = make_lattice(2); in.points_per_batch = 1; in.n = P;
   in.index = nullptr; in.small_tiles = 0;
   int rc;
-  for (int step = 0; step < max_steps; ++step) {
-    const int cur = step & 1, nxt = cur ^ 1;
-    trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.list[cur], w.counters + cur, w.counters + nxt);
+  const bool fused = impl == SDFR_MLP_TCGEN05 && mlp_tc_march_ok(dec);
+  if (fused) {
+    // ---- fused march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
+    // The lattice pass is good to ~3e-4 (its error near the surface is what the refine engine measures and bounds by
+    // 2.5e-3), so rays are handed to the full-precision finish well before that matters.
+    const float near_thr = 5e-3f;
+    RayMarch desc[6];
+    for (int k = 0; k < 6; ++k) {
+      RayMarch& m = desc[k];
+      m.p = tp; m.near_thr = near_thr; m.latent_unit = latent_unit_dev; m.tau = w.tau; m.tau_exit = w.tau_exit;
+      m.list = w.list[k & 1]; m.count = w.counters + (k % 3);
+      m.next_list = w.list[(k + 1) & 1]; m.next_count = w.counters + ((k + 1) % 3);
+      m.near_list = w.hits; m.near_count = w.counters + 3;
+      m.reset_count = w.counters + ((k + 2) % 3);
+    }
+    SDFR_CUDA(cudaMemcpyAsync(w.march, desc, sizeof(desc), cudaMemcpyHostToDevice, s));
+    MlpInputs im = in;
+    im.inputs = nullptr;
+    for (int step = 0; step < max_steps; ++step) {
+      im.march = w.march + (step % 6);
+      im.count_dev = w.counters + (step % 3);
+      if ((rc = launch_mlp_tc_coarse(dec, im, nullptr, s))) return rc;
+    }
+    // ---- finish at full precision: Newton steps along the ray, the last evaluation classifies and feeds the maps ----
+    const int newton = 3;
+    in.count_dev = w.counters + 3;
+    for (int it = 0; it <= newton; ++it) {
+      trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, w.counters + 3, nullptr);
+      SDFR_LAUNCH_CHECK();
+      if ((rc = launch_mlp_tc(dec, in, w.sdf, w.dinput, s))) return rc;
+      trace_newton_kernel<<<blocks, 256, 0, s>>>(tp, w, 4.f * near_thr, it == newton);
+      SDFR_LAUNCH_CHECK();
+    }
+  } else {
+    for (int step = 0; step < max_steps; ++step) {
+      const int cur = step & 1, nxt = cur ^ 1;
+      trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.list[cur], w.counters + cur, w.counters + nxt);
+      SDFR_LAUNCH_CHECK();
+      in.count_dev = w.counters + cur;
+      rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(dec, in, w.sdf, nullptr, s) : launch_mlp_ffma(dec, in, w.sdf, nullptr, s);
+      if (rc) return rc;
+      trace_advance_kernel<<<blocks, 256, 0, s>>>(tp, w, w.list[cur], w.counters + cur, w.list[nxt], w.counters + nxt,
+                                                 step == max_steps - 1);
+      SDFR_LAUNCH_CHECK();
+    }
+    // gradient-carrying evaluation at the hit points: every listed ray is a hit
+    SDFR_CUDA(cudaMemsetAsync(w.hit_flag, 1, (size_t)P, s));
+    SDFR_CUDA(cudaMemcpyAsync(w.counters + 4, w.counters + 3, 4, cudaMemcpyDeviceToDevice, s));
+    trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, w.counters + 3, nullptr);
     SDFR_LAUNCH_CHECK();
-    in.count_dev = w.counters + cur;
-    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(dec, in, w.sdf, nullptr, s) : launch_mlp_ffma(dec, in, w.sdf, nullptr, s);
+    in.count_dev = w.counters + 3;
+    rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(dec, in, w.sdf, w.dinput, s) : launch_mlp_ffma(dec, in, w.sdf, w.dinput, s);
     if (rc) return rc;
-    trace_advance_kernel<<<blocks, 256, 0, s>>>(tp, w, w.list[cur], w.counters + cur, w.list[nxt], w.counters + nxt,
-                                               step == max_steps - 1);
-    SDFR_LAUNCH_CHECK();
   }
-  // gradient-carrying evaluation at the hit points
-  trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, w.counters + 2, nullptr);
-  SDFR_LAUNCH_CHECK();
-  in.count_dev = w.counters + 2;
-  rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(dec, in, w.sdf, w.dinput, s) : launch_mlp_ffma(dec, in, w.sdf, w.dinput, s);
-  if (rc) return rc;
   trace_finalize_kernel<<<blocks, 256, 0, s>>>(tp, w, depth_dev, nmap_dev, nocs_dev, mask_dev);
   SDFR_LAUNCH_CHECK();
-  if (hit_count_dev) SDFR_CUDA(cudaMemcpyAsync(hit_count_dev, w.counters + 2, 4, cudaMemcpyDeviceToDevice, s));
+  if (hit_count_dev) SDFR_CUDA(cudaMemcpyAsync(hit_count_dev, w.counters + 4, 4, cudaMemcpyDeviceToDevice, s));
   return SDFR_OK;
 }
 

@@ -40,16 +40,42 @@ def test_trace_maps_and_gradients_vs_oracle(stock_prior_path, size):
     r = tracer(dec, lat_g, pose_g, normalize_latent=False)
     both = (r["mask"][0].cpu() > 0.5) & (ro["mask"][0] > 0.5)
     either = (r["mask"][0].cpu() > 0.5) | (ro["mask"][0] > 0.5)
-    assert both.sum() >= 0.995 * either.sum(), (int(both.sum()), int(either.sum()))   # hit sets agree up to borderline rays
-    d_err = (r["depth"][0].cpu() - ro["depth"][0].detach())[both].abs().max()
-    assert d_err < 1e-4 * 5.0, d_err
-    c_err = (r["color"].cpu() - ro["nocs"].detach())[:, both].abs().max()
-    assert c_err < 1e-4, c_err
-    n_err = (r["normals"].cpu() - ro["normals"].detach())[:, both].abs()
-    assert (n_err > 1e-3).float().mean() < 2e-3, float(n_err.max())
-    # gradients: restrict the cotangents to the common hit set so borderline rays do not enter
+    # hit sets agree up to borderline rays: a grazing ray that plain sphere tracing abandons after max_steps may still be
+    # resolved by the full-precision finish of the fused march (and the other way round); every such pixel must lie
+    # on the silhouette (a 4-neighbour of a miss)
+    diff = either & ~both
+    assert diff.sum() <= max(4, 0.01 * either.sum()), (int(both.sum()), int(either.sum()))
+    miss = torch.nn.functional.pad(~(ro["mask"][0] > 0.5), (1, 1, 1, 1), value=True)
+    edge = miss[:-2, 1:-1] | miss[2:, 1:-1] | miss[1:-1, :-2] | miss[1:-1, 2:] | miss[1:-1, 1:-1]
+    assert bool(edge[diff].all())
+    # the ray parameter of a hit is defined up to the stopping band |f| < eps, i.e. eps / |grad f . d| in tau
+    # (oracle/trace_oracle.py); the fused march polishes the root, the oracle stops at the band's outer edge
+    band = 1.5 * 1e-4 / ro["slope"][0].detach().clamp(min=1e-3) + 2e-5
+    d_err = (r["depth"][0].cpu() - ro["depth"][0].detach()).abs()
+    assert bool((d_err[both] <= band[both]).all()), float((d_err / band)[both].max())
+    c_err = (r["color"].cpu() - ro["nocs"].detach()).abs().max(dim=0)[0]
+    assert bool((c_err[both] <= 0.5 * band[both] + 1e-6).all()), float((c_err / band)[both].max())
+    assert float(d_err[both].median()) < 3e-4 and float(c_err[both].median()) < 1.5e-4     # the oracle stops at the band's edge
+    # our hits are roots by the specification's own measure: |f| < eps at OUR points, evaluated by the oracle decoder;
+    # and the normals are the oracle's gradient at those points (the field is piecewise linear with pieces far
+    # smaller than the stopping band, so normals are only comparable at the same point)
+    o_, d_, rn_ = T.rays(K, size, size, pose0)
+    idx = both.reshape(-1).nonzero().squeeze(1)
+    tau_ours = r["depth"][0].detach().cpu().reshape(-1)[idx] / rn_[idx, 2]
+    xg = (o_ + tau_ours[:, None] * d_[idx]).requires_grad_(True)
+    f_at = O.decoder_forward(prior, torch.cat([lat_o.detach().expand(idx.numel(), -1), xg], 1)).squeeze(1)
+    assert float(f_at.abs().max()) < 1e-4 + 2e-5, float(f_at.abs().max())
+    (G_at,) = torch.autograd.grad(f_at.sum(), xg)
+    n_want = ((G_at / G_at.norm(dim=1, keepdim=True)) @ pose0[:3, :3].t() + 1) / 2
+    n_err = (r["normals"].cpu().reshape(3, -1)[:, idx].t() - n_want).abs()
+    assert (n_err > 1e-3).float().mean() < 5e-3, float(n_err.max())
+    # gradients: the specification's implicit derivative evaluated at OUR hit points (same reason as the normals), with
+    # the cotangents restricted to the common hit set so that borderline rays do not enter
     w = both.float()
-    lo2 = (ro["depth"] * cd * w).sum() + (ro["nocs"] * cn * w).sum()
+    tau_all = torch.zeros(size * size)
+    tau_all[idx] = tau_ours
+    ro2 = T.render_hits(prior, lat_o, K, size, size, pose_o, tau_all, idx)
+    lo2 = (ro2["depth"] * cd * w).sum() + (ro2["nocs"] * cn * w).sum()
     g_lat_o, g_pose_o = torch.autograd.grad(lo2, [lat_o, pose_o])
     lg = (r["depth"] * (cd * w).to(cuda)).sum() + (r["color"] * (cn * w).to(cuda)).sum()
     g_lat, g_pose = torch.autograd.grad(lg, [lat_g, pose_g])
