@@ -1573,9 +1573,13 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
 // ---------------------------------------------------------------------------------------------
 constexpr int Q_THREADS = 320;
 constexpr int Q_NEPI = 256;
-constexpr int Q_STAGE_TILES = 2;                       // k-chunks (32 k) per ring stage
-constexpr int Q_STAGE_BYTES = Q_STAGE_TILES * TILE_BYTES;
-template <int NP> struct BandRing { static constexpr int value = NP <= 16 ? 5 : 3; };
+// NP = points per CTA.  16: short row lists; the B operand is laid out [zeros | hi | lo] and a K step is TWO MMAs
+// (N = 4 NP).  64: long row lists (many detections per launch); the [hi | lo] layout without the zero groups is what
+// fits next to the ring, and a K step is THREE MMAs of N = 2 NP = 128 (W_hi x H_hi -> hh; W_hi x H_lo, W_lo x H_hi -> cross).
+// Either way every output sees the same two accumulation chains, in the same order, as in mlp_tc_kernel.
+template <int NP> struct BandPad { static constexpr bool value = NP <= 32; };
+template <int NP> struct BandStageTiles { static constexpr int value = NP <= 32 ? 2 : 1; };   // k-chunks (32 k) per ring stage
+template <int NP> struct BandRing { static constexpr int value = NP <= 16 ? 5 : (NP <= 32 ? 3 : 5); };
 
 struct BandPairPlan {
   uint32_t stages, b, inp, dinp, g, bars, tmem_slot, total;
@@ -1584,8 +1588,8 @@ template <int NP>
 __host__ __device__ inline BandPairPlan make_band_pair_plan(int in0) {
   BandPairPlan p;
   uint32_t o = 0;
-  p.stages = o; o += BandRing<NP>::value * Q_STAGE_BYTES;
-  p.b = o; o += 64 * (3 * NP * 16);                    // 64 8-k chunks x [zeros | hi | lo] point groups
+  p.stages = o; o += BandRing<NP>::value * BandStageTiles<NP>::value * TILE_BYTES;
+  p.b = o; o += 64 * ((BandPad<NP>::value ? 3 : 2) * NP * 16);   // 64 8-k chunks x [zeros |] hi | lo point groups
   const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
   p.inp = o; o += in_pad * 2 * NP * 4;                 // inputs of the whole pair tile
   p.dinp = o; o += 2 * in_pad * 2 * NP * 4;            // input-gradient partials, double-buffered by tile parity
@@ -1645,15 +1649,20 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
   constexpr int NSTAGE = BandRing<NP>::value;
+  constexpr int Q_STAGE_TILES = BandStageTiles<NP>::value;
+  constexpr int Q_STAGE_BYTES = Q_STAGE_TILES * TILE_BYTES;
+  constexpr bool kPad = BandPad<NP>::value;
   constexpr int NPP = 2 * NP;                          // points of the pair tile
-  constexpr int BCH = 3 * NP * 16;                     // bytes per 8-k chunk of B: zeros, hi, lo point groups
-  constexpr int HI = NP * 16, LO = NP * 16;            // hi region inside a chunk; lo region relative to hi
+  constexpr int BCH = (kPad ? 3 : 2) * NP * 16;        // bytes per 8-k chunk of B: [zeros,] hi, lo point groups
+  constexpr int HI = kPad ? NP * 16 : 0, LO = NP * 16; // hi region inside a chunk; lo region relative to hi
   constexpr int GW = 16;                               // points per TMEM load group
   constexpr int G = NP / GW;
   constexpr int PG = GW / 8;
   constexpr int TCOLS = 8 * NP;                        // two 256-feature blocks x 4 NP columns
-  constexpr uint32_t kId = idesc_band_pair(4 * NP);
-  static_assert(NP == 16 || NP == 32, "pair tiles of 2 x 16 or 2 x 32 points");
+  // columns of a block: padded [hh(0) | cross(0) | hh(1) | cross(1)], split [hh(0) | hh(1) | cross(0) | cross(1)]
+  constexpr int COL_PH = kPad ? 2 * NP : NP, COL_CROSS = kPad ? NP : 2 * NP;
+  constexpr uint32_t kId = idesc_band_pair(kPad ? 4 * NP : 2 * NP);
+  static_assert(NP == 16 || NP == 32 || NP == 64, "pair tiles of 2 x 16, 2 x 32 or 2 x 64 points");
   const BandPairPlan P = make_band_pair_plan<NP>(in0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -1684,10 +1693,11 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
     mbar_init(bar_x, Q_NEPI / 32);                     // the peer's epilogue warps: "my input-gradient partials are final"
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // the zero point groups of every chunk are written once and never again
-  for (int i = tid; i < 64 * (HI / 16); i += Q_THREADS)
-    *reinterpret_cast<uint4*>(bop + (i / (HI / 16)) * BCH + (i % (HI / 16)) * 16) = make_uint4(0u, 0u, 0u, 0u);
-  fence_async_smem();
+  if (kPad) {   // the zero point groups of every chunk are written once and never again
+    for (int i = tid; i < 64 * NP; i += Q_THREADS)
+      *reinterpret_cast<uint4*>(bop + (i / NP) * BCH + (i % NP) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
+  }
   if (warp == 9) tmem_alloc_pair(smem_u32(smem + P.tmem_slot), TCOLS);
   tc_fence_before();
   __syncthreads();
@@ -1751,8 +1761,12 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
     uint32_t stage = 0, phase = 0, act_phase = 0;
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t desc_a_base = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);
-    const uint64_t desc_b_main = make_desc(smem_u32(bop) + HI, BCH, B_SBO);     // N-rows of a CTA: [hi ; lo]
-    const uint64_t desc_b_cross = make_desc(smem_u32(bop), BCH, B_SBO);         //                  [0 ; hi]
+    // padded layout: N-rows of a CTA [hi ; lo] (main) and [0 ; hi] (cross); split layout: hi and lo separately
+    const uint64_t desc_b_main = make_desc(smem_u32(bop) + HI, BCH, B_SBO);
+    const uint64_t desc_b_cross = make_desc(smem_u32(bop), BCH, B_SBO);
+    const uint64_t desc_b_lo = make_desc(smem_u32(bop) + HI + LO, BCH, B_SBO);
+    constexpr int GRP = 1;                               // ring stages per issuer iteration (2 was measured slower: the
+                                                         // issuer then waits for the later stage before starting the earlier)
     for (long long it = 0; it < my_tiles; ++it) {
       for (int p = 0; p < npass; ++p) {
         const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
@@ -1762,30 +1776,52 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
         tc_fence_after();
         for (int j = 0; j < nblocks; ++j) {
           const uint32_t d = tm + (uint32_t)(j * 4 * NP);
-          for (int kc = 0; kc < k_chunks; kc += Q_STAGE_TILES) {
-            const int cnt = min(Q_STAGE_TILES, k_chunks - kc);
-            mbar_wait(bar_full + 8 * stage, phase);
-            mbar_wait(bar_peer + 8 * stage, phase);
+          for (int kc = 0; kc < k_chunks; kc += Q_STAGE_TILES * GRP) {
+            uint32_t st[GRP];
+            int nst = 0;
+#pragma unroll
+            for (int g = 0; g < GRP; ++g) {
+              if (kc + g * Q_STAGE_TILES < k_chunks) {
+                st[g] = stage;
+                mbar_wait(bar_full + 8 * stage, phase);
+                mbar_wait(bar_peer + 8 * stage, phase);
+                if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+                nst = g + 1;
+              }
+            }
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int i = 0; i < Q_STAGE_TILES; ++i) {
-                if (i < cnt) {
-                  const uint64_t da_hi = desc_a_base + (uint64_t)((stage * Q_STAGE_BYTES + i * TILE_BYTES) >> 4);
-                  const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
-                  const uint64_t koff = (uint64_t)(((kc + i) * (KC / 8) * BCH) >> 4);
+              for (int g = 0; g < GRP; ++g) {
+                if (g < nst) {
+                  const int kc0 = kc + g * Q_STAGE_TILES;
+                  const int cnt = min(Q_STAGE_TILES, k_chunks - kc0);
 #pragma unroll
-                  for (int t = 0; t < KC / 16; ++t) {
-                    const uint64_t ka = (uint64_t)((t * 2 * A_LBO) >> 4), kb = koff + (uint64_t)((t * 2 * BCH) >> 4);
-                    umma_f16_pair(d, da_hi + ka, desc_b_main + kb, kId, (kc | i | t) ? 1u : 0u);   // W_hi x [H_hi ; H_lo]
-                    umma_f16_pair(d, da_lo + ka, desc_b_cross + kb, kId, 1u);                     // W_lo x [0 ; H_hi]
+                  for (int i = 0; i < Q_STAGE_TILES; ++i) {
+                    if (i < cnt) {
+                      const uint64_t da_hi = desc_a_base + (uint64_t)((st[g] * Q_STAGE_BYTES + i * TILE_BYTES) >> 4);
+                      const uint64_t da_lo = da_hi + (uint64_t)(TILE_HALF_BYTES >> 4);
+                      const uint64_t koff = (uint64_t)(((kc0 + i) * (KC / 8) * BCH) >> 4);
+#pragma unroll
+                      for (int t = 0; t < KC / 16; ++t) {
+                        const uint64_t ka = (uint64_t)((t * 2 * A_LBO) >> 4), kb = koff + (uint64_t)((t * 2 * BCH) >> 4);
+                        const uint32_t acc = (kc0 | i | t) ? 1u : 0u;
+                        if (kPad) {
+                          umma_f16_pair(d, da_hi + ka, desc_b_main + kb, kId, acc);                   // W_hi x [H_hi ; H_lo]
+                          umma_f16_pair(d, da_lo + ka, desc_b_cross + kb, kId, 1u);                   // W_lo x [0 ; H_hi]
+                        } else {
+                          umma_f16_pair(d, da_hi + ka, desc_b_main + kb, kId, acc);                   // W_hi x H_hi -> hh
+                          umma_f16_pair(d + COL_CROSS, da_hi + ka, desc_b_lo + kb, kId, acc);         // W_hi x H_lo -> cross
+                          umma_f16_pair(d + COL_CROSS, da_lo + ka, desc_b_main + kb, kId, 1u);        // W_lo x H_hi -> cross
+                        }
+                      }
+                    }
                   }
+                  umma_commit_pair(bar_empty + 8 * st[g], (uint16_t)3);   // the stage is free in both CTAs
                 }
               }
-              umma_commit_pair(bar_empty + 8 * stage, (uint16_t)3);   // the stage is free in both CTAs
             }
             __syncwarp();
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
           }
         }
         if (elect_one()) umma_commit_pair(bar_acc, (uint16_t)3);      // the accumulators of the pass are complete
@@ -1802,7 +1838,10 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
     const uint32_t b_dst = mapa_u32(smem_u32(bop), (uint32_t)ph) + HI;      // hi region of the owner's B operand
     const uint32_t act_bar = mapa_u32(bar_act, 0u);
     const uint32_t peer_x = mapa_u32(bar_x, rank ^ 1u);
-    uint32_t* masks32 = reinterpret_cast<uint32_t*>(masks);   // [layer][feature][point half]
+    // ReLU sign words: [layer][feature of this CTA (block j, lane t)][point half], one u64 each
+    auto mask_at = [&](const int layer, const int j) -> unsigned long long& {
+      return masks[((size_t)layer * 256 + (size_t)(j * 128 + t)) * 2 + ph];
+    };
     uint32_t acc_phase = 0, x_phase = 0;
     float amax = 0.f;
     auto publish = [&]() {                             // this warp's operand rows (own and remote) are written, TMEM read
@@ -1865,8 +1904,8 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               uint32_t vm[GW], vc[GW];
-              tmem_ld16(lane_base + ph * 2 * NP + g * GW, vm);
-              tmem_ld16(lane_base + ph * 2 * NP + NP + g * GW, vc);
+              tmem_ld16(lane_base + ph * COL_PH + g * GW, vm);
+              tmem_ld16(lane_base + ph * COL_PH + COL_CROSS + g * GW, vc);
               tmem_ld_wait();
               if (lane == 0) {
 #pragma unroll
@@ -1891,13 +1930,13 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
             for (int j = 0; j < 2; ++j) {
               const int f = (2 * j + (int)rank) * 128 + t;
               const float w = f < hidden ? __ldg(T.last_w + f) * BWD_SCALE : 0.f;
-              const uint32_t mk = f < hidden ? masks32[((size_t)(num_layers - 2) * 512 + f) * 2 + ph] : 0u;
+              const unsigned long long mk = f < hidden ? mask_at(num_layers - 2, j) : 0ull;
               const uint32_t row = b_dst + (uint32_t)((f >> 3) * BCH + (f & 7) * 16);
 #pragma unroll
               for (int g = 0; g < NP / 8; ++g) {
                 float h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (g * 8 + e)) & 1u) ? w * gbuf[ph * NP + g * 8 + e] : 0.f;
+                for (int e = 0; e < 8; ++e) h[e] = ((mk >> (g * 8 + e)) & 1ull) ? w * gbuf[ph * NP + g * 8 + e] : 0.f;
                 amax = fmaxf(amax, pack8_store_cluster(row, LO, g, h));
               }
             }
@@ -1912,8 +1951,8 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
 #pragma unroll
             for (int g = 0; g < G; ++g) {
               uint32_t vm[GW], vc[GW];
-              tmem_ld16(lane_base + ph * 2 * NP + g * GW, vm);
-              tmem_ld16(lane_base + ph * 2 * NP + NP + g * GW, vc);
+              tmem_ld16(lane_base + ph * COL_PH + g * GW, vm);
+              tmem_ld16(lane_base + ph * COL_PH + COL_CROSS + g * GW, vc);
               tmem_ld_wait();
               if (f < in0) {
 #pragma unroll
@@ -1945,17 +1984,17 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
         for (int j = 0; j < nblocks; ++j) {
           const int f = (2 * j + (int)rank) * 128 + t;
           const int cls = f < split ? 0 : (f < split + Ps.cat_dim ? 1 : 2);
-          const uint32_t tb = lane_base + (uint32_t)(j * 4 * NP + ph * 2 * NP);
+          const uint32_t tb = lane_base + (uint32_t)(j * 4 * NP + ph * COL_PH);
           const uint32_t row = b_dst + (uint32_t)((f >> 3) * BCH + (f & 7) * 16);
           const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
-          const uint32_t pmask = (!fwd && cls == 0) ? masks32[((size_t)(Ps.layer - 1) * 512 + f) * 2 + ph] : 0u;
+          const unsigned long long pmask = (!fwd && cls == 0) ? mask_at(Ps.layer - 1, j) : 0ull;
           const int cat_row = (Ps.cat_off + f - split) * NPP + ph * NP;
-          uint32_t mk = 0u;
+          unsigned long long mk = 0ull;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             uint32_t vm[GW], vc[GW];
             tmem_ld16(tb + g * GW, vm);
-            tmem_ld16(tb + NP + g * GW, vc);
+            tmem_ld16(tb + COL_CROSS + g * GW, vc);
             tmem_ld_wait();
             float x[GW];
 #pragma unroll
@@ -1968,7 +2007,7 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
                 for (int qq = 0; qq < GW; ++qq) {
                   const float y = x[qq] + bias;
                   const bool on = y > 0.f;
-                  if (on) mk |= 1u << (g * GW + qq);
+                  if (on) mk |= 1ull << (g * GW + qq);
                   h[qq] = on ? y * Ps.out_scale : 0.f;
                 }
               } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
@@ -1981,7 +2020,7 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
             } else {
               if (cls == 0) {
 #pragma unroll
-                for (int qq = 0; qq < GW; ++qq) h[qq] = ((pmask >> (g * GW + qq)) & 1u) ? x[qq] * Ps.out_scale : 0.f;
+                for (int qq = 0; qq < GW; ++qq) h[qq] = ((pmask >> (g * GW + qq)) & 1ull) ? x[qq] * Ps.out_scale : 0.f;
               } else {
                 if (cls == 1) {                                    // gradient of the concatenated input columns
 #pragma unroll
@@ -1999,7 +2038,7 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
               amax = fmaxf(amax, pack8_store_cluster(row, LO, g * PG + pk, h8));
             }
           }
-          if (fwd && want_grad) masks32[((size_t)Ps.layer * 512 + f) * 2 + ph] = mk;   // only the backward reads them
+          if (fwd && want_grad) mask_at(Ps.layer, j) = mk;   // only the backward reads them
         }
         publish();
       }
@@ -2206,18 +2245,26 @@ int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s) {
   return SDFR_OK;
 }
 
-// CTA pairs the band-pair kernel can keep resident (0: the kernel cannot run here), queried once per tile width.
+// CTA pairs the band-pair kernel can keep resident (0: the kernel cannot run here), queried once per tile width and
+// input width (the shared-memory plan grows with the decoder's input).
 template <int NP>
 static int band_pair_slots(int in0) {
-  static int init = 0, slots = 0, smem_max = 0;
-  if (!init) {
-    init = 1;
-    int devid = 0;
-    const BandPairPlan plan = make_band_pair_plan<NP>(KC);   // the widest input the tensor-core path accepts
-    if (cudaGetDevice(&devid) == cudaSuccess &&
-        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) == cudaSuccess &&
-        (int)plan.total <= smem_max &&
-        cudaFuncSetAttribute(mlp_tc_band_pair_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.total) == cudaSuccess) {
+  static int cache[5] = {-1, -1, -1, -1, -1};
+  static int smem_max = -1;
+  if (in0 <= 0 || in0 > KC) return 0;
+  const int key = (in0 + 7) / 8;
+  if (cache[key] < 0) {
+    cache[key] = 0;
+    if (smem_max < 0) {
+      int devid = 0;
+      smem_max = 0;
+      if (cudaGetDevice(&devid) != cudaSuccess ||
+          cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, devid) != cudaSuccess ||
+          cudaFuncSetAttribute(mlp_tc_band_pair_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) != cudaSuccess)
+        smem_max = 0;
+    }
+    const BandPairPlan plan = make_band_pair_plan<NP>(in0);
+    if ((int)plan.total <= smem_max) {
       cudaLaunchConfig_t q;
       memset(&q, 0, sizeof(q));
       q.gridDim = dim3((unsigned)(2 * 64));
@@ -2228,11 +2275,11 @@ static int band_pair_slots(int in0) {
       qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.attrs = qa; q.numAttrs = 1;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_band_pair_kernel<NP>, &q) == cudaSuccess && nc >= 1) slots = nc;
+      if (cudaOccupancyMaxActiveClusters(&nc, mlp_tc_band_pair_kernel<NP>, &q) == cudaSuccess && nc >= 1) cache[key] = nc;
     }
     cudaGetLastError();
   }
-  return in0 <= KC ? slots : 0;
+  return cache[key];
 }
 
 // The band-pair kernel takes pass tables whose hidden passes are an even number of 128-feature blocks and whose
@@ -2240,7 +2287,7 @@ static int band_pair_slots(int in0) {
 static bool band_pair_ok(const sdfr_decoder* dec, const TcHostState* st, bool want_grad) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("SDFR_BAND_PAIR"); enabled = e ? atoi(e) : 1; }   // 0: A/B runs of the single-CTA kernel
-  if (!enabled || band_pair_slots<16>(dec->dev.in0) <= 0) return false;
+  if (!enabled) return false;
   const int npass = want_grad ? st->table.num_passes : st->table.num_layers;
   for (int p = 0; p < npass; ++p) {
     const TcPassDev& ps = st->table.pass[p];
@@ -2290,8 +2337,11 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
   // 64-point tile waits on the weight stream and loses 10 % by waiting for two stages of its 5-stage ring.
   const int group = np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
   unsigned long long* masks = in.mask_scratch ? in.mask_scratch : st->mask_dev;
-  if (small && band_pair_ok(dec, st, dinput != nullptr))
-    return launch_band_pair<16>(dec, st, in, sdf, dinput, masks, s);   // short row lists: 2 x 16 points per CTA pair
+  if (band_pair_ok(dec, st, dinput != nullptr)) {
+    // CTA pairs, M = 256 features per instruction: 2 x 16 points per pair for short row lists, 2 x 64 otherwise
+    if (small && band_pair_slots<16>(dec->dev.in0) > 0) return launch_band_pair<16>(dec, st, in, sdf, dinput, masks, s);
+    if (!small && band_pair_slots<64>(dec->dev.in0) > 0) return launch_band_pair<64>(dec, st, in, sdf, dinput, masks, s);
+  }
   if (small)
     mlp_tc_kernel<16><<<grid, NTHREADS, make_plan<16>(dec->dev.num_layers, dec->dev.in0).total, s>>>(
         st->table_dev, st->tiles_dev, in, sdf, dinput, st->overflow_dev, masks, point_tiles, group);
