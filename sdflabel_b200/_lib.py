@@ -111,6 +111,8 @@ _lib = None
 def load() -> C.CDLL:
     """Loads libsdfr.so (raises SdfrError when it has not been built)."""
     global _lib
+    if _lib is not None:
+        return _lib
     with _lock:
         if _lib is not None:
             return _lib
@@ -140,8 +142,13 @@ def require_cuda() -> None:
 
 
 def stream_ptr() -> int:
+    """cudaStream_t of torch's current stream on the current device.  The raw accessor is used when this torch has it
+    (0.3 us instead of the 5 - 15 us of building a torch.cuda.Stream object: the refine loop asks six times per call)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:
+        return torch.cuda.current_stream().cuda_stream
 
 
 def ptr(t) -> int:

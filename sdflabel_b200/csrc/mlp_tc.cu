@@ -1578,8 +1578,15 @@ constexpr int Q_NEPI = 256;
 // fits next to the ring, and a K step is THREE MMAs of N = 2 NP = 128 (W_hi x H_hi -> hh; W_hi x H_lo, W_lo x H_hi -> cross).
 // Either way every output sees the same two accumulation chains, in the same order, as in mlp_tc_kernel.
 template <int NP> struct BandPad { static constexpr bool value = NP <= 32; };
-template <int NP> struct BandStageTiles { static constexpr int value = NP <= 32 ? 2 : 1; };   // k-chunks (32 k) per ring stage
-template <int NP> struct BandRing { static constexpr int value = NP <= 16 ? 5 : (NP <= 32 ? 3 : 5); };
+// BandPipe double-buffers the B operand, so that the epilogue of a 256-feature block runs under the MMAs of the next
+// block / the next pass.  Implemented and bit-identical, but measured SLOWER for NP = 16 (115 us against 106 us):
+// the kernel is bound by the L2 -> SM weight stream (57 pairs x 14.9 MB in ~100 us is ~8 TB/s of L2 reads), and the
+// 96 KB of a second operand come out of the weight ring (112 KB in flight instead of 160 KB).  So it stays off, and
+// what remains of it is the half-granular hand-over: the MMAs of the next pass start on k-chunks 0-7 while the
+// epilogue is still writing the rows of k-chunks 8-15.
+template <int NP> struct BandPipe { static constexpr bool value = false; };
+template <int NP> struct BandStageTiles { static constexpr int value = BandPipe<NP>::value ? 1 : (NP <= 32 ? 2 : 1); };   // k-chunks (32 k) per ring stage
+template <int NP> struct BandRing { static constexpr int value = BandPipe<NP>::value ? 7 : (NP <= 16 ? 5 : (NP <= 32 ? 3 : 5)); };
 
 struct BandPairPlan {
   uint32_t stages, b, inp, dinp, g, bars, tmem_slot, total;
@@ -1589,7 +1596,7 @@ __host__ __device__ inline BandPairPlan make_band_pair_plan(int in0) {
   BandPairPlan p;
   uint32_t o = 0;
   p.stages = o; o += BandRing<NP>::value * BandStageTiles<NP>::value * TILE_BYTES;
-  p.b = o; o += 64 * ((BandPad<NP>::value ? 3 : 2) * NP * 16);   // 64 8-k chunks x [zeros |] hi | lo point groups
+  p.b = o; o += (BandPipe<NP>::value ? 2 : 1) * 64 * ((BandPad<NP>::value ? 3 : 2) * NP * 16);   // 64 8-k chunks x [zeros |] hi | lo
   const uint32_t in_pad = (uint32_t)((in0 + 7) & ~7);
   p.inp = o; o += in_pad * 2 * NP * 4;                 // inputs of the whole pair tile
   p.dinp = o; o += 2 * in_pad * 2 * NP * 4;            // input-gradient partials, double-buffered by tile parity
@@ -1652,8 +1659,14 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
   constexpr int Q_STAGE_TILES = BandStageTiles<NP>::value;
   constexpr int Q_STAGE_BYTES = Q_STAGE_TILES * TILE_BYTES;
   constexpr bool kPad = BandPad<NP>::value;
+  constexpr bool kPipe = BandPipe<NP>::value;          // two B operands: the epilogue of a block runs under the MMAs of the next
+  // hand-over between epilogue and issuer per 256-feature block / k-half (the next pass starts on k-chunks 0-7 while
+  // the rows of 8-15 are still being written), or once per pass: the finer protocol costs two more barrier rounds per
+  // pass, which pays for the long epilogues of 2 x 64 points (1 246 -> 1 217 us) and not for 2 x 16 (106 -> 112 us)
+  constexpr bool kSplit = kPipe || NP > 16;
   constexpr int NPP = 2 * NP;                          // points of the pair tile
   constexpr int BCH = (kPad ? 3 : 2) * NP * 16;        // bytes per 8-k chunk of B: [zeros,] hi, lo point groups
+  constexpr int BBYTES = 64 * BCH;                     // one B operand
   constexpr int HI = kPad ? NP * 16 : 0, LO = NP * 16; // hi region inside a chunk; lo region relative to hi
   constexpr int GW = 16;                               // points per TMEM load group
   constexpr int G = NP / GW;
@@ -1666,14 +1679,17 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
   const BandPairPlan P = make_band_pair_plan<NP>(in0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
-  unsigned char* bop = smem + P.b;
+  unsigned char* bop = smem + P.b;                     // B operand(s): pass g reads operand (g & 1) when kPipe
   unsigned long long* masks = mask_scratch + (size_t)blockIdx.x * (size_t)(num_layers - 1) * 512;
   float* inp = reinterpret_cast<float*>(smem + P.inp);         // [in_pad][2 NP]
   float* gbuf = reinterpret_cast<float*>(smem + P.g);
   const uint32_t bars = smem_u32(smem + P.bars);
+  // bar_acc[j]: the MMAs of 256-feature block j of the pass have completed (commit multicast to both CTAs);
+  // bar_half[h] (rank 0's copy is used): k-chunks [8 h, 8 h + 8) of the NEXT pass's B operand are written in both
+  // CTAs and TMEM block h has been read - one arrival per epilogue warp of both CTAs, every pass
   const uint32_t bar_full = bars, bar_peer = bars + 8 * NSTAGE, bar_empty = bars + 8 * (2 * NSTAGE),
-                 bar_acc = bars + 8 * (3 * NSTAGE), bar_act = bars + 8 * (3 * NSTAGE + 1),
-                 bar_x = bars + 8 * (3 * NSTAGE + 2);
+                 bar_acc = bars + 8 * (3 * NSTAGE), bar_half = bars + 8 * (3 * NSTAGE + 2),
+                 bar_x = bars + 8 * (3 * NSTAGE + 4);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
   const int in_pad = (in0 + 7) & ~7;
   const bool want_grad = dinput_out != nullptr;
@@ -1688,13 +1704,15 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
       mbar_init(bar_peer + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_act, 2 * (Q_NEPI / 32));             // one arrival per epilogue warp of both CTAs (rank 0's copy is used)
+    for (int j = 0; j < 2; ++j) {
+      mbar_init(bar_acc + 8 * j, 1);
+      mbar_init(bar_half + 8 * j, 2 * (Q_NEPI / 32));
+    }
     mbar_init(bar_x, Q_NEPI / 32);                     // the peer's epilogue warps: "my input-gradient partials are final"
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (kPad) {   // the zero point groups of every chunk are written once and never again
-    for (int i = tid; i < 64 * NP; i += Q_THREADS)
+    for (int i = tid; i < (kPipe ? 2 : 1) * 64 * NP; i += Q_THREADS)
       *reinterpret_cast<uint4*>(bop + (i / NP) * BCH + (i % NP) * 16) = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
   }
@@ -1758,25 +1776,37 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
     __syncwarp();
   } else if (warp == 9) {
     // ===================== rank 0: MMA issuer for the pair =====================
-    uint32_t stage = 0, phase = 0, act_phase = 0;
+    uint32_t stage = 0, phase = 0, half_phase = 0, gpass = 0;
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t desc_a_base = make_desc(smem_u32(smem + P.stages), A_LBO, A_SBO);
-    // padded layout: N-rows of a CTA [hi ; lo] (main) and [0 ; hi] (cross); split layout: hi and lo separately
-    const uint64_t desc_b_main = make_desc(smem_u32(bop) + HI, BCH, B_SBO);
-    const uint64_t desc_b_cross = make_desc(smem_u32(bop), BCH, B_SBO);
-    const uint64_t desc_b_lo = make_desc(smem_u32(bop) + HI + LO, BCH, B_SBO);
-    constexpr int GRP = 1;                               // ring stages per issuer iteration (2 was measured slower: the
-                                                         // issuer then waits for the later stage before starting the earlier)
+    // ring stages per issuer iteration: eight MMAs per iteration either way (the fixed cost of an iteration - barrier
+    // waits, fence, election - is ~170 cycles; sixteen per iteration was measured slower: the issuer then waits for the
+    // later stage before it starts on the earlier one)
+    constexpr int GRP = kPipe ? 2 : 1;
     for (long long it = 0; it < my_tiles; ++it) {
-      for (int p = 0; p < npass; ++p) {
+      for (int p = 0; p < npass; ++p, ++gpass) {
         const int m_blocks = __ldg(&T.pass[p].m_blocks), k_chunks = __ldg(&T.pass[p].k_chunks);
         const int nblocks = m_blocks == 1 ? 1 : m_blocks >> 1;
-        mbar_wait_cluster(bar_act, act_phase);         // B operand of both CTAs staged, TMEM of both drained
-        act_phase ^= 1;
-        tc_fence_after();
+        const uint32_t bsrc = smem_u32(bop) + (kPipe ? (gpass & 1u) * BBYTES : 0u);
+        // padded layout: N-rows of a CTA [hi ; lo] (main) and [0 ; hi] (cross); split layout: hi and lo separately
+        const uint64_t desc_b_main = make_desc(bsrc + HI, BCH, B_SBO);
+        const uint64_t desc_b_cross = make_desc(bsrc, BCH, B_SBO);
+        const uint64_t desc_b_lo = make_desc(bsrc + HI + LO, BCH, B_SBO);
+        uint32_t waited = 0;                           // bit h: bar_half[h] of this pass has been consumed
+        auto need = [&](const int h_) {
+          const int h = kSplit ? h_ : 0;
+          if (!((waited >> h) & 1u)) {
+            mbar_wait_cluster(bar_half + 8 * h, half_phase);
+            waited |= 1u << h;
+            tc_fence_after();
+          }
+        };
+        need(0);                                       // k-chunks 0-7 staged in both CTAs, TMEM block 0 drained
         for (int j = 0; j < nblocks; ++j) {
           const uint32_t d = tm + (uint32_t)(j * 4 * NP);
+          if (j == 1) need(1);                         // TMEM block 1 drained
           for (int kc = 0; kc < k_chunks; kc += Q_STAGE_TILES * GRP) {
+            if (kc >= 8) need(1);
             uint32_t st[GRP];
             int nst = 0;
 #pragma unroll
@@ -1823,9 +1853,17 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
             }
             __syncwarp();
           }
+          if (kSplit || j == nblocks - 1) {
+            if (elect_one()) umma_commit_pair(bar_acc + (kSplit ? 8 * j : 0), (uint16_t)3);   // block j (the pass) is complete in both CTAs
+            __syncwarp();
+          }
         }
-        if (elect_one()) umma_commit_pair(bar_acc, (uint16_t)3);      // the accumulators of the pass are complete
-        __syncwarp();
+        if (kSplit && nblocks == 1) {                  // keep the second block's barriers in step
+          if (elect_one()) umma_commit_pair(bar_acc + 8, (uint16_t)3);
+          __syncwarp();
+        }
+        need(1);
+        half_phase ^= 1;
       }
     }
   } else {
@@ -1835,20 +1873,28 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
     const int et = tid;
     const bool own = ph == (int)rank;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t b_dst = mapa_u32(smem_u32(bop), (uint32_t)ph) + HI;      // hi region of the owner's B operand
-    const uint32_t act_bar = mapa_u32(bar_act, 0u);
+    const uint32_t b_remote = mapa_u32(smem_u32(bop), (uint32_t)ph) + HI;   // hi region of the point owner's first B operand
+    const uint32_t half_bar[2] = {mapa_u32(bar_half, 0u), mapa_u32(bar_half + 8, 0u)};
     const uint32_t peer_x = mapa_u32(bar_x, rank ^ 1u);
     // ReLU sign words: [layer][feature of this CTA (block j, lane t)][point half], one u64 each
     auto mask_at = [&](const int layer, const int j) -> unsigned long long& {
       return masks[((size_t)layer * 256 + (size_t)(j * 128 + t)) * 2 + ph];
     };
-    uint32_t acc_phase = 0, x_phase = 0;
+    uint32_t acc_phase = 0, x_phase = 0, gpass = 0;
     float amax = 0.f;
-    auto publish = [&]() {                             // this warp's operand rows (own and remote) are written, TMEM read
+    auto publish = [&](const int h) {                  // this warp's rows of k-half h (own and remote) are written, TMEM block h read
+      if (!kSplit && h == 0) return;                   // one hand-over per pass: after the last block
       fence_async_all();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_release(act_bar);
+      if (lane == 0) mbar_arrive_cluster_release(half_bar[kSplit ? h : 0]);
+    };
+    auto wait_acc = [&](const int j_) {
+      if (!kSplit && j_ == 0) return;                  // one commit per pass
+      const int j = kSplit ? j_ : 0;
+      mbar_wait(bar_acc + 8 * j, (acc_phase >> j) & 1u);
+      acc_phase ^= 1u << j;
+      tc_fence_after();
     };
     for (long long it = 0; it < my_tiles; ++it) {
       const long long ptile = it * num_pairs + pair_id;
@@ -1878,10 +1924,10 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
         dinp[i] = 0.f;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // B operand of layer 0 (own points): k = input column, one 32-k chunk
+      // B operand of layer 0 (own points): k = input column, one 32-k chunk, into the operand the first pass reads
       if (q == 0 && own) {
         const int k = lane;
-        unsigned char* row = bop + (k >> 3) * BCH + HI + (k & 7) * 16;
+        unsigned char* row = bop + (kPipe ? (gpass & 1u) * BBYTES : 0u) + (k >> 3) * BCH + HI + (k & 7) * 16;
 #pragma unroll
         for (int g = 0; g < NP / 8; ++g) {
           float h[8];
@@ -1890,15 +1936,18 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
           amax = fmaxf(amax, pack8_store_t<LO>(row, g, h));
         }
       }
-      publish();
+      publish(0);
+      publish(1);
 
-      for (int p = 0; p < npass; ++p) {
+      for (int p = 0; p < npass; ++p, ++gpass) {
         const TcPassDev Ps = T.pass[p];
-        mbar_wait(bar_acc, acc_phase);
-        acc_phase ^= 1;
-        tc_fence_after();
+        // rows of the next pass's operand: the other buffer when double-buffered, in place otherwise (then only
+        // once every MMA of this pass has completed)
+        const uint32_t b_dst = b_remote + (kPipe ? ((gpass + 1u) & 1u) * BBYTES : 0u);
         if (Ps.kind == 1) {
           // ---- last Linear (both CTAs hold row 0 for all 2 NP points): sdf and the tanh slope ----
+          wait_acc(0);
+          wait_acc(1);
           if (q == 0) {
             const float bias0 = __ldg(Ps.bias);
 #pragma unroll
@@ -1939,13 +1988,15 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
                 for (int e = 0; e < 8; ++e) h[e] = ((mk >> (g * 8 + e)) & 1ull) ? w * gbuf[ph * NP + g * 8 + e] : 0.f;
                 amax = fmaxf(amax, pack8_store_cluster(row, LO, g, h));
               }
+              publish(j);
             }
-            publish();
           }
           continue;
         }
         if (Ps.kind == 3) {
           // ---- gradient with respect to the input rows (single block, both CTAs hold it): own points only ----
+          wait_acc(0);
+          wait_acc(1);
           if (q == 0 && own) {
             const int f = t;
 #pragma unroll
@@ -1981,66 +2032,73 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
         const bool fwd = Ps.kind == 0;
         const int split = fwd ? Ps.rows : Ps.prev_rows;       // rows below: regular outputs
         const int nblocks = Ps.m_blocks >> 1;
-        for (int j = 0; j < nblocks; ++j) {
-          const int f = (2 * j + (int)rank) * 128 + t;
-          const int cls = f < split ? 0 : (f < split + Ps.cat_dim ? 1 : 2);
-          const uint32_t tb = lane_base + (uint32_t)(j * 4 * NP + ph * COL_PH);
-          const uint32_t row = b_dst + (uint32_t)((f >> 3) * BCH + (f & 7) * 16);
-          const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
-          const unsigned long long pmask = (!fwd && cls == 0) ? mask_at(Ps.layer - 1, j) : 0ull;
-          const int cat_row = (Ps.cat_off + f - split) * NPP + ph * NP;
-          unsigned long long mk = 0ull;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            uint32_t vm[GW], vc[GW];
-            tmem_ld16(tb + g * GW, vm);
-            tmem_ld16(tb + COL_CROSS + g * GW, vc);
-            tmem_ld_wait();
-            float x[GW];
-#pragma unroll
-            for (int qq = 0; qq < GW; ++qq)
-              x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
-            float h[GW];
-            if (fwd) {
-              if (cls == 0) {
-#pragma unroll
-                for (int qq = 0; qq < GW; ++qq) {
-                  const float y = x[qq] + bias;
-                  const bool on = y > 0.f;
-                  if (on) mk |= 1ull << (g * GW + qq);
-                  h[qq] = on ? y * Ps.out_scale : 0.f;
-                }
-              } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
-#pragma unroll
-                for (int qq = 0; qq < GW; ++qq) h[qq] = inp[cat_row + g * GW + qq] * Ps.out_scale;
-              } else {
-#pragma unroll
-                for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
-              }
-            } else {
-              if (cls == 0) {
-#pragma unroll
-                for (int qq = 0; qq < GW; ++qq) h[qq] = ((pmask >> (g * GW + qq)) & 1ull) ? x[qq] * Ps.out_scale : 0.f;
-              } else {
-                if (cls == 1) {                                    // gradient of the concatenated input columns
-#pragma unroll
-                  for (int qq = 0; qq < GW; ++qq) dinp[cat_row + g * GW + qq] += x[qq];
-                }
-#pragma unroll
-                for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
-              }
-            }
-#pragma unroll
-            for (int pk = 0; pk < PG; ++pk) {
-              float h8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h8[e] = h[pk * 8 + e];
-              amax = fmaxf(amax, pack8_store_cluster(row, LO, g * PG + pk, h8));
-            }
-          }
-          if (fwd && want_grad) mask_at(Ps.layer, j) = mk;   // only the backward reads them
+        if (!kPipe) {                                  // in place: the operand may only change once nothing reads it any more
+          wait_acc(0);
+          wait_acc(1);
         }
-        publish();
+        for (int j = 0; j < 2; ++j) {
+          if (kPipe) wait_acc(j);
+          if (j < nblocks) {
+            const int f = (2 * j + (int)rank) * 128 + t;
+            const int cls = f < split ? 0 : (f < split + Ps.cat_dim ? 1 : 2);
+            const uint32_t tb = lane_base + (uint32_t)(j * 4 * NP + ph * COL_PH);
+            const uint32_t row = b_dst + (uint32_t)((f >> 3) * BCH + (f & 7) * 16);
+            const float bias = (fwd && cls == 0) ? __ldg(Ps.bias + f) : 0.f;
+            const unsigned long long pmask = (!fwd && cls == 0) ? mask_at(Ps.layer - 1, j) : 0ull;
+            const int cat_row = (Ps.cat_off + f - split) * NPP + ph * NP;
+            unsigned long long mk = 0ull;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              uint32_t vm[GW], vc[GW];
+              tmem_ld16(tb + g * GW, vm);
+              tmem_ld16(tb + COL_CROSS + g * GW, vc);
+              tmem_ld_wait();
+              float x[GW];
+#pragma unroll
+              for (int qq = 0; qq < GW; ++qq)
+                x[qq] = (__uint_as_float(vm[qq]) + __uint_as_float(vc[qq])) * Ps.inv_scale;
+              float h[GW];
+              if (fwd) {
+                if (cls == 0) {
+#pragma unroll
+                  for (int qq = 0; qq < GW; ++qq) {
+                    const float y = x[qq] + bias;
+                    const bool on = y > 0.f;
+                    if (on) mk |= 1ull << (g * GW + qq);
+                    h[qq] = on ? y * Ps.out_scale : 0.f;
+                  }
+                } else if (cls == 1) {                               // cat[x, input] feeds the next Linear
+#pragma unroll
+                  for (int qq = 0; qq < GW; ++qq) h[qq] = inp[cat_row + g * GW + qq] * Ps.out_scale;
+                } else {
+#pragma unroll
+                  for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
+                }
+              } else {
+                if (cls == 0) {
+#pragma unroll
+                  for (int qq = 0; qq < GW; ++qq) h[qq] = ((pmask >> (g * GW + qq)) & 1ull) ? x[qq] * Ps.out_scale : 0.f;
+                } else {
+                  if (cls == 1) {                                    // gradient of the concatenated input columns
+#pragma unroll
+                    for (int qq = 0; qq < GW; ++qq) dinp[cat_row + g * GW + qq] += x[qq];
+                  }
+#pragma unroll
+                  for (int qq = 0; qq < GW; ++qq) h[qq] = 0.f;
+                }
+              }
+#pragma unroll
+              for (int pk = 0; pk < PG; ++pk) {
+                float h8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h8[e] = h[pk * 8 + e];
+                amax = fmaxf(amax, pack8_store_cluster(row, LO, g * PG + pk, h8));
+              }
+            }
+            if (fwd && want_grad) mask_at(Ps.layer, j) = mk;   // only the backward reads them
+          }
+          publish(j);
+        }
       }
       // the next pair tile re-stages inp: every local epilogue thread must be past its last read
       asm volatile("bar.sync 1, 256;" ::: "memory");
