@@ -509,7 +509,10 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         if i >= 3:
             e2e_times.append(time.perf_counter() - t0)
-    e2e_s = float(np.mean(e2e_times))
+    # median of the K per-step times: a host-timed 0.5 ms call is hit by millisecond hiccups of the host now and then
+    # (e.g. the nvidia-smi poll of the clock sampler holding a driver lock); mean and max are reported beside it
+    e2e_s = float(np.median(e2e_times))
+    e2e_mean_s, e2e_max_s = float(np.mean(e2e_times)), float(np.max(e2e_times))
     if dist:
         t = torch.tensor([e2e_s], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -654,7 +657,8 @@ def run_ours(args, rank, world, local_rank):
                         "product default): an iteration evaluates only the lattice points the decoder's certified "
                         "Lipschitz bound cannot exclude from the band; identical surfels and results",
                 "ms_per_step": p_ms, "value": B * SIZE * SIZE / (p_ms * 1e-3), "unit": "rays/s",
-                "e2e_ms_per_step": float(np.mean(pe2e)) * 1e3, "e2e_value": SIZE * SIZE / float(np.mean(pe2e)),
+                "e2e_ms_per_step": float(np.median(pe2e)) * 1e3, "e2e_value": SIZE * SIZE / float(np.median(pe2e)),
+                "e2e_ms_per_step_mean": float(np.mean(pe2e)) * 1e3,
                 "lattice_points_per_iteration": rows / max(its, 1), "lattice_points_full": DENSITY ** 3,
                 "latent_lipschitz_bound": float(dec.native().latent_lipschitz),
                 "params_bit_identical_to_whole_lattice": bool(np.array_equal(pp, fp))}
@@ -723,7 +727,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": head_clocks if head_clocks and head_clocks.get("samples") else clocks,
             "clocks_whole_run": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3, "api": "sdflabel_b200.pipelines.optimizer.Optimizer.optimize(1, ...)"},
+                    "ms_per_step": e2e_s * 1e3, "estimator": "median of the K per-step times",
+                    "ms_per_step_mean": e2e_mean_s * 1e3, "ms_per_step_max": e2e_max_s * 1e3,
+                    "api": "sdflabel_b200.pipelines.optimizer.Optimizer.optimize(1, ...)"},
             "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": tgb,
             "frames_per_s": frames_block["frames_per_s"] if frames_block else None,
             "frames": frames_block,

@@ -435,7 +435,7 @@ int sdfr_splat_forward(const sdfr_raster_cfg* cfg, const float* coords_dev, cons
   int rc;
   if ((rc = launch_project(vd, 1, (int)m, s))) return rc;
   if (cfg->primitive == SDFR_PRIM_DISC) {
-    if ((rc = launch_splat_forward(vd, 1, cfg->width, cfg->height, s))) return rc;
+    if ((rc = launch_splat_forward(vd, 1, cfg->width, cfg->height, cfg->width * cfg->height <= kFineCropPixelsHost, s))) return rc;
     if (cfg->bg_dev && (rc = launch_disc_background(vd, 1, (int)P, s))) return rc;
   } else {
     if ((rc = launch_circle_forward(vd, 1, (int)P, s))) return rc;

@@ -211,7 +211,8 @@ struct SplatView {
 };
 
 int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStream_t s);
-int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, cudaStream_t s);
+int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, int any_fine, cudaStream_t s);
+constexpr int kFineCropPixelsHost = 64 * 64;   // = kFineCropPixels of splat.cu: crops up to this size use 4 x 4 pixel tiles
 int launch_pixel_grad_prep(const SplatView* views_dev, int batch, int max_pixels, const float* g_color,
                            const float* g_mask, const float* g_depth, const float* g_nmap, cudaStream_t s);
 int launch_splat_backward(const SplatView* views_dev, int batch, int max_count, cudaStream_t s);

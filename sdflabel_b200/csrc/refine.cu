@@ -606,10 +606,12 @@ int pow2_ceil(int v, int lo) {
 
 // launch shape of the per-pixel kernels: the largest crop among the active detections, rounded up to a power
 // of two (>= 32) and clamped to the capacity; kernels exit early outside each detection's own crop
-void active_shape(const sdfr_refine* r, int* qw, int* qh) {
+void active_shape(const sdfr_refine* r, int* qw, int* qh, int* any_fine) {
   int mw = 0, mh = 0;
+  *any_fine = 0;
   for (int b = 0; b < r->active; ++b) {
     mw = std::max(mw, r->det_w[b]); mh = std::max(mh, r->det_h[b]);
+    *any_fine |= r->det_w[b] * r->det_h[b] <= kFineCropPixelsHost;     // picks the splat tiling of that detection
   }
   *qw = std::min(pow2_ceil(mw, 32), std::max(r->cfg.max_width, mw));
   *qh = std::min(pow2_ceil(mh, 32), std::max(r->cfg.max_height, mh));
@@ -922,14 +924,14 @@ int enqueue_begin(sdfr_refine* r, int B, cudaStream_t s) {
 }
 
 // enqueues the NINE kernels of one refine iteration of detections [0, B) on `s`
-int enqueue_iteration(sdfr_refine* r, int B, int qw, int qh, cudaStream_t s, StageClock* clk = nullptr) {
+int enqueue_iteration(sdfr_refine* r, int B, int qw, int qh, int any_fine, cudaStream_t s, StageClock* clk = nullptr) {
   EngineDev E = r->E;
   E.batch = B;
   const IterPlan p = make_iter_plan(r, B);
   int rc;
   STAGE_MARK(clk);
   if ((rc = enqueue_surface(r, p, s, clk))) return rc;             // lattice, select, band pass, isosurface + projection
-  if ((rc = launch_splat_forward(E.views, B, qw, qh, s))) return rc;
+  if ((rc = launch_splat_forward(E.views, B, qw, qh, any_fine, s))) return rc;
   STAGE_MARK(clk);
   const int n2 = (qw * qh + LB - 1) / LB;
   losses_batch_kernel<<<dim3(n2 + E.nb3, B), LB, 0, s>>>(E, n2);
@@ -954,8 +956,8 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   const int B = r->active;
   for (int b = 0; b < B; ++b)
     SDFR_REQUIRE(r->det_w[b] > 0, SDFR_E_INVALID, "detection %d of the %d active ones has not been set", b, B);
-  int qw, qh;
-  active_shape(r, &qw, &qh);
+  int qw, qh, any_fine;
+  active_shape(r, &qw, &qh, &any_fine);
   for (int b = 0; b < B; ++b) r->iters_enqueued[b] = (int)std::min<long long>((long long)r->iters_enqueued[b] + iters, 1 << 30);
   static int use_graph = -1;
   if (use_graph < 0) { const char* e = getenv("SDFR_REFINE_GRAPH"); use_graph = e ? atoi(e) : 1; }
@@ -965,18 +967,18 @@ extern "C" int sdfr_refine_run(sdfr_refine* r, int iters, void* stream) {
   // The first call runs un-captured (lazy attribute setup inside the launchers must not happen during capture).
   if (!use_graph || r->runs == 0) {
     for (; done < (use_graph ? std::min(iters, 1) : iters); ++done)
-      if ((rc = enqueue_iteration(r, B, qw, qh, s))) return rc;
+      if ((rc = enqueue_iteration(r, B, qw, qh, any_fine, s))) return rc;
   }
   r->runs += 1;
   if (done == iters) return SDFR_OK;
-  const auto key = std::make_tuple(B, qw, qh);
+  const auto key = std::make_tuple(B, qw * 2 + any_fine, qh);
   auto it = r->graphs.find(key);
   if (it == r->graphs.end()) {
     cudaGraph_t graph = nullptr;
     const long long before = sdfr_launch_count();
     if (!r->capture_stream) SDFR_CUDA(cudaStreamCreateWithFlags(&r->capture_stream, cudaStreamNonBlocking));
     SDFR_CUDA(cudaStreamBeginCapture(r->capture_stream, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_iteration(r, B, qw, qh, r->capture_stream);
+    rc = enqueue_iteration(r, B, qw, qh, any_fine, r->capture_stream);
     cudaError_t ce = cudaStreamEndCapture(r->capture_stream, &graph);
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     SDFR_CUDA(ce);
@@ -1106,15 +1108,15 @@ extern "C" int sdfr_refine_profile(sdfr_refine* r, int iters, float* stage_ms_ho
   const int B = r->active;
   for (int b = 0; b < B; ++b)
     SDFR_REQUIRE(r->det_w[b] > 0, SDFR_E_INVALID, "detection %d of the %d active ones has not been set", b, B);
-  int qw, qh;
-  active_shape(r, &qw, &qh);
+  int qw, qh, any_fine;
+  active_shape(r, &qw, &qh, &any_fine);
   std::vector<double> acc(kNumStages, 0.0);
   int rc = SDFR_OK;
   for (int it = 0; it < iters && rc == SDFR_OK; ++it) {
     StageClock clk;
     clk.s = s;
     if (it == 0 && (rc = enqueue_begin(r, B, s))) break;
-    rc = enqueue_iteration(r, B, qw, qh, s, &clk);
+    rc = enqueue_iteration(r, B, qw, qh, any_fine, s, &clk);
     r->iters_enqueued.assign(r->iters_enqueued.size(), 1 << 30);     // the history is read through D.iter
     cudaStreamSynchronize(s);
     if (rc == SDFR_OK && (int)clk.ev.size() == kNumStages + 1)

@@ -13,6 +13,8 @@
 // whose box meets the tile (two sweeps: sum zeta^2 / max, then the softmax), the
 // backward a gather per surfel (one warp) over the pixels of its box.  Both are
 // deterministic (no atomics).  Traffic: 44 B per surfel in, 8 floats per pixel out.
+#include <algorithm>
+
 #include "common.cuh"
 #include "project.cuh"
 
@@ -51,24 +53,29 @@ __device__ __forceinline__ Hit disc_test(float rx, float ry, float rz, float vx,
   return h;
 }
 
-constexpr int TILE = 8;        // pixels per tile side
-constexpr int SPLIT = 4;       // threads per pixel, each sweeping a quarter of the tile's surfel list
-constexpr int CHUNK = 256;     // = threads per block = TILE * TILE * SPLIT
+constexpr int CHUNK = 256;     // threads per block = tile * tile * split
 constexpr int LCAP = 1024;     // surfels of one tile kept resident in shared memory for both sweeps
-// 8 x 8 pixel tiles with FOUR threads per pixel at every crop size: a 32 x 32 crop (the reference's default regime,
-// configs/config_refine.ini:12) is 16 CTAs, a 256 x 256 crop 1024, and the ~1 600 surfels of a detection are a few
-// hundred per tile instead of overflowing the resident list; the critical path of a busy tile is a quarter of
-// what one thread per pixel on 16 x 16 tiles pays (256 x 256: 66 -> 30 us).
+// Crops above kFineCropPixels: 8 x 8 pixel tiles with FOUR threads per pixel, each sweeping a quarter of the tile's surfel
+// list (a 256 x 256 crop is 1024 CTAs; the critical path of a busy tile is a quarter of what one thread per pixel on
+// 16 x 16 tiles pays: 66 -> 30 us).  Crops up to kFineCropPixels (the reference's default regime: rendering_area 32 - 64,
+// configs/config_refine.ini:12): 4 x 4 tiles with SIXTEEN threads per pixel - a 32 x 32 crop is 64 CTAs instead of 16,
+// and the ~900 surfels that meet a central 8 x 8 tile there (close to the list's capacity: one tile past it ran the
+// chunk-serial path and took 96 us) become ~400.  The mode depends on the detection's OWN crop only, so its bits do not
+// depend on what else is in the batch.
+constexpr int kFineCropPixels = 64 * 64;
+
 __global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* __restrict__ views) {
   extern __shared__ __align__(16) float s_list[];
   const SplatView& V = views[blockIdx.z];
-  constexpr int tile = TILE, split = SPLIT, lcap = LCAP;
+  constexpr int lcap = LCAP;
+  const bool fine = V.width * V.height <= kFineCropPixels;
+  const int tile = fine ? 4 : 8, split = fine ? 16 : 4;
   const int tx0 = blockIdx.x * tile, ty0 = blockIdx.y * tile;
   if (tx0 >= V.width || ty0 >= V.height) return;
   const int m = min(V.count ? *V.count : V.static_count, V.capacity);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pix = tid >> 2, part = tid & 3;
-  const int x = tx0 + (pix & 7), y = ty0 + (pix >> 3);
+  const int pix = fine ? tid >> 4 : tid >> 2, part = fine ? tid & 15 : tid & 3;
+  const int x = tx0 + (fine ? pix & 3 : pix & 7), y = ty0 + (fine ? pix >> 2 : pix >> 3);
   const bool live = x < V.width && y < V.height;
   const int tx1 = min(tx0 + tile - 1, V.width - 1), ty1 = min(ty0 + tile - 1, V.height - 1);
 
@@ -115,19 +122,17 @@ __global__ void __launch_bounds__(CHUNK) splat_forward_kernel(const SplatView* _
       acc[7] += e * ((s_m[k][2] + 1.f) / 2.f);
     }
   };
-  // the four threads of a pixel hold partial results over their quarters of the list: combine them in a fixed
-  // order (lanes 4p .. 4p+3 of one warp)
+  // the threads of a pixel hold partial results over their shares of the list: combine them in a fixed order
+  // (consecutive lanes of one warp)
   auto combine_sweep0 = [&]() {
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
+    for (int o = 1; o < split; o <<= 1) {
       sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
       zeta_max = fmaxf(zeta_max, __shfl_xor_sync(0xffffffffu, zeta_max, o));
       hits += __shfl_xor_sync(0xffffffffu, hits, o);
     }
   };
   auto combine_sweep1 = [&]() {
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
+    for (int o = 1; o < split; o <<= 1) {
       den += __shfl_xor_sync(0xffffffffu, den, o);
 #pragma unroll
       for (int c = 0; c < 8; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
@@ -244,12 +249,7 @@ __global__ void pixel_grad_prep_kernel(const SplatView* __restrict__ views, cons
 }
 
 // One warp per surfel: gathers d loss / d (v, m, composited colour) over the surfel's pixel box.
-__global__ void __launch_bounds__(256) splat_backward_kernel(const SplatView* __restrict__ views) {
-  const SplatView& V = views[blockIdx.y];
-  const int m = min(V.count ? *V.count : V.static_count, V.capacity);
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= m) return;
+__device__ __forceinline__ void splat_backward_surfel(const SplatView& V, const int i, const int lane) {
   const float vx = V.cam_v[i * 3], vy = V.cam_v[i * 3 + 1], vz = V.cam_v[i * 3 + 2];
   const float mx = V.cam_m[i * 3], my = V.cam_m[i * 3 + 1], mz = V.cam_m[i * 3 + 2];
   const float cx = V.cam_c[i * 3], cy = V.cam_c[i * 3 + 1], cz = V.cam_c[i * 3 + 2];
@@ -313,6 +313,16 @@ __global__ void __launch_bounds__(256) splat_backward_kernel(const SplatView* __
   }
 }
 
+// One warp per surfel; the grid covers a few thousand surfels per sweep (a detection has ~2 000) instead of the whole
+// capacity, whose empty blocks used to be most of this kernel's time in large batches.
+__global__ void __launch_bounds__(256) splat_backward_kernel(const SplatView* __restrict__ views) {
+  const SplatView& V = views[blockIdx.y];
+  const int m = min(V.count ? *V.count : V.static_count, V.capacity);
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < m; i += gridDim.x * (blockDim.x >> 5))
+    splat_backward_surfel(V, i, lane);
+}
+
 }  // namespace
 
 int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStream_t s) {
@@ -323,14 +333,17 @@ int launch_project(const SplatView* views_dev, int batch, int max_count, cudaStr
   return SDFR_OK;
 }
 
-int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, cudaStream_t s) {
+int launch_splat_forward(const SplatView* views_dev, int batch, int max_w, int max_h, int any_fine, cudaStream_t s) {
   if (max_w <= 0 || max_h <= 0 || batch <= 0) return SDFR_OK;
+  // any_fine: some detection of the launch is a small crop (4 x 4 tiles); the grid then covers the finer tiling and the
+  // blocks of the other detections beyond their 8 x 8 tiling exit at once
+  const int tile = any_fine ? 4 : 8;
   static bool attr_set = false;
   if (!attr_set) {
     SDFR_CUDA(cudaFuncSetAttribute(splat_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LCAP * 56));
     attr_set = true;
   }
-  dim3 grid((max_w + TILE - 1) / TILE, (max_h + TILE - 1) / TILE, batch);
+  dim3 grid((max_w + tile - 1) / tile, (max_h + tile - 1) / tile, batch);
   splat_forward_kernel<<<grid, CHUNK, (size_t)LCAP * 56, s>>>(views_dev);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
@@ -347,7 +360,7 @@ int launch_pixel_grad_prep(const SplatView* views_dev, int batch, int max_pixels
 
 int launch_splat_backward(const SplatView* views_dev, int batch, int max_count, cudaStream_t s) {
   if (max_count <= 0 || batch <= 0) return SDFR_OK;
-  dim3 grid((max_count + 7) / 8, batch);
+  dim3 grid(std::min((max_count + 7) / 8, 512), batch);
   splat_backward_kernel<<<grid, 256, 0, s>>>(views_dev);
   SDFR_LAUNCH_CHECK();
   return SDFR_OK;
