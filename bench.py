@@ -352,6 +352,56 @@ def _run_cfg3_once(dec, grid, weights, dev):
             "lattice_points_per_detection_iteration": (rows / its) if its else float(DENSITY ** 3)}
 
 
+def run_trace(dec, sc, dev):
+    """configs[4] (slice) / north_star's trace mode: sphere-traced render of one latent, forward and forward + backward
+    (implicit differentiation at the hits), through the public ``SphereTracer`` module; device-timed."""
+    import torch
+    from sdflabel_b200.renderer.tracer import SphereTracer
+    lat = torch.tensor(sc["init"]["latent"], device=dev)
+    pose = torch.eye(4)
+    cy, sy = float(np.cos(0.6)), float(np.sin(0.6))
+    pose[:3, :3] = torch.diag(torch.tensor([1.0, -1.0, 1.0])) @ torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    pose[:3, 3] = torch.tensor([0.0, 0.0, 5.0])                       # optimizer.py:87-90 at yaw 0.6, 5 units away
+    pose = pose.to(dev)
+    rows = []
+    for size in (256, 1024):
+        K = torch.from_numpy(sc["K"]).clone()
+        K[:2] *= size / float(SIZE)
+        tracer = SphereTracer(K, (size, size)).to(dev)
+
+        def fwd():
+            with torch.no_grad():
+                return tracer(dec, lat, pose)
+
+        def both():
+            l, p = lat.clone().requires_grad_(True), pose.clone().requires_grad_(True)
+            out = tracer(dec, l, p)
+            (out["depth"].sum() + out["color"].sum()).backward()
+
+        res = {}
+        for name, fn in (("fwd", fwd), ("fwd_bwd", both)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ev = []
+            for _ in range(5):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                ev.append((a, b))
+            torch.cuda.synchronize()
+            res[name] = float(np.median([a.elapsed_time(b) for a, b in ev]))
+        hits = int(fwd()["mask"].sum().item())
+        rows.append({"resolution": f"{size}x{size}", "hit_rays": hits, "fwd_ms": res["fwd"],
+                     "fwd_rays_per_s": size * size / (res["fwd"] * 1e-3), "fwd_bwd_ms": res["fwd_bwd"],
+                     "fwd_bwd_rays_per_s": size * size / (res["fwd_bwd"] * 1e-3)})
+    return {"what": "trace mode (sdflabel_b200.renderer.tracer.SphereTracer): distance cache on a regular 40^3 lattice, "
+                    "speculative sphere tracing on the tcgen05 lattice-pass kernel, Newton finish at full precision, "
+                    "implicit-differentiation backward; one latent, stock prior, eps 1e-4; median of 5 device-timed calls",
+            "per_resolution": rows}
+
+
 def run_frames(args, dec, grid, weights, dev, rank, world, dist):
     """configs[3]: the frame loop, frames sharded by detection count, label all-gather at dump time."""
     import torch
@@ -682,6 +732,10 @@ def run_ours(args, rank, world, local_rank):
             extras["cfg3"] = run_cfg3(dec, grid, sc["weights"], dev)
         except Exception as e:   # noqa: BLE001
             extras["cfg3"] = {"error": repr(e)}
+        try:
+            extras["trace"] = run_trace(dec, sc, dev)
+        except Exception as e:   # noqa: BLE001
+            extras["trace"] = {"error": repr(e)[:300]}
     frames_block = None
     if args.frames > 0 and not args.quick:
         frames_block = run_frames(args, dec, grid, sc["weights"], dev, rank, world, dist)

@@ -140,6 +140,15 @@ inline LatticeParams make_lattice(int density) {
   return lp;
 }
 
+// regular lattice of d^3 nodes over [-1, hi]^3 (no half-cell shift): the distance cache of trace mode
+inline LatticeParams make_regular_lattice(int density, double hi) {
+  LatticeParams lp;
+  lp.density = density;
+  lp.step = (hi + 1.0) / (double)(density - 1);
+  lp.shift = 0.0;
+  return lp;
+}
+
 __device__ __forceinline__ void lattice_point(const LatticeParams& lp, long long idx, float& x, float& y,
                                               float& z) {
   const int d = lp.density;
@@ -241,6 +250,10 @@ struct MlpInputs {
   // lattice-pass kernel only: march mode (trace.cuh).  The rows are the rays of march->list (count_dev = march->count),
   // and instead of writing sdf the epilogue advances every ray and sorts it into the next / near lists.
   const RayMarch* march = nullptr;
+  // CTA-pair band kernels: the launch runs only when count_lo < *count_dev <= count_hi (adaptive_tiles: launch_mlp_tc
+  // enqueues the 16- and the 64-point tiling with complementary windows)
+  int count_lo = 0, count_hi = 0x7fffffff;
+  int adaptive_tiles = 0;
 };
 
 __device__ __forceinline__ long long mlp_rows(const MlpInputs& in) {
@@ -254,6 +267,7 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
 // forward only, fp16 operand precision (hi halves only): the band pre-selection pass of the fused engine
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s);
 bool mlp_tc_march_ok(const sdfr_decoder* dec);   // the lattice-pass kernel can run trace mode's fused march for this decoder
+int mlp_tc_round_rows(const sdfr_decoder* dec);  // rows of one round of the lattice-pass grid (0: no pair kernel)
 size_t mlp_tc_mask_scratch_bytes(const sdfr_decoder* dec);
 int build_tc_tables(sdfr_decoder* dec, const sdfr_decoder_spec* spec, const float* const* weights_host);
 void free_tc_tables(sdfr_decoder* dec);

@@ -1172,7 +1172,9 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
                  bar_acc = bars + 8 * (3 * P_STAGES), bar_a = bars + 8 * (3 * P_STAGES + 2);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.tmem_slot);
   const int in_pad = (in0 + 7) & ~7;
-  const long long n_rows = mlp_rows(in);
+  // march mode: 2^march_lk sample points per listed ray (trace.cuh)
+  const int march_lk = in.march ? march_log2k(*in.march, *in.march->count) : 0;
+  const long long n_rows = in.march ? march_rows(*in.march) : mlp_rows(in);
   const long long num_pair_tiles = (n_rows + 2 * P_PTS - 1) / (2 * P_PTS);
   const long long num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   // The last Linear (hidden -> 1) is a dot product per point: when the layer before it is a plain hidden layer
@@ -1337,7 +1339,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
         const long long gi = base + n;
         float v = 0.f;
         if (gi < n_rows && c < in0 && in.march) {
-          v = march_input(*in.march, gi, c);
+          v = march_input(*in.march, gi, c, march_lk);
         } else if (gi < n_rows && c < in0) {
           const long long src = in.index ? (long long)in.index[gi] : gi;
           if (in.inputs) {
@@ -1388,7 +1390,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
             float y = __uint_as_float(v[0]) * Ps.inv_scale + __ldg(Ps.bias);
             if (use_tanh) y = tanhf(y);
             y = tanhf(y);
-            if (in.march) march_advance(*in.march, base + pt_l < n_rows, base + pt_l, y);
+            if (in.march) march_advance(*in.march, base + pt_l < n_rows, base + pt_l, y, march_lk);
             else if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
           }
           tc_fence_before();
@@ -1440,7 +1442,7 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
                       __ldg(T.pass[num_layers - 1].bias);
             if (use_tanh) y = tanhf(y);
             y = tanhf(y);
-            if (in.march) march_advance(*in.march, base + pt_l < n_rows, base + pt_l, y);
+            if (in.march) march_advance(*in.march, base + pt_l < n_rows, base + pt_l, y, march_lk);
             else if (base + pt_l < n_rows) sdf_out[base + pt_l] = y;
           }
           continue;
@@ -1652,7 +1654,8 @@ mlp_tc_band_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char* _
                         float* __restrict__ sdf_out, float* __restrict__ dinput_out, int* __restrict__ overflow_flag,
                         unsigned long long* __restrict__ mask_scratch) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  if (in.count_dev && *in.count_dev <= 0) return;     // uniform over the grid: before any cluster traffic
+  // uniform over the grid, before any cluster traffic: nothing to evaluate, or a row count outside this launch's window
+  if (in.count_dev && (*in.count_dev <= in.count_lo || *in.count_dev > in.count_hi)) return;
   const TcTable& T = *tabp;
   const int num_layers = T.num_layers, in0 = T.in0, latent = T.latent, use_tanh = T.use_tanh;
   constexpr int NSTAGE = BandRing<NP>::value;
@@ -2396,6 +2399,14 @@ int launch_mlp_tc(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, floa
   const int group = np == 16 ? 4 : (point_tiles > grid ? 2 : 1);
   unsigned long long* masks = in.mask_scratch ? in.mask_scratch : st->mask_dev;
   if (band_pair_ok(dec, st, dinput != nullptr)) {
+    // The row count lives on the device and may be anything (trace mode's Newton rounds): both tilings are enqueued,
+    // each with a window on the count, and the one whose window it misses returns at once (~3 us)
+    if (in.adaptive_tiles && in.count_dev && band_pair_slots<16>(dec->dev.in0) > 0 && band_pair_slots<64>(dec->dev.in0) > 0) {
+      MlpInputs lo = in, hi = in;
+      lo.count_hi = hi.count_lo = 2 * 32 * band_pair_slots<16>(dec->dev.in0);      // two rounds of 2 x 16 ~ one of 2 x 64
+      int rc = launch_band_pair<16>(dec, st, lo, sdf, dinput, masks, s);
+      return rc ? rc : launch_band_pair<64>(dec, st, hi, sdf, dinput, masks, s);
+    }
     // CTA pairs, M = 256 features per instruction: 2 x 16 points per pair for short row lists, 2 x 64 otherwise
     if (small && band_pair_slots<16>(dec->dev.in0) > 0) return launch_band_pair<16>(dec, st, in, sdf, dinput, masks, s);
     if (!small && band_pair_slots<64>(dec->dev.in0) > 0) return launch_band_pair<64>(dec, st, in, sdf, dinput, masks, s);
@@ -2465,6 +2476,8 @@ static bool coarse_pair_ok(const sdfr_decoder* dec) {
 
 // march mode of trace.cu lives in the pair kernel only
 bool mlp_tc_march_ok(const sdfr_decoder* dec) { return coarse_pair_ok(dec); }
+// rows one round of the lattice-pass grid evaluates (every resident CTA pair one tile)
+int mlp_tc_round_rows(const sdfr_decoder* dec) { return coarse_pair_ok(dec) ? coarse_pair_slots() * 2 * P_PTS : 0; }
 
 int launch_mlp_tc_coarse(const sdfr_decoder* dec, const MlpInputs& in, float* sdf, cudaStream_t s) {
   SDFR_REQUIRE(dec->tc.ok && dec->tc_ptr, SDFR_E_UNSUPPORTED, "tcgen05 MLP kernel does not cover this decoder");

@@ -6,19 +6,29 @@
 //
 // Rays are "points" for the decoder kernels.  Two forms of the march, no host synchronisation in either:
 //
-//  * fused (tensor-core decoder with a CTA-pair pass table): ONE kernel per march step - the lattice-pass kernel
-//    (mlp_tc.cu, fp16 operands, 0.74 of the tensor roofline) in march mode generates its rows from the active rays
-//    (o + tau d), and its epilogue advances every ray (tau += sdf), drops it when it leaves the box, or - once
-//    |sdf| < near_thr - hands it to the `near` list (warp-ballot compaction, one atomic per warp and list).  Far from
-//    the surface the 3e-4 error of that pass only perturbs the step length.  The near rays are then finished at full
-//    precision by Newton steps along the ray, tau -= sdf / (grad sdf . d), using the accurate forward + input-gradient
-//    kernel whose last evaluation also yields the normals and d sdf / d latent: a hit is a root with |sdf| < eps.
+//  * fused (tensor-core decoder with a CTA-pair pass table):
+//      1. distance cache: the lattice-pass kernel (mlp_tc.cu, fp16 operands, 0.74 of the tensor roofline) evaluates a
+//         regular 40^3 lattice over the box once (190 us); every ray then marches through its trilinear interpolant
+//         minus a safety margin in registers (trace_grid_march_kernel) until it is within ~1.5 cells of the surface
+//         or leaves the box.  Rays that never come near the surface cost no decoder evaluation at all.
+//      2. speculative march (trace.cuh): ONE launch of the lattice-pass kernel per step; it generates its rows from
+//         the active rays - 2^lk look-ahead samples per ray, as many as fit one round of the grid - and its epilogue
+//         advances every ray over all samples whose unbounding spheres connect, drops it when it leaves the box, or -
+//         once |sdf| < near_thr - hands it to the `near` list (warp-ballot compaction, one atomic per warp and list).
+//         A launch costs one pass over the weights however few rays are left, so the long tail of grazing rays
+//         (60 plain steps) collapses to ~10 launches.  Far from the surface the 3e-4 error of that pass only
+//         perturbs the step length.
+//      3. the near rays are finished at full precision by Newton steps along the ray, tau -= sdf / (grad sdf . d),
+//         using the accurate forward + input-gradient kernel whose last evaluation also yields the normals and
+//         d sdf / d latent: a hit is a root with |sdf| < eps.
 //  * stepwise (any decoder, SDFR_MLP_FFMA): three launches per step at full precision - trace_points, the decoder
 //    forward over `count` rows, trace_advance - and one gradient-carrying evaluation at the hits.
 //
 // The backward is implicit differentiation of f(l, o + tau d) = 0 at the hit: no storage
 // of the march, one gradient evaluation per hit ray.
 #include "trace.cuh"
+
+#include <algorithm>
 
 
 namespace sdfr {
@@ -30,13 +40,26 @@ struct TraceWs {
   float* tau_exit;   // [P]
   int* list[2];      // [P] active ray ids (ping-pong)
   int* hits;         // [P] rows of the final evaluation: the hit rays (stepwise) / the near rays (fused)
-  int* counters;     // [8] march counters (3, rotating), rows of the final evaluation [3], hits [4]
+  int* counters;     // [16] march counters (3, rotating), near rays [3], hits [4], Newton work lists [5..8]
   unsigned char* hit_flag;   // [P] per row of the final evaluation: 1 = hit
   float* inputs;     // [P, in0] decoder inputs of the rows being evaluated
   float* sdf;        // [P]
   float* dinput;     // [P, in0] for the rows of the final evaluation
   RayMarch* march;   // [6] per-step descriptors of the fused march
+  float* fh;         // [P] fused march: predicted sdf at tau, slope estimate, last evaluated sample (trace.cuh)
+  float* mh;
+  float* ls;
+  float* lf;
+  float* cache;      // [GRID_D^3] distance cache: coarse sdf on the regular lattice over the box
+  float* esdf;       // [P] fused finish: sdf / input gradient of the rows evaluated in this Newton round (compact);
+  float* edinput;    // [P, in0]  sdf / dinput above hold the LAST evaluation of every near ray, by near index
 };
+
+constexpr int GRID_D = 40;            // nodes per axis of the distance cache (spacing 0.052 over [-1, 1.025])
+constexpr float GRID_MARGIN = 0.04f;  // subtracted from the interpolated distance: trilinear error of a 1-Lipschitz
+                                      // field is below the distance to the nearest node (<= 0.045 at a cell centre);
+                                      // measured 0.02 on the stock prior
+constexpr float GRID_STOP = 0.08f;    // hand-over to the decoder march below this interpolated distance
 
 __global__ void __launch_bounds__(256) trace_init_kernel(TraceParams p, TraceWs w) {
   const int P = p.width * p.height;
@@ -64,15 +87,85 @@ __global__ void __launch_bounds__(256) trace_init_kernel(TraceParams p, TraceWs 
   ray_append(active, j, w.list[0], w.counters + 0);
 }
 
-// decoder inputs [latent_unit, o + tau d] for the rows of `list` (also resets the next list's counter)
+// Fused form of the start: box entry / exit of every pixel ray, then the march through the distance cache
+// (trilinear, GRID_MARGIN subtracted) up to the hand-over distance.  Rays that get there join the active list with a
+// predicted distance and slope (the interpolant and its directional derivative) for the speculative march.
+__global__ void __launch_bounds__(256) trace_grid_march_kernel(TraceParams p, TraceWs w) {
+  const int P = p.width * p.height;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool active = false;
+  if (j < P) {
+    float o[3], d[3], rn[3];
+    ray_of_pixel(p, j, o, d, rn);
+    float t0 = 0.f, t1 = 1e30f;
+    for (int a = 0; a < 3; ++a) {
+      const float inv = 1.f / d[a];
+      float ta = (p.lo - o[a]) * inv, tb = (p.hi - o[a]) * inv;
+      if (ta > tb) { const float s = ta; ta = tb; tb = s; }
+      if (d[a] == 0.f) {
+        if (o[a] < p.lo || o[a] > p.hi) { t0 = 1.f; t1 = 0.f; }
+        continue;
+      }
+      t0 = fmaxf(t0, ta);
+      t1 = fminf(t1, tb);
+    }
+    float tau = t0, fv = 0.f, mv = -1.f;
+    if (t0 <= t1) {
+      const float inv_h = (float)(GRID_D - 1) / (p.hi - p.lo);
+      const float* __restrict__ G = w.cache;
+      for (int it = 0; it < 96; ++it) {
+        float u[3], fr[3];
+        int i0[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          u[a] = fminf(fmaxf((o[a] + tau * d[a] - p.lo) * inv_h, 0.f), (float)(GRID_D - 1) - 1e-3f);
+          i0[a] = (int)u[a];
+          fr[a] = u[a] - (float)i0[a];
+        }
+        const float* c = G + ((size_t)i0[0] * GRID_D + i0[1]) * GRID_D + i0[2];
+        const float c000 = c[0], c001 = c[1], c010 = c[GRID_D], c011 = c[GRID_D + 1];
+        const float c100 = c[GRID_D * GRID_D], c101 = c[GRID_D * GRID_D + 1], c110 = c[GRID_D * GRID_D + GRID_D],
+                    c111 = c[GRID_D * GRID_D + GRID_D + 1];
+        const float x00 = c000 + fr[2] * (c001 - c000), x01 = c010 + fr[2] * (c011 - c010);
+        const float x10 = c100 + fr[2] * (c101 - c100), x11 = c110 + fr[2] * (c111 - c110);
+        const float y0 = x00 + fr[1] * (x01 - x00), y1 = x10 + fr[1] * (x11 - x10);
+        const float f = y0 + fr[0] * (y1 - y0);
+        if (f < GRID_STOP) {
+          // directional derivative of the interpolant along the ray
+          const float gx = (y1 - y0) * inv_h;
+          const float gy = ((x01 - x00) + fr[0] * ((x11 - x10) - (x01 - x00))) * inv_h;
+          const float z00 = c001 - c000, z01 = c011 - c010, z10 = c101 - c100, z11 = c111 - c110;
+          const float zy0 = z00 + fr[1] * (z01 - z00), zy1 = z10 + fr[1] * (z11 - z10);
+          const float gz = (zy0 + fr[0] * (zy1 - zy0)) * inv_h;
+          fv = fmaxf(f, 0.25f * GRID_STOP);
+          mv = fminf(fmaxf(gx * d[0] + gy * d[1] + gz * d[2], -1.f), 0.f);
+          active = true;
+          break;
+        }
+        tau += f - GRID_MARGIN;
+        if (tau > t1) break;
+      }
+    }
+    w.tau[j] = tau;
+    w.tau_exit[j] = t1;
+    w.fh[j] = fv;
+    w.mh[j] = mv;
+    w.ls[j] = -1e30f;
+    w.lf[j] = 0.f;
+  }
+  ray_append(active, j, w.list[0], w.counters + 0);
+}
+
+// decoder inputs [latent_unit, o + tau d] for the rows of `list` (also resets the next list's counter); with `via`,
+// row i is the ray list[via[i]] (the work list of a Newton round indexes the near list)
 __global__ void __launch_bounds__(256) trace_points_kernel(TraceParams p, TraceWs w, const float* __restrict__ latent_unit,
-                                                           const int* __restrict__ list, const int* __restrict__ count,
-                                                           int* __restrict__ reset_counter) {
+                                                           const int* __restrict__ list, const int* __restrict__ via,
+                                                           const int* __restrict__ count, int* __restrict__ reset_counter) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && reset_counter) *reset_counter = 0;
   const int n = *count;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int j = list[i];
+  const int j = list[via ? via[i] : i];
   float o[3], d[3], rn[3];
   ray_of_pixel(p, j, o, d, rn);
   const float tau = w.tau[j];
@@ -103,34 +196,44 @@ __global__ void __launch_bounds__(256) trace_advance_kernel(TraceParams p, Trace
   ray_append(hit, j, w.hits, w.counters + 3);
 }
 
-// Newton step of the near rays along their ray, from the accurate evaluation (sdf, grad sdf) at o + tau d;
-// the LAST evaluation classifies: a hit is a root with |sdf| < eps inside the box.
-__global__ void __launch_bounds__(256) trace_newton_kernel(TraceParams p, TraceWs w, float max_step, int last) {
-  const int n = w.counters[3];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool hit = false;
-  if (i < n) {
+// One Newton round of the near rays along their ray, from the accurate evaluation (sdf, grad sdf) at o + tau d of the
+// rows of the work list (`work` = indices into the near list, null = all of it).  A row whose |sdf| < stay_thr is a
+// root: its evaluation is final (sdf / dinput by near index, hit flag) and it leaves the work list; the others step,
+// tau -= sdf / (grad sdf . d), and are evaluated again.  The last round classifies what is left: a hit is a root with
+// |sdf| < eps inside the box.
+__global__ void __launch_bounds__(256) trace_newton_kernel(TraceParams p, TraceWs w, const int* __restrict__ work,
+                                                           const int* __restrict__ work_count, int* __restrict__ next_work,
+                                                           int* __restrict__ next_count, float max_step, float stay_thr,
+                                                           int last) {
+  const int n = *work_count;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = false, again = false;
+  int i = 0;
+  if (r < n) {
+    i = work ? work[r] : r;
     const int j = w.hits[i];
-    const float f = w.sdf[i];
+    const float f = w.esdf[r];
     const float tau = w.tau[j];
-    if (last) {
+    const float* G = w.edinput + (size_t)r * p.in0;
+    if (last || fabsf(f) < stay_thr) {
       hit = fabsf(f) < p.eps && tau >= 0.f && tau <= w.tau_exit[j];
       w.hit_flag[i] = hit ? 1 : 0;
-    } else if (fabsf(f) >= 0.25f * p.eps) {     // already well inside the stopping band: stay
+      w.sdf[i] = f;
+      for (int c = 0; c < p.in0; ++c) w.dinput[(size_t)i * p.in0 + c] = G[c];
+    } else {
       float o[3], d[3], rn[3];
       ray_of_pixel(p, j, o, d, rn);
-      const float* G = w.dinput + (size_t)i * p.in0 + p.latent;
-      const float Gd = G[0] * d[0] + G[1] * d[1] + G[2] * d[2];
+      const float Gd = G[p.latent] * d[0] + G[p.latent + 1] * d[1] + G[p.latent + 2] * d[2];
       // f(tau + s) ~ f + s (G . d); a ray that runs (nearly) along the level set falls back to the sphere-tracing step
       float step = fabsf(Gd) > 1e-3f ? -f / Gd : f;
       step = fminf(fmaxf(step, -max_step), max_step);
       if (step == step) w.tau[j] = tau + step;
+      again = true;
     }
   }
-  if (last) {
-    const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(w.counters + 4, __popc(ballot));
-  }
+  ray_append(again, i, next_work, next_count);
+  const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(w.counters + 4, __popc(ballot));
 }
 
 // maps of the hit rays from the gradient-carrying evaluation at the hit points
@@ -229,12 +332,20 @@ TraceWs carve(void* ws, int64_t P, int in0) {
   w.inputs = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
   w.sdf = reinterpret_cast<float*>(take((size_t)P * 4));
   w.dinput = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
+  w.fh = reinterpret_cast<float*>(take((size_t)P * 4));
+  w.mh = reinterpret_cast<float*>(take((size_t)P * 4));
+  w.ls = reinterpret_cast<float*>(take((size_t)P * 4));
+  w.lf = reinterpret_cast<float*>(take((size_t)P * 4));
+  w.cache = reinterpret_cast<float*>(take((size_t)GRID_D * GRID_D * GRID_D * 4));
+  w.esdf = reinterpret_cast<float*>(take((size_t)P * 4));
+  w.edinput = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
   return w;
 }
 
 size_t ws_bytes(int64_t P, int in0) {
   auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  return r(64) + r(6 * sizeof(RayMarch)) + 6 * r((size_t)P * 4) + r((size_t)P) + 2 * r((size_t)P * in0 * 4);
+  return r(64) + r(6 * sizeof(RayMarch)) + 11 * r((size_t)P * 4) + r((size_t)P) + 3 * r((size_t)P * in0 * 4) +
+         r((size_t)GRID_D * GRID_D * GRID_D * 4);
 }
 
 int fill_params(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec, const float* pose_host, float eps, TraceParams* tp) {
@@ -280,49 +391,72 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
   if (nmap_dev) SDFR_CUDA(cudaMemsetAsync(nmap_dev, 0, (size_t)P * 12, s));
   if (nocs_dev) SDFR_CUDA(cudaMemsetAsync(nocs_dev, 0, (size_t)P * 12, s));
   const unsigned blocks = (unsigned)((P + 255) / 256);
-  trace_init_kernel<<<blocks, 256, 0, s>>>(tp, w);
-  SDFR_LAUNCH_CHECK();
   MlpInputs in;
   in.inputs = w.inputs; in.latent_unit = nullptr; in.lattice = make_lattice(2); in.points_per_batch = 1; in.n = P;
   in.index = nullptr; in.small_tiles = 0;
   int rc;
   const bool fused = impl == SDFR_MLP_TCGEN05 && mlp_tc_march_ok(dec);
   if (fused) {
-    // ---- fused march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
+    // ---- distance cache and the march through it ----
+    MlpInputs ig;
+    ig.inputs = nullptr; ig.latent_unit = latent_unit_dev; ig.lattice = make_regular_lattice(GRID_D, (double)tp.hi);
+    ig.points_per_batch = (long long)GRID_D * GRID_D * GRID_D; ig.n = ig.points_per_batch;
+    ig.index = nullptr; ig.count_dev = nullptr; ig.small_tiles = 0;
+    if ((rc = launch_mlp_tc_coarse(dec, ig, w.cache, s))) return rc;
+    trace_grid_march_kernel<<<blocks, 256, 0, s>>>(tp, w);
+    SDFR_LAUNCH_CHECK();
+    // ---- speculative march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
     // The lattice pass is good to ~3e-4 (its error near the surface is what the refine engine measures and bounds by
     // 2.5e-3), so rays are handed to the full-precision finish well before that matters.
     const float near_thr = 5e-3f;
+    const int round_rows = mlp_tc_round_rows(dec);
     RayMarch desc[6];
     for (int k = 0; k < 6; ++k) {
       RayMarch& m = desc[k];
-      m.p = tp; m.near_thr = near_thr; m.latent_unit = latent_unit_dev; m.tau = w.tau; m.tau_exit = w.tau_exit;
+      m.p = tp; m.near_thr = near_thr; m.spacing = 1.2f; m.latent_unit = latent_unit_dev; m.tau = w.tau; m.tau_exit = w.tau_exit;
+      m.fh = w.fh; m.mh = w.mh; m.ls = w.ls; m.lf = w.lf;
       m.list = w.list[k & 1]; m.count = w.counters + (k % 3);
       m.next_list = w.list[(k + 1) & 1]; m.next_count = w.counters + ((k + 1) % 3);
       m.near_list = w.hits; m.near_count = w.counters + 3;
       m.reset_count = w.counters + ((k + 2) % 3);
+      m.round_rows = round_rows; m.max_log2k = 5;
     }
     SDFR_CUDA(cudaMemcpyAsync(w.march, desc, sizeof(desc), cudaMemcpyHostToDevice, s));
     MlpInputs im = in;
     im.inputs = nullptr;
-    for (int step = 0; step < max_steps; ++step) {
+    im.n = std::max<long long>(P, round_rows);
+    // a launch advances every ray by at least one plain sphere-tracing step and a grazing ray by up to 32: a third of
+    // the step budget covers what max_steps plain steps reach from the hand-over distance; launches that find their
+    // list empty return at once
+    const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 3)));
+    for (int step = 0; step < launches; ++step) {
       im.march = w.march + (step % 6);
       im.count_dev = w.counters + (step % 3);
       if ((rc = launch_mlp_tc_coarse(dec, im, nullptr, s))) return rc;
     }
-    // ---- finish at full precision: Newton steps along the ray, the last evaluation classifies and feeds the maps ----
+    // ---- finish at full precision: Newton rounds along the ray over a shrinking work list; the evaluation that finds
+    //      |sdf| < eps / 2 (or the last one) classifies the ray and feeds the maps ----
     const int newton = 3;
-    in.count_dev = w.counters + 3;
+    MlpInputs ia = in;
+    ia.inputs = w.inputs;
+    ia.adaptive_tiles = 1;
     for (int it = 0; it <= newton; ++it) {
-      trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, w.counters + 3, nullptr);
+      const int* work = it == 0 ? nullptr : w.list[(it - 1) & 1];
+      const int* work_count = it == 0 ? w.counters + 3 : w.counters + 4 + it;
+      trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, work, work_count, nullptr);
       SDFR_LAUNCH_CHECK();
-      if ((rc = launch_mlp_tc(dec, in, w.sdf, w.dinput, s))) return rc;
-      trace_newton_kernel<<<blocks, 256, 0, s>>>(tp, w, 4.f * near_thr, it == newton);
+      ia.count_dev = work_count;
+      if ((rc = launch_mlp_tc(dec, ia, w.esdf, w.edinput, s))) return rc;
+      trace_newton_kernel<<<blocks, 256, 0, s>>>(tp, w, work, work_count, w.list[it & 1], w.counters + 5 + it,
+                                                 4.f * near_thr, 0.5f * eps, it == newton);
       SDFR_LAUNCH_CHECK();
     }
   } else {
+    trace_init_kernel<<<blocks, 256, 0, s>>>(tp, w);
+    SDFR_LAUNCH_CHECK();
     for (int step = 0; step < max_steps; ++step) {
       const int cur = step & 1, nxt = cur ^ 1;
-      trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.list[cur], w.counters + cur, w.counters + nxt);
+      trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.list[cur], nullptr, w.counters + cur, w.counters + nxt);
       SDFR_LAUNCH_CHECK();
       in.count_dev = w.counters + cur;
       rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(dec, in, w.sdf, nullptr, s) : launch_mlp_ffma(dec, in, w.sdf, nullptr, s);
@@ -334,7 +468,7 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     // gradient-carrying evaluation at the hit points: every listed ray is a hit
     SDFR_CUDA(cudaMemsetAsync(w.hit_flag, 1, (size_t)P, s));
     SDFR_CUDA(cudaMemcpyAsync(w.counters + 4, w.counters + 3, 4, cudaMemcpyDeviceToDevice, s));
-    trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, w.counters + 3, nullptr);
+    trace_points_kernel<<<blocks, 256, 0, s>>>(tp, w, latent_unit_dev, w.hits, nullptr, w.counters + 3, nullptr);
     SDFR_LAUNCH_CHECK();
     in.count_dev = w.counters + 3;
     rc = impl == SDFR_MLP_TCGEN05 ? launch_mlp_tc(dec, in, w.sdf, w.dinput, s) : launch_mlp_ffma(dec, in, w.sdf, w.dinput, s);

@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import math
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, Iterable, List, Optional, Sequence
 
@@ -102,7 +103,10 @@ class FrameRefiner:
                                        getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
             # (the tensor-core decoder keeps its scratch per engine; the CUDA-core kernel's LayerNorm scratch is
             #  per decoder, so with that kernel the two engines must not overlap: same stream)
-            self.init_stream = torch.cuda.Stream(device=self.device) if dsdf.native().tcgen05 else \
+            # High priority: the initialisation kernels are short and the host waits for each of them, the refinement
+            # is a long asynchronous train of launches; pending blocks of the side streams go first.
+            self.concurrent_init = bool(dsdf.native().tcgen05)
+            self.init_stream = torch.cuda.Stream(device=self.device, priority=-1) if self.concurrent_init else \
                 torch.cuda.current_stream(self.device)
         # the host part of the pose initialisation (sample draw, 4-point fits, read-backs) runs on a few threads:
         # its C / LAPACK / CUDA calls release the GIL; every detection draws from a generator of its own
@@ -111,8 +115,12 @@ class FrameRefiner:
             init_threads = max(1, min(6, (os.cpu_count() or 2) // local_ranks - 1))
         self.init_threads = int(init_threads)
         self.pool = ThreadPoolExecutor(max_workers=self.init_threads) if self.init_threads > 1 else None
-        self.timing = {'init_s': 0.0, 'refine_wait_s': 0.0, 'label_s': 0.0, 'detections': 0, 'batches': 0,
-                       'no_pose': 0}
+        # every worker thread initialises its detections on a stream of its own: its read-backs wait for its own
+        # kernels only
+        self._tls = threading.local()
+        self._events = []           # (start, end) CUDA events around the refinement of each batch
+        self.timing = {'init_s': 0.0, 'refine_wait_s': 0.0, 'label_s': 0.0, 'refine_gpu_s': 0.0, 'detections': 0,
+                       'batches': 0, 'no_pose': 0}
 
     # ---- stage 1: model clouds + pose RANSAC of a batch (side stream) ---------------------------------
     def _prepare(self, items):
@@ -126,6 +134,8 @@ class FrameRefiner:
                 chunk = items[s:s + eng.cfg.batch]
                 lat = np.stack([np.asarray(d['latent_pred'], dtype=np.float32) for _, _, d in chunk])
                 clouds = eng.surface_clouds(lat)
+                self._clouds_ready = torch.cuda.Event()
+                self._clouds_ready.record(self.init_stream)
                 work = list(zip(chunk, clouds))
                 params = list(self.pool.map(self._initial, work)) if self.pool else [self._initial(w) for w in work]
                 out.extend((fid, di, det, p) for ((fid, di, det), _), p in zip(work, params))
@@ -139,7 +149,13 @@ class FrameRefiner:
         # the reference consumes numpy's global RNG in file order; a generator seeded per detection keeps a
         # detection's hypotheses independent of which rank / batch / thread it lands in
         rng = np.random.RandomState((self.seed * 1000003 + fid * 131 + di) % (2 ** 32))
-        with torch.cuda.device(self.device), torch.cuda.stream(self.init_stream):
+        stream = self.init_stream
+        if self.pool is not None and self.concurrent_init:
+            stream = getattr(self._tls, 'stream', None)
+            if stream is None:
+                stream = self._tls.stream = torch.cuda.Stream(device=self.device, priority=-1)
+            stream.wait_event(self._clouds_ready)
+        with torch.cuda.device(self.device), torch.cuda.stream(stream):
             return initial_params(det, cloud, self.estimator, rng)
 
     # ---- stage 2: refinement of a prepared batch (main stream, asynchronous) ---------------------------
@@ -155,7 +171,11 @@ class FrameRefiner:
             for b, (fid, di, det, p) in enumerate(live):
                 eng.set_detection(b, det['K'], int(det['crop_size'][1]), int(det['crop_size'][0]), det['nocs_pred'],
                                   det['lidar'], p['yaw'], p['trans'], p['scale'], p['latent'])
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
             eng.run(self.iters)
+            ev[1].record()
+            self._events.append(ev)
         return live
 
     # ---- stage 3: read-back, labels ----------------------------------------------------------------------
@@ -168,6 +188,9 @@ class FrameRefiner:
         with torch.cuda.device(self.device):
             out, hists = eng.get_batch()
             self.timing['refine_wait_s'] += time.perf_counter() - t0
+            for a, b in self._events:                       # device time from the first to the last launch of the batch
+                self.timing['refine_gpu_s'] += a.elapsed_time(b) * 1e-3
+            self._events = []
             t1 = time.perf_counter()
             ext = eng.label_extents()
         results = []

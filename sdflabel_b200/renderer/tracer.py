@@ -75,9 +75,9 @@ class SphereTracer(torch.nn.Module):
         self._k_cache = None
 
     def _intrinsics(self):
-        key = (self.K.data_ptr(), self.K._version)
+        k32 = self.K.detach().float().cpu()
+        key = k32.numpy().tobytes()                       # by value: 36 bytes, never a stale pointer / version pair
         if self._k_cache is None or self._k_cache[0] != key:
-            k32 = self.K.detach().float().cpu()
             self._k_cache = (key, k32.inverse().reshape(-1).tolist(), k32.reshape(-1).tolist())
         return self._k_cache[1], self._k_cache[2]
 

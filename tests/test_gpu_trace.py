@@ -84,6 +84,40 @@ def test_trace_maps_and_gradients_vs_oracle(stock_prior_path, size):
     assert np.abs(gp - gpo).max() < 2e-3 * np.abs(gpo).max(), (gp, gpo)
 
 
+@pytest.mark.parametrize("view", [(0.6, (0.0, 0.0, 5.0), 128), (2.3, (0.2, -0.1, 3.6), 160), (-1.1, (-0.3, 0.15, 7.0), 64)])
+def test_trace_fused_march_matches_plain_march(stock_prior_path, view):
+    """The fused form (distance cache, speculative look-ahead samples, Newton finish) finds the hits of the plain
+    full-precision march (one decoder evaluation per step, tau += sdf; SDFR_MLP_FFMA selects it): same silhouette up to
+    rays on its edge, same ray parameter up to the stopping band |f| < eps."""
+    from sdflabel_b200 import _lib
+    from sdflabel_b200.deepsdf.workspace import setup_dsdf
+    yaw, trans, size = view
+    dec, prior, K, tracer = _setup(stock_prior_path, size)
+    plain, _ = setup_dsdf(stock_prior_path, precision=torch.float32)
+    plain = plain.to(cuda)
+    plain.mlp_impl = _lib.MLP_FFMA
+    lat = torch.nn.functional.normalize(torch.tensor([0.6, 0.6, 0.5]), dim=0).to(cuda)
+    pose = O.yaw_pose(torch.tensor([yaw]), torch.tensor(trans)).to(cuda)
+    with torch.no_grad():
+        a = tracer(dec, lat, pose, normalize_latent=False)
+        b = tracer(plain, lat, pose, normalize_latent=False)
+    ma, mb = a["mask"][0] > 0.5, b["mask"][0] > 0.5
+    both, either = ma & mb, ma | mb
+    assert int(both.sum()) > 100
+    diff = either & ~both
+    assert int(diff.sum()) <= max(4, 0.01 * int(either.sum())), (int(both.sum()), int(either.sum()))
+    miss = torch.nn.functional.pad(~mb, (1, 1, 1, 1), value=True)
+    edge = miss[:-2, 1:-1] | miss[2:, 1:-1] | miss[1:-1, :-2] | miss[1:-1, 2:] | miss[1:-1, 1:-1]
+    assert bool(edge[diff].all())
+    # |grad f . d| from the normals: the plain march stops at the outer edge of the band, the fused one at the root
+    o_, d_, rn_ = T.rays(K, size, size, pose.cpu())
+    n_obj = ((b["normals"].reshape(3, -1).t() * 2 - 1) @ pose[:3, :3]).cpu()          # rows: R^T n_cam
+    slope = (n_obj * d_).sum(1).abs().reshape(size, size).clamp(min=2e-2)
+    d_err = (a["depth"][0] - b["depth"][0]).abs().cpu()
+    band = 1.6 * 1e-4 / slope + 3e-5
+    assert bool((d_err[both.cpu()] <= band[both.cpu()]).all()), float((d_err / band)[both.cpu()].max())
+
+
 def test_trace_agrees_with_splat_mode(stock_prior_path):
     """Sanity (not parity): both renderers see the same surface (SURVEY.md T10 bands)."""
     from sdflabel_b200.grid import Grid3D
