@@ -1175,6 +1175,10 @@ mlp_tc_coarse_pair_kernel(const TcTable* __restrict__ tabp, const unsigned char*
   // march mode: 2^march_lk sample points per listed ray (trace.cuh)
   const int march_lk = in.march ? march_log2k(*in.march, *in.march->count) : 0;
   const long long n_rows = in.march ? march_rows(*in.march) : mlp_rows(in);
+#ifdef SDFR_TRACE_DEBUG
+  if (in.march && blockIdx.x == 0 && threadIdx.x == 0)
+    printf("march launch: %d rays x %d samples, near so far %d\n", *in.march->count, 1 << march_lk, *in.march->near_count);
+#endif
   const long long num_pair_tiles = (n_rows + 2 * P_PTS - 1) / (2 * P_PTS);
   const long long num_pairs = gridDim.x >> 1, pair_id = blockIdx.x >> 1;
   // The last Linear (hidden -> 1) is a dot product per point: when the layer before it is a plain hidden layer

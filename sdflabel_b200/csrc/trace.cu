@@ -50,6 +50,7 @@ struct TraceWs {
   float* mh;
   float* ls;
   float* lf;
+  int* nsteps;       // [P] fused march: connected samples consumed per ray
   float* cache;      // [GRID_D^3] distance cache: coarse sdf on the regular lattice over the box
   float* esdf;       // [P] fused finish: sdf / input gradient of the rows evaluated in this Newton round (compact);
   float* edinput;    // [P, in0]  sdf / dinput above hold the LAST evaluation of every near ray, by near index
@@ -146,12 +147,16 @@ __global__ void __launch_bounds__(256) trace_grid_march_kernel(TraceParams p, Tr
         if (tau > t1) break;
       }
     }
+#ifdef SDFR_TRACE_DEBUG
+    if (j == SDFR_TRACE_DEBUG) printf("grid ray %d: t0 %.5f t1 %.5f tau %.5f fv %.5f mv %.3f active %d\n", j, t0, t1, tau, fv, mv, (int)active);
+#endif
     w.tau[j] = tau;
     w.tau_exit[j] = t1;
     w.fh[j] = fv;
     w.mh[j] = mv;
     w.ls[j] = -1e30f;
     w.lf[j] = 0.f;
+    w.nsteps[j] = 0;
   }
   ray_append(active, j, w.list[0], w.counters + 0);
 }
@@ -215,6 +220,9 @@ __global__ void __launch_bounds__(256) trace_newton_kernel(TraceParams p, TraceW
     const float f = w.esdf[r];
     const float tau = w.tau[j];
     const float* G = w.edinput + (size_t)r * p.in0;
+#ifdef SDFR_TRACE_DEBUG
+    if (j == SDFR_TRACE_DEBUG) printf("newton ray %d row %d near-index %d: tau %.6f f %.3e G %.4f %.4f %.4f last %d\n", j, r, i, tau, f, G[p.latent], G[p.latent + 1], G[p.latent + 2], last);
+#endif
     if (last || fabsf(f) < stay_thr) {
       hit = fabsf(f) < p.eps && tau >= 0.f && tau <= w.tau_exit[j];
       w.hit_flag[i] = hit ? 1 : 0;
@@ -336,6 +344,7 @@ TraceWs carve(void* ws, int64_t P, int in0) {
   w.mh = reinterpret_cast<float*>(take((size_t)P * 4));
   w.ls = reinterpret_cast<float*>(take((size_t)P * 4));
   w.lf = reinterpret_cast<float*>(take((size_t)P * 4));
+  w.nsteps = reinterpret_cast<int*>(take((size_t)P * 4));
   w.cache = reinterpret_cast<float*>(take((size_t)GRID_D * GRID_D * GRID_D * 4));
   w.esdf = reinterpret_cast<float*>(take((size_t)P * 4));
   w.edinput = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
@@ -344,7 +353,7 @@ TraceWs carve(void* ws, int64_t P, int in0) {
 
 size_t ws_bytes(int64_t P, int in0) {
   auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  return r(64) + r(6 * sizeof(RayMarch)) + 11 * r((size_t)P * 4) + r((size_t)P) + 3 * r((size_t)P * in0 * 4) +
+  return r(64) + r(6 * sizeof(RayMarch)) + 12 * r((size_t)P * 4) + r((size_t)P) + 3 * r((size_t)P * in0 * 4) +
          r((size_t)GRID_D * GRID_D * GRID_D * 4);
 }
 
@@ -408,13 +417,13 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     // ---- speculative march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
     // The lattice pass is good to ~3e-4 (its error near the surface is what the refine engine measures and bounds by
     // 2.5e-3), so rays are handed to the full-precision finish well before that matters.
-    const float near_thr = 5e-3f;
+    const float near_thr = 2.5e-3f, near_reach = 0.01f;
     const int round_rows = mlp_tc_round_rows(dec);
     RayMarch desc[6];
     for (int k = 0; k < 6; ++k) {
       RayMarch& m = desc[k];
-      m.p = tp; m.near_thr = near_thr; m.spacing = 1.2f; m.latent_unit = latent_unit_dev; m.tau = w.tau; m.tau_exit = w.tau_exit;
-      m.fh = w.fh; m.mh = w.mh; m.ls = w.ls; m.lf = w.lf;
+      m.p = tp; m.near_thr = near_thr; m.near_reach = near_reach; m.spacing = 1.2f; m.latent_unit = latent_unit_dev; m.tau = w.tau; m.tau_exit = w.tau_exit;
+      m.fh = w.fh; m.mh = w.mh; m.ls = w.ls; m.lf = w.lf; m.nsteps = w.nsteps; m.step_budget = 4 * max_steps;
       m.list = w.list[k & 1]; m.count = w.counters + (k % 3);
       m.next_list = w.list[(k + 1) & 1]; m.next_count = w.counters + ((k + 1) % 3);
       m.near_list = w.hits; m.near_count = w.counters + 3;
@@ -425,10 +434,12 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     MlpInputs im = in;
     im.inputs = nullptr;
     im.n = std::max<long long>(P, round_rows);
-    // a launch advances every ray by at least one plain sphere-tracing step and a grazing ray by up to 32: a third of
-    // the step budget covers what max_steps plain steps reach from the hand-over distance; launches that find their
-    // list empty return at once
-    const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 3)));
+    // A launch advances every ray by at least one plain sphere-tracing step and a grazing ray by up to 32; a ray is
+    // abandoned (a miss, the plain march's max_steps rule) once it has consumed 4 max_steps connected samples -
+    // without that, the few rays that run parallel to a flat side a millimetre away keep every launch busy.
+    // Launches that find their list empty return at once (3.5 us): while more rays are active than fit one round every
+    // launch is a plain step for all of them, so large images need their ~25 launches.
+    const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 2)));
     for (int step = 0; step < launches; ++step) {
       im.march = w.march + (step % 6);
       im.count_dev = w.counters + (step % 3);
@@ -448,7 +459,7 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
       ia.count_dev = work_count;
       if ((rc = launch_mlp_tc(dec, ia, w.esdf, w.edinput, s))) return rc;
       trace_newton_kernel<<<blocks, 256, 0, s>>>(tp, w, work, work_count, w.list[it & 1], w.counters + 5 + it,
-                                                 4.f * near_thr, 0.5f * eps, it == newton);
+                                                 2.f * near_reach, 0.5f * eps, it == newton);
       SDFR_LAUNCH_CHECK();
     }
   } else {

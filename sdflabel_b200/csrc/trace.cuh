@@ -31,6 +31,7 @@ struct TraceParams {
 struct RayMarch {
   TraceParams p;
   float near_thr;
+  float near_reach;           // hand-over only when the predicted root |sdf| / |slope| is within this distance
   float spacing;              // c above
   const float* latent_unit;   // [latent]
   float* tau;                 // [P] safe front of the ray
@@ -39,6 +40,8 @@ struct RayMarch {
   float* mh;                  // [P] slope estimate d sdf / d tau in [-1, 0]
   float* ls;                  // [P] ray parameter of the last evaluated connected sample (-1e30: none yet)
   float* lf;                  // [P] its sdf
+  int* nsteps;                // [P] connected samples the ray has consumed (each is worth one plain step)
+  int step_budget;            // a ray that has consumed more is abandoned (the plain march's max_steps rule)
   const int* list;
   const int* count;
   int* next_list;
@@ -63,7 +66,7 @@ __device__ __forceinline__ long long march_rows(const RayMarch& m) {
 // ray parameter of sample k of a ray (explicitly rounded operations: the row generator and the epilogue agree)
 __device__ __forceinline__ float march_sample(const RayMarch& m, float tau, float fh, float mh, int k) {
   const float r = fminf(fmaxf(__fmaf_rn(m.spacing, mh, 1.f), 0.3f), 1.f);
-  float dt = __fmul_rn(m.spacing, fmaxf(fh, m.near_thr));
+  float dt = __fmul_rn(m.spacing, fmaxf(fh, 0.4f * m.near_thr));   // floor: 1e-3, the resolution of this pass
   float s = tau;
   for (int i = 0; i < k; ++i) {
     s = __fadd_rn(s, dt);
@@ -120,10 +123,15 @@ __device__ __forceinline__ void march_advance(const RayMarch& m, bool valid, lon
   const float s_own = march_sample(m, tau0, fh, mh, k);
   float front = tau0, tnear = 0.f, prevs = -1e30f, prevf = 0.f;
   bool alive = valid, isnear = false, dead = false, inside = false;
+  int used = 0;
   for (int kk = 0; kk < K; ++kk) {
     const float fk = __shfl_sync(0xffffffffu, f, g0 + kk), sk = __shfl_sync(0xffffffffu, s_own, g0 + kk);
     const bool reach = alive && (kk == 0 || sk - fabsf(fk) <= front) && sk <= texit && fk == fk;
-    const bool nr = reach && fabsf(fk) < m.near_thr;
+    // hand-over to the Newton finish: close to the surface AND the root within Newton's reach - a ray that runs at a
+    // shallow angle (|d sdf / d tau| small) keeps marching here, where a launch is cheap, until it is within 1e-3
+    // (three times the error of this pass)
+    const float slope_k = kk > 0 || lasts > -1e29f ? (fk - lastf) / fmaxf(sk - lasts, 1e-9f) : mh;
+    const bool nr = reach && fabsf(fk) < m.near_thr && (fabsf(fk) < 1e-3f || fabsf(fk) <= m.near_reach * fabsf(slope_k));
     const bool ok = reach && !nr && fk > 0.f;
     if (nr) { isnear = true; tnear = sk; }
     if (reach && !nr && !ok) {
@@ -135,6 +143,7 @@ __device__ __forceinline__ void march_advance(const RayMarch& m, bool valid, lon
       dead = true;                                         // NaN
     }
     if (ok) {
+      ++used;
       prevs = lasts; prevf = lastf;
       lasts = sk; lastf = fk;
       front = fmaxf(front, sk + fk);
@@ -143,11 +152,17 @@ __device__ __forceinline__ void march_advance(const RayMarch& m, bool valid, lon
   }
   bool keep = false;
   const bool leader = valid && k == 0;
+#ifdef SDFR_TRACE_DEBUG
+  if (valid && j == SDFR_TRACE_DEBUG)
+    printf("march ray %d sample %d/%d: s %.6f f %.6f | tau0 %.6f fh %.5f mh %.3f front %.6f near %d tnear %.6f dead %d inside %d texit %.4f\n",
+           j, k, K, s_own, f, tau0, fh, mh, front, (int)isnear, tnear, (int)dead, (int)inside, texit);
+#endif
   if (leader) {
     if (isnear) {
       m.tau[j] = tnear;                  // tau stays at the evaluated point
-    } else if (!dead && front <= texit && front >= 0.f) {
+    } else if (!dead && front <= texit && front >= 0.f && (used += m.nsteps[j]) <= m.step_budget) {
       keep = true;
+      m.nsteps[j] = used;
       float slope = mh;
       if (prevs > -1e29f && lasts > prevs) slope = fminf(fmaxf((lastf - prevf) / (lasts - prevs), -1.f), 0.f);
       const float ahead = front - lasts;

@@ -11,7 +11,7 @@ dev = torch.device("cuda")
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 yaw = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6
 dec, L = setup_dsdf("assets/deepsdf_synth.pt", precision=torch.float32); dec = dec.to(dev)
-plain, _ = setup_dsdf("assets/deepsdf_synth.pt", precision=torch.float32); plain = plain.to(dev); plain.mlp_impl = _lib.MLP_FFMA
+plain, _ = setup_dsdf("assets/deepsdf_synth.pt", precision=torch.float32); plain = plain.to(dev); plain.mlp_impl = _lib.MLP_FFMA; STEPS = 256
 prior = P.load_prior("assets/deepsdf_synth.pt")
 lat = torch.nn.functional.normalize(torch.tensor([0.6, 0.6, 0.5]), dim=0)
 pose = O.yaw_pose(torch.tensor([yaw]), torch.tensor([0.0, 0.0, 5.0]))
@@ -19,7 +19,7 @@ K = scenes.intrinsics(size)
 tr = SphereTracer(K, (size, size)).to(dev)
 with torch.no_grad():
     a = tr(dec, lat.to(dev), pose.to(dev), normalize_latent=False)
-    b = tr(plain, lat.to(dev), pose.to(dev), normalize_latent=False)
+    b = SphereTracer(K, (size, size), max_steps=STEPS).to(dev)(plain, lat.to(dev), pose.to(dev), normalize_latent=False)
 ma, mb = (a["mask"][0] > 0.5).cpu(), (b["mask"][0] > 0.5).cpu()
 print("hits fused", int(ma.sum()), "plain", int(mb.sum()), "diff", int((ma ^ mb).sum()))
 o, d, rn = T.rays(K, size, size, pose)
