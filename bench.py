@@ -219,6 +219,17 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    # Where the reference tree is reachable (the build container; never the GPU box), its UNMODIFIED Optimizer.optimize is
+    # timed beside the port at cfg1 - the largest crop its M x P x 3 tensors hold - to show what the port is worth
+    try:
+        from oracle import ref_harness
+        if ref_harness.available():
+            import subprocess
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_vs_port.py"), "64"], capture_output=True,
+                                 text=True, timeout=600).stdout.strip().splitlines()
+            line["reference_unmodified_cfg1"] = json.loads(out[-1])
+    except Exception as e:   # noqa: BLE001
+        line["reference_unmodified_cfg1"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line), flush=True)
 
 

@@ -91,6 +91,8 @@ class FrameRefiner:
                  pose_estimator='kabsch', init_scale=2.0, device='cuda', seed=0, init_threads=None):
         self.dsdf, self.grid, self.weights, self.iters = dsdf, grid, weights, int(iters)
         self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:      # pin the index now: the current device is per THREAD, the workers start on 0
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.max_batch = int(max_batch)
         self.estimator = PoseEstimator(pose_estimator, init_scale)
         self.seed = int(seed)
