@@ -332,6 +332,19 @@ const char* sdfr_refine_stage_name(int stage);
 int sdfr_refine_export(sdfr_refine* r, int b, float* yaw_dev, float* trans_dev, float* scale_dev, float* latent_dev,
                        void* stream);
 
+/* Optimizer.optimize of ONE detection as a single call (optimizer.py:56-164 as its caller sees it,
+ * refine_css.py:216-231): sdfr_refine_set_detection(b, host inputs) -> sdfr_refine_import(params from the
+ * caller's DEVICE tensors) -> Adam state restored when *adam_t > 0 (the solver of optimizer.py:46-52 lives as
+ * long as the Optimizer) -> `iters` iterations -> sdfr_refine_export (the params tensors updated in place) ->
+ * sdfr_refine_get (one synchronisation; params_host [5+L], history_host [iters,4] / n_history may be NULL) ->
+ * adam_m_host [4] / adam_v_host [4] / *adam_t updated (may be NULL: a fresh solver, state not returned).
+ * The host buffers only have to stay valid for the duration of the call. */
+int sdfr_refine_optimize(sdfr_refine* r, int b, const float* k_host, const float* kinv_host, int width, int height,
+                         const float* nocs_host, int th, int tw, const float* lidar_host, int n_lidar,
+                         float* yaw_dev, float* trans_dev, float* scale_dev, float* latent_dev, float* adam_m_host,
+                         float* adam_v_host, int* adam_t, int iters, float* params_host, float* history_host,
+                         int* n_history, void* stream);
+
 /* Device views of the last iteration's intermediates of detection b (for
  * parity tests and label dumps): kind 0 sdf [D^3], 1 d sdf/d[latent,x] of the band points of the
  * whole batch (compact, [sum m, L+3]),

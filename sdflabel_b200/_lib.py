@@ -95,6 +95,8 @@ SIGNATURES = {
     "sdfr_refine_lattice_rows": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int, vp]),
     "sdfr_refine_get": (C.c_int, [vp, C.c_int, c_float_p, c_float_p, C.POINTER(C.c_int), vp]),
     "sdfr_refine_export": (C.c_int, [vp, C.c_int, vp, vp, vp, vp, vp]),
+    "sdfr_refine_optimize": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int,
+                                       vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp]),
     "sdfr_refine_view": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(C.c_int64)]),
     "sdfr_refine_copy_view": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64, vp]),
     "sdfr_rotate_iou": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp]),

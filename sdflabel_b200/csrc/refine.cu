@@ -576,6 +576,11 @@ struct sdfr_refine {
   int runs;
   std::vector<int> iters_enqueued;   // per detection: iterations launched since its last set_detection
   std::vector<DetState> host_state;  // what the last sdfr_refine_get / get_batch read back
+  // Page-locked landing zone of the read-back: [DetState x batch | latent x batch*L | presel, overflow | history].
+  // A device->host copy into pageable memory blocks the host until it has completed, so five small copies were
+  // five round trips; into this block they are enqueued back to back and waited for once.
+  char* rb;
+  size_t rb_det, rb_lat, rb_flags, rb_hist, rb_bytes;
 };
 
 namespace {
@@ -629,6 +634,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   r->dec = dec;
   r->cfg = *cfg;
   r->capture_stream = nullptr; r->runs = 0;
+  r->rb = nullptr;
   r->active = cfg->batch;
   r->iters_enqueued.assign((size_t)cfg->batch, 0);
   r->det_w.assign((size_t)cfg->batch, 0);
@@ -674,6 +680,17 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   A(E.presel_err, 4); A(E.extents, (size_t)B * 8);
   A(E.mask_scratch, mlp_tc_mask_scratch_bytes(dec) / 8 + 1);
   A(E.views, B);
+  r->rb_det = 0;
+  r->rb_lat = r->rb_det + sizeof(DetState) * (size_t)B;
+  r->rb_flags = r->rb_lat + sizeof(float) * (size_t)B * L;
+  r->rb_hist = r->rb_flags + 4 * sizeof(int);
+  r->rb_bytes = r->rb_hist + sizeof(float) * (size_t)B * E.max_iters * 4;
+  if (cudaHostAlloc(reinterpret_cast<void**>(&r->rb), r->rb_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    r->rb = nullptr;
+    sdfr_refine_destroy(r);
+    SDFR_REQUIRE(false, SDFR_E_CUDA, "cudaHostAlloc of the %zu-byte read-back block failed", r->rb_bytes);
+  }
+  memset(r->rb, 0, r->rb_bytes);
   r->views_host.resize(B);
   r->nocs_dev.assign(B, nullptr);
   r->nocs_cap.assign(B, 0);
@@ -709,6 +726,7 @@ extern "C" void sdfr_refine_destroy(sdfr_refine* r) {
   if (r->capture_stream) cudaStreamDestroy(r->capture_stream);
   for (void* p : r->allocs) cudaFree(p);
   for (float* p : r->nocs_dev) if (p) cudaFree(p);
+  if (r->rb) cudaFreeHost(r->rb);
   delete r;
 }
 
@@ -1024,30 +1042,36 @@ extern "C" int sdfr_refine_get(sdfr_refine* r, int b, float* params_host, float*
   SDFR_REQUIRE(r && params_host && b >= 0 && b < r->cfg.batch, SDFR_E_INVALID, "bad argument");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   EngineDev& E = r->E;
-  DetState& D = r->host_state[b];
-  int overflow = 0, presel_bits = 0;
   // everything the caller reads back rides on ONE stream synchronisation: state, latent, the history rows
-  // the host knows were enqueued, and the two decoder flags
+  // the host knows were enqueued, and the two decoder flags - all into the page-locked block
+  DetState* rb_det = reinterpret_cast<DetState*>(r->rb + r->rb_det) + b;
+  float* rb_lat = reinterpret_cast<float*>(r->rb + r->rb_lat) + (size_t)b * E.L;
+  int* rb_flags = reinterpret_cast<int*>(r->rb + r->rb_flags);
+  float* rb_hist = reinterpret_cast<float*>(r->rb + r->rb_hist) + (size_t)b * E.max_iters * 4;
   const int nh_host = std::min(r->iters_enqueued[b], E.max_iters);
-  SDFR_CUDA(cudaMemcpyAsync(&D, E.det + b, sizeof(D), cudaMemcpyDeviceToHost, s));
-  SDFR_CUDA(cudaMemcpyAsync(params_host + 5, E.latent + (size_t)b * E.L, E.L * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(rb_det, E.det + b, sizeof(DetState), cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(rb_lat, E.latent + (size_t)b * E.L, E.L * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (history_host && nh_host > 0)
-    SDFR_CUDA(cudaMemcpyAsync(history_host, E.history + (size_t)b * E.max_iters * 4, (size_t)nh_host * 4 * sizeof(float),
+    SDFR_CUDA(cudaMemcpyAsync(rb_hist, E.history + (size_t)b * E.max_iters * 4, (size_t)nh_host * 4 * sizeof(float),
                               cudaMemcpyDeviceToHost, s));
-  SDFR_CUDA(cudaMemcpyAsync(&presel_bits, E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
-  int rc = tc_overflow_flag_enqueue(r->dec, &overflow, s);
+  SDFR_CUDA(cudaMemcpyAsync(rb_flags, E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int rc = tc_overflow_flag_enqueue(r->dec, rb_flags + 1, s);
   if (rc) return rc;
   SDFR_CUDA(cudaStreamSynchronize(s));
+  DetState& D = r->host_state[b];
+  D = *rb_det;
   params_host[0] = D.yaw; params_host[1] = D.trans[0]; params_host[2] = D.trans[1]; params_host[3] = D.trans[2];
   params_host[4] = D.scale;
+  memcpy(params_host + 5, rb_lat, E.L * sizeof(float));
   const int nh = std::min(D.iter, E.max_iters);
   if (n_history) *n_history = nh;
   if (history_host && nh > nh_host) {      // iterations this handle did not count (not reachable through the ABI)
-    SDFR_CUDA(cudaMemcpyAsync(history_host, E.history + (size_t)b * E.max_iters * 4, (size_t)nh * 4 * sizeof(float),
+    SDFR_CUDA(cudaMemcpyAsync(rb_hist, E.history + (size_t)b * E.max_iters * 4, (size_t)nh * 4 * sizeof(float),
                               cudaMemcpyDeviceToHost, s));
     SDFR_CUDA(cudaStreamSynchronize(s));
   }
-  return check_decoder_flags(r, overflow, presel_bits, s);
+  if (history_host && nh > 0) memcpy(history_host, rb_hist, (size_t)nh * 4 * sizeof(float));
+  return check_decoder_flags(r, rb_flags[1], rb_flags[0], s);
 }
 
 extern "C" int sdfr_refine_get_batch(sdfr_refine* r, float* params_host, float* history_host, int* n_history,
@@ -1056,24 +1080,49 @@ extern "C" int sdfr_refine_get_batch(sdfr_refine* r, float* params_host, float* 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   EngineDev& E = r->E;
   const int B = r->active, L = E.L, W = 5 + L;
-  int overflow = 0, presel_bits = 0;
-  std::vector<float> lat((size_t)B * L);
-  SDFR_CUDA(cudaMemcpyAsync(r->host_state.data(), E.det, sizeof(DetState) * (size_t)B, cudaMemcpyDeviceToHost, s));
-  SDFR_CUDA(cudaMemcpyAsync(lat.data(), E.latent, sizeof(float) * (size_t)B * L, cudaMemcpyDeviceToHost, s));
+  DetState* rb_det = reinterpret_cast<DetState*>(r->rb + r->rb_det);
+  float* rb_lat = reinterpret_cast<float*>(r->rb + r->rb_lat);
+  int* rb_flags = reinterpret_cast<int*>(r->rb + r->rb_flags);
+  float* rb_hist = reinterpret_cast<float*>(r->rb + r->rb_hist);
+  SDFR_CUDA(cudaMemcpyAsync(rb_det, E.det, sizeof(DetState) * (size_t)B, cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(rb_lat, E.latent, sizeof(float) * (size_t)B * L, cudaMemcpyDeviceToHost, s));
   if (history_host)
-    SDFR_CUDA(cudaMemcpyAsync(history_host, E.history, sizeof(float) * (size_t)B * E.max_iters * 4, cudaMemcpyDeviceToHost, s));
-  SDFR_CUDA(cudaMemcpyAsync(&presel_bits, E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
-  int rc = tc_overflow_flag_enqueue(r->dec, &overflow, s);
+    SDFR_CUDA(cudaMemcpyAsync(rb_hist, E.history, sizeof(float) * (size_t)B * E.max_iters * 4, cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaMemcpyAsync(rb_flags, E.presel_err, sizeof(int), cudaMemcpyDeviceToHost, s));
+  int rc = tc_overflow_flag_enqueue(r->dec, rb_flags + 1, s);
   if (rc) return rc;
   SDFR_CUDA(cudaStreamSynchronize(s));
+  memcpy(r->host_state.data(), rb_det, sizeof(DetState) * (size_t)B);
+  if (history_host) memcpy(history_host, rb_hist, sizeof(float) * (size_t)B * E.max_iters * 4);
   for (int b = 0; b < B; ++b) {
     const DetState& D = r->host_state[b];
     float* p = params_host + (size_t)b * W;
     p[0] = D.yaw; p[1] = D.trans[0]; p[2] = D.trans[1]; p[3] = D.trans[2]; p[4] = D.scale;
-    memcpy(p + 5, lat.data() + (size_t)b * L, sizeof(float) * L);
+    memcpy(p + 5, rb_lat + (size_t)b * L, sizeof(float) * L);
     if (n_history) n_history[b] = std::min(D.iter, E.max_iters);
   }
-  return check_decoder_flags(r, overflow, presel_bits, s);
+  return check_decoder_flags(r, rb_flags[1], rb_flags[0], s);
+}
+
+// Optimizer.optimize as ONE call (optimizer.py:56-164 seen from its caller): inputs of slot b from host buffers,
+// parameters from / to the caller's device tensors, `iters` iterations, one synchronisation, read-back.
+extern "C" int sdfr_refine_optimize(sdfr_refine* r, int b, const float* k_host, const float* kinv_host, int width,
+                                    int height, const float* nocs_host, int th, int tw, const float* lidar_host,
+                                    int n_lidar, float* yaw_dev, float* trans_dev, float* scale_dev, float* latent_dev,
+                                    float* adam_m_host, float* adam_v_host, int* adam_t, int iters, float* params_host,
+                                    float* history_host, int* n_history, void* stream) {
+  SDFR_REQUIRE(r && yaw_dev && trans_dev && scale_dev && latent_dev && params_host, SDFR_E_INVALID, "null argument");
+  SDFR_REQUIRE(b >= 0 && b < r->active, SDFR_E_INVALID, "slot %d is not among the %d active ones", b, r ? r->active : 0);
+  int rc;
+  if ((rc = sdfr_refine_set_detection(r, b, k_host, kinv_host, width, height, nocs_host, th, tw, lidar_host, n_lidar,
+                                      nullptr, nullptr, nullptr, nullptr, stream))) return rc;
+  if ((rc = sdfr_refine_import(r, b, yaw_dev, trans_dev, scale_dev, latent_dev, stream))) return rc;
+  if (adam_m_host && adam_v_host && adam_t && *adam_t > 0 &&
+      (rc = sdfr_refine_set_optimizer_state(r, b, adam_m_host, adam_v_host, *adam_t, stream))) return rc;
+  if ((rc = sdfr_refine_run(r, iters, stream))) return rc;
+  if ((rc = sdfr_refine_export(r, b, yaw_dev, trans_dev, scale_dev, latent_dev, stream))) return rc;
+  if ((rc = sdfr_refine_get(r, b, params_host, history_host, n_history, stream))) return rc;
+  return sdfr_refine_get_optimizer_state(r, b, adam_m_host, adam_v_host, adam_t);
 }
 
 extern "C" int sdfr_refine_preselect_error(sdfr_refine* r, float* err_host, void* stream) {

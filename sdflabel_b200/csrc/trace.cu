@@ -440,9 +440,17 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     // Launches that find their list empty return at once (3.5 us): while more rays are active than fit one round every
     // launch is a plain step for all of them, so large images need their ~25 launches.
     const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 2)));
+    static int stats = -1;       // SDFR_TRACE_STATS=1: per-launch ray counts on stderr (synchronises; a dev aid)
+    if (stats < 0) { const char* e = getenv("SDFR_TRACE_STATS"); stats = e ? atoi(e) : 0; }
     for (int step = 0; step < launches; ++step) {
       im.march = w.march + (step % 6);
       im.count_dev = w.counters + (step % 3);
+      if (stats) {
+        int c[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(c, w.counters, sizeof(c), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "trace march launch %d: active %d near %d\n", step, c[step % 3], c[3]);
+      }
       if ((rc = launch_mlp_tc_coarse(dec, im, nullptr, s))) return rc;
     }
     // ---- finish at full precision: Newton rounds along the ray over a shrinking work list; the evaluation that finds
@@ -461,6 +469,12 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
       trace_newton_kernel<<<blocks, 256, 0, s>>>(tp, w, work, work_count, w.list[it & 1], w.counters + 5 + it,
                                                  2.f * near_reach, 0.5f * eps, it == newton);
       SDFR_LAUNCH_CHECK();
+      if (stats) {
+        int c[16];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(c, w.counters, sizeof(c), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "trace newton round %d: rows %d -> again %d, hits so far %d\n", it, it == 0 ? c[3] : c[4 + it], c[5 + it], c[4]);
+      }
     }
   } else {
     trace_init_kernel<<<blocks, 256, 0, s>>>(tp, w);

@@ -81,6 +81,7 @@ class _Engine:
         self._pinned: Dict = {}     # persistent pinned staging buffers, keyed by (name, detection)
         self._dirty = set()         # detections whose staging buffers may still be in flight
         self._kcache: Dict = {}
+        self._out = None            # read-back arrays of optimize_slot
 
     def __del__(self):
         try:
@@ -161,6 +162,37 @@ class _Engine:
     def set_active(self, n):
         _lib.check(_lib.load().sdfr_refine_set_active(self.handle, int(n)))
         self.active = int(n)
+
+    @staticmethod
+    def _host_f32(arr):
+        """contiguous float32 host array sharing memory with ``arr`` when it already is one (tensor or ndarray)."""
+        if isinstance(arr, torch.Tensor):
+            arr = arr.detach()
+            arr = (arr if arr.device.type == 'cpu' else arr.cpu()).numpy()
+        return np.ascontiguousarray(arr, dtype=np.float32)
+
+    def optimize_slot(self, b, K, width, height, nocs_pred, lidar_np, p, adam, iters):
+        """``Optimizer.optimize`` of slot b as ONE C-ABI call (sdfr_refine_optimize): host inputs in, the device
+        tensors of ``p`` read and updated in place, ``adam`` = (m[4], v[4], c_int t) continued and updated, one
+        stream synchronisation.  The call is synchronous, so the host arrays are handed over as they are (page-locked
+        or not) without staging copies."""
+        k32, kinv = self._intrinsics(K)
+        nocs = self._host_f32(nocs_pred)
+        lidar = self._host_f32(lidar_np).reshape(-1, 3)
+        out = self._out
+        if out is None or out[1].shape[0] < self.cfg.max_iters:
+            out = self._out = (np.zeros(5 + self.latent_size, dtype=np.float32),
+                               np.zeros((self.cfg.max_iters, 4), dtype=np.float32), C.c_int(0))
+        if self._dirty:                      # staged copies of an earlier set_detection may still be in flight
+            torch.cuda.current_stream().synchronize()
+            self._dirty.clear()
+        _lib.check(_lib.load().sdfr_refine_optimize(
+            self.handle, b, k32.data_ptr(), kinv.data_ptr(), int(width), int(height), nocs.ctypes.data,
+            int(nocs.shape[1]), int(nocs.shape[2]), lidar.ctypes.data, int(lidar.shape[0]), p['yaw'].data_ptr(),
+            p['trans'].data_ptr(), p['scale'].data_ptr(), p['latent'].data_ptr(), adam[0].ctypes.data,
+            adam[1].ctypes.data, C.addressof(adam[2]), int(iters), out[0].ctypes.data, out[1].ctypes.data,
+            C.addressof(out[2]), _lib.stream_ptr()))
+        return out[0].copy(), out[1][:out[2].value].copy()
 
     def set_optimizer_state(self, b, state):
         m, v, t = state
@@ -400,20 +432,21 @@ class Optimizer:
             if eng.active != 1:
                 eng.set_active(1)
             if direct:
-                eng.set_detection(0, K, width, height, nocs_pred, lidar)
-                eng.import_params(0, p)
+                # one C-ABI call: inputs, parameters in / out on the device, Adam state, iterations, read-back
+                if self._adam is None:
+                    self._adam = (np.zeros(4, dtype=np.float32), np.zeros(4, dtype=np.float32), C.c_int(0))
+                out, hist = eng.optimize_slot(0, K, width, height, nocs_pred, lidar, p, self._adam, iters_optim)
             else:
                 host = {k: p[k].detach().cpu().numpy() for k in keys}
                 eng.set_detection(0, K, width, height, nocs_pred, lidar, host['yaw'], host['trans'], host['scale'],
                                   host['latent'])
-            if self._adam is not None:
-                eng.set_optimizer_state(0, self._adam)
-            eng.run(iters_optim)
-            if direct:
-                eng.export_params(0, p)
-            # read back (one stream sync; it also carries the decoder's fp16-range and pre-selection guards)
-            out, hist = eng.get(0)
-            self._adam = eng.get_optimizer_state(0)
+                if self._adam is not None:
+                    eng.set_optimizer_state(0, (self._adam[0], self._adam[1], self._adam[2].value))
+                eng.run(iters_optim)
+                # read back (one stream sync; it also carries the decoder's fp16-range and pre-selection guards)
+                out, hist = eng.get(0)
+                m, v, t = eng.get_optimizer_state(0)
+                self._adam = (m, v, C.c_int(t))
         self.engine = eng
         self.history = hist
         if not direct:
