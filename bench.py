@@ -363,53 +363,100 @@ def _run_cfg3_once(dec, grid, weights, dev):
             "lattice_points_per_detection_iteration": (rows / its) if its else float(DENSITY ** 3)}
 
 
-def run_trace(dec, sc, dev):
+def run_trace(dec, sc, dev, flop_pt, pk):
     """configs[4] (slice) / north_star's trace mode: sphere-traced render of one latent, forward and forward + backward
     (implicit differentiation at the hits), through the public ``SphereTracer`` module; device-timed."""
+    import ctypes as C
     import torch
+    from sdflabel_b200 import _lib
     from sdflabel_b200.renderer.tracer import SphereTracer
+    lib = _lib.load()
     lat = torch.tensor(sc["init"]["latent"], device=dev)
-    pose = torch.eye(4)
-    cy, sy = float(np.cos(0.6)), float(np.sin(0.6))
-    pose[:3, :3] = torch.diag(torch.tensor([1.0, -1.0, 1.0])) @ torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
-    pose[:3, 3] = torch.tensor([0.0, 0.0, 5.0])                       # optimizer.py:87-90 at yaw 0.6, 5 units away
-    pose = pose.to(dev)
+
+    def pose_of(yaw, dist=5.0):
+        pose = torch.eye(4)
+        cy, sy = float(np.cos(yaw)), float(np.sin(yaw))
+        pose[:3, :3] = torch.diag(torch.tensor([1.0, -1.0, 1.0])) @ torch.tensor([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        pose[:3, 3] = torch.tensor([0.0, 0.0, dist])                   # optimizer.py:87-90, `dist` units away
+        return pose
+
+    pose_h = pose_of(0.6)
+    pose = pose_h.to(dev)
+    views = [pose_of(0.6 + 0.7 * i) for i in range(8)]                 # host poses: no read-back per view
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        return float(np.median([a.elapsed_time(b) for a, b in ev]))
+
     rows = []
     for size in (256, 1024):
         K = torch.from_numpy(sc["K"]).clone()
         K[:2] *= size / float(SIZE)
         tracer = SphereTracer(K, (size, size)).to(dev)
+        fresh = SphereTracer(K, (size, size), reuse_cache=False).to(dev)
 
         def fwd():
             with torch.no_grad():
                 return tracer(dec, lat, pose)
+
+        def fwd_fresh():
+            with torch.no_grad():
+                return fresh(dec, lat, pose)
 
         def both():
             l, p = lat.clone().requires_grad_(True), pose.clone().requires_grad_(True)
             out = tracer(dec, l, p)
             (out["depth"].sum() + out["color"].sum()).backward()
 
-        res = {}
-        for name, fn in (("fwd", fwd), ("fwd_bwd", both)):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            ev = []
-            for _ in range(5):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                b.record()
-                ev.append((a, b))
-            torch.cuda.synchronize()
-            res[name] = float(np.median([a.elapsed_time(b) for a, b in ev]))
+        def many():
+            return tracer.render_views(dec, lat, views, views_in_flight=4)
+
+        res = {"fwd": timed(fwd), "fwd_fresh": timed(fwd_fresh), "fwd_bwd": timed(both), "views": timed(many, 3)}
         hits = int(fwd()["mask"].sum().item())
-        rows.append({"resolution": f"{size}x{size}", "hit_rays": hits, "fwd_ms": res["fwd"],
-                     "fwd_rays_per_s": size * size / (res["fwd"] * 1e-3), "fwd_bwd_ms": res["fwd_bwd"],
-                     "fwd_bwd_rays_per_s": size * size / (res["fwd_bwd"] * 1e-3)})
-    return {"what": "trace mode (sdflabel_b200.renderer.tracer.SphereTracer): distance cache on a regular 40^3 lattice, "
-                    "speculative sphere tracing on the tcgen05 lattice-pass kernel, Newton finish at full precision, "
-                    "implicit-differentiation backward; one latent, stock prior, eps 1e-4; median of 5 device-timed calls",
+        view_hits = int(sum(float(v["mask"].sum().item()) for v in many()))
+        # decoder rows one forward issues (counted in an un-timed instrumented call) -> tensor-pipe utilisation:
+        # a march / cache row is one fp16-operand forward (F flop), a Newton row the full-precision forward + input
+        # gradient (2 F algorithmic; issued as 3 MMAs per product)
+        lib.sdfr_trace_set_stats(1)
+        fwd_fresh()
+        torch.cuda.synchronize()
+        cnt = (C.c_int64 * 4)()
+        lib.sdfr_trace_get_stats(cnt)
+        lib.sdfr_trace_set_stats(0)
+        flops = flop_pt * (cnt[0] + cnt[1] + 2.0 * cnt[3])
+        rows.append({"resolution": f"{size}x{size}", "hit_rays": hits,
+                     "fwd_ms": res["fwd"], "fwd_rays_per_s": size * size / (res["fwd"] * 1e-3),
+                     "fwd_new_latent_ms": res["fwd_fresh"], "fwd_new_latent_rays_per_s": size * size / (res["fwd_fresh"] * 1e-3),
+                     "fwd_bwd_ms": res["fwd_bwd"], "fwd_bwd_rays_per_s": size * size / (res["fwd_bwd"] * 1e-3),
+                     "views_in_flight": {"views": len(views), "streams": 4, "ms": res["views"], "hit_rays": view_hits,
+                                         "fwd_rays_per_s": len(views) * size * size / (res["views"] * 1e-3)},
+                     "decoder_rows_new_latent": {"distance_cache": int(cnt[0]), "march": int(cnt[1]),
+                                                 "march_launches": int(cnt[2]), "newton": int(cnt[3])},
+                     "roofline": {"bound": "tensor", "achieved": flops / (res["fwd_fresh"] * 1e-3) / 1e12,
+                                  "peak": pk["tensor"], "unit": "TFLOP/s",
+                                  "frac": flops / (res["fwd_fresh"] * 1e-3) / 1e12 / pk["tensor"],
+                                  "frac_views_in_flight": (flop_pt * (cnt[1] + 2.0 * cnt[3]) * len(views) /
+                                                           (res["views"] * 1e-3) / 1e12 / pk["tensor"]),
+                                  "note": "algorithmic decoder flops of the rows the trace evaluates / device time; a "
+                                          "single view is a chain of ~25 dependent launches bound by the latency of one "
+                                          "decoder tile, which independent views in flight fill (their figure assumes "
+                                          "the per-view rows of the single view and no cache rows)"}})
+    return {"what": "trace mode (sdflabel_b200.renderer.tracer.SphereTracer): distance cache on a regular 40^3 lattice "
+                    "(kept across calls while the latent stays within the decoder's Lipschitz slack: `fwd` = same "
+                    "latent, `fwd_new_latent` = cache rebuilt every call), speculative sphere tracing on the tcgen05 "
+                    "lattice-pass kernel, Newton finish at full precision, implicit-differentiation backward; "
+                    "`views_in_flight`: SphereTracer.render_views, 8 poses of the latent on 4 CUDA streams; stock "
+                    "prior, eps 1e-4; median of device-timed calls",
             "per_resolution": rows}
 
 
@@ -744,7 +791,7 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:   # noqa: BLE001
             extras["cfg3"] = {"error": repr(e)}
         try:
-            extras["trace"] = run_trace(dec, sc, dev)
+            extras["trace"] = run_trace(dec, sc, dev, flop_pt, pk)
         except Exception as e:   # noqa: BLE001
             extras["trace"] = {"error": repr(e)[:300]}
     frames_block = None

@@ -190,8 +190,22 @@ int64_t sdfr_trace_workspace_bytes(const sdfr_raster_cfg* cfg, const sdfr_decode
  * the object frame, mask [1,H,W]; zero where no hit.  latent_unit_dev: [L] normalised latent. */
 int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg, const float* latent_unit_dev,
                        const float* pose_host, int max_steps, float eps, float* depth_dev, float* nmap_dev,
-                       float* nocs_dev, float* mask_dev, int32_t* hit_count_dev, void* workspace_dev, int impl,
-                       void* stream);
+                       float* nocs_dev, float* mask_dev, int32_t* hit_count_dev, void* workspace_dev,
+                       void* cache_dev, float latent_lipschitz, int impl, void* stream);
+
+/* Optional persistent block for the distance cache of the fused march (cache_dev above; NULL = rebuilt every
+ * call): sdfr_trace_cache_bytes() bytes of device memory, zero-filled by the caller once, private to one decoder.
+ * The cache (the decoder on a regular 40^3 lattice, 190 us) depends on the latent only; it is reused while
+ * latent_lipschitz * |latent - latent of the cache| <= 0.01 with that product added to the march's safety margin
+ * (latent_lipschitz: the certified bound of sdfr_refine_cfg; 0 = never reuse), and renewed otherwise - decided
+ * on the device, no synchronisation.  Rendering one shape from many poses pays for the cache once. */
+int64_t sdfr_trace_cache_bytes(void);
+
+/* Measurement aid: with on != 0 every fused-march forward synchronises after each launch and counts the decoder rows
+ * it issued (process-wide; resets the counts).  counts4 = [distance-cache rows, march rows (fp16-operand forward),
+ * non-empty march launches, Newton rows (full-precision forward + input gradient)].  Never on in a timed call. */
+void sdfr_trace_set_stats(int on);
+void sdfr_trace_get_stats(int64_t* counts4);
 
 /* Gradient of a loss on the depth / NOCS maps with respect to the pose (12 floats, rows of
  * [R|t]) and the unit latent, by implicit differentiation of sdf(l, o + tau d) = 0 at the hits

@@ -73,7 +73,10 @@ SIGNATURES = {
                                       vp, vp, vp, vp]),
     "sdfr_trace_workspace_bytes": (C.c_int64, [C.POINTER(RasterCfg), vp]),
     "sdfr_trace_forward": (C.c_int, [vp, C.POINTER(RasterCfg), vp, c_float_p, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp,
-                                     C.c_int, vp]),
+                                     vp, C.c_float, C.c_int, vp]),
+    "sdfr_trace_cache_bytes": (C.c_int64, []),
+    "sdfr_trace_set_stats": (None, [C.c_int]),
+    "sdfr_trace_get_stats": (None, [C.POINTER(C.c_int64)]),
     "sdfr_trace_backward": (C.c_int, [vp, C.POINTER(RasterCfg), c_float_p, C.c_float, vp, vp, vp, vp, vp, vp]),
     "sdfr_loss3d": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_double, vp, vp, vp, vp]),
     "sdfr_loss2d": (C.c_int, [vp, vp, C.c_int, C.c_int, vp, vp, vp]),

@@ -52,6 +52,10 @@ struct TraceWs {
   float* lf;
   int* nsteps;       // [P] fused march: connected samples consumed per ray
   float* cache;      // [GRID_D^3] distance cache: coarse sdf on the regular lattice over the box
+  float* z_ref;      // [CACHE_LATENT] unit latent the cache was evaluated at
+  int* cstate;       // [4] cache state: valid, lattice rows this call evaluates (0 = cache reused), extra margin (float)
+  unsigned long long* mask_scratch;   // ReLU sign scratch of the full-precision decoder launches of THIS workspace (views
+                                      // in flight on different streams must not share the decoder's own)
   float* esdf;       // [P] fused finish: sdf / input gradient of the rows evaluated in this Newton round (compact);
   float* edinput;    // [P, in0]  sdf / dinput above hold the LAST evaluation of every near ray, by near index
 };
@@ -60,7 +64,35 @@ constexpr int GRID_D = 40;            // nodes per axis of the distance cache (s
 constexpr float GRID_MARGIN = 0.04f;  // subtracted from the interpolated distance: trilinear error of a 1-Lipschitz
                                       // field is below the distance to the nearest node (<= 0.045 at a cell centre);
                                       // measured 0.02 on the stock prior
-constexpr float GRID_STOP = 0.08f;    // hand-over to the decoder march below this interpolated distance
+constexpr float GRID_STOP = 0.05f;    // hand-over to the decoder march below this interpolated distance (0.08: 17 march
+                                      // launches at 256^2, 0.05: 15; the last steps of the grid march are 0.01 long)
+constexpr int GRID_ITERS = 192;       // step cap of the grid march
+constexpr int CACHE_LATENT = 512;     // floats reserved for the cache's reference latent
+constexpr float CACHE_SLACK = 0.01f;  // the cache is reused while lipschitz * |z - z_ref| stays below this (it widens the margin)
+constexpr size_t CACHE_BYTES = (((size_t)GRID_D * GRID_D * GRID_D * 4 + 255) & ~(size_t)255) + CACHE_LATENT * 4 + 256;
+
+// Distance cache across calls (caller-owned block, sdfr_trace_cache_bytes): the cache only depends on the latent, and the
+// decoder is Lipschitz in it (sdfr_refine_cfg.latent_lipschitz):
+//   sdf(x; z) >= sdf(x; z_ref) - lip |z - z_ref| ,
+// so the lattice values at z_ref stay a conservative distance bound for z once lip |z - z_ref| is added to the margin.
+// One warp decides on the device: reuse (no lattice rows this call) or renew (whole lattice, new reference).
+__global__ void trace_cache_check_kernel(const float* __restrict__ z, int L, float lip, int n_rows, float* __restrict__ z_ref,
+                                         int* __restrict__ cstate) {
+  const int lane = threadIdx.x;
+  float acc = 0.f;
+  for (int c = lane; c < L; c += 32) { const float dz = z[c] - z_ref[c]; acc += dz * dz; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const float extra = lip * sqrtf(acc);
+  const bool reuse = cstate[0] == 1 && lip > 0.f && extra <= CACHE_SLACK;   // also false for a NaN latent
+  __syncwarp();
+  if (!reuse) for (int c = lane; c < L; c += 32) z_ref[c] = z[c];
+  if (lane == 0) {
+    cstate[0] = 1;
+    cstate[1] = reuse ? 0 : n_rows;
+    cstate[2] = __float_as_int(reuse ? extra : 0.f);
+  }
+}
 
 __global__ void __launch_bounds__(256) trace_init_kernel(TraceParams p, TraceWs w) {
   const int P = p.width * p.height;
@@ -91,7 +123,7 @@ __global__ void __launch_bounds__(256) trace_init_kernel(TraceParams p, TraceWs 
 // Fused form of the start: box entry / exit of every pixel ray, then the march through the distance cache
 // (trilinear, GRID_MARGIN subtracted) up to the hand-over distance.  Rays that get there join the active list with a
 // predicted distance and slope (the interpolant and its directional derivative) for the speculative march.
-__global__ void __launch_bounds__(256) trace_grid_march_kernel(TraceParams p, TraceWs w) {
+__global__ void __launch_bounds__(256) trace_grid_march_kernel(TraceParams p, TraceWs w, float stop) {
   const int P = p.width * p.height;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   bool active = false;
@@ -112,9 +144,13 @@ __global__ void __launch_bounds__(256) trace_grid_march_kernel(TraceParams p, Tr
     }
     float tau = t0, fv = 0.f, mv = -1.f;
     if (t0 <= t1) {
+      const float extra = __int_as_float(w.cstate[2]);     // lip |z - z_ref| of a reused cache
+      const float grid_margin = GRID_MARGIN + extra, grid_stop = stop + extra;
       const float inv_h = (float)(GRID_D - 1) / (p.hi - p.lo);
       const float* __restrict__ G = w.cache;
-      for (int it = 0; it < 96; ++it) {
+      // steps are >= stop - margin = 0.01, the box diagonal is 3.5: a ray that has not arrived after GRID_ITERS steps
+      // (it runs along a surface at the hand-over distance) continues in the decoder march from where it is
+      for (int it = 0; it <= GRID_ITERS; ++it) {
         float u[3], fr[3];
         int i0[3];
 #pragma unroll
@@ -131,19 +167,19 @@ __global__ void __launch_bounds__(256) trace_grid_march_kernel(TraceParams p, Tr
         const float x10 = c100 + fr[2] * (c101 - c100), x11 = c110 + fr[2] * (c111 - c110);
         const float y0 = x00 + fr[1] * (x01 - x00), y1 = x10 + fr[1] * (x11 - x10);
         const float f = y0 + fr[0] * (y1 - y0);
-        if (f < GRID_STOP) {
+        if (f < grid_stop || it == GRID_ITERS) {
           // directional derivative of the interpolant along the ray
           const float gx = (y1 - y0) * inv_h;
           const float gy = ((x01 - x00) + fr[0] * ((x11 - x10) - (x01 - x00))) * inv_h;
           const float z00 = c001 - c000, z01 = c011 - c010, z10 = c101 - c100, z11 = c111 - c110;
           const float zy0 = z00 + fr[1] * (z01 - z00), zy1 = z10 + fr[1] * (z11 - z10);
           const float gz = (zy0 + fr[0] * (zy1 - zy0)) * inv_h;
-          fv = fmaxf(f, 0.25f * GRID_STOP);
+          fv = fmaxf(f - extra, 0.25f * stop);
           mv = fminf(fmaxf(gx * d[0] + gy * d[1] + gz * d[2], -1.f), 0.f);
           active = true;
           break;
         }
-        tau += f - GRID_MARGIN;
+        tau += f - grid_margin;
         if (tau > t1) break;
       }
     }
@@ -325,7 +361,10 @@ __global__ void __launch_bounds__(256) trace_backward_kernel(TraceParams p, Trac
   }
 }
 
-TraceWs carve(void* ws, int64_t P, int in0) {
+int g_trace_stats = -1;                 // row counting of the fused march (sdfr_trace_set_stats)
+long long g_trace_counts[4] = {0, 0, 0, 0};   // distance-cache rows, march rows, non-empty march launches, Newton rows
+
+TraceWs carve(void* ws, int64_t P, int in0, size_t mask_bytes) {
   TraceWs w;
   char* p = reinterpret_cast<char*>(ws);
   auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) & ~(size_t)255; return r; };
@@ -346,15 +385,18 @@ TraceWs carve(void* ws, int64_t P, int in0) {
   w.lf = reinterpret_cast<float*>(take((size_t)P * 4));
   w.nsteps = reinterpret_cast<int*>(take((size_t)P * 4));
   w.cache = reinterpret_cast<float*>(take((size_t)GRID_D * GRID_D * GRID_D * 4));
+  w.z_ref = reinterpret_cast<float*>(take((size_t)CACHE_LATENT * 4));
+  w.cstate = reinterpret_cast<int*>(take(256));
+  w.mask_scratch = mask_bytes ? reinterpret_cast<unsigned long long*>(take(mask_bytes)) : nullptr;
   w.esdf = reinterpret_cast<float*>(take((size_t)P * 4));
   w.edinput = reinterpret_cast<float*>(take((size_t)P * in0 * 4));
   return w;
 }
 
-size_t ws_bytes(int64_t P, int in0) {
+size_t ws_bytes(int64_t P, int in0, size_t mask_bytes) {
   auto r = [](size_t b) { return (b + 255) & ~(size_t)255; };
   return r(64) + r(6 * sizeof(RayMarch)) + 12 * r((size_t)P * 4) + r((size_t)P) + 3 * r((size_t)P * in0 * 4) +
-         r((size_t)GRID_D * GRID_D * GRID_D * 4);
+         r((size_t)GRID_D * GRID_D * GRID_D * 4) + r((size_t)CACHE_LATENT * 4) + 256 + r(mask_bytes);
 }
 
 int fill_params(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec, const float* pose_host, float eps, TraceParams* tp) {
@@ -378,13 +420,23 @@ using namespace sdfr;
 
 extern "C" int64_t sdfr_trace_workspace_bytes(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec) {
   if (!cfg || !dec) return -1;
-  return (int64_t)ws_bytes((int64_t)cfg->width * cfg->height, dec->dev.in0);
+  return (int64_t)ws_bytes((int64_t)cfg->width * cfg->height, dec->dev.in0, mlp_tc_mask_scratch_bytes(dec));
+}
+
+extern "C" int64_t sdfr_trace_cache_bytes(void) { return (int64_t)CACHE_BYTES; }
+
+extern "C" void sdfr_trace_set_stats(int on) {
+  g_trace_stats = on;
+  for (long long& c : g_trace_counts) c = 0;
+}
+extern "C" void sdfr_trace_get_stats(int64_t* counts4) {
+  for (int i = 0; i < 4; ++i) counts4[i] = g_trace_counts[i];
 }
 
 extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg, const float* latent_unit_dev,
                                   const float* pose_host, int max_steps, float eps, float* depth_dev, float* nmap_dev,
-                                  float* nocs_dev, float* mask_dev, int32_t* hit_count_dev, void* workspace_dev, int impl,
-                                  void* stream) {
+                                  float* nocs_dev, float* mask_dev, int32_t* hit_count_dev, void* workspace_dev,
+                                  void* cache_dev, float latent_lipschitz, int impl, void* stream) {
   SDFR_REQUIRE(dec && cfg && latent_unit_dev && pose_host && workspace_dev, SDFR_E_INVALID, "null argument");
   SDFR_REQUIRE(cfg->width > 0 && cfg->height > 0 && max_steps > 0 && eps > 0.f, SDFR_E_INVALID, "bad trace configuration");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -392,7 +444,17 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
   const int in0 = dec->dev.in0;
   TraceParams tp;
   fill_params(cfg, dec, pose_host, eps, &tp);
-  TraceWs w = carve(workspace_dev, P, in0);
+  TraceWs w = carve(workspace_dev, P, in0, mlp_tc_mask_scratch_bytes(dec));
+  SDFR_REQUIRE(dec->dev.latent_size <= CACHE_LATENT, SDFR_E_UNSUPPORTED, "latent size %d > %d", dec->dev.latent_size,
+               CACHE_LATENT);
+  if (cache_dev) {      // the caller's persistent block replaces the per-call cache of the workspace
+    char* c = reinterpret_cast<char*>(cache_dev);
+    w.cache = reinterpret_cast<float*>(c);
+    w.z_ref = reinterpret_cast<float*>(c + (((size_t)GRID_D * GRID_D * GRID_D * 4 + 255) & ~(size_t)255));
+    w.cstate = reinterpret_cast<int*>(w.z_ref + CACHE_LATENT);
+  } else {
+    SDFR_CUDA(cudaMemsetAsync(w.cstate, 0, 16, s));
+  }
   if (impl == SDFR_MLP_AUTO) impl = dec->tc.ok ? SDFR_MLP_TCGEN05 : SDFR_MLP_FFMA;
   SDFR_CUDA(cudaMemsetAsync(w.counters, 0, 64, s));
   if (depth_dev) SDFR_CUDA(cudaMemsetAsync(depth_dev, 0, (size_t)P * 4, s));
@@ -403,6 +465,7 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
   MlpInputs in;
   in.inputs = w.inputs; in.latent_unit = nullptr; in.lattice = make_lattice(2); in.points_per_batch = 1; in.n = P;
   in.index = nullptr; in.small_tiles = 0;
+  in.mask_scratch = w.mask_scratch;
   int rc;
   const bool fused = impl == SDFR_MLP_TCGEN05 && mlp_tc_march_ok(dec);
   if (fused) {
@@ -410,9 +473,16 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     MlpInputs ig;
     ig.inputs = nullptr; ig.latent_unit = latent_unit_dev; ig.lattice = make_regular_lattice(GRID_D, (double)tp.hi);
     ig.points_per_batch = (long long)GRID_D * GRID_D * GRID_D; ig.n = ig.points_per_batch;
-    ig.index = nullptr; ig.count_dev = nullptr; ig.small_tiles = 0;
+    ig.index = nullptr; ig.small_tiles = 0;
+    // reuse the lattice values of an earlier call while the latent has not moved beyond the slack (device-side decision)
+    trace_cache_check_kernel<<<1, 32, 0, s>>>(latent_unit_dev, dec->dev.latent_size, cache_dev ? latent_lipschitz : 0.f,
+                                              (int)ig.n, w.z_ref, w.cstate);
+    SDFR_LAUNCH_CHECK();
+    ig.count_dev = w.cstate + 1;
     if ((rc = launch_mlp_tc_coarse(dec, ig, w.cache, s))) return rc;
-    trace_grid_march_kernel<<<blocks, 256, 0, s>>>(tp, w);
+    static float grid_stop = -1.f;   // SDFR_TRACE_GRID_STOP: dev override of the hand-over distance
+    if (grid_stop < 0.f) { const char* e = getenv("SDFR_TRACE_GRID_STOP"); grid_stop = e ? (float)atof(e) : GRID_STOP; }
+    trace_grid_march_kernel<<<blocks, 256, 0, s>>>(tp, w, grid_stop);
     SDFR_LAUNCH_CHECK();
     // ---- speculative march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
     // The lattice pass is good to ~3e-4 (its error near the surface is what the refine engine measures and bounds by
@@ -437,11 +507,24 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     // A launch advances every ray by at least one plain sphere-tracing step and a grazing ray by up to 32; a ray is
     // abandoned (a miss, the plain march's max_steps rule) once it has consumed 4 max_steps connected samples -
     // without that, the few rays that run parallel to a flat side a millimetre away keep every launch busy.
-    // Launches that find their list empty return at once (3.5 us): while more rays are active than fit one round every
-    // launch is a plain step for all of them, so large images need their ~25 launches.
-    const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 2)));
-    static int stats = -1;       // SDFR_TRACE_STATS=1: per-launch ray counts on stderr (synchronises; a dev aid)
-    if (stats < 0) { const char* e = getenv("SDFR_TRACE_STATS"); stats = e ? atoi(e) : 0; }
+    // Launches that find their list empty return at once (3.5 us).  While more rays are active than fit half a round
+    // every launch is a plain step for all of them, and the count falls by ~7 % per launch there: a 1024^2 image hands
+    // 160 k rays to the march and still had 10 k active after 32 launches (they were dropped: 0.4 % of the hits
+    // missing), so large images get three more launches per doubling of the pixel count, up to the max_steps of the
+    // plain march.
+    int extra_launches = 0;
+    for (int64_t q = 65536; q < P; q *= 2) extra_launches += 3;
+    const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 2) + extra_launches));
+    // sdfr_trace_set_stats(1) / SDFR_TRACE_STATS=1: count the rows of every launch (synchronises after each: a
+    // measurement aid for bench.py's utilisation figure, never on in a timed call)
+    if (g_trace_stats < 0) { const char* e = getenv("SDFR_TRACE_STATS"); g_trace_stats = e ? atoi(e) : 0; }
+    const int stats = g_trace_stats;
+    if (stats) {
+      int c[4];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(c, w.cstate, sizeof(c), cudaMemcpyDeviceToHost);
+      g_trace_counts[0] += c[1];
+    }
     for (int step = 0; step < launches; ++step) {
       im.march = w.march + (step % 6);
       im.count_dev = w.counters + (step % 3);
@@ -449,7 +532,14 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
         int c[16];
         cudaStreamSynchronize(s);
         cudaMemcpy(c, w.counters, sizeof(c), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "trace march launch %d: active %d near %d\n", step, c[step % 3], c[3]);
+        if (stats > 1) fprintf(stderr, "trace march launch %d: active %d near %d\n", step, c[step % 3], c[3]);
+        const int n = c[step % 3];
+        if (n > 0) {
+          int lk = 0;
+          while (lk < 5 && ((long long)n << (lk + 1)) <= (long long)round_rows) ++lk;
+          g_trace_counts[1] += (long long)n << lk;
+          g_trace_counts[2] += 1;
+        }
       }
       if ((rc = launch_mlp_tc_coarse(dec, im, nullptr, s))) return rc;
     }
@@ -473,7 +563,8 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
         int c[16];
         cudaStreamSynchronize(s);
         cudaMemcpy(c, w.counters, sizeof(c), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "trace newton round %d: rows %d -> again %d, hits so far %d\n", it, it == 0 ? c[3] : c[4 + it], c[5 + it], c[4]);
+        if (stats > 1) fprintf(stderr, "trace newton round %d: rows %d -> again %d, hits so far %d\n", it, it == 0 ? c[3] : c[4 + it], c[5 + it], c[4]);
+        g_trace_counts[3] += it == 0 ? c[3] : c[4 + it];
       }
     }
   } else {
@@ -513,7 +604,7 @@ extern "C" int sdfr_trace_backward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg
   const int64_t P = (int64_t)cfg->width * cfg->height;
   TraceParams tp;
   fill_params(cfg, dec, pose_host, eps, &tp);
-  TraceWs w = carve(workspace_dev, P, dec->dev.in0);
+  TraceWs w = carve(workspace_dev, P, dec->dev.in0, mlp_tc_mask_scratch_bytes(dec));
   if (d_pose_dev) SDFR_CUDA(cudaMemsetAsync(d_pose_dev, 0, 12 * sizeof(float), s));
   if (d_latent_unit_dev) SDFR_CUDA(cudaMemsetAsync(d_latent_unit_dev, 0, dec->dev.latent_size * sizeof(float), s));
   trace_backward_kernel<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(tp, w, g_depth_dev, g_nocs_dev, d_pose_dev,

@@ -24,7 +24,7 @@ from .. import _lib
 
 class _Trace(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, latent_unit, pose, native, cfg_tuple, max_steps, eps, impl):
+    def forward(ctx, latent_unit, pose, native, cfg_tuple, max_steps, eps, impl, cache):
         lib = _lib.load()
         width, height, kinv, kmat = cfg_tuple
         dev = latent_unit.device
@@ -42,7 +42,9 @@ class _Trace(torch.autograd.Function):
         with torch.cuda.device(dev):
             _lib.check(lib.sdfr_trace_forward(native.handle, cfg, lat.data_ptr(), _lib.fptr(pose_h), int(max_steps),
                                               float(eps), depth.data_ptr(), nmap.data_ptr(), nocs.data_ptr(),
-                                              mask.data_ptr(), 0, ws.data_ptr(), impl, _lib.stream_ptr()))
+                                              mask.data_ptr(), 0, ws.data_ptr(), _lib.ptr(cache),
+                                              float(native.latent_lipschitz) if cache is not None else 0.0, impl,
+                                              _lib.stream_ptr()))
         ctx.native, ctx.cfg, ctx.ws, ctx.pose_h, ctx.eps = native, cfg, ws, pose_h, float(eps)
         ctx.meta = (latent_unit.dtype, pose.dtype, pose.device, tuple(pose.shape), latent_unit.shape[0])
         ctx.mark_non_differentiable(nmap, mask)
@@ -63,16 +65,36 @@ class _Trace(torch.autograd.Function):
                                                _lib.stream_ptr()))
         g_pose = torch.zeros(pose_shape, device=dev, dtype=torch.float32)
         g_pose[:3, :4] = d_pose.view(3, 4)
-        return d_lat.to(lat_dtype), g_pose.to(pose_dev, pose_dtype), None, None, None, None, None
+        return d_lat.to(lat_dtype), g_pose.to(pose_dev, pose_dtype), None, None, None, None, None, None
 
 
 class SphereTracer(torch.nn.Module):
-    def __init__(self, K, resolution_px, max_steps=64, eps=1e-4, precision=torch.float32):
+    def __init__(self, K, resolution_px, max_steps=64, eps=1e-4, precision=torch.float32, reuse_cache=True):
         super().__init__()
         self.res_x_px, self.res_y_px = resolution_px
         self.max_steps, self.eps = int(max_steps), float(eps)
         self.register_buffer('K', K.to(precision))
         self._k_cache = None
+        # distance cache of the fused march, kept across calls (sdfr_trace_cache_bytes): it depends on the latent
+        # only, so rendering one shape from many poses - or a latent that moves by less than the decoder's
+        # Lipschitz slack - pays for it once.  One block per native decoder handle.
+        self.reuse_cache = bool(reuse_cache)
+        self._dist_cache = None
+        self._view_caches = {}
+        self._view_streams = []
+
+    def _cache_for(self, native, device, slot=None):
+        if not self.reuse_cache:
+            return None
+        ent = self._dist_cache if slot is None else self._view_caches.get(slot)
+        if ent is None or ent[0] is not native or ent[1].device != device:
+            buf = torch.zeros((_lib.load().sdfr_trace_cache_bytes(),), device=device, dtype=torch.uint8)
+            ent = (native, buf)
+            if slot is None:
+                self._dist_cache = ent
+            else:
+                self._view_caches[slot] = ent
+        return ent[1]
 
     def _intrinsics(self):
         k32 = self.K.detach().float().cpu()
@@ -88,6 +110,50 @@ class SphereTracer(torch.nn.Module):
         lat = torch.nn.functional.normalize(latent, p=2, dim=0) if normalize_latent else latent
         kinv, kmat = self._intrinsics()
         cfg = (int(self.res_x_px), int(self.res_y_px), kinv, kmat)
-        depth, nmap, nocs, mask = _Trace.apply(lat, camera_matrix, dsdf.native(), cfg, self.max_steps, self.eps,
-                                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO))
+        native = dsdf.native()
+        depth, nmap, nocs, mask = _Trace.apply(lat, camera_matrix, native, cfg, self.max_steps, self.eps,
+                                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO),
+                                               self._cache_for(native, lat.device))
         return {'depth': depth, 'normals': nmap, 'color': nocs, 'mask': mask}
+
+    def render_views(self, dsdf, latent, camera_matrices, normalize_latent=True, views_in_flight=4):
+        """Forward-only renders of one latent from several poses, ``views_in_flight`` of them concurrently on
+        separate CUDA streams.  A single trace is a chain of ~25 dependent launches, most of them bound by the latency
+        of one decoder tile rather than by throughput (few rays are left after the first march steps and CTAs
+        without rows exit at once), so independent views fill the SMs a single view leaves idle.  Each stream keeps
+        its own distance cache.  Pass the poses as HOST tensors: reading a device pose back synchronises its stream.
+        Returns one dict per pose, ordered like ``camera_matrices``, usable on the current stream."""
+        if not latent.is_cuda:
+            raise _lib.SdfrError("SphereTracer runs on a CUDA device only (no CPU path)")
+        dev = latent.device
+        native = dsdf.native()
+        kinv, kmat = self._intrinsics()
+        cfg = (int(self.res_x_px), int(self.res_y_px), kinv, kmat)
+        impl = getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO)
+        n_streams = max(1, min(int(views_in_flight), len(camera_matrices)))
+        if not native.tcgen05 or impl == _lib.MLP_FFMA:
+            n_streams = 1          # the CUDA-core decoder kernel spills to a scratch buffer the launches of a decoder share
+        with torch.cuda.device(dev), torch.no_grad():
+            while len(self._view_streams) < n_streams:
+                self._view_streams.append(torch.cuda.Stream(device=dev))
+            cur = torch.cuda.current_stream()
+            lat = torch.nn.functional.normalize(latent, p=2, dim=0) if normalize_latent else latent
+            lat = lat.detach().contiguous().float()
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            outs = []
+            for i, pose in enumerate(camera_matrices):
+                st = self._view_streams[i % n_streams]
+                if i < n_streams:
+                    st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    maps = _Trace.apply(lat, pose, native, cfg, self.max_steps, self.eps, impl,
+                                        self._cache_for(native, dev, slot=i % n_streams))
+                for t in maps:
+                    t.record_stream(cur)
+                outs.append(dict(zip(('depth', 'normals', 'color', 'mask'), maps)))
+            lat.record_stream(self._view_streams[0])
+            for st in self._view_streams[:n_streams]:
+                lat.record_stream(st)
+                cur.wait_stream(st)
+        return outs

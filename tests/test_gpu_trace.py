@@ -153,6 +153,65 @@ def test_trace_agrees_with_splat_mode(stock_prior_path):
     assert float((r["normals"][:, m] - rendering["normals"][:, m]).abs().median()) < 3e-2
 
 
+def test_trace_distance_cache_reuse(stock_prior_path):
+    """The distance cache of the fused march is kept across calls: another pose of the same latent, and a latent
+    moved by less than the Lipschitz slack (lip |dz| <= 0.01, added to the march's margin), must render what a
+    tracer that rebuilds the cache every call renders - and a latent moved further must renew the cache."""
+    from sdflabel_b200.renderer.tracer import SphereTracer
+    size = 96
+    dec, prior, K, tracer = _setup(stock_prior_path, size)
+    fresh = SphereTracer(K, (size, size), reuse_cache=False).to(cuda)
+    lip = float(dec.native().latent_lipschitz)
+    assert lip > 0
+    z0 = torch.nn.functional.normalize(torch.tensor([0.6, 0.6, 0.5]), dim=0)
+    step = torch.tensor([1.0, -1.0, 0.0]) / np.sqrt(2.0)
+    cases = [(z0, 0.6), (z0, 2.0),                                   # same latent, two poses: reuse with no extra margin
+             (z0 + step * (0.006 / lip), 2.0),                       # inside the slack: reuse with a wider margin
+             (torch.nn.functional.normalize(z0 + step * 0.05, dim=0), 1.2)]   # far: renewed
+    state = lambda: tracer._dist_cache[1][-256:-240].view(torch.int32).cpu().tolist()
+    rows = []
+    for z, yaw in cases:
+        pose = O.yaw_pose(torch.tensor([yaw]), torch.tensor([0.0, 0.0, 5.0])).to(cuda)
+        with torch.no_grad():
+            a = tracer(dec, z.to(cuda), pose, normalize_latent=False)
+            b = fresh(dec, z.to(cuda), pose, normalize_latent=False)
+        rows.append(state()[1])
+        ma, mb = a["mask"][0] > 0.5, b["mask"][0] > 0.5
+        both, either = ma & mb, ma | mb
+        assert int(both.sum()) > 100
+        assert int((either & ~both).sum()) <= max(2, 0.005 * int(either.sum()))
+        # both stop within |f| < eps / 2 of the same root
+        o_, d_, rn_ = T.rays(K, size, size, pose.cpu())
+        idx = both.reshape(-1).nonzero().squeeze(1).cpu()
+        tau_all = torch.zeros(size * size)
+        tau_all[idx] = a["depth"][0].reshape(-1).cpu()[idx] / rn_[idx, 2]
+        slope = T.render_hits(prior, z, K, size, size, pose.cpu(), tau_all, idx)["slope"][0].detach()
+        steep = both.cpu() & (slope > 0.05)
+        d_err = (a["depth"][0] - b["depth"][0]).abs().cpu()
+        band = 1.25 * 1e-4 / slope.clamp(min=1e-3) + 3e-5
+        assert bool((d_err[steep] <= band[steep]).all()), float((d_err / band)[steep].max())
+    assert rows[0] == 40 ** 3 and rows[1] == 0 and rows[2] == 0 and rows[3] == 40 ** 3, rows
+
+
+def test_trace_views_in_flight_match_sequential(stock_prior_path):
+    """render_views (several poses of one latent on concurrent CUDA streams, a distance cache per stream) returns
+    what one forward per pose returns: the rays of a view do not interact with anything else in flight."""
+    size = 64
+    dec, prior, K, tracer = _setup(stock_prior_path, size)
+    lat = torch.tensor([0.6, 0.6, 0.5], device=cuda)
+    poses = [O.yaw_pose(torch.tensor([0.3 + 0.9 * i]), torch.tensor([0.05 * i, 0.0, 4.0 + 0.5 * i])) for i in range(6)]
+    for _ in range(2):                                    # second pass: every stream reuses its cache
+        outs = tracer.render_views(dec, lat, poses, views_in_flight=3)
+        assert len(outs) == len(poses)
+        for pose, got in zip(poses, outs):
+            with torch.no_grad():
+                want = tracer(dec, lat, pose.to(cuda))
+            assert int(want["mask"].sum()) > 50
+            assert torch.equal(got["mask"], want["mask"])
+            for key in ("depth", "color", "normals"):
+                assert float((got[key] - want[key]).abs().max()) <= 1e-6, key
+
+
 def test_trace_empty_view(stock_prior_path):
     """Camera looking away from the object: no hits, zero maps, zero gradients."""
     dec, prior, K, tracer = _setup(stock_prior_path, 32)
