@@ -200,6 +200,11 @@ int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg, const floa
  * (latent_lipschitz: the certified bound of sdfr_refine_cfg; 0 = never reuse), and renewed otherwise - decided
  * on the device, no synchronisation.  Rendering one shape from many poses pays for the cache once. */
 int64_t sdfr_trace_cache_bytes(void);
+/* Brings the block up to date for this latent on `stream` (reuse or renew, as sdfr_trace_forward would).  Renders
+ * that follow with latent_lipschitz < 0 use the block as it is: strips or views of one latent rendered
+ * concurrently on several streams share one cache (order them after this call with an event). */
+int sdfr_trace_cache_update(sdfr_decoder* dec, const float* latent_unit_dev, void* cache_dev, float latent_lipschitz,
+                            void* stream);
 
 /* Measurement aid: with on != 0 every fused-march forward synchronises after each launch and counts the decoder rows
  * it issued (process-wide; resets the counts).  counts4 = [distance-cache rows, march rows (fp16-operand forward),

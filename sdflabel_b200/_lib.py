@@ -75,6 +75,7 @@ SIGNATURES = {
     "sdfr_trace_forward": (C.c_int, [vp, C.POINTER(RasterCfg), vp, c_float_p, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp,
                                      vp, C.c_float, C.c_int, vp]),
     "sdfr_trace_cache_bytes": (C.c_int64, []),
+    "sdfr_trace_cache_update": (C.c_int, [vp, vp, vp, C.c_float, vp]),
     "sdfr_trace_set_stats": (None, [C.c_int]),
     "sdfr_trace_get_stats": (None, [C.POINTER(C.c_int64)]),
     "sdfr_trace_backward": (C.c_int, [vp, C.POINTER(RasterCfg), c_float_p, C.c_float, vp, vp, vp, vp, vp, vp]),

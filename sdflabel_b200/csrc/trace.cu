@@ -399,6 +399,22 @@ size_t ws_bytes(int64_t P, int in0, size_t mask_bytes) {
          r((size_t)GRID_D * GRID_D * GRID_D * 4) + r((size_t)CACHE_LATENT * 4) + 256 + r(mask_bytes);
 }
 
+// reuse the lattice values of an earlier call while the latent has not moved beyond the slack (device-side decision),
+// evaluate the lattice otherwise
+int update_distance_cache(const sdfr_decoder* dec, const float* latent_unit_dev, float lip, float hi, float* cache,
+                          float* z_ref, int* cstate, cudaStream_t s) {
+  MlpInputs ig;
+  ig.inputs = nullptr; ig.latent_unit = latent_unit_dev; ig.lattice = make_regular_lattice(GRID_D, (double)hi);
+  ig.points_per_batch = (long long)GRID_D * GRID_D * GRID_D; ig.n = ig.points_per_batch;
+  ig.index = nullptr; ig.small_tiles = 0;
+  trace_cache_check_kernel<<<1, 32, 0, s>>>(latent_unit_dev, dec->dev.latent_size, lip, (int)ig.n, z_ref, cstate);
+  SDFR_LAUNCH_CHECK();
+  ig.count_dev = cstate + 1;
+  return launch_mlp_tc_coarse(dec, ig, cache, s);
+}
+
+constexpr float BOX_LO = -1.0f, BOX_HI = 1.025f;   // Grid3D(40) extent the priors are sampled on (grid.py:38)
+
 int fill_params(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec, const float* pose_host, float eps, TraceParams* tp) {
   tp->width = cfg->width; tp->height = cfg->height;
   tp->in0 = dec->dev.in0; tp->latent = dec->dev.latent_size;
@@ -408,7 +424,7 @@ int fill_params(const sdfr_raster_cfg* cfg, const sdfr_decoder* dec, const float
     tp->t[r] = pose_host[r * 4 + 3];
   }
   tp->eps = eps;
-  tp->lo = -1.0f; tp->hi = 1.025f;   // Grid3D(40) extent the priors are sampled on (grid.py:38)
+  tp->lo = BOX_LO; tp->hi = BOX_HI;
   return SDFR_OK;
 }
 
@@ -424,6 +440,27 @@ extern "C" int64_t sdfr_trace_workspace_bytes(const sdfr_raster_cfg* cfg, const 
 }
 
 extern "C" int64_t sdfr_trace_cache_bytes(void) { return (int64_t)CACHE_BYTES; }
+
+extern "C" int sdfr_trace_cache_update(sdfr_decoder* dec, const float* latent_unit_dev, void* cache_dev,
+                                       float latent_lipschitz, void* stream) {
+  SDFR_REQUIRE(dec && latent_unit_dev && cache_dev, SDFR_E_INVALID, "null argument");
+  SDFR_REQUIRE(dec->tc.ok && mlp_tc_march_ok(dec), SDFR_E_UNSUPPORTED, "the distance cache belongs to the fused march");
+  SDFR_REQUIRE(dec->dev.latent_size <= CACHE_LATENT, SDFR_E_UNSUPPORTED, "latent size %d > %d", dec->dev.latent_size,
+               CACHE_LATENT);
+  char* c = reinterpret_cast<char*>(cache_dev);
+  float* z_ref = reinterpret_cast<float*>(c + (((size_t)GRID_D * GRID_D * GRID_D * 4 + 255) & ~(size_t)255));
+  int* cstate = reinterpret_cast<int*>(z_ref + CACHE_LATENT);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = update_distance_cache(dec, latent_unit_dev, latent_lipschitz > 0.f ? latent_lipschitz : 0.f, BOX_HI,
+                                 reinterpret_cast<float*>(c), z_ref, cstate, s);
+  if (!rc && g_trace_stats > 0) {
+    int st[4];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(st, cstate, sizeof(st), cudaMemcpyDeviceToHost);
+    g_trace_counts[0] += st[1];
+  }
+  return rc;
+}
 
 extern "C" void sdfr_trace_set_stats(int on) {
   g_trace_stats = on;
@@ -470,16 +507,11 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
   const bool fused = impl == SDFR_MLP_TCGEN05 && mlp_tc_march_ok(dec);
   if (fused) {
     // ---- distance cache and the march through it ----
-    MlpInputs ig;
-    ig.inputs = nullptr; ig.latent_unit = latent_unit_dev; ig.lattice = make_regular_lattice(GRID_D, (double)tp.hi);
-    ig.points_per_batch = (long long)GRID_D * GRID_D * GRID_D; ig.n = ig.points_per_batch;
-    ig.index = nullptr; ig.small_tiles = 0;
-    // reuse the lattice values of an earlier call while the latent has not moved beyond the slack (device-side decision)
-    trace_cache_check_kernel<<<1, 32, 0, s>>>(latent_unit_dev, dec->dev.latent_size, cache_dev ? latent_lipschitz : 0.f,
-                                              (int)ig.n, w.z_ref, w.cstate);
-    SDFR_LAUNCH_CHECK();
-    ig.count_dev = w.cstate + 1;
-    if ((rc = launch_mlp_tc_coarse(dec, ig, w.cache, s))) return rc;
+    // (a negative latent_lipschitz: the caller has brought the block up to date for this latent with
+    //  sdfr_trace_cache_update - renders of one latent that run concurrently share one cache)
+    if (!(cache_dev && latent_lipschitz < 0.f) &&
+        (rc = update_distance_cache(dec, latent_unit_dev, cache_dev ? latent_lipschitz : 0.f, tp.hi, w.cache, w.z_ref,
+                                    w.cstate, s))) return rc;
     static float grid_stop = -1.f;   // SDFR_TRACE_GRID_STOP: dev override of the hand-over distance
     if (grid_stop < 0.f) { const char* e = getenv("SDFR_TRACE_GRID_STOP"); grid_stop = e ? (float)atof(e) : GRID_STOP; }
     trace_grid_march_kernel<<<blocks, 256, 0, s>>>(tp, w, grid_stop);
@@ -519,7 +551,7 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     // measurement aid for bench.py's utilisation figure, never on in a timed call)
     if (g_trace_stats < 0) { const char* e = getenv("SDFR_TRACE_STATS"); g_trace_stats = e ? atoi(e) : 0; }
     const int stats = g_trace_stats;
-    if (stats) {
+    if (stats && !(cache_dev && latent_lipschitz < 0.f)) {
       int c[4];
       cudaStreamSynchronize(s);
       cudaMemcpy(c, w.cstate, sizeof(c), cudaMemcpyDeviceToHost);

@@ -120,8 +120,12 @@ class _Engine:
         """(K, K^-1) as contiguous fp32 host tensors; the inverse is torch's own K.float().inverse()
         (primitives.py:204).  Cached by VALUE (the 36 bytes of K): a fresh K tensor per detection usually
         lands in the allocation the previous one just freed, so nothing about the tensor object identifies it."""
-        k32 = K.detach().float().cpu().contiguous() if isinstance(K, torch.Tensor) else \
-            torch.from_numpy(np.ascontiguousarray(np.asarray(K, dtype=np.float32)))
+        if isinstance(K, torch.Tensor):
+            k32 = K.detach()
+            if k32.device.type != 'cpu' or k32.dtype != torch.float32 or not k32.is_contiguous():
+                k32 = k32.float().cpu().contiguous()
+        else:
+            k32 = torch.from_numpy(np.ascontiguousarray(np.asarray(K, dtype=np.float32)))
         key = k32.numpy().tobytes()
         hit = self._kcache.get(key)
         if hit is None:

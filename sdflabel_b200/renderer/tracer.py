@@ -24,7 +24,7 @@ from .. import _lib
 
 class _Trace(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, latent_unit, pose, native, cfg_tuple, max_steps, eps, impl, cache):
+    def forward(ctx, latent_unit, pose, native, cfg_tuple, max_steps, eps, impl, cache, trusted=False, pose_h=None):
         lib = _lib.load()
         width, height, kinv, kmat = cfg_tuple
         dev = latent_unit.device
@@ -32,7 +32,8 @@ class _Trace(torch.autograd.Function):
         cfg.kinv[:] = kinv
         cfg.k[:] = kmat
         lat = latent_unit.detach().contiguous().float()
-        pose_h = np.ascontiguousarray(pose.detach().cpu().float().numpy().reshape(16))
+        if pose_h is None:
+            pose_h = np.ascontiguousarray(pose.detach().cpu().float().numpy().reshape(16))
         f32 = dict(device=dev, dtype=torch.float32)
         depth = torch.empty((1, height, width), **f32)
         nmap = torch.empty((3, height, width), **f32)
@@ -43,8 +44,8 @@ class _Trace(torch.autograd.Function):
             _lib.check(lib.sdfr_trace_forward(native.handle, cfg, lat.data_ptr(), _lib.fptr(pose_h), int(max_steps),
                                               float(eps), depth.data_ptr(), nmap.data_ptr(), nocs.data_ptr(),
                                               mask.data_ptr(), 0, ws.data_ptr(), _lib.ptr(cache),
-                                              float(native.latent_lipschitz) if cache is not None else 0.0, impl,
-                                              _lib.stream_ptr()))
+                                              (-1.0 if trusted else float(native.latent_lipschitz)) if cache is not None
+                                              else 0.0, impl, _lib.stream_ptr()))
         ctx.native, ctx.cfg, ctx.ws, ctx.pose_h, ctx.eps = native, cfg, ws, pose_h, float(eps)
         ctx.meta = (latent_unit.dtype, pose.dtype, pose.device, tuple(pose.shape), latent_unit.shape[0])
         ctx.mark_non_differentiable(nmap, mask)
@@ -65,7 +66,7 @@ class _Trace(torch.autograd.Function):
                                                _lib.stream_ptr()))
         g_pose = torch.zeros(pose_shape, device=dev, dtype=torch.float32)
         g_pose[:3, :4] = d_pose.view(3, 4)
-        return d_lat.to(lat_dtype), g_pose.to(pose_dev, pose_dtype), None, None, None, None, None, None
+        return d_lat.to(lat_dtype), g_pose.to(pose_dev, pose_dtype), None, None, None, None, None, None, None, None
 
 
 class SphereTracer(torch.nn.Module):
@@ -80,20 +81,15 @@ class SphereTracer(torch.nn.Module):
         # Lipschitz slack - pays for it once.  One block per native decoder handle.
         self.reuse_cache = bool(reuse_cache)
         self._dist_cache = None
-        self._view_caches = {}
         self._view_streams = []
 
-    def _cache_for(self, native, device, slot=None):
+    def _cache_for(self, native, device):
         if not self.reuse_cache:
             return None
-        ent = self._dist_cache if slot is None else self._view_caches.get(slot)
+        ent = self._dist_cache
         if ent is None or ent[0] is not native or ent[1].device != device:
             buf = torch.zeros((_lib.load().sdfr_trace_cache_bytes(),), device=device, dtype=torch.uint8)
-            ent = (native, buf)
-            if slot is None:
-                self._dist_cache = ent
-            else:
-                self._view_caches[slot] = ent
+            ent = self._dist_cache = (native, buf)
         return ent[1]
 
     def _intrinsics(self):
@@ -111,8 +107,8 @@ class SphereTracer(torch.nn.Module):
         kinv, kmat = self._intrinsics()
         cfg = (int(self.res_x_px), int(self.res_y_px), kinv, kmat)
         native = dsdf.native()
-        depth, nmap, nocs, mask = _Trace.apply(lat, camera_matrix, native, cfg, self.max_steps, self.eps,
-                                               getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO),
+        impl = getattr(dsdf, 'mlp_impl', _lib.MLP_AUTO)
+        depth, nmap, nocs, mask = _Trace.apply(lat, camera_matrix, native, cfg, self.max_steps, self.eps, impl,
                                                self._cache_for(native, lat.device))
         return {'depth': depth, 'normals': nmap, 'color': nocs, 'mask': mask}
 
@@ -120,8 +116,9 @@ class SphereTracer(torch.nn.Module):
         """Forward-only renders of one latent from several poses, ``views_in_flight`` of them concurrently on
         separate CUDA streams.  A single trace is a chain of ~25 dependent launches, most of them bound by the latency
         of one decoder tile rather than by throughput (few rays are left after the first march steps and CTAs
-        without rows exit at once), so independent views fill the SMs a single view leaves idle.  Each stream keeps
-        its own distance cache.  Pass the poses as HOST tensors: reading a device pose back synchronises its stream.
+        without rows exit at once), so independent views fill the SMs a single view leaves idle.  The views share ONE
+        distance cache, brought up to date for the latent before they start (sdfr_trace_cache_update).  Pass the
+        poses as HOST tensors: reading a device pose back synchronises its stream.
         Returns one dict per pose, ordered like ``camera_matrices``, usable on the current stream."""
         if not latent.is_cuda:
             raise _lib.SdfrError("SphereTracer runs on a CUDA device only (no CPU path)")
@@ -139,6 +136,16 @@ class SphereTracer(torch.nn.Module):
             cur = torch.cuda.current_stream()
             lat = torch.nn.functional.normalize(latent, p=2, dim=0) if normalize_latent else latent
             lat = lat.detach().contiguous().float()
+            fused = bool(native.tcgen05 and impl != _lib.MLP_FFMA)
+            cache = None
+            if fused:
+                if self.reuse_cache:
+                    cache, lip = self._cache_for(native, dev), float(native.latent_lipschitz)
+                else:                        # rebuilt every call, still one block for all views of the call
+                    cache = torch.zeros((_lib.load().sdfr_trace_cache_bytes(),), device=dev, dtype=torch.uint8)
+                    lip = 0.0
+                _lib.check(_lib.load().sdfr_trace_cache_update(native.handle, lat.data_ptr(), cache.data_ptr(), lip,
+                                                               _lib.stream_ptr()))
             ready = torch.cuda.Event()
             ready.record(cur)
             outs = []
@@ -147,13 +154,13 @@ class SphereTracer(torch.nn.Module):
                 if i < n_streams:
                     st.wait_event(ready)
                 with torch.cuda.stream(st):
-                    maps = _Trace.apply(lat, pose, native, cfg, self.max_steps, self.eps, impl,
-                                        self._cache_for(native, dev, slot=i % n_streams))
+                    maps = _Trace.apply(lat, pose, native, cfg, self.max_steps, self.eps, impl, cache, fused)
                 for t in maps:
                     t.record_stream(cur)
                 outs.append(dict(zip(('depth', 'normals', 'color', 'mask'), maps)))
-            lat.record_stream(self._view_streams[0])
             for st in self._view_streams[:n_streams]:
                 lat.record_stream(st)
+                if cache is not None:
+                    cache.record_stream(st)
                 cur.wait_stream(st)
         return outs

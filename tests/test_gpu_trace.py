@@ -194,7 +194,7 @@ def test_trace_distance_cache_reuse(stock_prior_path):
 
 
 def test_trace_views_in_flight_match_sequential(stock_prior_path):
-    """render_views (several poses of one latent on concurrent CUDA streams, a distance cache per stream) returns
+    """render_views (several poses of one latent on concurrent CUDA streams, one shared distance cache) returns
     what one forward per pose returns: the rays of a view do not interact with anything else in flight."""
     size = 64
     dec, prior, K, tracer = _setup(stock_prior_path, size)
