@@ -519,7 +519,13 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     // ---- speculative march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
     // The lattice pass is good to ~3e-4 (its error near the surface is what the refine engine measures and bounds by
     // 2.5e-3), so rays are handed to the full-precision finish well before that matters.
-    const float near_thr = 2.5e-3f, near_reach = 0.01f;
+    static float near_thr = -1.f, near_reach = -1.f;
+    static int newton = -1;
+    if (near_thr < 0.f) {      // dev overrides: SDFR_TRACE_NEAR_THR / _NEAR_REACH / _NEWTON
+      const char* e = getenv("SDFR_TRACE_NEAR_THR"); near_thr = e ? (float)atof(e) : 2.5e-3f;
+      e = getenv("SDFR_TRACE_NEAR_REACH"); near_reach = e ? (float)atof(e) : 0.01f;
+      e = getenv("SDFR_TRACE_NEWTON"); newton = e ? atoi(e) : 3;
+    }
     const int round_rows = mlp_tc_round_rows(dec);
     RayMarch desc[6];
     for (int k = 0; k < 6; ++k) {
@@ -577,7 +583,6 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     }
     // ---- finish at full precision: Newton rounds along the ray over a shrinking work list; the evaluation that finds
     //      |sdf| < eps / 2 (or the last one) classifies the ray and feeds the maps ----
-    const int newton = 3;
     MlpInputs ia = in;
     ia.inputs = w.inputs;
     ia.adaptive_tiles = 1;

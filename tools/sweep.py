@@ -48,12 +48,19 @@ for size in (64, 256):
         print(f"| {B} | {size}x{size} | {ms:.3f} | {B / ms * 1e3:,.0f} | {B * size * size / ms * 1e3:,.0f} |", flush=True)
         eng.get(0)
 
-print("\n## Trace mode: sphere tracing of one latent (64 march steps max, eps 1e-4), stock prior\n")
-print("| resolution | hit rays | fwd ms | fwd rays / s | fwd+bwd ms | fwd+bwd rays / s |")
-print("|---|---|---|---|---|---|")
+print("\n## Trace mode (cfg5): sphere tracing of one latent (eps 1e-4), stock prior; batch = poses rendered per call "
+      "(`SphereTracer.render_views`, 4 / 8 CUDA streams); tensor fraction = algorithmic decoder flops of the evaluated rows / "
+      "time / measured dense bf16 peak\n")
+print("| resolution | hit rays / view | batch | streams | fwd ms / call | fwd rays / s | tensor frac | fwd+bwd ms (batch 1) |")
+print("|---|---|---|---|---|---|---|---|")
+import ctypes as C, json
+lib = _lib.load()
+spec = json.load(open(os.path.splitext(bench.PRIOR)[0] + ".json"))
+flop_pt, pk = bench.mlp_flops_per_point(spec), bench.peaks()
 lat = torch.tensor(sc["init"]["latent"], device=dev)
 from oracle import sdf_oracle as O   # pose helper only (test infrastructure; this script is a dev tool)
-pose = O.yaw_pose(torch.tensor([0.6]), torch.tensor([0.0, 0.0, 5.0])).to(dev)
+pose_h = O.yaw_pose(torch.tensor([0.6]), torch.tensor([0.0, 0.0, 5.0]))
+pose = pose_h.to(dev)
 for size in (64, 128, 256, 512, 1024):
     K = torch.from_numpy(sc["K"]).clone()
     K[:2] *= size / 256.0
@@ -62,10 +69,24 @@ for size in (64, 128, 256, 512, 1024):
         r = tracer(dec, lat, pose)
         hits = int(r["mask"].sum().item())
         fwd = timed(lambda: tracer(dec, lat, pose), n=5, warm=2)
+        lib.sdfr_trace_set_stats(1)
+        tracer(dec, lat, pose)
+        torch.cuda.synchronize()
+        cnt = (C.c_int64 * 4)()
+        lib.sdfr_trace_get_stats(cnt)
+        lib.sdfr_trace_set_stats(0)
+    flops = flop_pt * (cnt[1] + 2.0 * cnt[3])          # march rows + Newton rows (forward + input gradient), cache reused
 
     def fb():
         l = lat.clone().requires_grad_(True); p = pose.clone().requires_grad_(True)
         out = tracer(dec, l, p)
         (out["depth"].sum() + out["color"].sum()).backward()
     both = timed(fb, n=5, warm=2)
-    print(f"| {size}x{size} | {hits} | {fwd:.2f} | {size * size / fwd * 1e3:,.0f} | {both:.2f} | {size * size / both * 1e3:,.0f} |", flush=True)
+    print(f"| {size}x{size} | {hits} | 1 | 1 | {fwd:.2f} | {size * size / fwd * 1e3:,.0f} | {flops / (fwd * 1e-3) / 1e12 / pk['tensor']:.2f} | {both:.2f} |", flush=True)
+    for batch in ((4, 16, 64, 128) if size <= 256 else (4, 16)):
+        views = [O.yaw_pose(torch.tensor([0.6 + 0.05 * i]), torch.tensor([0.0, 0.0, 5.0])) for i in range(batch)]
+        for streams in (4, 8):
+            if streams > batch:
+                continue
+            ms = timed(lambda: tracer.render_views(dec, lat, views, views_in_flight=streams), n=3, warm=1)
+            print(f"| {size}x{size} | {hits} | {batch} | {streams} | {ms:.2f} | {batch * size * size / ms * 1e3:,.0f} | {batch * flops / (ms * 1e-3) / 1e12 / pk['tensor']:.2f} | |", flush=True)
