@@ -274,6 +274,7 @@ void free_tc_tables(sdfr_decoder* dec);
 int tc_overflow_flag(const sdfr_decoder* dec, int* flag);
 int tc_overflow_flag_enqueue(const sdfr_decoder* dec, int* flag_host, cudaStream_t s);
 int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s);
+const int* tc_overflow_ptr(const sdfr_decoder* dec);   // the device flag itself (null: no tensor-core tables)
 
 // surface.cu
 int launch_lattice_points(int density, float* pts, cudaStream_t s);

@@ -2303,6 +2303,10 @@ int tc_overflow_flag_enqueue(const sdfr_decoder* dec, int* flag_host, cudaStream
   SDFR_CUDA(cudaMemcpyAsync(flag_host, st->overflow_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
   return SDFR_OK;
 }
+const int* tc_overflow_ptr(const sdfr_decoder* dec) {
+  if (!dec->tc.ok || !dec->tc_ptr) return nullptr;
+  return reinterpret_cast<const TcHostState*>(dec->tc_ptr)->overflow_dev;
+}
 int tc_overflow_reset(const sdfr_decoder* dec, cudaStream_t s) {
   if (!dec->tc.ok || !dec->tc_ptr) return SDFR_OK;
   const TcHostState* st = reinterpret_cast<const TcHostState*>(dec->tc_ptr);

@@ -499,6 +499,65 @@ __global__ void export_params_kernel(const DetState* __restrict__ det, const flo
   if (latent_out) for (int i = t; i < L; i += blockDim.x) latent_out[i] = latent[i];
 }
 
+// ---- Optimizer.optimize as one call (sdfr_refine_optimize): packed staging in, packed read-back out ----
+// Prologue: block 0 unpacks the staged [DetState | SplatView | lidar] block of slot b (ONE host->device copy) and takes
+// the parameters from the caller's device tensors (import_params); every block resizes its pixels of the NOCS target
+// (optimizer.py:135-137).
+__global__ void __launch_bounds__(256) optimize_prologue_kernel(EngineDev E, int b, const unsigned int* __restrict__ stage,
+                                                                const float* __restrict__ nocs_src, int th, int tw,
+                                                                const float* __restrict__ yaw, const float* __restrict__ trans,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ latent_in, int n_lidar, int H, int W) {
+  const int t = threadIdx.x;
+  if (blockIdx.x == 0) {
+    constexpr int DW = (int)(sizeof(DetState) / 4), VW = (int)(sizeof(SplatView) / 4);
+    unsigned int* det = reinterpret_cast<unsigned int*>(E.det + b);
+    unsigned int* view = reinterpret_cast<unsigned int*>(E.views + b);
+    for (int i = t; i < DW; i += 256) det[i] = stage[i];
+    for (int i = t; i < VW; i += 256) view[i] = stage[DW + i];
+    float* lidar = E.lidar + (size_t)b * E.max_lidar * 3;
+    const float* ls = reinterpret_cast<const float*>(stage + DW + VW);
+    for (int i = t; i < n_lidar * 3; i += 256) lidar[i] = ls[i];
+    for (int i = t; i < E.L; i += 256) E.latent[(size_t)b * E.L + i] = latent_in[i];
+    __syncthreads();
+    DetState& D = E.det[b];
+    if (t == 0) { D.yaw = yaw[0]; D.scale = scale[0]; }
+    if (t < 3) D.trans[t] = trans[t];
+  }
+  const int j = blockIdx.x * 256 + t;
+  if (j >= H * W) return;
+  const int h = j / W, w = j - h * W;
+  const float sh = (float)th / (float)H, sw = (float)tw / (float)W;
+  const int ih = min((int)floorf((float)h * sh), th - 1), iw = min((int)floorf((float)w * sw), tw - 1);
+  float* dst = E.target + (size_t)b * 3 * E.max_pixels;
+  for (int c = 0; c < 3; ++c) dst[c * (H * W) + j] = nocs_src[(c * th + ih) * tw + iw];
+}
+
+// Epilogue: the params tensors updated in place (export_params) and everything the host reads packed into one block
+// [DetState | latent | presel_err, overflow | history rows] for ONE device->host copy.
+__global__ void __launch_bounds__(256) optimize_epilogue_kernel(EngineDev E, int b, float* __restrict__ yaw,
+                                                                float* __restrict__ trans, float* __restrict__ scale,
+                                                                float* __restrict__ latent_out,
+                                                                unsigned int* __restrict__ rb, const int* __restrict__ overflow,
+                                                                int hist_rows) {
+  const int t = threadIdx.x;
+  constexpr int DW = (int)(sizeof(DetState) / 4);
+  const DetState& D = E.det[b];
+  if (t == 0) { yaw[0] = D.yaw; scale[0] = D.scale; }
+  if (t < 3) trans[t] = D.trans[t];
+  const float* lat = E.latent + (size_t)b * E.L;
+  for (int i = t; i < E.L; i += 256) latent_out[i] = lat[i];
+  const unsigned int* det = reinterpret_cast<const unsigned int*>(E.det + b);
+  for (int i = t; i < DW; i += 256) rb[i] = det[i];
+  for (int i = t; i < E.L; i += 256) rb[DW + i] = __float_as_uint(lat[i]);
+  if (t == 0) {
+    rb[DW + E.L] = (unsigned int)*E.presel_err;
+    rb[DW + E.L + 1] = overflow ? (unsigned int)*overflow : 0u;
+  }
+  const unsigned int* hist = reinterpret_cast<const unsigned int*>(E.history + (size_t)b * E.max_iters * 4);
+  for (int i = t; i < hist_rows * 4; i += 256) rb[DW + E.L + 2 + i] = hist[i];
+}
+
 // ---- dump-time label extents (utils/refinement.py:527-541) ------------------------------------------
 // get_kitti_label evaluates the decoder with the refined latent AS IS (not normalised, refine_css.py:229)
 __global__ void raw_latent_kernel(EngineDev E) {
@@ -581,6 +640,13 @@ struct sdfr_refine {
   // five round trips; into this block they are enqueued back to back and waited for once.
   char* rb;
   size_t rb_det, rb_lat, rb_flags, rb_hist, rb_bytes;
+  // sdfr_refine_optimize: page-locked [DetState | SplatView | lidar] staging and its device copy; packed read-back
+  // [DetState | latent | 2 flags | history] on the device and its page-locked landing zone
+  char* opt_stage_host;
+  char* opt_stage_dev;
+  char* opt_rb_host;
+  char* opt_rb_dev;
+  size_t opt_stage_bytes, opt_rb_bytes;
 };
 
 namespace {
@@ -635,6 +701,7 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
   r->cfg = *cfg;
   r->capture_stream = nullptr; r->runs = 0;
   r->rb = nullptr;
+  r->opt_stage_host = r->opt_rb_host = r->opt_stage_dev = r->opt_rb_dev = nullptr;
   r->active = cfg->batch;
   r->iters_enqueued.assign((size_t)cfg->batch, 0);
   r->det_w.assign((size_t)cfg->batch, 0);
@@ -691,6 +758,14 @@ extern "C" int sdfr_refine_create(sdfr_decoder* dec, const sdfr_refine_cfg* cfg,
     SDFR_REQUIRE(false, SDFR_E_CUDA, "cudaHostAlloc of the %zu-byte read-back block failed", r->rb_bytes);
   }
   memset(r->rb, 0, r->rb_bytes);
+  r->opt_stage_bytes = sizeof(DetState) + sizeof(SplatView) + sizeof(float) * 3 * (size_t)E.max_lidar;
+  r->opt_rb_bytes = sizeof(DetState) + sizeof(float) * (size_t)(L + 2) + sizeof(float) * 4 * (size_t)E.max_iters;
+  A(r->opt_stage_dev, r->opt_stage_bytes); A(r->opt_rb_dev, r->opt_rb_bytes);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&r->opt_stage_host), r->opt_stage_bytes, cudaHostAllocDefault) != cudaSuccess ||
+      cudaHostAlloc(reinterpret_cast<void**>(&r->opt_rb_host), r->opt_rb_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    sdfr_refine_destroy(r);
+    SDFR_REQUIRE(false, SDFR_E_CUDA, "cudaHostAlloc of the optimize staging blocks failed");
+  }
   r->views_host.resize(B);
   r->nocs_dev.assign(B, nullptr);
   r->nocs_cap.assign(B, 0);
@@ -727,6 +802,8 @@ extern "C" void sdfr_refine_destroy(sdfr_refine* r) {
   for (void* p : r->allocs) cudaFree(p);
   for (float* p : r->nocs_dev) if (p) cudaFree(p);
   if (r->rb) cudaFreeHost(r->rb);
+  if (r->opt_stage_host) cudaFreeHost(r->opt_stage_host);
+  if (r->opt_rb_host) cudaFreeHost(r->opt_rb_host);
   delete r;
 }
 
@@ -1106,22 +1183,84 @@ extern "C" int sdfr_refine_get_batch(sdfr_refine* r, float* params_host, float* 
 
 // Optimizer.optimize as ONE call (optimizer.py:56-164 seen from its caller): inputs of slot b from host buffers,
 // parameters from / to the caller's device tensors, `iters` iterations, one synchronisation, read-back.
+// Two host->device copies (the packed [DetState | SplatView | lidar] block, the NOCS prediction), a prologue kernel, the
+// iterations, an epilogue kernel, one device->host copy.
 extern "C" int sdfr_refine_optimize(sdfr_refine* r, int b, const float* k_host, const float* kinv_host, int width,
                                     int height, const float* nocs_host, int th, int tw, const float* lidar_host,
                                     int n_lidar, float* yaw_dev, float* trans_dev, float* scale_dev, float* latent_dev,
                                     float* adam_m_host, float* adam_v_host, int* adam_t, int iters, float* params_host,
                                     float* history_host, int* n_history, void* stream) {
-  SDFR_REQUIRE(r && yaw_dev && trans_dev && scale_dev && latent_dev && params_host, SDFR_E_INVALID, "null argument");
-  SDFR_REQUIRE(b >= 0 && b < r->active, SDFR_E_INVALID, "slot %d is not among the %d active ones", b, r ? r->active : 0);
+  SDFR_REQUIRE(r && k_host && nocs_host && yaw_dev && trans_dev && scale_dev && latent_dev && params_host, SDFR_E_INVALID,
+               "null argument");
+  SDFR_REQUIRE(b >= 0 && b < r->active, SDFR_E_INVALID, "slot %d is not among the %d active ones", b, r->active);
+  SDFR_REQUIRE(width > 0 && height > 0 && width <= r->cfg.max_width && height <= r->cfg.max_height, SDFR_E_CAPACITY,
+               "crop %dx%d exceeds the configured capacity %dx%d", width, height, r->cfg.max_width, r->cfg.max_height);
+  SDFR_REQUIRE(n_lidar >= 0 && n_lidar <= r->E.max_lidar, SDFR_E_CAPACITY, "%d lidar points exceed capacity %d",
+               n_lidar, r->E.max_lidar);
+  SDFR_REQUIRE(n_lidar == 0 || lidar_host, SDFR_E_INVALID, "null lidar array");
+  SDFR_REQUIRE(th > 0 && tw > 0 && iters >= 0, SDFR_E_INVALID, "bad argument");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  EngineDev& E = r->E;
+  // ---- staging: what sdfr_refine_set_detection + sdfr_refine_set_optimizer_state would copy piecewise ----
+  DetState D;
+  memset(&D, 0, sizeof(D));     // fresh optimiser state unless the caller continues one (optimizer.py:46-52)
+  D.width = width; D.height = height; D.n_lidar = n_lidar; D.target_ready = 1;
+  if (adam_m_host && adam_v_host && adam_t && *adam_t > 0) {
+    memcpy(D.adam_m, adam_m_host, sizeof(D.adam_m));
+    memcpy(D.adam_v, adam_v_host, sizeof(D.adam_v));
+    D.adam_t = *adam_t;
+  }
+  SplatView& V = r->views_host[b];
+  V.width = width; V.height = height;
+  for (int i = 0; i < 9; ++i) V.k[i] = k_host[i];
+  if (kinv_host) for (int i = 0; i < 9; ++i) V.kinv[i] = kinv_host[i];
+  else invert3x3(k_host, V.kinv);
+  memcpy(r->opt_stage_host, &D, sizeof(D));
+  memcpy(r->opt_stage_host + sizeof(D), &V, sizeof(V));
+  if (n_lidar > 0) memcpy(r->opt_stage_host + sizeof(D) + sizeof(V), lidar_host, sizeof(float) * 3 * (size_t)n_lidar);
+  SDFR_CUDA(cudaMemcpyAsync(r->opt_stage_dev, r->opt_stage_host, sizeof(D) + sizeof(V) + sizeof(float) * 3 * (size_t)n_lidar,
+                            cudaMemcpyHostToDevice, s));
+  const size_t nocs_count = (size_t)3 * th * tw;
+  if (r->nocs_cap[b] < nocs_count) {
+    if (r->nocs_dev[b]) SDFR_CUDA(cudaFree(r->nocs_dev[b]));
+    r->nocs_dev[b] = nullptr;
+    r->nocs_cap[b] = 0;
+    SDFR_CUDA(cudaMalloc(&r->nocs_dev[b], nocs_count * sizeof(float)));
+    r->nocs_cap[b] = nocs_count;
+  }
+  SDFR_CUDA(cudaMemcpyAsync(r->nocs_dev[b], nocs_host, nocs_count * sizeof(float), cudaMemcpyHostToDevice, s));
+  const int P = width * height;
+  optimize_prologue_kernel<<<(P + 255) / 256, 256, 0, s>>>(E, b, reinterpret_cast<const unsigned int*>(r->opt_stage_dev),
+                                                           r->nocs_dev[b], th, tw, yaw_dev, trans_dev, scale_dev, latent_dev,
+                                                           n_lidar, height, width);
+  SDFR_LAUNCH_CHECK();
+  r->det_w[b] = width;
+  r->det_h[b] = height;
+  r->iters_enqueued[b] = 0;
   int rc;
-  if ((rc = sdfr_refine_set_detection(r, b, k_host, kinv_host, width, height, nocs_host, th, tw, lidar_host, n_lidar,
-                                      nullptr, nullptr, nullptr, nullptr, stream))) return rc;
-  if ((rc = sdfr_refine_import(r, b, yaw_dev, trans_dev, scale_dev, latent_dev, stream))) return rc;
-  if (adam_m_host && adam_v_host && adam_t && *adam_t > 0 &&
-      (rc = sdfr_refine_set_optimizer_state(r, b, adam_m_host, adam_v_host, *adam_t, stream))) return rc;
   if ((rc = sdfr_refine_run(r, iters, stream))) return rc;
-  if ((rc = sdfr_refine_export(r, b, yaw_dev, trans_dev, scale_dev, latent_dev, stream))) return rc;
-  if ((rc = sdfr_refine_get(r, b, params_host, history_host, n_history, stream))) return rc;
+  // ---- packed read-back ----
+  const int nh_host = std::min(r->iters_enqueued[b], E.max_iters);
+  optimize_epilogue_kernel<<<1, 256, 0, s>>>(E, b, yaw_dev, trans_dev, scale_dev, latent_dev,
+                                             reinterpret_cast<unsigned int*>(r->opt_rb_dev), tc_overflow_ptr(r->dec),
+                                             history_host ? nh_host : 0);
+  SDFR_LAUNCH_CHECK();
+  const size_t head = sizeof(DetState) + sizeof(float) * (size_t)(E.L + 2);
+  SDFR_CUDA(cudaMemcpyAsync(r->opt_rb_host, r->opt_rb_dev, head + (history_host ? sizeof(float) * 4 * (size_t)nh_host : 0),
+                            cudaMemcpyDeviceToHost, s));
+  SDFR_CUDA(cudaStreamSynchronize(s));
+  DetState& H = r->host_state[b];
+  memcpy(&H, r->opt_rb_host, sizeof(DetState));
+  const float* lat = reinterpret_cast<const float*>(r->opt_rb_host + sizeof(DetState));
+  params_host[0] = H.yaw; params_host[1] = H.trans[0]; params_host[2] = H.trans[1]; params_host[3] = H.trans[2];
+  params_host[4] = H.scale;
+  memcpy(params_host + 5, lat, sizeof(float) * (size_t)E.L);
+  const int nh = std::min(H.iter, nh_host);
+  if (n_history) *n_history = nh;
+  if (history_host && nh > 0) memcpy(history_host, r->opt_rb_host + head, sizeof(float) * 4 * (size_t)nh);
+  int flags[2];
+  memcpy(flags, lat + E.L, sizeof(flags));
+  if ((rc = check_decoder_flags(r, flags[1], flags[0], s))) return rc;
   return sdfr_refine_get_optimizer_state(r, b, adam_m_host, adam_v_host, adam_t);
 }
 
