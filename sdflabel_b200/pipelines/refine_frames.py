@@ -215,17 +215,21 @@ class FrameRefiner:
         ``<idx>.pkl`` and frames whose dump exists are skipped (the reference's resume rule)."""
         todo = [i for i in frame_ids if not (path_autolabels and F.frame_done(path_autolabels, i))]
         # batches of whole frames, at most max_batch detections each (a larger frame gets a batch of its own slices)
+        # The FIRST batch is a quarter of that: nothing overlaps its initialisation (the GPU waits for it), and with the
+        # frames of a run sharded over many ranks that pipeline fill is a visible share of a rank's few batches.
         batches, cur = [], []
         for fid in todo:
             dets = frames[fid]['detections']
             items = [(fid, di, d) for di, d in enumerate(dets)]
-            while len(items) > self.max_batch:
+            limit = self.max_batch if batches else max(1, min(self.max_batch, max(4, self.max_batch // 4)))
+            while len(items) > limit:
                 if cur:
                     batches.append(cur)
                     cur = []
-                batches.append(items[:self.max_batch])
-                items = items[self.max_batch:]
-            if len(cur) + len(items) > self.max_batch:
+                batches.append(items[:limit])
+                items = items[limit:]
+                limit = self.max_batch
+            if len(cur) + len(items) > limit:
                 batches.append(cur)
                 cur = []
             cur = cur + items
