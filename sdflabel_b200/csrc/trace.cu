@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) trace_backward_kernel(TraceParams p, Trac
   }
 }
 
-int g_trace_stats = -1;                 // row counting of the fused march (sdfr_trace_set_stats)
+int g_trace_stats = 0;                  // row counting of the fused march (sdfr_trace_set_stats)
 long long g_trace_counts[4] = {0, 0, 0, 0};   // distance-cache rows, march rows, non-empty march launches, Newton rows
 
 TraceWs carve(void* ws, int64_t P, int in0, size_t mask_bytes) {
@@ -512,20 +512,15 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     if (!(cache_dev && latent_lipschitz < 0.f) &&
         (rc = update_distance_cache(dec, latent_unit_dev, cache_dev ? latent_lipschitz : 0.f, tp.hi, w.cache, w.z_ref,
                                     w.cstate, s))) return rc;
-    static float grid_stop = -1.f;   // SDFR_TRACE_GRID_STOP: dev override of the hand-over distance
-    if (grid_stop < 0.f) { const char* e = getenv("SDFR_TRACE_GRID_STOP"); grid_stop = e ? (float)atof(e) : GRID_STOP; }
-    trace_grid_march_kernel<<<blocks, 256, 0, s>>>(tp, w, grid_stop);
+    trace_grid_march_kernel<<<blocks, 256, 0, s>>>(tp, w, GRID_STOP);
     SDFR_LAUNCH_CHECK();
     // ---- speculative march: one launch per step; lists ping-pong, counters rotate (read / append / clear) ----
     // The lattice pass is good to ~3e-4 (its error near the surface is what the refine engine measures and bounds by
     // 2.5e-3), so rays are handed to the full-precision finish well before that matters.
-    static float near_thr = -1.f, near_reach = -1.f;
-    static int newton = -1;
-    if (near_thr < 0.f) {      // dev overrides: SDFR_TRACE_NEAR_THR / _NEAR_REACH / _NEWTON
-      const char* e = getenv("SDFR_TRACE_NEAR_THR"); near_thr = e ? (float)atof(e) : 2.5e-3f;
-      e = getenv("SDFR_TRACE_NEAR_REACH"); near_reach = e ? (float)atof(e) : 0.01f;
-      e = getenv("SDFR_TRACE_NEWTON"); newton = e ? atoi(e) : 3;
-    }
+    // (a wider hand-over - 5e-3 / 0.02 - saves two march launches at 256^2 but the second Newton round then outgrows the
+    //  16-point tiling of the band kernel: measured, no gain)
+    const float near_thr = 2.5e-3f, near_reach = 0.01f;
+    const int newton = 3;
     const int round_rows = mlp_tc_round_rows(dec);
     RayMarch desc[6];
     for (int k = 0; k < 6; ++k) {
@@ -553,9 +548,8 @@ extern "C" int sdfr_trace_forward(sdfr_decoder* dec, const sdfr_raster_cfg* cfg,
     int extra_launches = 0;
     for (int64_t q = 65536; q < P; q *= 2) extra_launches += 3;
     const int launches = std::max(1, std::min(max_steps, std::max(8, max_steps / 2) + extra_launches));
-    // sdfr_trace_set_stats(1) / SDFR_TRACE_STATS=1: count the rows of every launch (synchronises after each: a
-    // measurement aid for bench.py's utilisation figure, never on in a timed call)
-    if (g_trace_stats < 0) { const char* e = getenv("SDFR_TRACE_STATS"); g_trace_stats = e ? atoi(e) : 0; }
+    // sdfr_trace_set_stats(1): count the rows of every launch (synchronises after each: a measurement aid for
+    // bench.py's utilisation figure, never on in a timed call; 2 also prints the per-launch counts)
     const int stats = g_trace_stats;
     if (stats && !(cache_dev && latent_lipschitz < 0.f)) {
       int c[4];

@@ -11,7 +11,11 @@ dec, L = setup_dsdf("assets/deepsdf_synth.pt", precision=torch.float32)
 dec = dec.to(dev)
 lat = torch.nn.functional.normalize(torch.tensor([0.6, 0.6, 0.5]), dim=0).to(dev)
 pose = O.yaw_pose(torch.tensor([0.6]), torch.tensor([0.0, 0.0, 5.0])).to(dev)
-sizes = [int(a) for a in sys.argv[1:]] or [64, 256]
+stats = "--stats" in sys.argv          # per-launch ray counts on stderr (sdfr_trace_set_stats(2): synchronises every launch)
+sizes = [int(a) for a in sys.argv[1:] if a != "--stats"] or [64, 256]
+if stats:
+    from sdflabel_b200 import _lib
+    _lib.load().sdfr_trace_set_stats(2)
 for size in sizes:
     K = scenes.intrinsics(size)
     tracer = SphereTracer(K, (size, size)).to(dev)
