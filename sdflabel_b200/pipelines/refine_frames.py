@@ -84,6 +84,32 @@ def initial_params(det: Dict, model_pts: torch.Tensor, estimator: PoseEstimator,
             'latent': np.asarray(det['latent_pred'], dtype=np.float32).copy()}
 
 
+def plan_batches(frames: Sequence[Dict], todo: Sequence[int], max_batch: int) -> List[List]:
+    """Batches of whole frames, at most ``max_batch`` detections each (a larger frame gets batches of its own slices),
+    as lists of (frame_id, detection_index, detection).  The FIRST batch is a quarter of that: nothing overlaps its
+    initialisation (the GPU waits for it), and with the frames of a run sharded over many ranks that pipeline fill is
+    a visible share of a rank's few batches.  Results do not depend on the grouping."""
+    batches, cur = [], []
+    for fid in todo:
+        dets = frames[fid]['detections']
+        items = [(fid, di, d) for di, d in enumerate(dets)]
+        limit = max_batch if batches else max(1, min(max_batch, max(4, max_batch // 4)))
+        while len(items) > limit:
+            if cur:
+                batches.append(cur)
+                cur = []
+            batches.append(items[:limit])
+            items = items[limit:]
+            limit = max_batch
+        if len(cur) + len(items) > limit:
+            batches.append(cur)
+            cur = []
+        cur = cur + items
+    if cur:
+        batches.append(cur)
+    return batches
+
+
 class FrameRefiner:
     """Refines frames on this process's GPU; see the module docstring."""
 
@@ -214,27 +240,7 @@ class FrameRefiner:
         is None where no initial pose was found).  With ``path_autolabels`` every finished frame is dumped as
         ``<idx>.pkl`` and frames whose dump exists are skipped (the reference's resume rule)."""
         todo = [i for i in frame_ids if not (path_autolabels and F.frame_done(path_autolabels, i))]
-        # batches of whole frames, at most max_batch detections each (a larger frame gets a batch of its own slices)
-        # The FIRST batch is a quarter of that: nothing overlaps its initialisation (the GPU waits for it), and with the
-        # frames of a run sharded over many ranks that pipeline fill is a visible share of a rank's few batches.
-        batches, cur = [], []
-        for fid in todo:
-            dets = frames[fid]['detections']
-            items = [(fid, di, d) for di, d in enumerate(dets)]
-            limit = self.max_batch if batches else max(1, min(self.max_batch, max(4, self.max_batch // 4)))
-            while len(items) > limit:
-                if cur:
-                    batches.append(cur)
-                    cur = []
-                batches.append(items[:limit])
-                items = items[limit:]
-                limit = self.max_batch
-            if len(cur) + len(items) > limit:
-                batches.append(cur)
-                cur = []
-            cur = cur + items
-        if cur:
-            batches.append(cur)
+        batches = plan_batches(frames, todo, self.max_batch)
         done: Dict[int, List] = {fid: [None] * len(frames[fid]['detections']) for fid in todo}
         remaining = {fid: len(frames[fid]['detections']) for fid in todo}
         for fid in todo:

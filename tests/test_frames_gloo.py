@@ -130,3 +130,26 @@ def test_sharded_dumps_cover_every_frame_and_resume(tmp_path):
         if f != 2:
             assert pred[f]['location'].shape == (f % 3 + 1, 3) and gt[f]['bbox'].shape == (f % 3 + 1, 4)
     assert not [p for p in os.listdir(out) if p.endswith('.tmp')]     # atomic writes leave nothing behind
+
+
+def test_batch_plan_covers_every_detection_once_in_order():
+    """refine_frames.plan_batches: whole frames per batch up to the limit, oversized frames sliced, the first batch a
+    quarter of the limit (pipeline fill), every detection exactly once and in (frame, detection) order."""
+    from sdflabel_b200.pipelines.refine_frames import plan_batches
+    rng = np.random.RandomState(3)
+    for max_batch in (1, 5, 32):
+        counts = rng.randint(0, 9, size=40).tolist() + [70, 0, 33, 1]
+        frames = [{'detections': [{'id': (f, d)} for d in range(c)]} for f, c in enumerate(counts)]
+        todo = [i for i in range(len(frames)) if i % 7 != 3]
+        batches = plan_batches(frames, todo, max_batch)
+        flat = [(fid, di) for b in batches for fid, di, det in b]
+        assert flat == [(fid, di) for fid in todo for di in range(counts[fid])]
+        assert all(det is frames[fid]['detections'][di] for b in batches for fid, di, det in b)
+        assert all(0 < len(b) <= max_batch for b in batches)
+        assert len(batches[0]) <= max(1, min(max_batch, max(4, max_batch // 4)))
+        # a frame that fits a batch is never split across two
+        for b in batches:
+            for fid in {f for f, _, _ in b}:
+                if counts[fid] <= max(1, min(max_batch, max(4, max_batch // 4))):
+                    assert sum(1 for f, _, _ in b if f == fid) == counts[fid]
+    assert plan_batches([], [], 8) == [] and plan_batches([{'detections': []}], [0], 8) == []
